@@ -1,0 +1,52 @@
+"""basix_b200 -- B200-native (sm_100a) implementation of the FEniCS/basix hot path:
+``FiniteElement.tabulate``, ``push_forward`` / ``pull_back`` and the per-cell DOF
+transformations, behind the reference's Python names.
+
+Everything is computed by hand-written CUDA kernels in ``libbasix_b200.so`` (C ABI in
+``include/basix_b200.h``).  There is no CPU fallback: without the built library, or without a
+CUDA device, the compute calls raise ``RuntimeError``.
+"""
+
+from . import _capi
+from .finite_element import (
+    CellType,
+    DPCVariant,
+    ElementFamily,
+    FiniteElement,
+    LagrangeVariant,
+    MapType,
+    PolysetType,
+    polyset_dim,
+    polyset_nderivs,
+    tabulate_polynomial_set,
+)
+
+__version__ = "0.1.0"
+
+
+def device_count() -> int:
+    return _capi.lib().bx_device_count()
+
+
+def set_device(device: int) -> None:
+    _capi.check(_capi.lib().bx_set_device(int(device)))
+
+
+def kernel_launch_count() -> int:
+    return int(_capi.lib().bx_kernel_launch_count())
+
+
+def index(p: int, q: int | None = None, r: int | None = None) -> int:
+    """``basix.index`` (python/basix/utils.py; cpp/basix/indexing.h:13-34)."""
+    if q is None:
+        return p
+    if r is None:
+        return (p + q + 1) * (p + q) // 2 + q
+    return (p + q + r) * (p + q + r + 1) * (p + q + r + 2) // 6 + (q + r) * (q + r + 1) // 2 + r
+
+
+__all__ = [
+    "CellType", "DPCVariant", "ElementFamily", "FiniteElement", "LagrangeVariant", "MapType", "PolysetType",
+    "device_count", "index", "kernel_launch_count", "polyset_dim", "polyset_nderivs", "set_device",
+    "tabulate_polynomial_set",
+]

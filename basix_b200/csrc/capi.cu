@@ -1,0 +1,574 @@
+// extern "C" boundary (include/basix_b200.h): argument validation, error plumbing and the
+// host-pointer staging pipelines.  No arithmetic lives here; every compute call ends in a CUDA
+// kernel of this library (there is no CPU fallback).
+#include "element.cuh"
+
+#include <algorithm>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+namespace bx
+{
+// ---- globals -------------------------------------------------------------------------------------
+std::atomic<uint64_t> g_launch_count{0};
+namespace
+{
+thread_local std::string t_error;
+}
+void set_last_error(const std::string& msg) { t_error = msg; }
+
+int sm_count()
+{
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  BX_CUDA(cudaGetDevice(&dev));
+  if (dev != cached_dev)
+  {
+    BX_CUDA(cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev));
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+// ---- cell topology: counts per dimension and face types (reference cell.cpp topology) ---------------
+int cell_tdim(int c)
+{
+  switch (c)
+  {
+  case BX_CELL_POINT: return 0;
+  case BX_CELL_INTERVAL: return 1;
+  case BX_CELL_TRIANGLE:
+  case BX_CELL_QUADRILATERAL: return 2;
+  case BX_CELL_TETRAHEDRON:
+  case BX_CELL_HEXAHEDRON:
+  case BX_CELL_PRISM:
+  case BX_CELL_PYRAMID: return 3;
+  default: fail(BX_ERR_INVALID_ARG, "Unsupported cell type");
+  }
+}
+
+int cell_num_entities(int c, int dim)
+{
+  static const int counts[8][4] = {
+      {1, 0, 0, 0},  // point
+      {2, 1, 0, 0},  // interval
+      {3, 3, 1, 0},  // triangle
+      {4, 6, 4, 1},  // tetrahedron
+      {4, 4, 1, 0},  // quadrilateral
+      {8, 12, 6, 1}, // hexahedron
+      {6, 9, 5, 1},  // prism
+      {5, 8, 5, 1},  // pyramid
+  };
+  if (c < 0 or c > 7 or dim < 0 or dim > 3)
+    fail(BX_ERR_INVALID_ARG, "Unsupported cell type");
+  return counts[c][dim];
+}
+
+int cell_sub_entity_type(int c, int dim, int index)
+{
+  const int tdim = cell_tdim(c);
+  if (dim == 0)
+    return BX_CELL_POINT;
+  if (dim == 1)
+    return BX_CELL_INTERVAL;
+  if (dim == tdim)
+    return c;
+  // dim == 2 faces of a 3-D cell
+  switch (c)
+  {
+  case BX_CELL_TETRAHEDRON: return BX_CELL_TRIANGLE;
+  case BX_CELL_HEXAHEDRON: return BX_CELL_QUADRILATERAL;
+  case BX_CELL_PRISM: return (index == 0 or index == 4) ? BX_CELL_TRIANGLE : BX_CELL_QUADRILATERAL;
+  case BX_CELL_PYRAMID: return index == 0 ? BX_CELL_QUADRILATERAL : BX_CELL_TRIANGLE;
+  default: fail(BX_ERR_INVALID_ARG, "Unsupported cell type");
+  }
+}
+
+// reference polyset.cpp:3003-3050
+int polyset_dim(int c, int ptype, int d)
+{
+  if (ptype == BX_POLYSET_STANDARD)
+  {
+    switch (c)
+    {
+    case BX_CELL_POINT: return 1;
+    case BX_CELL_INTERVAL: return d + 1;
+    case BX_CELL_TRIANGLE: return (d + 1) * (d + 2) / 2;
+    case BX_CELL_TETRAHEDRON: return (d + 1) * (d + 2) * (d + 3) / 6;
+    case BX_CELL_QUADRILATERAL: return (d + 1) * (d + 1);
+    case BX_CELL_HEXAHEDRON: return (d + 1) * (d + 1) * (d + 1);
+    case BX_CELL_PRISM: return (d + 1) * (d + 1) * (d + 2) / 2;
+    case BX_CELL_PYRAMID: return (d + 1) * (d + 1) * (d + 1);
+    default: return 1;
+    }
+  }
+  if (ptype == BX_POLYSET_MACROEDGE)
+  {
+    switch (c)
+    {
+    case BX_CELL_POINT: return 1;
+    case BX_CELL_INTERVAL: return 2 * d + 1;
+    case BX_CELL_TRIANGLE: return (d + 1) * (2 * d + 1);
+    case BX_CELL_TETRAHEDRON: return (d + 1) * (2 * d + 1) * (2 * d + 3) / 3;
+    case BX_CELL_QUADRILATERAL: return (2 * d + 1) * (2 * d + 1);
+    case BX_CELL_HEXAHEDRON: return (2 * d + 1) * (2 * d + 1) * (2 * d + 1);
+    default: return 1;
+    }
+  }
+  return 1;
+}
+
+// reference polyset.cpp:3052-3075
+int polyset_nderivs(int c, int n)
+{
+  switch (c)
+  {
+  case BX_CELL_POINT: return 1;
+  case BX_CELL_INTERVAL: return n + 1;
+  case BX_CELL_TRIANGLE:
+  case BX_CELL_QUADRILATERAL: return (n + 1) * (n + 2) / 2;
+  case BX_CELL_TETRAHEDRON:
+  case BX_CELL_HEXAHEDRON:
+  case BX_CELL_PRISM:
+  case BX_CELL_PYRAMID: return (n + 1) * (n + 2) * (n + 3) / 6;
+  default: return 1;
+  }
+}
+
+// ---- forward declarations of the device-pointer implementations ---------------------------------------
+template <typename T>
+void polyset_tabulate_device(int cell, int ptype, int degree, int nd, const T* x, size_t npts, T* P,
+                             cudaStream_t stream);
+void tabulate_device(const bx_element& e, int nd, const double* x, size_t npts, double* basis, size_t out_pts,
+                     cudaStream_t s);
+int tabulate_path(const bx_element& e, int nd);
+int map_value_size(int map_type, int pull, int in_vs, int gdim, int tdim);
+void map_device(int map_type, int pull, const double* U, const double* J, const double* detJ, const double* K,
+                size_t nc, size_t rows, int in_vs, int gdim, int tdim, double* out, cudaStream_t s);
+template <typename T>
+void dof_transform_device(const bx_element& e, int op, T* data, size_t nc, size_t cell_size, int n,
+                          const uint32_t* cell_info, cudaStream_t s);
+
+namespace
+{
+// ---- host-pointer staging -----------------------------------------------------------------------------
+// Two streams, each with its own device buffers; chunk i runs H2D -> kernels -> D2H in order on
+// stream i % 2, so the copies of one chunk overlap the kernels of the other.
+struct DevBuf
+{
+  void* p = nullptr;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  void alloc(size_t bytes)
+  {
+    release();
+    if (bytes)
+      BX_CUDA(cudaMalloc(&p, bytes));
+  }
+  void release()
+  {
+    if (p)
+      cudaFree(p);
+    p = nullptr;
+  }
+  ~DevBuf() { release(); }
+  template <typename T>
+  T* as() const
+  {
+    return static_cast<T*>(p);
+  }
+};
+
+struct TwoStreams
+{
+  cudaStream_t s[2] = {nullptr, nullptr};
+  TwoStreams()
+  {
+    BX_CUDA(cudaStreamCreateWithFlags(&s[0], cudaStreamNonBlocking));
+    BX_CUDA(cudaStreamCreateWithFlags(&s[1], cudaStreamNonBlocking));
+  }
+  void sync()
+  {
+    BX_CUDA(cudaStreamSynchronize(s[0]));
+    BX_CUDA(cudaStreamSynchronize(s[1]));
+  }
+  ~TwoStreams()
+  {
+    for (auto st : s)
+      if (st)
+      {
+        cudaStreamSynchronize(st);
+        cudaStreamDestroy(st);
+      }
+  }
+};
+
+constexpr size_t kStageBytes = size_t(256) << 20; // target size of one staged chunk (largest array)
+
+size_t chunk_units(size_t nunits, size_t bytes_per_unit, size_t align)
+{
+  size_t c = std::max<size_t>(1, kStageBytes / std::max<size_t>(1, bytes_per_unit));
+  c = std::max(align, c / align * align);
+  return std::min(c, nunits);
+}
+
+void require(bool ok, const char* msg)
+{
+  if (!ok)
+    fail(BX_ERR_INVALID_ARG, msg);
+}
+
+void check_mem(int mem) { require(mem == BX_MEM_HOST or mem == BX_MEM_DEVICE, "mem must be BX_MEM_HOST or BX_MEM_DEVICE"); }
+
+template <typename T>
+void polyset_any(int cell, int ptype, int degree, int nd, const T* x, size_t npts, T* P, int mem, bx_stream_t stream)
+{
+  check_mem(mem);
+  if (npts == 0)
+    return;
+  require(x and P, "polyset tabulate: null pointer");
+  const int tdim = cell_tdim(cell);
+  if (mem == BX_MEM_DEVICE)
+  {
+    polyset_tabulate_device<T>(cell, ptype, degree, nd, x, npts, P, static_cast<cudaStream_t>(stream));
+    return;
+  }
+  const size_t rows = size_t(polyset_nderivs(cell, nd)) * polyset_dim(cell, ptype, degree);
+  const size_t chunk = chunk_units(npts, rows * sizeof(T), 32);
+  TwoStreams st;
+  DevBuf dx[2], dP[2];
+  for (int b = 0; b < 2; ++b)
+  {
+    dx[b].alloc(chunk * std::max(tdim, 1) * sizeof(T));
+    dP[b].alloc(chunk * rows * sizeof(T));
+  }
+  size_t i = 0;
+  for (size_t p0 = 0; p0 < npts; p0 += chunk, ++i)
+  {
+    const int b = int(i & 1);
+    const size_t np = std::min(chunk, npts - p0);
+    if (tdim > 0)
+      BX_CUDA(cudaMemcpyAsync(dx[b].p, x + p0 * tdim, np * tdim * sizeof(T), cudaMemcpyHostToDevice, st.s[b]));
+    polyset_tabulate_device<T>(cell, ptype, degree, nd, dx[b].as<T>(), np, dP[b].as<T>(), st.s[b]);
+    // table rows are npts apart on the host, np apart on the device
+    BX_CUDA(cudaMemcpy2DAsync(P + p0, npts * sizeof(T), dP[b].p, np * sizeof(T), np * sizeof(T), rows,
+                              cudaMemcpyDeviceToHost, st.s[b]));
+  }
+  st.sync();
+}
+
+void tabulate_any(const bx_element& e, int nd, const double* x, size_t npts, int tdim_x, double* basis, int mem,
+                  bx_stream_t stream)
+{
+  check_mem(mem);
+  if (tdim_x != e.tdim)
+    fail(BX_ERR_INVALID_ARG, "Point dim (" + std::to_string(tdim_x) + ") does not match element dim ("
+                                 + std::to_string(e.tdim) + ").");
+  require(nd >= 0, "tabulate: negative derivative order");
+  if (npts == 0)
+    return;
+  require(x and basis, "tabulate: null pointer");
+  if (mem == BX_MEM_DEVICE)
+  {
+    tabulate_device(e, nd, x, npts, basis, npts, static_cast<cudaStream_t>(stream));
+    return;
+  }
+  const int nder = polyset_nderivs(e.cell_type, nd);
+  const size_t per_pt = size_t(nder) * e.N * sizeof(double);
+  const size_t chunk = chunk_units(npts, per_pt, 32);
+  TwoStreams st;
+  DevBuf dx[2], dout[2];
+  for (int b = 0; b < 2; ++b)
+  {
+    dx[b].alloc(chunk * e.tdim * sizeof(double));
+    dout[b].alloc(chunk * per_pt);
+  }
+  size_t i = 0;
+  for (size_t p0 = 0; p0 < npts; p0 += chunk, ++i)
+  {
+    const int b = int(i & 1);
+    const size_t np = std::min(chunk, npts - p0);
+    BX_CUDA(cudaMemcpyAsync(dx[b].p, x + p0 * e.tdim, np * e.tdim * sizeof(double), cudaMemcpyHostToDevice, st.s[b]));
+    tabulate_device(e, nd, dx[b].as<double>(), np, dout[b].as<double>(), np, st.s[b]);
+    // each derivative slab of the chunk is one contiguous run of np * N values on both sides
+    BX_CUDA(cudaMemcpy2DAsync(basis + p0 * e.N, npts * e.N * sizeof(double), dout[b].p, np * e.N * sizeof(double),
+                              np * e.N * sizeof(double), nder, cudaMemcpyDeviceToHost, st.s[b]));
+  }
+  st.sync();
+}
+
+void map_any(int map_type, int pull, const double* U, const double* J, const double* detJ, const double* K, size_t nc,
+             size_t rows, int in_vs, int gdim, int tdim, double* out, int mem, bx_stream_t stream)
+{
+  check_mem(mem);
+  require(in_vs > 0 and gdim >= 1 and gdim <= 3 and tdim >= 1 and tdim <= 3, "map: bad value size or Jacobian shape");
+  const int out_vs = map_value_size(map_type, pull, in_vs, gdim, tdim);
+  if (nc == 0 or rows == 0)
+    return;
+  require(U and J and detJ and K and out, "map: null pointer");
+  if (mem == BX_MEM_DEVICE)
+  {
+    map_device(map_type, pull, U, J, detJ, K, nc, rows, in_vs, gdim, tdim, out, static_cast<cudaStream_t>(stream));
+    return;
+  }
+  const size_t jsz = size_t(gdim) * tdim;
+  const size_t per_cell = rows * std::max(in_vs, out_vs) * sizeof(double);
+  const size_t chunk = chunk_units(nc, per_cell, 1);
+  TwoStreams st;
+  DevBuf dU[2], dJ[2], dd[2], dK[2], dout[2];
+  for (int b = 0; b < 2; ++b)
+  {
+    dU[b].alloc(chunk * rows * in_vs * sizeof(double));
+    dJ[b].alloc(chunk * jsz * sizeof(double));
+    dd[b].alloc(chunk * sizeof(double));
+    dK[b].alloc(chunk * jsz * sizeof(double));
+    dout[b].alloc(chunk * rows * out_vs * sizeof(double));
+  }
+  size_t i = 0;
+  for (size_t c0 = 0; c0 < nc; c0 += chunk, ++i)
+  {
+    const int b = int(i & 1);
+    const size_t n = std::min(chunk, nc - c0);
+    cudaStream_t s = st.s[b];
+    BX_CUDA(cudaMemcpyAsync(dU[b].p, U + c0 * rows * in_vs, n * rows * in_vs * sizeof(double), cudaMemcpyHostToDevice, s));
+    BX_CUDA(cudaMemcpyAsync(dJ[b].p, J + c0 * jsz, n * jsz * sizeof(double), cudaMemcpyHostToDevice, s));
+    BX_CUDA(cudaMemcpyAsync(dd[b].p, detJ + c0, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    BX_CUDA(cudaMemcpyAsync(dK[b].p, K + c0 * jsz, n * jsz * sizeof(double), cudaMemcpyHostToDevice, s));
+    map_device(map_type, pull, dU[b].as<double>(), dJ[b].as<double>(), dd[b].as<double>(), dK[b].as<double>(), n, rows,
+               in_vs, gdim, tdim, dout[b].as<double>(), s);
+    BX_CUDA(cudaMemcpyAsync(out + c0 * rows * out_vs, dout[b].p, n * rows * out_vs * sizeof(double),
+                            cudaMemcpyDeviceToHost, s));
+  }
+  st.sync();
+}
+
+template <typename T>
+void transform_any(const bx_element* e, int op, T* data, size_t nc, size_t cell_size, int n, const uint32_t* cell_info,
+                   int mem, bx_stream_t stream)
+{
+  check_mem(mem);
+  require(e != nullptr, "T_apply: null element");
+  if (nc == 0)
+    return;
+  require(data and cell_info, "T_apply: null pointer");
+  if (mem == BX_MEM_DEVICE)
+  {
+    dof_transform_device<T>(*e, op, data, nc, cell_size, n, cell_info, static_cast<cudaStream_t>(stream));
+    return;
+  }
+  // validate once (throws on bad arguments) and return early for identity elements, before staging
+  if (e->identity or e->tdim < 2 or e->slots.empty())
+  {
+    dof_transform_device<T>(*e, op, static_cast<T*>(nullptr), 0, cell_size, n, nullptr, nullptr);
+    return;
+  }
+  const size_t chunk = chunk_units(nc, cell_size * sizeof(T), 1);
+  TwoStreams st;
+  DevBuf dd[2], dc[2];
+  for (int b = 0; b < 2; ++b)
+  {
+    dd[b].alloc(chunk * cell_size * sizeof(T));
+    dc[b].alloc(chunk * sizeof(uint32_t));
+  }
+  size_t i = 0;
+  for (size_t c0 = 0; c0 < nc; c0 += chunk, ++i)
+  {
+    const int b = int(i & 1);
+    const size_t m = std::min(chunk, nc - c0);
+    cudaStream_t s = st.s[b];
+    BX_CUDA(cudaMemcpyAsync(dd[b].p, data + c0 * cell_size, m * cell_size * sizeof(T), cudaMemcpyHostToDevice, s));
+    BX_CUDA(cudaMemcpyAsync(dc[b].p, cell_info + c0, m * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    dof_transform_device<T>(*e, op, dd[b].as<T>(), m, cell_size, n, dc[b].as<uint32_t>(), s);
+    BX_CUDA(cudaMemcpyAsync(data + c0 * cell_size, dd[b].p, m * cell_size * sizeof(T), cudaMemcpyDeviceToHost, s));
+  }
+  st.sync();
+}
+} // namespace
+} // namespace bx
+
+// =====================================================================================================
+extern "C"
+{
+  const char* bx_last_error(void) { return bx::t_error.c_str(); }
+  const char* bx_version(void) { return "basix_b200 0.1.0 (sm_100a)"; }
+
+  int bx_device_count(void)
+  {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+    {
+      cudaGetLastError();
+      return 0;
+    }
+    return n;
+  }
+
+  int bx_set_device(int device)
+  {
+    return bx::guarded([&]() { BX_CUDA(cudaSetDevice(device)); });
+  }
+
+  int bx_stream_synchronize(bx_stream_t stream)
+  {
+    return bx::guarded([&]() { BX_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream))); });
+  }
+
+  uint64_t bx_kernel_launch_count(void) { return bx::g_launch_count.load(); }
+
+  int bx_polyset_dim(int cell_type, int polyset_type, int degree)
+  {
+    return bx::polyset_dim(cell_type, polyset_type, degree);
+  }
+  int bx_polyset_nderivs(int cell_type, int nderiv) { return bx::polyset_nderivs(cell_type, nderiv); }
+
+  int bx_polyset_tabulate_f64(int cell_type, int polyset_type, int degree, int nderiv, const double* x, size_t npts,
+                              double* P, int mem, bx_stream_t stream)
+  {
+    return bx::guarded([&]() { bx::polyset_any<double>(cell_type, polyset_type, degree, nderiv, x, npts, P, mem, stream); });
+  }
+  int bx_polyset_tabulate_f32(int cell_type, int polyset_type, int degree, int nderiv, const float* x, size_t npts,
+                              float* P, int mem, bx_stream_t stream)
+  {
+    return bx::guarded([&]() { bx::polyset_any<float>(cell_type, polyset_type, degree, nderiv, x, npts, P, mem, stream); });
+  }
+
+  int bx_element_create_from_arrays(const bx_element_desc* desc, bx_element** out)
+  {
+    return bx::guarded(
+        [&]()
+        {
+          bx::require(desc and out, "create_element: null argument");
+          *out = nullptr;
+          *out = bx::element_from_desc(*desc);
+        });
+  }
+
+  void bx_element_destroy(bx_element* e) { delete e; }
+
+  int bx_element_info(const bx_element* e, int32_t info[10])
+  {
+    return bx::guarded(
+        [&]()
+        {
+          bx::require(e and info, "element_info: null argument");
+          info[0] = e->cell_type;
+          info[1] = e->polyset_type;
+          info[2] = e->tdim;
+          info[3] = e->ndofs;
+          info[4] = e->vs;
+          info[5] = e->map_type;
+          info[6] = e->superdegree;
+          info[7] = e->perms;
+          info[8] = e->identity;
+          info[9] = e->psize;
+        });
+  }
+
+  int bx_element_tabulate_shape(const bx_element* e, int nd, size_t npts, size_t shape[4])
+  {
+    return bx::guarded(
+        [&]()
+        {
+          bx::require(e and shape, "tabulate_shape: null argument");
+          shape[0] = size_t(bx::polyset_nderivs(e->cell_type, nd));
+          shape[1] = npts;
+          shape[2] = size_t(e->ndofs);
+          shape[3] = size_t(e->vs);
+        });
+  }
+
+  int bx_element_net_operator(const bx_element* e, int op, uint32_t cell_info, int32_t* src, double* A)
+  {
+    return bx::guarded(
+        [&]()
+        {
+          bx::require(e != nullptr, "net_operator: null element");
+          bx::require(op >= 0 and op <= 7, "net_operator: unknown operator");
+          static const int kind_of[8] = {0, 1, 2, 3, 0, 2, 1, 3};
+          bx::element_net_operator(*e, kind_of[op], cell_info, src, A);
+        });
+  }
+
+  int bx_element_tabulate_path(const bx_element* e, int nd) { return e ? bx::tabulate_path(*e, nd) : -1; }
+
+  int bx_tabulate_f64(const bx_element* e, int nd, const double* x, size_t npts, int tdim_x, double* basis, int mem,
+                      bx_stream_t stream)
+  {
+    return bx::guarded(
+        [&]()
+        {
+          bx::require(e != nullptr, "tabulate: null element");
+          bx::tabulate_any(*e, nd, x, npts, tdim_x, basis, mem, stream);
+        });
+  }
+
+  int bx_map_value_size(int map_type, int pull, int in_vs, int gdim, int tdim)
+  {
+    int v = -1;
+    bx::guarded([&]() { v = bx::map_value_size(map_type, pull, in_vs, gdim, tdim); });
+    return v;
+  }
+
+  int bx_map_f64(int map_type, int pull, const double* U, const double* J, const double* detJ, const double* K,
+                 size_t nc, size_t rows, int in_vs, int gdim, int tdim, double* out, int mem, bx_stream_t stream)
+  {
+    return bx::guarded([&]() { bx::map_any(map_type, pull, U, J, detJ, K, nc, rows, in_vs, gdim, tdim, out, mem, stream); });
+  }
+
+  int bx_push_forward_f64(const bx_element* e, const double* U, const double* J, const double* detJ, const double* K,
+                          size_t nc, size_t rows, int in_vs, int gdim, int tdim, double* out, int mem,
+                          bx_stream_t stream)
+  {
+    return bx::guarded(
+        [&]()
+        {
+          bx::require(e != nullptr, "push_forward: null element");
+          bx::map_any(e->map_type, 0, U, J, detJ, K, nc, rows, in_vs, gdim, tdim, out, mem, stream);
+        });
+  }
+
+  int bx_pull_back_f64(const bx_element* e, const double* u, const double* J, const double* detJ, const double* K,
+                       size_t nc, size_t rows, int in_vs, int gdim, int tdim, double* out, int mem, bx_stream_t stream)
+  {
+    return bx::guarded(
+        [&]()
+        {
+          bx::require(e != nullptr, "pull_back: null element");
+          bx::map_any(e->map_type, 1, u, J, detJ, K, nc, rows, in_vs, gdim, tdim, out, mem, stream);
+        });
+  }
+
+  int bx_T_apply_f64(const bx_element* e, int op, double* data, size_t nc, size_t cell_size, int n,
+                     const uint32_t* cell_info, int mem, bx_stream_t stream)
+  {
+    return bx::guarded([&]() { bx::transform_any<double>(e, op, data, nc, cell_size, n, cell_info, mem, stream); });
+  }
+  int bx_T_apply_f32(const bx_element* e, int op, float* data, size_t nc, size_t cell_size, int n,
+                     const uint32_t* cell_info, int mem, bx_stream_t stream)
+  {
+    return bx::guarded([&]() { bx::transform_any<float>(e, op, data, nc, cell_size, n, cell_info, mem, stream); });
+  }
+  int bx_T_apply_i32(const bx_element* e, int op, int32_t* data, size_t nc, size_t cell_size, int n,
+                     const uint32_t* cell_info, int mem, bx_stream_t stream)
+  {
+    return bx::guarded([&]() { bx::transform_any<int32_t>(e, op, data, nc, cell_size, n, cell_info, mem, stream); });
+  }
+
+  int bx_permute_i32(const bx_element* e, int inverse, int32_t* d, size_t nc, const uint32_t* cell_info, int mem,
+                     bx_stream_t stream)
+  {
+    return bx::guarded(
+        [&]()
+        {
+          bx::require(e != nullptr, "permute: null element");
+          if (!e->perms)
+            bx::fail(BX_ERR_RUNTIME, "The DOF transformations for this element are not permutations");
+          // permute -> permute_data<false>(_eperm) = T_apply's operator; permute_inv ->
+          // permute_data<true>(_eperm_inv) = Tt_apply's operator (finite-element.h:800-843)
+          bx::transform_any<int32_t>(e, inverse ? BX_TT_APPLY : BX_T_APPLY, d, nc, size_t(e->ndofs), 1, cell_info, mem,
+                                     stream);
+        });
+  }
+}

@@ -1,0 +1,491 @@
+// Host-side construction of bx_element (tables + device mirror).
+//
+// Reference behaviour restated here (set-up only, runs once per element on the host):
+//   permutation / identity detection        cpp/basix/finite-element.cpp:1260-1295
+//   _eperm / _eperm_inv from the matrices   cpp/basix/finite-element.cpp:1302-1347
+//   _etrans, _etransT, _etrans_inv, _etrans_invT (M^-1 = M^2 / M^3 for rotations)
+//                                           cpp/basix/finite-element.cpp:1349-1445
+//   order of application per cell_info      cpp/basix/finite-element.h:1703-1837
+#include "element.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <limits>
+#include <memory>
+#include <numeric>
+
+namespace bx
+{
+namespace
+{
+// ---- tiny dense helpers (n <= a few dozen) -------------------------------------------------------
+using Mat = std::vector<double>; // row-major n x n
+
+Mat mat_identity(int n)
+{
+  Mat I(size_t(n) * n, 0.0);
+  for (int i = 0; i < n; ++i)
+    I[size_t(i) * n + i] = 1.0;
+  return I;
+}
+Mat mat_mul(const Mat& A, const Mat& B, int n)
+{
+  Mat C(size_t(n) * n, 0.0);
+  for (int i = 0; i < n; ++i)
+    for (int k = 0; k < n; ++k)
+    {
+      const double a = A[size_t(i) * n + k];
+      if (a == 0.0)
+        continue;
+      for (int j = 0; j < n; ++j)
+        C[size_t(i) * n + j] += a * B[size_t(k) * n + j];
+    }
+  return C;
+}
+Mat mat_transpose(const Mat& A, int n)
+{
+  Mat T(size_t(n) * n);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j)
+      T[size_t(j) * n + i] = A[size_t(i) * n + j];
+  return T;
+}
+
+template <typename T>
+T* upload(const std::vector<T>& v)
+{
+  if (v.empty())
+    return nullptr;
+  T* d = nullptr;
+  BX_CUDA(cudaMalloc(&d, v.size() * sizeof(T)));
+  BX_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return d;
+}
+
+int num_states(int mask) { return mask + 1; }
+} // namespace
+
+bx_element* element_from_desc(const bx_element_desc& d)
+{
+  if (d.cell_type < BX_CELL_POINT or d.cell_type > BX_CELL_PYRAMID)
+    fail(BX_ERR_INVALID_ARG, "create_element: unknown cell type");
+  if (d.ndofs <= 0 or d.value_size <= 0 or !d.coeffs)
+    fail(BX_ERR_INVALID_ARG, "create_element: empty coefficient matrix");
+  auto e = std::make_unique<bx_element>();
+  e->cell_type = d.cell_type;
+  e->polyset_type = d.polyset_type;
+  e->degree = d.degree;
+  e->superdegree = d.embedded_superdegree;
+  e->map_type = d.map_type;
+  e->ndofs = d.ndofs;
+  e->vs = d.value_size;
+  e->tdim = cell_tdim(d.cell_type);
+  e->psize = polyset_dim(d.cell_type, d.polyset_type, d.embedded_superdegree);
+  {
+    // device is optional at construction: host tables are always built
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) == cudaSuccess and ndev > 0)
+    {
+      BX_CUDA(cudaGetDevice(&e->device));
+      e->on_device = true;
+    }
+    else
+      cudaGetLastError();
+  }
+
+  const int ndofs = e->ndofs, vs = e->vs, psize = e->psize;
+  e->coeffs.assign(d.coeffs, d.coeffs + size_t(ndofs) * vs * psize);
+  if (d.n_dof_ordering != 0)
+  {
+    if (d.n_dof_ordering != ndofs or !d.dof_ordering)
+      fail(BX_ERR_INVALID_ARG, "Incorrect number of dofs in ordering.");
+    e->dof_ordering.assign(d.dof_ordering, d.dof_ordering + ndofs);
+    std::vector<int> check(ndofs, 0);
+    for (int q : e->dof_ordering)
+    {
+      if (q < 0 or q >= ndofs)
+        fail(BX_ERR_INVALID_ARG, "Out of range: dof_ordering.");
+      check[q] += 1;
+    }
+    for (int q : check)
+      if (q != 1)
+        fail(BX_ERR_INVALID_ARG, "Dof ordering not a permutation.");
+  }
+
+  // ---- contraction operand: rows = output column (dof_ordering[dof]*vs + j), zero padded to 8 x 4 ---
+  e->N = ndofs * vs;
+  e->K = psize;
+  e->Npad = int(ceil_div(e->N, 8) * 8);
+  e->Kpad = int(ceil_div(e->K, 4) * 4);
+  e->Cp.assign(size_t(e->Npad) * e->Kpad, 0.0);
+  for (int dof = 0; dof < ndofs; ++dof)
+  {
+    const int tgt = e->dof_ordering.empty() ? dof : e->dof_ordering[dof];
+    for (int j = 0; j < vs; ++j)
+      for (int k = 0; k < psize; ++k)
+        e->Cp[size_t(tgt * vs + j) * e->Kpad + k] = e->coeffs[size_t(dof) * vs * psize + size_t(j) * psize + k];
+  }
+  if (e->on_device)
+    e->d_Cp = upload(e->Cp);
+
+  // ---- entity dofs -----------------------------------------------------------------------------------
+  if (!d.entity_dof_offsets or !d.entity_dofs)
+    fail(BX_ERR_INVALID_ARG, "create_element: entity dofs missing");
+  e->edofs.resize(e->tdim + 1);
+  {
+    int ent = 0;
+    for (int dim = 0; dim <= e->tdim; ++dim)
+    {
+      const int ne = cell_num_entities(d.cell_type, dim);
+      e->edofs[dim].resize(ne);
+      for (int i = 0; i < ne; ++i, ++ent)
+      {
+        const int b = d.entity_dof_offsets[ent], f = d.entity_dof_offsets[ent + 1];
+        if (b < 0 or f < b)
+          fail(BX_ERR_INVALID_ARG, "create_element: bad entity dof offsets");
+        for (int k = b; k < f; ++k)
+        {
+          if (d.entity_dofs[k] < 0 or d.entity_dofs[k] >= ndofs)
+            fail(BX_ERR_INVALID_ARG, "create_element: entity dof out of range");
+          e->edofs[dim][i].push_back(d.entity_dofs[k]);
+        }
+      }
+    }
+  }
+
+  // ---- entity transformations ------------------------------------------------------------------------
+  auto take = [&](int cls, const double* p, int n, int ntrans)
+  {
+    e->etrans_dim[cls] = p ? n : -1;
+    if (p and n > 0)
+      e->etrans[cls].assign(p, p + size_t(ntrans) * n * n);
+  };
+  for (auto& v : e->etrans_dim)
+    v = -1;
+  take(BX_CELL_INTERVAL, d.etrans_interval, d.etrans_interval_dim, 1);
+  take(BX_CELL_TRIANGLE, d.etrans_triangle, d.etrans_triangle_dim, 2);
+  take(BX_CELL_QUADRILATERAL, d.etrans_quadrilateral, d.etrans_quadrilateral_dim, 2);
+
+  // Permutation / identity detection, same test as finite-element.cpp:1260-1295
+  e->perms = true;
+  e->identity = true;
+  {
+    const double eps = 10.0 * d.degree * d.degree * std::numeric_limits<double>::epsilon();
+    for (int cls : {BX_CELL_INTERVAL, BX_CELL_TRIANGLE, BX_CELL_QUADRILATERAL})
+    {
+      const int n = e->etrans_dim[cls];
+      if (n <= 0)
+        continue;
+      const int ntrans = cls == BX_CELL_INTERVAL ? 1 : 2;
+      for (int i = 0; e->perms and i < ntrans; ++i)
+      {
+        const double* M = e->etrans[cls].data() + size_t(i) * n * n;
+        for (int row = 0; row < n; ++row)
+        {
+          double rmin = 0, rmax = 0, rtot = 0;
+          for (int k = 0; k < n; ++k)
+          {
+            const double r = M[size_t(row) * n + k];
+            rmin = std::min(r, rmin);
+            rmax = std::max(r, rmax);
+            rtot += r;
+          }
+          if ((n != 1 and std::abs(rmin) > eps) or std::abs(rmax - 1.0) > eps or std::abs(rtot - 1.0) > eps)
+          {
+            e->perms = false;
+            e->identity = false;
+            break;
+          }
+          if (std::abs(M[size_t(row) * n + row] - 1) > eps)
+            e->identity = false;
+        }
+      }
+      if (!e->perms)
+        break;
+    }
+  }
+
+  e->dof_slot.assign(ndofs, -1);
+  e->dof_loc.assign(ndofs, 0);
+  e->lo_dof = e->hi_dof = 0;
+  if (e->identity or e->tdim < 2)
+    return e.release();
+
+  // ---- slots in the reference's processing order ------------------------------------------------------
+  const int nfaces = e->tdim == 3 ? int(e->edofs[2].size()) : 0;
+  const int face_start = e->tdim == 3 ? 3 * nfaces : 0;
+  int dofstart = 0;
+  for (auto& v : e->edofs[0])
+    dofstart += int(v.size());
+  auto add_slot = [&](int shift, int mask, int cls, const std::vector<int>& dofs)
+  {
+    bx_element::Slot s;
+    s.shift = shift;
+    s.mask = mask;
+    s.cls = cls;
+    s.first = dofstart;
+    s.dofs = dofs;
+    s.dim = int(dofs.size());
+    dofstart += s.dim;
+    if (s.dim == 0)
+      return;
+    if (e->etrans_dim[cls] != s.dim)
+      fail(BX_ERR_INVALID_ARG, "create_element: entity transformation size does not match entity dofs");
+    if (!e->perms)
+    {
+      // transform_data walks contiguous blocks (running dofstart), finite-element.h:1772-1835
+      s.dofs.resize(s.dim);
+      std::iota(s.dofs.begin(), s.dofs.end(), s.first);
+      if (s.first + s.dim > ndofs)
+        fail(BX_ERR_INVALID_ARG, "create_element: entity dof blocks exceed the element dimension");
+    }
+    e->slots.push_back(std::move(s));
+  };
+  for (size_t ed = 0; ed < e->edofs[1].size(); ++ed)
+    add_slot(face_start + int(ed), 1, BX_CELL_INTERVAL, e->edofs[1][ed]);
+  if (e->tdim == 3)
+    for (int f = 0; f < nfaces; ++f)
+      add_slot(3 * f, 7, cell_sub_entity_type(d.cell_type, 2, f), e->edofs[2][f]);
+
+  int lo = ndofs, hi = 0;
+  for (size_t s = 0; s < e->slots.size(); ++s)
+    for (int l = 0; l < e->slots[s].dim; ++l)
+    {
+      const int dof = e->slots[s].dofs[l];
+      e->dof_slot[dof] = int16_t(s);
+      e->dof_loc[dof] = int16_t(l);
+      lo = std::min(lo, dof);
+      hi = std::max(hi, dof + 1);
+    }
+  e->lo_dof = lo < hi ? lo : 0;
+  e->hi_dof = lo < hi ? hi : 0;
+
+  // ---- per-class step operators -----------------------------------------------------------------------
+  // index maps (permutation elements): new[r] = old[map[r]]
+  std::array<std::array<std::vector<int>, 2>, 8> fwd, inv;
+  // matrices (general elements): new = M old ; [cls][i] for the four stored flavours
+  std::array<std::array<Mat, 2>, 8> M_, MT_, Minv_, MinvT_;
+  for (int cls : {BX_CELL_INTERVAL, BX_CELL_TRIANGLE, BX_CELL_QUADRILATERAL})
+  {
+    const int n = e->etrans_dim[cls];
+    if (n <= 0)
+      continue;
+    const int ntrans = cls == BX_CELL_INTERVAL ? 1 : 2;
+    for (int i = 0; i < ntrans; ++i)
+    {
+      const double* T = e->etrans[cls].data() + size_t(i) * n * n;
+      if (e->perms)
+      {
+        std::vector<int> perm(n, 0), iperm(n, 0);
+        for (int row = 0; row < n; ++row)
+          for (int col = 0; col < n; ++col)
+            if (T[size_t(row) * n + col] > 0.5)
+            {
+              perm[row] = col;
+              iperm[col] = row;
+              break;
+            }
+        fwd[cls][i] = perm;
+        inv[cls][i] = iperm;
+      }
+      else
+      {
+        Mat M(T, T + size_t(n) * n);
+        Mat Minv = M;
+        if (cls == BX_CELL_QUADRILATERAL and i == 0)
+          Minv = mat_mul(mat_mul(M, M, n), M, n);
+        else if (cls == BX_CELL_TRIANGLE and i == 0)
+          Minv = mat_mul(M, M, n);
+        M_[cls][i] = M;
+        MT_[cls][i] = mat_transpose(M, n);
+        Minv_[cls][i] = Minv;
+        MinvT_[cls][i] = mat_transpose(Minv, n);
+      }
+    }
+  }
+
+  // ---- compose net operator per (op, slot/class, state) --------------------------------------------
+  // op kinds: 0 T, 1 Tt, 2 Tt_inv, 3 Tinv.  `post` (reflect after rotate) for 1 and 3.
+  std::vector<int4> slot_info(e->slots.size());
+  std::vector<int2> slot_mat(e->slots.size());
+  int gsize = 0;
+  for (size_t s = 0; s < e->slots.size(); ++s)
+  {
+    slot_info[s] = make_int4(e->slots[s].shift, e->slots[s].mask, e->slots[s].dim, gsize);
+    gsize += num_states(e->slots[s].mask) * e->slots[s].dim;
+  }
+  std::array<int, 8> cls_base{};
+  int msize = 0;
+  if (!e->perms)
+    for (int cls : {BX_CELL_INTERVAL, BX_CELL_TRIANGLE, BX_CELL_QUADRILATERAL})
+    {
+      const int n = e->etrans_dim[cls];
+      cls_base[cls] = msize;
+      if (n > 0)
+        msize += (cls == BX_CELL_INTERVAL ? 2 : 8) * n * n;
+    }
+  for (size_t s = 0; s < e->slots.size(); ++s)
+    slot_mat[s] = make_int2(e->slots[s].first, cls_base[e->slots[s].cls]);
+
+  std::vector<int16_t> gather(e->perms ? size_t(4) * gsize : 0);
+  std::vector<double> mats(e->perms ? 0 : size_t(4) * msize);
+  for (int op = 0; op < 4; ++op)
+  {
+    const bool post = (op == 1 or op == 3);
+    if (e->perms)
+    {
+      const auto& steps = (op == 0 or op == 2) ? fwd : inv; // _eperm for T/Tt_inv, _eperm_inv for Tt/Tinv
+      for (size_t s = 0; s < e->slots.size(); ++s)
+      {
+        const auto& sl = e->slots[s];
+        const int n = sl.dim;
+        for (int state = 0; state < num_states(sl.mask); ++state)
+        {
+          std::vector<int> src(n);
+          std::iota(src.begin(), src.end(), 0);
+          auto apply = [&](const std::vector<int>& m)
+          {
+            std::vector<int> t(n);
+            for (int r = 0; r < n; ++r)
+              t[r] = src[m[r]];
+            src.swap(t);
+          };
+          if (sl.mask == 1)
+          {
+            if (state & 1)
+              apply(steps[sl.cls][0]);
+          }
+          else
+          {
+            const int refl = state & 1, rots = (state >> 1) & 3;
+            if (!post and refl)
+              apply(steps[sl.cls][1]);
+            for (int r = 0; r < rots; ++r)
+              apply(steps[sl.cls][0]);
+            if (post and refl)
+              apply(steps[sl.cls][1]);
+          }
+          for (int r = 0; r < n; ++r)
+            gather[size_t(op) * gsize + slot_info[s].w + state * n + r] = int16_t(sl.dofs[src[r]]);
+        }
+      }
+    }
+    else
+    {
+      const auto& steps = op == 0 ? M_ : op == 1 ? MT_ : op == 2 ? MinvT_ : Minv_;
+      for (int cls : {BX_CELL_INTERVAL, BX_CELL_TRIANGLE, BX_CELL_QUADRILATERAL})
+      {
+        const int n = e->etrans_dim[cls];
+        if (n <= 0)
+          continue;
+        const int nst = cls == BX_CELL_INTERVAL ? 2 : 8;
+        for (int state = 0; state < nst; ++state)
+        {
+          Mat A = mat_identity(n);
+          if (cls == BX_CELL_INTERVAL)
+          {
+            if (state & 1)
+              A = mat_mul(steps[cls][0], A, n);
+          }
+          else
+          {
+            const int refl = state & 1, rots = (state >> 1) & 3;
+            if (!post and refl)
+              A = mat_mul(steps[cls][1], A, n);
+            for (int r = 0; r < rots; ++r)
+              A = mat_mul(steps[cls][0], A, n);
+            if (post and refl)
+              A = mat_mul(steps[cls][1], A, n);
+          }
+          std::copy(A.begin(), A.end(), mats.begin() + size_t(op) * msize + cls_base[cls] + size_t(state) * n * n);
+        }
+      }
+    }
+  }
+  e->gather_size = gsize;
+  e->mats_size = msize;
+  e->h_slot_info = slot_info;
+  e->h_slot_mat = slot_mat;
+  e->h_gather = gather;
+  e->h_mats = mats;
+  if (e->on_device)
+  {
+    e->d_dof_slot = upload(e->dof_slot);
+    e->d_dof_loc = upload(e->dof_loc);
+    e->d_slot_info = upload(slot_info);
+    e->d_slot_mat = upload(slot_mat);
+    e->d_gather = upload(gather);
+    e->d_mats = upload(mats);
+  }
+  return e.release();
+}
+
+void require_device(const bx_element& e)
+{
+  if (!e.on_device)
+    fail(BX_ERR_CUDA, "basix_b200: no usable CUDA device (the element holds host tables only; there is no CPU fallback)");
+}
+
+void element_net_operator(const bx_element& e, int kind, uint32_t cell_info, int32_t* src, double* A)
+{
+  if (kind < 0 or kind > 3)
+    fail(BX_ERR_INVALID_ARG, "net_operator: kind must be 0..3");
+  const int n = e.ndofs;
+  if (src)
+  {
+    if (!e.perms)
+      fail(BX_ERR_RUNTIME, "The DOF transformations for this element are not permutations");
+    for (int i = 0; i < n; ++i)
+      src[i] = i;
+  }
+  if (A)
+  {
+    std::fill(A, A + size_t(n) * n, 0.0);
+    for (int i = 0; i < n; ++i)
+      A[size_t(i) * n + i] = 1.0;
+  }
+  if (e.identity or e.tdim < 2)
+    return;
+  for (size_t s = 0; s < e.slots.size(); ++s)
+  {
+    const auto& sl = e.slots[s];
+    const int state = int((cell_info >> sl.shift) & uint32_t(sl.mask));
+    if (state == 0)
+      continue;
+    for (int l = 0; l < sl.dim; ++l)
+    {
+      const int dof = sl.dofs[l];
+      if (e.perms)
+      {
+        const int sd = e.h_gather[size_t(kind) * e.gather_size + e.h_slot_info[s].w + state * sl.dim + l];
+        if (src)
+          src[dof] = sd;
+        if (A)
+        {
+          A[size_t(dof) * n + dof] = 0.0;
+          A[size_t(dof) * n + sd] = 1.0;
+        }
+      }
+      else if (A)
+      {
+        const double* row
+            = e.h_mats.data() + size_t(kind) * e.mats_size + e.h_slot_mat[s].y + (size_t(state) * sl.dim + l) * sl.dim;
+        for (int i = 0; i < sl.dim; ++i)
+          A[size_t(dof) * n + sl.first + i] = row[i];
+      }
+    }
+  }
+}
+} // namespace bx
+
+bx_element::~bx_element()
+{
+  // best effort; errors at teardown are ignored
+  cudaFree(d_Cp);
+  cudaFree(d_dof_slot);
+  cudaFree(d_dof_loc);
+  cudaFree(d_slot_info);
+  cudaFree(d_gather);
+  cudaFree(d_slot_mat);
+  cudaFree(d_mats);
+}

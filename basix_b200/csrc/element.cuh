@@ -1,0 +1,88 @@
+// Host-side element object + its device mirror.
+//
+// Mirrors the immutable members of the reference's basix::FiniteElement<F> that the hot path
+// reads (cpp/basix/finite-element.h:1429-1554).  The DOF-transformation data is NOT kept in the
+// reference's "prepared swap sequence / in-place LU" form (precompute.h); instead, at creation
+// time, the host composes -- for each transformable sub-entity and each value of that entity's
+// cell_info bit-field -- the net operator the reference's sequence of swaps / matrix sweeps
+// produces, so a device thread can produce one output entry with one table lookup (gather for
+// permutation elements, one short dot product for matrix elements) instead of replaying a
+// data-dependent sequence of in-place updates.
+#pragma once
+
+#include "common.cuh"
+
+#include <array>
+#include <vector>
+
+struct bx_element
+{
+  // ---- scalar facts -------------------------------------------------------------------------
+  int cell_type = 0, polyset_type = 0, degree = 0, superdegree = 0, map_type = 0;
+  int ndofs = 0, vs = 1, tdim = 0, psize = 0;
+  bool perms = false, identity = true; // dof_transformations_are_{permutations,identity}
+  int device = 0;
+
+  // ---- host copies ----------------------------------------------------------------------------
+  std::vector<double> coeffs;                           // [ndofs][vs*psize]
+  std::vector<int> dof_ordering;                        // empty or [ndofs]
+  std::vector<std::vector<std::vector<int>>> edofs;     // [dim][entity][k]
+  std::array<std::vector<double>, 8> etrans;            // per sub-entity cell type: [ntrans][n][n]
+  std::array<int, 8> etrans_dim{};                      // n per sub-entity cell type
+
+  // ---- tabulate: contraction operand ----------------------------------------------------------
+  // Cp[Npad][Kpad]: row (dof_ordering[dof]*vs + j) = coeffs[dof][j*psize .. (j+1)*psize), zero padded
+  int N = 0, K = 0, Npad = 0, Kpad = 0;
+  std::vector<double> Cp;
+  double* d_Cp = nullptr;
+
+  // ---- DOF transformations ----------------------------------------------------------------------
+  // "slots" = transformable sub-entities in the reference's processing order (edges, then faces)
+  struct Slot
+  {
+    int shift;      // first cell_info bit of this entity
+    int mask;       // 1 (edge: reversed?) or 7 (face: reflect | rotations<<1)
+    int dim;        // number of dofs on the entity
+    int cls;        // sub-entity cell type (interval / triangle / quadrilateral)
+    int first;      // matrix path: first dof of the contiguous block (running dofstart)
+    std::vector<int> dofs; // permutation path: _edofs[dim][entity]
+  };
+  std::vector<Slot> slots;
+  std::vector<int16_t> dof_slot, dof_loc; // per dof: owning slot (-1: never moves) and local index
+  int lo_dof = 0, hi_dof = 0;             // [lo, hi): smallest dof range containing all movable dofs
+
+  // Host tables (all four operator kinds packed), uploaded verbatim to the device.
+  std::vector<int4> h_slot_info;  // [nslots] {shift, mask, dim, gather base}
+  std::vector<int2> h_slot_mat;   // [nslots] {first dof, matrix base of the slot's class}
+  std::vector<int16_t> h_gather;  // [4][gather_size]
+  std::vector<double> h_mats;     // [4][mats_size]
+  bool on_device = false;         // false when the element was built without a usable CUDA device
+
+  // Device tables (all ops packed).  See dof_transform.cu for the layout.
+  int16_t* d_dof_slot = nullptr;  // [ndofs]
+  int16_t* d_dof_loc = nullptr;   // [ndofs]
+  int4* d_slot_info = nullptr;    // [nslots] {shift, mask, dim, table base}
+  int16_t* d_gather = nullptr;    // [4 ops][gather_size]: source dof for (slot, state, loc)
+  int gather_size = 0;
+  int2* d_slot_mat = nullptr;     // [nslots] {first dof, matrix base of its class}
+  double* d_mats = nullptr;       // [4 ops][mats_size]: dense [state][dim][dim] per class
+  int mats_size = 0;
+
+  ~bx_element();
+  bx_element() = default;
+  bx_element(const bx_element&) = delete;
+  bx_element& operator=(const bx_element&) = delete;
+};
+
+namespace bx
+{
+// Build host tables and upload the device mirror (current device).  Without a usable device the
+// host tables are still built (so they can be inspected) and every compute call fails.
+bx_element* element_from_desc(const bx_element_desc& d);
+// Throws BX_ERR_CUDA unless the device mirror exists.
+void require_device(const bx_element& e);
+// Net operator of T-kind `kind` (0 T, 1 Tt, 2 Tt_inv, 3 Tinv) for one cell_info, from the host tables:
+// permutation elements fill src[ndofs] (out[i] = in[src[i]]); all elements can fill the dense
+// A[ndofs][ndofs] (out = A in).  Either pointer may be null.
+void element_net_operator(const bx_element& e, int kind, uint32_t cell_info, int32_t* src, double* A);
+} // namespace bx

@@ -1,0 +1,225 @@
+// Batched push_forward / pull_back (Piola maps) over many cells.
+//
+// Replaces FiniteElement::push_forward / pull_back (reference cpp/basix/finite-element.cpp:1971-2042)
+// and the per-cell kernels of cpp/basix/maps.h:56-192.  pull_back is the same kernel with
+// (K, 1/detJ, J) in place of (J, detJ, K), exactly as finite-element.cpp:2038 does.
+//
+// Bandwidth-bound: every thread owns one (cell, row) pair, reads the row's reference values and the
+// cell's small matrix, writes the mapped row.  The accumulation order of maps.h is kept and the file
+// is compiled with -fmad=false, so results are bit-identical to a reference built without FMA
+// contraction.
+#include "common.cuh"
+
+namespace bx
+{
+namespace
+{
+constexpr int kThreads = 256;
+
+// A is the matrix the reference kernel actually reads (RA x CA, row-major):
+//   covariant          A = "K" argument:  out[i] = sum_k A[k][i] in[k]                 maps.h:73-94
+//   contravariant      A = "J" argument:  out[i] = (sum_k A[i][k] in[k]) / det         maps.h:100-124
+//   double covariant   A = "K" argument:  out = A^T in A                                maps.h:128-160
+//   double contravar.  A = "J" argument:  out = A in A^T / det^2                        maps.h:163-192
+template <int MAP, int RA, int CA>
+__global__ void __launch_bounds__(kThreads)
+    map_kernel(const double* __restrict__ in, const double* __restrict__ A, const double* __restrict__ detJ,
+               int invert_det, size_t nc, size_t rows, double* __restrict__ out)
+{
+  constexpr int IN_VS = MAP == BX_MAP_COVARIANT_PIOLA            ? RA
+                        : MAP == BX_MAP_CONTRAVARIANT_PIOLA      ? CA
+                        : MAP == BX_MAP_DOUBLE_COVARIANT_PIOLA   ? RA * RA
+                                                                 : CA * CA;
+  constexpr int OUT_VS = MAP == BX_MAP_COVARIANT_PIOLA            ? CA
+                         : MAP == BX_MAP_CONTRAVARIANT_PIOLA      ? RA
+                         : MAP == BX_MAP_DOUBLE_COVARIANT_PIOLA   ? CA * CA
+                                                                  : RA * RA;
+  const size_t total = nc * rows;
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += stride)
+  {
+    const size_t c = t / rows;
+    double a[RA][CA];
+#pragma unroll
+    for (int i = 0; i < RA; ++i)
+#pragma unroll
+      for (int j = 0; j < CA; ++j)
+        a[i][j] = A[c * (RA * CA) + i * CA + j];
+    double u[IN_VS];
+#pragma unroll
+    for (int i = 0; i < IN_VS; ++i)
+      u[i] = in[t * IN_VS + i];
+    double r[OUT_VS];
+    if constexpr (MAP == BX_MAP_COVARIANT_PIOLA)
+    {
+#pragma unroll
+      for (int i = 0; i < CA; ++i)
+      {
+        double acc = 0;
+#pragma unroll
+        for (int k = 0; k < RA; ++k)
+          acc += a[k][i] * u[k];
+        r[i] = acc;
+      }
+    }
+    else if constexpr (MAP == BX_MAP_CONTRAVARIANT_PIOLA)
+    {
+      const double det = invert_det ? 1.0 / detJ[c] : detJ[c];
+#pragma unroll
+      for (int i = 0; i < RA; ++i)
+      {
+        double acc = 0;
+#pragma unroll
+        for (int k = 0; k < CA; ++k)
+          acc += a[i][k] * u[k];
+        r[i] = acc / det;
+      }
+    }
+    else if constexpr (MAP == BX_MAP_DOUBLE_COVARIANT_PIOLA)
+    {
+#pragma unroll
+      for (int i = 0; i < CA; ++i)
+#pragma unroll
+        for (int j = 0; j < CA; ++j)
+        {
+          double acc = 0;
+#pragma unroll
+          for (int k = 0; k < RA; ++k)
+#pragma unroll
+            for (int l = 0; l < RA; ++l)
+              acc += a[k][i] * u[k * RA + l] * a[l][j];
+          r[i * CA + j] = acc;
+        }
+    }
+    else
+    {
+      const double det = invert_det ? 1.0 / detJ[c] : detJ[c];
+      const double det2 = det * det;
+#pragma unroll
+      for (int i = 0; i < RA; ++i)
+#pragma unroll
+        for (int j = 0; j < RA; ++j)
+        {
+          double acc = 0;
+#pragma unroll
+          for (int k = 0; k < CA; ++k)
+#pragma unroll
+            for (int l = 0; l < CA; ++l)
+              acc += a[i][k] * u[k * CA + l] * a[j][l];
+          r[i * RA + j] = acc / det2;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < OUT_VS; ++i)
+      out[t * OUT_VS + i] = r[i];
+  }
+}
+
+// identity map: u(i, j) = U(i, j)  (finite-element.h:632-640)
+__global__ void __launch_bounds__(kThreads) copy_kernel(const double* __restrict__ in, size_t n, double* __restrict__ out)
+{
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += stride)
+    out[t] = in[t];
+}
+
+int grid_for(size_t n)
+{
+  const size_t want = ceil_div(n, size_t(kThreads));
+  const size_t cap = size_t(sm_count()) * 8;
+  return int(want < cap ? (want == 0 ? 1 : want) : cap);
+}
+
+template <int MAP, int RA>
+void launch_ca(int ca, const double* in, const double* A, const double* detJ, int inv, size_t nc, size_t rows,
+               double* out, cudaStream_t s)
+{
+  const int g = grid_for(nc * rows);
+  switch (ca)
+  {
+  case 1: map_kernel<MAP, RA, 1><<<g, kThreads, 0, s>>>(in, A, detJ, inv, nc, rows, out); break;
+  case 2: map_kernel<MAP, RA, 2><<<g, kThreads, 0, s>>>(in, A, detJ, inv, nc, rows, out); break;
+  case 3: map_kernel<MAP, RA, 3><<<g, kThreads, 0, s>>>(in, A, detJ, inv, nc, rows, out); break;
+  default: fail(BX_ERR_INVALID_ARG, "map: Jacobian dimensions must be between 1 and 3");
+  }
+  BX_LAUNCHED();
+}
+
+template <int MAP>
+void launch_ra(int ra, int ca, const double* in, const double* A, const double* detJ, int inv, size_t nc,
+               size_t rows, double* out, cudaStream_t s)
+{
+  switch (ra)
+  {
+  case 1: launch_ca<MAP, 1>(ca, in, A, detJ, inv, nc, rows, out, s); break;
+  case 2: launch_ca<MAP, 2>(ca, in, A, detJ, inv, nc, rows, out, s); break;
+  case 3: launch_ca<MAP, 3>(ca, in, A, detJ, inv, nc, rows, out, s); break;
+  default: fail(BX_ERR_INVALID_ARG, "map: Jacobian dimensions must be between 1 and 3");
+  }
+}
+} // namespace
+
+// Value size of the mapped data: push -> compute_value_size (finite-element.cpp:42-59) with
+// dim = gdim; pull -> the reference value size (tdim-based).
+int map_value_size(int map_type, int pull, int in_vs, int gdim, int tdim)
+{
+  const int dim = pull ? tdim : gdim;
+  switch (map_type)
+  {
+  case BX_MAP_IDENTITY: return pull ? in_vs : 1;
+  case BX_MAP_COVARIANT_PIOLA:
+  case BX_MAP_CONTRAVARIANT_PIOLA: return dim;
+  case BX_MAP_DOUBLE_COVARIANT_PIOLA:
+  case BX_MAP_DOUBLE_CONTRAVARIANT_PIOLA: return dim * dim;
+  case BX_MAP_L2_PIOLA: fail(BX_ERR_UNSUPPORTED, "Map not implemented");
+  default: fail(BX_ERR_INVALID_ARG, "Mapping not yet implemented");
+  }
+}
+
+// Device pointers.  U[nc][rows][in_vs], J[nc][gdim][tdim], detJ[nc], K[nc][tdim][gdim].
+void map_device(int map_type, int pull, const double* U, const double* J, const double* detJ, const double* K,
+                size_t nc, size_t rows, int in_vs, int gdim, int tdim, double* out, cudaStream_t s)
+{
+  const int out_vs = map_value_size(map_type, pull, in_vs, gdim, tdim);
+  if (nc == 0 or rows == 0)
+    return;
+  // The reference kernel's "J" and "K" arguments: push (J, K); pull (K, J).
+  const double* Jarg = pull ? K : J;
+  const double* Karg = pull ? J : K;
+  const int Jr = pull ? tdim : gdim, Jc = pull ? gdim : tdim; // shape of the "J" argument
+  const int Kr = Jc, Kc = Jr;                                  // shape of the "K" argument
+  const int dim_in = pull ? gdim : tdim;
+  auto need = [&](int want)
+  {
+    if (in_vs != want)
+      fail(BX_ERR_INVALID_ARG, "map: value size of the input (" + std::to_string(in_vs)
+                                   + ") does not match the map (" + std::to_string(want) + ")");
+  };
+  switch (map_type)
+  {
+  case BX_MAP_IDENTITY:
+    if (in_vs != out_vs)
+      fail(BX_ERR_INVALID_ARG, "map: identity map needs matching value sizes");
+    copy_kernel<<<grid_for(nc * rows * in_vs), kThreads, 0, s>>>(U, nc * rows * in_vs, out);
+    BX_LAUNCHED();
+    return;
+  case BX_MAP_COVARIANT_PIOLA:
+    need(dim_in);
+    launch_ra<BX_MAP_COVARIANT_PIOLA>(Kr, Kc, U, Karg, detJ, pull, nc, rows, out, s);
+    return;
+  case BX_MAP_CONTRAVARIANT_PIOLA:
+    need(dim_in);
+    launch_ra<BX_MAP_CONTRAVARIANT_PIOLA>(Jr, Jc, U, Jarg, detJ, pull, nc, rows, out, s);
+    return;
+  case BX_MAP_DOUBLE_COVARIANT_PIOLA:
+    need(dim_in * dim_in);
+    launch_ra<BX_MAP_DOUBLE_COVARIANT_PIOLA>(Kr, Kc, U, Karg, detJ, pull, nc, rows, out, s);
+    return;
+  case BX_MAP_DOUBLE_CONTRAVARIANT_PIOLA:
+    need(dim_in * dim_in);
+    launch_ra<BX_MAP_DOUBLE_CONTRAVARIANT_PIOLA>(Jr, Jc, U, Jarg, detJ, pull, nc, rows, out, s);
+    return;
+  default: fail(BX_ERR_UNSUPPORTED, "Map not implemented");
+  }
+}
+} // namespace bx

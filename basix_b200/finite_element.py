@@ -1,0 +1,565 @@
+"""Host-side mirror of the reference's ``basix.finite_element.FiniteElement``
+(python/basix/finite_element.py:50-592) over the CUDA C ABI.
+
+Same method names, argument order and error behaviour as the reference for the
+hot-path calls (``tabulate``, ``push_forward``, ``pull_back``, ``T_apply``,
+``Tt_apply_right``, ``Tt_inv_apply`` ...), plus batched variants the reference
+cannot express (one ``cell_info`` per cell).  Arrays may be
+
+* numpy arrays (host memory): the library stages them through the GPU and
+  returns numpy arrays -- the drop-in behaviour;
+* torch CUDA tensors (device memory): kernels are enqueued on torch's current
+  stream and torch tensors are returned without any host round trip.
+
+All arithmetic happens in ``libbasix_b200.so``; nothing here computes.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from enum import IntEnum
+
+import numpy as np
+
+from . import _capi
+from ._capi import BX_MEM_DEVICE, BX_MEM_HOST, ElementDesc, check, lib
+
+
+class CellType(IntEnum):
+    """basix::cell::type, cpp/basix/cell.h:20-30."""
+
+    point = 0
+    interval = 1
+    triangle = 2
+    tetrahedron = 3
+    quadrilateral = 4
+    hexahedron = 5
+    prism = 6
+    pyramid = 7
+
+
+class ElementFamily(IntEnum):
+    """basix::element::family, cpp/basix/element-families.h:44-61."""
+
+    custom = 0
+    P = 1
+    RT = 2
+    N1E = 3
+    BDM = 4
+    N2E = 5
+    CR = 6
+    Regge = 7
+    DPC = 8
+    bubble = 9
+    serendipity = 10
+    HHJ = 11
+    Hermite = 12
+    iso = 13
+
+
+class LagrangeVariant(IntEnum):
+    """basix::element::lagrange_variant, cpp/basix/element-families.h:12-27."""
+
+    unset = 0
+    equispaced = 1
+    gll_warped = 2
+    gll_isaac = 3
+    gll_centroid = 4
+    chebyshev_warped = 5
+    chebyshev_isaac = 6
+    chebyshev_centroid = 7
+    gl_warped = 8
+    gl_isaac = 9
+    gl_centroid = 10
+    legendre = 11
+    bernstein = 12
+
+
+class DPCVariant(IntEnum):
+    """basix::element::dpc_variant, cpp/basix/element-families.h:32-42."""
+
+    unset = 0
+    simplex_equispaced = 1
+    simplex_gll = 2
+    horizontal_equispaced = 3
+    horizontal_gll = 4
+    diagonal_equispaced = 5
+    diagonal_gll = 6
+    legendre = 7
+
+
+class MapType(IntEnum):
+    """basix::maps::type, cpp/basix/maps.h:39-47."""
+
+    identity = 0
+    L2Piola = 1
+    covariantPiola = 2
+    contravariantPiola = 3
+    doubleCovariantPiola = 4
+    doubleContravariantPiola = 5
+
+
+class PolysetType(IntEnum):
+    """basix::polyset::type, cpp/basix/polyset.h:136-140."""
+
+    standard = 0
+    macroedge = 1
+
+
+_TDIM = {0: 0, 1: 1, 2: 2, 3: 3, 4: 2, 5: 3, 6: 3, 7: 3}
+_NUM_ENTITIES = {0: (1,), 1: (2, 1), 2: (3, 3, 1), 3: (4, 6, 4, 1), 4: (4, 4, 1), 5: (8, 12, 6, 1),
+                 6: (6, 9, 5, 1), 7: (5, 8, 5, 1)}
+
+T_OPS = {"T_apply": 0, "Tt_apply": 1, "Tt_inv_apply": 2, "Tinv_apply": 3, "Tt_apply_right": 4,
+         "Tinv_apply_right": 5, "T_apply_right": 6, "Tt_inv_apply_right": 7}
+
+
+# ---- array plumbing ------------------------------------------------------------------------------
+def _is_torch(a) -> bool:
+    return type(a).__module__.startswith("torch")
+
+
+class _Arg:
+    """A C-contiguous array argument: pointer + memory kind (+ keeps the owner alive)."""
+
+    __slots__ = ("owner", "ptr", "mem", "shape")
+
+    def __init__(self, a, dtype, name: str, writable: bool = False):
+        if _is_torch(a):
+            import torch
+
+            want = {np.float64: torch.float64, np.float32: torch.float32, np.int32: torch.int32,
+                    np.uint32: torch.uint32}[dtype]
+            if not a.is_cuda:
+                raise TypeError(f"{name}: torch tensors must live on a CUDA device (use numpy for host data)")
+            if want == torch.uint32 and a.dtype == torch.int32:
+                a = a.view(torch.uint32)  # same bits
+            if a.dtype != want:
+                if writable:
+                    raise TypeError(f"{name}: expected dtype {want}, got {a.dtype}")
+                a = a.to(want)
+            if not a.is_contiguous():
+                if writable:
+                    raise TypeError(f"{name}: in-place argument must be contiguous")
+                a = a.contiguous()
+            self.owner, self.ptr, self.mem, self.shape = a, a.data_ptr(), BX_MEM_DEVICE, tuple(a.shape)
+        else:
+            if writable:
+                if not isinstance(a, np.ndarray) or a.dtype != dtype or not a.flags.c_contiguous:
+                    # the reference binds in-place arguments with .noconvert() (basix_wrappers.h:135,205)
+                    raise TypeError(f"{name}: in-place argument must be a C-contiguous numpy array of {dtype.__name__}")
+                if not a.flags.writeable:
+                    raise TypeError(f"{name}: array is read-only")
+            else:
+                a = np.ascontiguousarray(a, dtype=dtype)
+            self.owner, self.ptr, self.mem, self.shape = a, a.ctypes.data, BX_MEM_HOST, a.shape
+
+
+def _same_mem(*args: _Arg) -> int:
+    mems = {a.mem for a in args}
+    if len(mems) != 1:
+        raise TypeError("all array arguments must be of one kind: numpy (host) or torch CUDA tensors (device)")
+    return mems.pop()
+
+
+def _stream_and_like(arg: _Arg):
+    """(cuda stream handle, allocator for outputs of the same kind)."""
+    if arg.mem == BX_MEM_DEVICE:
+        import torch
+
+        dev = arg.owner.device
+        stream = torch.cuda.current_stream(dev).cuda_stream
+
+        def alloc(shape, dtype):
+            td = {np.float64: torch.float64, np.float32: torch.float32, np.int32: torch.int32}[dtype]
+            return torch.empty(shape, dtype=td, device=dev)
+
+        return stream, alloc
+    return None, lambda shape, dtype: np.empty(shape, dtype=dtype)
+
+
+def _ptr_of(a) -> int:
+    return a.data_ptr() if _is_torch(a) else a.ctypes.data
+
+
+# ---- polynomial sets -------------------------------------------------------------------------------
+def polyset_dim(celltype: int, ptype: int, degree: int) -> int:
+    return lib().bx_polyset_dim(int(celltype), int(ptype), int(degree))
+
+
+def polyset_nderivs(celltype: int, nderiv: int) -> int:
+    return lib().bx_polyset_nderivs(int(celltype), int(nderiv))
+
+
+def tabulate_polynomial_set(celltype: int, ptype: int, degree: int, nderiv: int, x):
+    """``basix._basixcpp.tabulate_polynomial_set_float64`` (basix_wrappers.h:467-475):
+    returns P with shape (nderivs, psize, npts)."""
+    tdim = _TDIM[int(celltype)]
+    xa = _Arg(x, np.float64, "x")
+    shape = xa.shape
+    if len(shape) == 1:
+        shape = (shape[0], 1)
+    if len(shape) != 2 or (tdim > 0 and shape[1] != tdim):
+        raise RuntimeError(f"Point dim ({shape[1] if len(shape) == 2 else '?'}) does not match cell dim ({tdim}).")
+    stream, alloc = _stream_and_like(xa)
+    P = alloc((polyset_nderivs(celltype, nderiv), polyset_dim(celltype, ptype, degree), shape[0]), np.float64)
+    check(lib().bx_polyset_tabulate_f64(int(celltype), int(ptype), int(degree), int(nderiv), xa.ptr, shape[0],
+                                        _ptr_of(P), xa.mem, stream))
+    return P
+
+
+# ---- element ----------------------------------------------------------------------------------------
+class FiniteElement:
+    """B200-backed finite element: the hot-path subset of ``basix.finite_element.FiniteElement``."""
+
+    def __init__(self, *, cell_type, polyset_type, degree, embedded_superdegree, map_type, value_shape,
+                 coefficient_matrix, entity_dofs, entity_transformations, dof_ordering=None, family=0,
+                 lagrange_variant=0, dpc_variant=0, discontinuous=False):
+        self._h = None
+        self._cell_type = CellType(int(cell_type))
+        self._polyset_type = PolysetType(int(polyset_type))
+        self._degree = int(degree)
+        self._embedded_superdegree = int(embedded_superdegree)
+        self._map_type = MapType(int(map_type))
+        self._value_shape = tuple(int(s) for s in value_shape)
+        self._family = ElementFamily(int(family))
+        self._lagrange_variant = LagrangeVariant(int(lagrange_variant))
+        self._dpc_variant = DPCVariant(int(dpc_variant))
+        self._discontinuous = bool(discontinuous)
+        vs = int(np.prod(self._value_shape)) if self._value_shape else 1
+        coeffs = np.ascontiguousarray(coefficient_matrix, dtype=np.float64)
+        if coeffs.ndim != 2:
+            raise ValueError("coefficient_matrix must be 2-D")
+        self._coeffs = coeffs
+        tdim = _TDIM[int(cell_type)]
+        counts = _NUM_ENTITIES[int(cell_type)]
+        if len(entity_dofs) != tdim + 1 or any(len(entity_dofs[d]) != counts[d] for d in range(tdim + 1)):
+            raise ValueError("entity_dofs does not match the cell topology")
+        self._entity_dofs = [[[int(v) for v in e] for e in row] for row in entity_dofs]
+        flat, offs = [], [0]
+        for row in self._entity_dofs:
+            for e in row:
+                flat.extend(e)
+                offs.append(len(flat))
+        offs_a = np.asarray(offs, dtype=np.int32)
+        flat_a = np.asarray(flat if flat else [0], dtype=np.int32)
+        self._entity_transformations = {int(k): np.ascontiguousarray(v, dtype=np.float64)
+                                        for k, v in entity_transformations.items()}
+        self._dof_ordering = (np.asarray(dof_ordering, dtype=np.int32)
+                              if dof_ordering is not None and len(dof_ordering) else np.zeros(0, dtype=np.int32))
+
+        d = ElementDesc()
+        d.cell_type, d.polyset_type, d.degree = int(cell_type), int(polyset_type), int(degree)
+        d.embedded_superdegree, d.map_type = int(embedded_superdegree), int(map_type)
+        d.ndofs, d.value_size = coeffs.shape[0], vs
+        d.coeffs = coeffs.ctypes.data
+        d.dof_ordering = self._dof_ordering.ctypes.data if len(self._dof_ordering) else None
+        d.n_dof_ordering = len(self._dof_ordering)
+        d.entity_dof_offsets, d.entity_dofs = offs_a.ctypes.data, flat_a.ctypes.data
+        keep = []
+        for ct, name in ((1, "interval"), (2, "triangle"), (4, "quadrilateral")):
+            m = self._entity_transformations.get(ct)
+            if m is not None:
+                if m.ndim != 3 or m.shape[1] != m.shape[2] or m.shape[0] != (1 if ct == 1 else 2):
+                    raise ValueError(f"entity_transformations[{name}] has a bad shape {m.shape}")
+                keep.append(m)
+                # a zero-sized matrix still needs a non-null pointer so "present, n = 0" is expressible
+                setattr(d, f"etrans_{name}", m.ctypes.data if m.size else flat_a.ctypes.data)
+                setattr(d, f"etrans_{name}_dim", m.shape[1])
+        if coeffs.shape[1] != vs * polyset_dim(cell_type, polyset_type, embedded_superdegree):
+            raise ValueError("coefficient_matrix has the wrong number of columns for this polyset")
+        h = C.c_void_p()
+        check(lib().bx_element_create_from_arrays(C.byref(d), C.byref(h)))
+        self._h = h
+        info = (C.c_int32 * 10)()
+        check(lib().bx_element_info(self._h, info))
+        self._tdim, self._ndofs, self._vs = info[2], info[3], info[4]
+        self._perms, self._identity, self._psize = bool(info[7]), bool(info[8]), info[9]
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                lib().bx_element_destroy(h)
+            except Exception:
+                pass
+
+    # ---- serialisation of the defining arrays (fixtures, caches) ---------------------------------
+    def to_arrays(self) -> dict:
+        out = {
+            "meta": np.asarray([int(self._cell_type), int(self._polyset_type), self._degree,
+                                self._embedded_superdegree, int(self._map_type), int(self._family),
+                                int(self._lagrange_variant), int(self._dpc_variant), int(self._discontinuous)],
+                               dtype=np.int64),
+            "value_shape": np.asarray(self._value_shape, dtype=np.int64),
+            "coefficient_matrix": self._coeffs,
+            "dof_ordering": self._dof_ordering,
+        }
+        flat, offs = [], [0]
+        for row in self._entity_dofs:
+            for e in row:
+                flat.extend(e)
+                offs.append(len(flat))
+        out["entity_dof_offsets"] = np.asarray(offs, dtype=np.int32)
+        out["entity_dofs_flat"] = np.asarray(flat, dtype=np.int32)
+        for ct, m in self._entity_transformations.items():
+            out[f"etrans_{ct}"] = m
+        return out
+
+    @classmethod
+    def from_arrays(cls, arrs) -> "FiniteElement":
+        meta = [int(v) for v in arrs["meta"]]
+        cell = meta[0]
+        counts = _NUM_ENTITIES[cell]
+        offs, flat = arrs["entity_dof_offsets"], arrs["entity_dofs_flat"]
+        edofs, k = [], 0
+        for n in counts:
+            row = []
+            for _ in range(n):
+                row.append([int(v) for v in flat[offs[k]:offs[k + 1]]])
+                k += 1
+            edofs.append(row)
+        etrans = {int(key.split("_")[1]): arrs[key] for key in arrs.keys() if key.startswith("etrans_")}
+        return cls(cell_type=cell, polyset_type=meta[1], degree=meta[2], embedded_superdegree=meta[3],
+                   map_type=meta[4], family=meta[5], lagrange_variant=meta[6], dpc_variant=meta[7],
+                   discontinuous=bool(meta[8]), value_shape=tuple(int(v) for v in arrs["value_shape"]),
+                   coefficient_matrix=arrs["coefficient_matrix"], entity_dofs=edofs,
+                   entity_transformations=etrans, dof_ordering=arrs["dof_ordering"])
+
+    # ---- properties (finite_element.py:407-592 of the reference) --------------------------------------
+    @property
+    def cell_type(self) -> CellType:
+        return self._cell_type
+
+    @property
+    def polyset_type(self) -> PolysetType:
+        return self._polyset_type
+
+    @property
+    def degree(self) -> int:
+        return self._degree
+
+    @property
+    def embedded_superdegree(self) -> int:
+        return self._embedded_superdegree
+
+    @property
+    def family(self) -> ElementFamily:
+        return self._family
+
+    @property
+    def lagrange_variant(self) -> LagrangeVariant:
+        return self._lagrange_variant
+
+    @property
+    def dpc_variant(self) -> DPCVariant:
+        return self._dpc_variant
+
+    @property
+    def discontinuous(self) -> bool:
+        return self._discontinuous
+
+    @property
+    def dim(self) -> int:
+        return self._ndofs
+
+    @property
+    def value_size(self) -> int:
+        return self._vs
+
+    @property
+    def value_shape(self) -> tuple:
+        return self._value_shape
+
+    @property
+    def map_type(self) -> MapType:
+        return self._map_type
+
+    @property
+    def dof_transformations_are_permutations(self) -> bool:
+        return self._perms
+
+    @property
+    def dof_transformations_are_identity(self) -> bool:
+        return self._identity
+
+    @property
+    def coefficient_matrix(self) -> np.ndarray:
+        return self._coeffs
+
+    @property
+    def entity_dofs(self):
+        return self._entity_dofs
+
+    @property
+    def dof_ordering(self):
+        return [int(v) for v in self._dof_ordering]
+
+    def entity_transformations(self) -> dict:
+        names = {1: "interval", 2: "triangle", 4: "quadrilateral"}
+        return {names[k]: v for k, v in self._entity_transformations.items()}
+
+    def net_permutation(self, cell_info: int, op: str = "T_apply") -> np.ndarray:
+        """Host tables: src with out[i] = in[src[i]] for this cell_info (permutation elements)."""
+        src = np.empty(self._ndofs, dtype=np.int32)
+        check(lib().bx_element_net_operator(self._h, T_OPS[op], int(cell_info) & 0xFFFFFFFF, src.ctypes.data, None))
+        return src
+
+    def net_operator(self, cell_info: int, op: str = "T_apply") -> np.ndarray:
+        """Host tables: dense (ndofs, ndofs) matrix A with out = A @ in for this cell_info."""
+        A = np.empty((self._ndofs, self._ndofs), dtype=np.float64)
+        check(lib().bx_element_net_operator(self._h, T_OPS[op], int(cell_info) & 0xFFFFFFFF, None, A.ctypes.data))
+        return A
+
+    def tabulate_shape(self, nd: int, npts: int):
+        shape = (C.c_size_t * 4)()
+        check(lib().bx_element_tabulate_shape(self._h, int(nd), int(npts), shape))
+        return tuple(int(s) for s in shape)
+
+    def tabulate_path(self, nd: int) -> str:
+        return {0: "generic", 1: "fused", 2: "tensor-product"}.get(lib().bx_element_tabulate_path(self._h, int(nd)), "?")
+
+    # ---- hot path ---------------------------------------------------------------------------------------
+    def tabulate(self, n: int, x, out=None):
+        """``FiniteElement.tabulate`` (finite_element.py:63-95): shape (nderivs, npts, ndofs, value_size).
+
+        ``out`` (optional, same kind as ``x``) mirrors the reference's C++ overload with the basis data as an
+        out argument (finite-element.h:454-455), avoiding the allocation on repeated calls."""
+        xa = _Arg(x, np.float64, "x")
+        if len(xa.shape) != 2:
+            raise TypeError("x must be a 2-D array of shape (npts, tdim)")
+        npts, xdim = xa.shape
+        stream, alloc = _stream_and_like(xa)
+        if xdim != self._tdim:
+            raise RuntimeError(f"Point dim ({xdim}) does not match element dim ({self._tdim}).")
+        shape = self.tabulate_shape(n, npts)
+        if out is None:
+            out = alloc(shape, np.float64)
+        else:
+            oa = _Arg(out, np.float64, "out", writable=True)
+            if oa.mem != xa.mem or tuple(oa.shape) != shape:
+                raise RuntimeError(f"out must have shape {shape} and live where x lives")
+        check(lib().bx_tabulate_f64(self._h, int(n), xa.ptr, npts, xdim, _ptr_of(out), xa.mem, stream))
+        return out
+
+    def _map(self, pull: int, U, J, detJ, K):
+        Ua, Ja = _Arg(U, np.float64, "U"), _Arg(J, np.float64, "J")
+        da, Ka = _Arg(detJ, np.float64, "detJ"), _Arg(K, np.float64, "K")
+        mem = _same_mem(Ua, Ja, da, Ka)
+        if len(Ua.shape) != 3 or len(Ja.shape) != 3 or len(Ka.shape) != 3 or len(da.shape) != 1:
+            raise TypeError("expected U (nc, rows, vs), J (nc, gdim, tdim), detJ (nc,), K (nc, tdim, gdim)")
+        nc, rows, in_vs = Ua.shape
+        gdim, tdim = Ja.shape[1], Ja.shape[2]
+        if Ja.shape[0] != nc or da.shape[0] != nc or Ka.shape != (nc, tdim, gdim):
+            raise RuntimeError("push_forward/pull_back: inconsistent array shapes")
+        out_vs = lib().bx_map_value_size(int(self._map_type), pull, in_vs, gdim, tdim)
+        if out_vs < 0:
+            check(1)
+        stream, alloc = _stream_and_like(Ua)
+        out = alloc((nc, rows, out_vs), np.float64)
+        fn = lib().bx_pull_back_f64 if pull else lib().bx_push_forward_f64
+        check(fn(self._h, Ua.ptr, Ja.ptr, da.ptr, Ka.ptr, nc, rows, in_vs, gdim, tdim, _ptr_of(out), mem, stream))
+        return out
+
+    def push_forward(self, U, J, detJ, K):
+        """``FiniteElement.push_forward`` (finite_element.py:112-134)."""
+        return self._map(0, U, J, detJ, K)
+
+    def pull_back(self, u, J, detJ, K):
+        """``FiniteElement.pull_back`` (finite_element.py:136-151)."""
+        return self._map(1, u, J, detJ, K)
+
+    def _transform(self, op: str, data, block_size: int, cell_info, batched: bool):
+        if _is_torch(data):
+            dt = {"torch.float64": np.float64, "torch.float32": np.float32, "torch.int32": np.int32}.get(str(data.dtype))
+        else:
+            dt = {np.dtype(np.float64): np.float64, np.dtype(np.float32): np.float32,
+                  np.dtype(np.int32): np.int32}.get(getattr(data, "dtype", None))
+        if dt is None:
+            raise TypeError("data must be float64, float32 or int32")
+        da = _Arg(data, dt, "data", writable=True)
+        if batched:
+            if len(da.shape) != 2:
+                raise TypeError("batched data must have shape (ncells, ndofs * block_size)")
+            nc, cs = da.shape
+            ca = _Arg(cell_info, np.uint32, "cell_info")
+            if ca.shape != (nc,):
+                raise RuntimeError("cell_info must have one entry per cell")
+            mem = _same_mem(da, ca)
+        else:
+            nc, cs = 1, int(np.prod(da.shape))
+            if da.mem == BX_MEM_DEVICE:
+                import torch
+
+                ca = _Arg(torch.tensor([int(cell_info) & 0xFFFFFFFF], dtype=torch.int64, device=data.device)
+                          .to(torch.uint32), np.uint32, "cell_info")
+            else:
+                ca = _Arg(np.asarray([int(cell_info) & 0xFFFFFFFF], dtype=np.uint32), np.uint32, "cell_info")
+            mem = da.mem
+        stream, _ = _stream_and_like(da)
+        fn = {np.float64: lib().bx_T_apply_f64, np.float32: lib().bx_T_apply_f32, np.int32: lib().bx_T_apply_i32}[dt]
+        check(fn(self._h, T_OPS[op], da.ptr, nc, cs, int(block_size), ca.ptr, mem, stream))
+
+    # single-cell calls, reference signatures (finite_element.py:153-194; finite-element.h:1067-1159)
+    def T_apply(self, data, block_size: int, cell_info: int) -> None:
+        self._transform("T_apply", data, block_size, cell_info, False)
+
+    def Tt_apply(self, data, block_size: int, cell_info: int) -> None:
+        self._transform("Tt_apply", data, block_size, cell_info, False)
+
+    def Tt_inv_apply(self, data, block_size: int, cell_info: int) -> None:
+        self._transform("Tt_inv_apply", data, block_size, cell_info, False)
+
+    def Tinv_apply(self, data, block_size: int, cell_info: int) -> None:
+        self._transform("Tinv_apply", data, block_size, cell_info, False)
+
+    def Tt_apply_right(self, data, block_size: int, cell_info: int) -> None:
+        self._transform("Tt_apply_right", data, block_size, cell_info, False)
+
+    def Tinv_apply_right(self, data, block_size: int, cell_info: int) -> None:
+        self._transform("Tinv_apply_right", data, block_size, cell_info, False)
+
+    def T_apply_right(self, data, block_size: int, cell_info: int) -> None:
+        self._transform("T_apply_right", data, block_size, cell_info, False)
+
+    def Tt_inv_apply_right(self, data, block_size: int, cell_info: int) -> None:
+        self._transform("Tt_inv_apply_right", data, block_size, cell_info, False)
+
+    # batched additions: data[ncells][ndofs * block_size], cell_info[ncells]
+    def T_apply_batch(self, data, block_size: int, cell_info, op: str = "T_apply") -> None:
+        self._transform(op, data, block_size, cell_info, True)
+
+    def _permute(self, inverse: int, d, cell_info, batched: bool):
+        da = _Arg(d, np.int32, "d", writable=True)
+        if batched:
+            if len(da.shape) != 2 or da.shape[1] != self._ndofs:
+                raise TypeError("batched d must have shape (ncells, ndofs)")
+            nc = da.shape[0]
+            ca = _Arg(cell_info, np.uint32, "cell_info")
+            if ca.shape != (nc,):
+                raise RuntimeError("cell_info must have one entry per cell")
+            mem = _same_mem(da, ca)
+        else:
+            if int(np.prod(da.shape)) != self._ndofs:
+                raise RuntimeError("d must have one entry per dof")
+            nc = 1
+            ca = _Arg(np.asarray([int(cell_info) & 0xFFFFFFFF], dtype=np.uint32), np.uint32, "cell_info")
+            if da.mem == BX_MEM_DEVICE:
+                import torch
+
+                ca = _Arg(torch.tensor([int(cell_info) & 0xFFFFFFFF], dtype=torch.int64, device=d.device)
+                          .to(torch.uint32), np.uint32, "cell_info")
+            mem = da.mem
+        stream, _ = _stream_and_like(da)
+        check(lib().bx_permute_i32(self._h, inverse, da.ptr, nc, ca.ptr, mem, stream))
+
+    def permute(self, d, cell_info: int) -> None:
+        """``FiniteElement::permute`` (finite-element.h:800-812), in place."""
+        self._permute(0, d, cell_info, False)
+
+    def permute_inv(self, d, cell_info: int) -> None:
+        """``FiniteElement::permute_inv`` (finite-element.h:831-843), in place."""
+        self._permute(1, d, cell_info, False)
+
+    def permute_batch(self, d, cell_info, inverse: bool = False) -> None:
+        self._permute(int(bool(inverse)), d, cell_info, True)

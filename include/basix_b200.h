@@ -1,0 +1,220 @@
+/* basix_b200.h -- C ABI of the B200-native (sm_100a) basix hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.
+ * Each entry point cites the reference interface (FEniCS/basix, file:line under
+ * /root/reference) it replaces.  All functions return BX_OK (0) or an error
+ * code; the message for the calling thread is available via bx_last_error().
+ * There is NO CPU fallback anywhere below this boundary: if no CUDA device is
+ * usable every compute entry point fails with BX_ERR_CUDA.
+ *
+ * Pointer kinds: every compute call takes `mem`:
+ *   BX_MEM_DEVICE  pointers are device pointers valid on the current device;
+ *                  work is enqueued on `stream` and the call returns without
+ *                  synchronising (stream-ordered, re-entrant).
+ *   BX_MEM_HOST    pointers are host pointers (pageable or pinned); the library
+ *                  stages host<->device in chunks through pinned buffers on its
+ *                  own streams and returns when the result is in host memory.
+ *
+ * Integer enums keep the reference's values:
+ *   cell type     basix::cell::type            cpp/basix/cell.h:20-30
+ *   polyset type  basix::polyset::type         cpp/basix/polyset.h:136-140
+ *   map type      basix::maps::type            cpp/basix/maps.h:39-47
+ *   family        basix::element::family       cpp/basix/element-families.h:44-61
+ *   lagrange/dpc variant                       cpp/basix/element-families.h:12-41
+ */
+#ifndef BASIX_B200_H
+#define BASIX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+  typedef struct bx_element bx_element;
+  typedef void* bx_stream_t; /* a cudaStream_t; NULL = legacy default stream */
+
+  enum bx_status
+  {
+    BX_OK = 0,
+    BX_ERR_INVALID_ARG = 1,
+    BX_ERR_CUDA = 2,
+    BX_ERR_UNSUPPORTED = 3,
+    BX_ERR_RUNTIME = 4
+  };
+
+  enum bx_mem
+  {
+    BX_MEM_HOST = 0,
+    BX_MEM_DEVICE = 1
+  };
+
+  enum bx_cell
+  {
+    BX_CELL_POINT = 0,
+    BX_CELL_INTERVAL = 1,
+    BX_CELL_TRIANGLE = 2,
+    BX_CELL_TETRAHEDRON = 3,
+    BX_CELL_QUADRILATERAL = 4,
+    BX_CELL_HEXAHEDRON = 5,
+    BX_CELL_PRISM = 6,
+    BX_CELL_PYRAMID = 7
+  };
+
+  enum bx_polyset
+  {
+    BX_POLYSET_STANDARD = 0,
+    BX_POLYSET_MACROEDGE = 1
+  };
+
+  enum bx_map
+  {
+    BX_MAP_IDENTITY = 0,
+    BX_MAP_L2_PIOLA = 1,
+    BX_MAP_COVARIANT_PIOLA = 2,
+    BX_MAP_CONTRAVARIANT_PIOLA = 3,
+    BX_MAP_DOUBLE_COVARIANT_PIOLA = 4,
+    BX_MAP_DOUBLE_CONTRAVARIANT_PIOLA = 5
+  };
+
+  /* The eight DOF-transformation operators, finite-element.h:1839-1998. */
+  enum bx_top
+  {
+    BX_T_APPLY = 0,           /* T_apply            finite-element.h:1839-1854 */
+    BX_TT_APPLY = 1,          /* Tt_apply           finite-element.h:1856-1870 */
+    BX_TT_INV_APPLY = 2,      /* Tt_inv_apply       finite-element.h:1872-1886 */
+    BX_TINV_APPLY = 3,        /* Tinv_apply         finite-element.h:1888-1902 */
+    BX_TT_APPLY_RIGHT = 4,    /* Tt_apply_right     finite-element.h:1904-1926 */
+    BX_TINV_APPLY_RIGHT = 5,  /* Tinv_apply_right   finite-element.h:1928-1950 */
+    BX_T_APPLY_RIGHT = 6,     /* T_apply_right      finite-element.h:1952-1974 */
+    BX_TT_INV_APPLY_RIGHT = 7 /* Tt_inv_apply_right finite-element.h:1976-1998 */
+  };
+
+  /* ---- library / device ---------------------------------------------------------------- */
+
+  /* Message of the last failing call made by the calling thread ("" if none). */
+  const char* bx_last_error(void);
+  /* Library version string. */
+  const char* bx_version(void);
+  /* Number of visible CUDA devices (0 if the driver/device is missing). */
+  int bx_device_count(void);
+  /* cudaSetDevice for the calling thread. */
+  int bx_set_device(int device);
+  /* Block until `stream` has drained (cudaStreamSynchronize). */
+  int bx_stream_synchronize(bx_stream_t stream);
+  /* Number of kernels this library has launched since load (all threads);
+     bench.py reports it as gpu_launches. */
+  uint64_t bx_kernel_launch_count(void);
+
+  /* ---- polynomial sets -------------------------------------------------------------------
+   * Replaces polyset::dim (polyset.cpp:3003-3050), polyset::nderivs (polyset.cpp:3052-3075)
+   * and polyset::tabulate (dispatch polyset.cpp:2914-2978; python binding
+   * tabulate_polynomial_set_float64, basix_wrappers.h:467-475).
+   * x[npts][tdim] row-major; P[nderivs][psize][npts] (point index fastest). */
+  int bx_polyset_dim(int cell_type, int polyset_type, int degree);
+  int bx_polyset_nderivs(int cell_type, int nderiv);
+  int bx_polyset_tabulate_f64(int cell_type, int polyset_type, int degree, int nderiv, const double* x,
+                              size_t npts, double* P, int mem, bx_stream_t stream);
+  int bx_polyset_tabulate_f32(int cell_type, int polyset_type, int degree, int nderiv, const float* x,
+                              size_t npts, float* P, int mem, bx_stream_t stream);
+
+  /* ---- element object ---------------------------------------------------------------------
+   * Mirrors the immutable data members of basix::FiniteElement<F> that the hot path reads
+   * (finite-element.h:1429-1554): _coeffs, _edofs, _entity_transformations (from which
+   * _eperm/_etrans* are derived as in finite-element.cpp:1260-1447), _dof_ordering,
+   * _value_shape, _map_type, cell/polyset type, _embedded_superdegree. */
+  typedef struct bx_element_desc
+  {
+    int cell_type;            /* bx_cell */
+    int polyset_type;         /* bx_polyset */
+    int degree;               /* FiniteElement::degree() (tolerance in perm detection) */
+    int embedded_superdegree; /* polyset degree, FiniteElement::embedded_superdegree() */
+    int map_type;             /* bx_map */
+    int ndofs;                /* FiniteElement::dim() */
+    int value_size;           /* prod(value_shape) */
+    const double* coeffs;     /* coefficient_matrix(): [ndofs][value_size * psize] row-major */
+    const int32_t* dof_ordering; /* dof_ordering() or NULL */
+    int n_dof_ordering;          /* 0 or ndofs */
+    /* entity_dofs(): entities enumerated dimension-major (all vertices, all edges, ...);
+       dofs of entity k are entity_dofs[entity_dof_offsets[k] .. entity_dof_offsets[k+1]) */
+    const int32_t* entity_dof_offsets; /* length (total number of sub-entities)+1 */
+    const int32_t* entity_dofs;
+    /* entity_transformations() (finite-element.h:772-776) per sub-entity cell type:
+       interval [1][n][n]; triangle / quadrilateral [2][n][n] = {rotation, reflection}.
+       NULL / 0 when the cell has no such sub-entity. */
+    const double* etrans_interval;
+    int etrans_interval_dim;
+    const double* etrans_triangle;
+    int etrans_triangle_dim;
+    const double* etrans_quadrilateral;
+    int etrans_quadrilateral_dim;
+  } bx_element_desc;
+
+  /* Build an element (host tables + device mirror on the current device) from arrays. */
+  int bx_element_create_from_arrays(const bx_element_desc* desc, bx_element** out);
+  void bx_element_destroy(bx_element* e);
+
+  /* Accessors (reference: finite-element.h:487-561). info[0..9] = cell_type, polyset_type,
+     tdim, ndofs, value_size, map_type, embedded_superdegree, dof_transformations_are_permutations,
+     dof_transformations_are_identity, psize. */
+  int bx_element_info(const bx_element* e, int32_t info[10]);
+  /* FiniteElement::tabulate_shape, finite-element.h:364-376: {nderivs, npts, ndofs, value_size}. */
+  int bx_element_tabulate_shape(const bx_element* e, int nd, size_t npts, size_t shape[4]);
+  /* Host-side inspection of the composed DOF-transformation tables (no device needed): the net
+     operator that op (a bx_top; the *_right variants share the operator of their left twin) applies
+     for one cell_info.  src[ndofs] (permutation elements only): out[i] = in[src[i]];
+     A[ndofs][ndofs]: out = A in.  Either may be NULL.  Generalises
+     FiniteElement::base_transformations (finite-element.cpp:1902-1969) to arbitrary cell_info. */
+  int bx_element_net_operator(const bx_element* e, int op, uint32_t cell_info, int32_t* src, double* A);
+  /* Which device path tabulate() will take for derivative order nd:
+     0 generic (polyset kernel + DMMA contraction), 1 fused simplex kernel,
+     2 tensor-product kernel. */
+  int bx_element_tabulate_path(const bx_element* e, int nd);
+
+  /* ---- FiniteElement::tabulate ------------------------------------------------------------
+   * Replaces FiniteElement<F>::tabulate (finite-element.cpp:1834-1888; python
+   * FiniteElement.tabulate, finite_element.py:63-95, binding basix_wrappers.h:117-124).
+   * x[npts][tdim]; basis[nderivs][npts][ndofs][value_size].  `tdim_x` is x.shape[1] and is
+   * validated against the element ("Point dim (..) does not match element dim (..)."). */
+  int bx_tabulate_f64(const bx_element* e, int nd, const double* x, size_t npts, int tdim_x, double* basis,
+                      int mem, bx_stream_t stream);
+
+  /* ---- push_forward / pull_back -----------------------------------------------------------
+   * Replaces FiniteElement<F>::push_forward (finite-element.cpp:1971-2005), pull_back
+   * (finite-element.cpp:2007-2042) and the kernels of maps.h:56-192.
+   * U[nc][rows][in_vs], J[nc][gdim][tdim], detJ[nc], K[nc][tdim][gdim] -> out[nc][rows][out_vs].
+   * bx_map_value_size gives out_vs (compute_value_size, finite-element.cpp:42-59, for push;
+   * the reference value size for pull). */
+  int bx_map_value_size(int map_type, int pull, int in_vs, int gdim, int tdim);
+  int bx_map_f64(int map_type, int pull, const double* U, const double* J, const double* detJ,
+                 const double* K, size_t nc, size_t rows, int in_vs, int gdim, int tdim, double* out,
+                 int mem, bx_stream_t stream);
+  int bx_push_forward_f64(const bx_element* e, const double* U, const double* J, const double* detJ,
+                          const double* K, size_t nc, size_t rows, int in_vs, int gdim, int tdim,
+                          double* out, int mem, bx_stream_t stream);
+  int bx_pull_back_f64(const bx_element* e, const double* u, const double* J, const double* detJ,
+                       const double* K, size_t nc, size_t rows, int in_vs, int gdim, int tdim, double* out,
+                       int mem, bx_stream_t stream);
+
+  /* ---- DOF transformations ----------------------------------------------------------------
+   * Replaces T_apply and its 7 siblings (finite-element.h:1839-1998), i.e. permute_data
+   * (finite-element.h:1703-1760) / transform_data (finite-element.h:1762-1837) with
+   * precompute::apply_* (precompute.h:136-374), batched over cells: data[nc][cell_size] is
+   * transformed in place, cell c using cell_info[c]; cell_size = ndofs * n.  The reference
+   * API is the nc == 1 case.  op is a bx_top. */
+  int bx_T_apply_f64(const bx_element* e, int op, double* data, size_t nc, size_t cell_size, int n,
+                     const uint32_t* cell_info, int mem, bx_stream_t stream);
+  int bx_T_apply_f32(const bx_element* e, int op, float* data, size_t nc, size_t cell_size, int n,
+                     const uint32_t* cell_info, int mem, bx_stream_t stream);
+  int bx_T_apply_i32(const bx_element* e, int op, int32_t* data, size_t nc, size_t cell_size, int n,
+                     const uint32_t* cell_info, int mem, bx_stream_t stream);
+  /* Replaces FiniteElement::permute / permute_inv (finite-element.h:800-843): d[nc][ndofs]. */
+  int bx_permute_i32(const bx_element* e, int inverse, int32_t* d, size_t nc, const uint32_t* cell_info,
+                     int mem, bx_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BASIX_B200_H */

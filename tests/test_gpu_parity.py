@@ -1,0 +1,318 @@
+"""Parity of the CUDA path (through the C ABI) against the reference oracle on identical inputs.
+
+Bars (BASELINE.json north_star / SURVEY 8c):
+  * permutations / integer indexing: bit-exact (array_equal);
+  * polyset, tabulate, Piola maps, matrix DOF transformations: max|gpu-ref| <= 1e-12 * max|ref| per slab.
+The polyset (simplex) and Piola kernels mirror the reference's operation order without FMA contraction and
+are additionally checked for bit equality where that holds.
+"""
+
+import numpy as np
+import pytest
+
+from conftest import make_pair, random_points, slab_close
+
+pytestmark = pytest.mark.gpu
+
+P, RT, N1E = 1, 2, 3
+INTERVAL, TRI, TET, QUAD, HEX = 1, 2, 3, 4, 5
+GLL, EQ, LEG = 2, 1, 11
+
+
+# ---- polyset::tabulate -------------------------------------------------------------------------------
+@pytest.mark.parametrize("cell,degree,nd", [(INTERVAL, 0, 0), (INTERVAL, 1, 1), (INTERVAL, 7, 3), (TRI, 0, 2),
+                                            (TRI, 1, 1), (TRI, 2, 1), (TRI, 6, 3), (TET, 0, 1), (TET, 1, 0),
+                                            (TET, 3, 1), (TET, 5, 2), (TET, 4, 3), (QUAD, 0, 1), (QUAD, 3, 2),
+                                            (HEX, 1, 0), (HEX, 4, 1), (HEX, 2, 2)])
+def test_polyset_tabulate(ref, cell, degree, nd):
+    import basix_b200 as bx
+
+    x = random_points(cell, 1003)
+    want = ref.tabulate_polynomial_set(cell, 0, degree, nd, x)
+    got = bx.tabulate_polynomial_set(cell, 0, degree, nd, x)
+    assert got.shape == want.shape
+    slab_close(got, want, 1e-13)
+    if cell in (INTERVAL, TRI, TET):
+        # same operation order, no FMA contraction -> identical bits
+        assert np.array_equal(got, want)
+
+
+def test_polyset_golden_anchor():
+    """SURVEY 8c anchors (reference output): triangle degree 2, nd=1 at (0.3, 0.2); hex degree 1."""
+    import basix_b200 as bx
+
+    got = bx.tabulate_polynomial_set(TRI, 0, 2, 1, np.array([[0.3, 0.2]]))[:, :, 0]
+    want = np.array([[1.4142135623731, -0.8, -0.692820323027551, -0.489897948556636, 0, -1.42407864951343],
+                     [0, 0, 6.92820323027551, 0, 0, -6.57267069006199],
+                     [0, 6, 3.46410161513775, -9.79795897113271, -4.24264068711928, 1.09544511501033]])
+    assert np.allclose(got, want, rtol=0, atol=5e-14)
+    got = bx.tabulate_polynomial_set(HEX, 0, 1, 0, np.array([[.25, .5, .75]]))[0, :, 0]
+    assert np.allclose(got, [1, 0.866025403784439, 0, 0, -0.866025403784439, -0.75, 0, 0], rtol=0, atol=5e-15)
+
+
+def test_polyset_device_pointers(ref):
+    import torch
+
+    import basix_b200 as bx
+
+    x = random_points(TET, 4099)
+    want = ref.tabulate_polynomial_set(TET, 0, 4, 2, x)
+    got = bx.tabulate_polynomial_set(TET, 0, 4, 2, torch.from_numpy(x).cuda())
+    assert got.is_cuda
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+# ---- FiniteElement::tabulate ---------------------------------------------------------------------------
+ELEMENTS = [
+    (P, TRI, 1, GLL), (P, TRI, 4, GLL), (P, TET, 1, GLL), (P, TET, 2, EQ), (P, TET, 5, GLL), (P, INTERVAL, 3, GLL),
+    (P, QUAD, 2, GLL), (P, HEX, 1, GLL), (P, HEX, 4, GLL), (N1E, TET, 3, LEG), (RT, TET, 4, LEG), (RT, TRI, 2, LEG),
+    (N1E, TRI, 1, LEG),
+]
+
+
+@pytest.mark.parametrize("family,cell,degree,variant", ELEMENTS)
+@pytest.mark.parametrize("nd", [0, 1, 2])
+def test_tabulate(ref, family, cell, degree, variant, nd):
+    r, e = make_pair(ref, family, cell, degree, variant)
+    x = random_points(cell, 777, seed=degree + 10 * nd)
+    want = r.tabulate(nd, x)
+    got = e.tabulate(nd, x)
+    assert got.shape == want.shape == e.tabulate_shape(nd, len(x))
+    slab_close(got, want, 1e-12)
+
+
+def test_tabulate_golden_p1_triangle(ref):
+    r, e = make_pair(ref, P, TRI, 1, GLL)
+    got = e.tabulate(1, np.array([[0.3, 0.2]])).reshape(3, 3)
+    assert np.allclose(got, [[.5, .3, .2], [-1, 1, 0], [-1, 0, 1]], rtol=0, atol=1e-15)
+
+
+def test_tabulate_dof_ordering(ref):
+    """dof_ordering scatter, finite-element.cpp:1880-1886 (reference test: test_dof_ordering.py:21-57)."""
+    order = [3, 0, 5, 1, 4, 2]
+    r0, e0 = make_pair(ref, P, TRI, 2, GLL)
+    r1, e1 = make_pair(ref, P, TRI, 2, GLL, dof_ordering=order)
+    x = random_points(TRI, 200)
+    t0, t1 = e0.tabulate(1, x), e1.tabulate(1, x)
+    slab_close(t1, r1.tabulate(1, x), 1e-12)
+    for i, j in enumerate(order):
+        assert np.array_equal(t0[:, :, i, :], t1[:, :, j, :])
+
+
+def test_tabulate_ragged_and_device(ref):
+    import torch
+
+    r, e = make_pair(ref, P, TET, 3, GLL)
+    for npts in (1, 7, 31, 33, 257):
+        x = random_points(TET, npts, seed=npts)
+        slab_close(e.tabulate(1, x), r.tabulate(1, x), 1e-12)
+        xd = torch.from_numpy(x).cuda()
+        got = e.tabulate(1, xd)
+        assert got.is_cuda
+        slab_close(got.cpu().numpy(), r.tabulate(1, x), 1e-12)
+    assert e.tabulate(1, np.zeros((0, 3))).shape == (4, 0, 20, 1)
+
+
+def test_tabulate_wrong_point_dim(ref):
+    r, e = make_pair(ref, P, TET, 2, EQ)
+    with pytest.raises(RuntimeError, match=r"Point dim \(2\) does not match element dim \(3\)\."):
+        e.tabulate(0, np.zeros((4, 2)))
+
+
+def test_tabulate_partition_of_unity_large(ref):
+    """Size-independent property at a size the oracle is too slow for: Lagrange basis sums to 1 and
+    derivative slabs sum to 0 (reference test_lagrange.py:857-864)."""
+    import torch
+
+    r, e = make_pair(ref, P, TET, 5, GLL)
+    x = torch.from_numpy(random_points(TET, 300_000, seed=5)).cuda()
+    t = e.tabulate(2, x)
+    s = t.sum(dim=2)[..., 0]
+    assert float((s[0] - 1).abs().max()) < 1e-11
+    scale = float(t.abs().max())
+    assert float(s[1:].abs().max()) < 1e-11 * scale
+
+
+# ---- push_forward / pull_back ----------------------------------------------------------------------------
+def jacobians(nc, gdim, tdim, seed=7):
+    rng = np.random.default_rng(seed)
+    J = np.zeros((nc, gdim, tdim))
+    J[:, :tdim, :tdim] = np.eye(tdim)
+    J += 0.3 * rng.standard_normal((nc, gdim, tdim))
+    if gdim == tdim:
+        detJ = np.linalg.det(J)
+        K = np.linalg.inv(J)
+    else:
+        JtJ = np.einsum("cji,cjk->cik", J, J)
+        detJ = np.sqrt(np.linalg.det(JtJ))
+        K = np.einsum("cij,ckj->cik", np.linalg.inv(JtJ), J)
+    return np.ascontiguousarray(J), np.ascontiguousarray(detJ), np.ascontiguousarray(K)
+
+
+MAP_ELEMENTS = [(P, TET, 2, EQ, 1), (N1E, TET, 3, LEG, 3), (RT, TET, 4, LEG, 3), (N1E, TRI, 2, LEG, 2),
+                (RT, TRI, 2, LEG, 2), (7, TET, 1, 0, 9), (11, TRI, 1, 0, 4), (7, TRI, 2, 0, 4), (11, TET, 1, 0, 9)]
+
+
+@pytest.mark.parametrize("family,cell,degree,variant,vs", MAP_ELEMENTS)
+@pytest.mark.parametrize("rows", [1, 5])
+def test_push_pull_square(ref, family, cell, degree, variant, vs, rows):
+    r, e = make_pair(ref, family, cell, degree, variant)
+    tdim = 3 if cell == TET else 2
+    nc = 1234
+    J, detJ, K = jacobians(nc, tdim, tdim)
+    U = np.random.default_rng(1).standard_normal((nc, rows, vs))
+    want = r.push_forward(U, J, detJ, K)
+    got = e.push_forward(U, J, detJ, K)
+    assert got.shape == want.shape
+    assert np.array_equal(got, want), np.max(np.abs(got - want))
+    back_ref = r.pull_back(want, J, detJ, K)
+    back = e.pull_back(got, J, detJ, K)
+    assert np.array_equal(back, back_ref)
+    assert np.allclose(back, U, rtol=1e-9, atol=1e-9)  # reference test_mappings.py round trip
+
+
+@pytest.mark.parametrize("family,variant,vs", [(N1E, LEG, 2), (RT, LEG, 2), (7, 0, 4), (11, 0, 4), (P, GLL, 1)])
+def test_push_pull_manifold(ref, family, variant, vs):
+    """2-D cells embedded in 3-D: non-square J (reference test_mappings.py:66-81)."""
+    r, e = make_pair(ref, family, TRI, 2, variant)
+    nc = 301
+    J, detJ, K = jacobians(nc, 3, 2)
+    U = np.random.default_rng(2).standard_normal((nc, 4, vs))
+    want = r.push_forward(U, J, detJ, K)
+    got = e.push_forward(U, J, detJ, K)
+    assert got.shape == want.shape and np.array_equal(got, want)
+    assert np.array_equal(e.pull_back(got, J, detJ, K), r.pull_back(want, J, detJ, K))
+
+
+def test_map_device_pointers_and_golden(ref):
+    import torch
+
+    r, e = make_pair(ref, N1E, TET, 3, LEG)
+    J = np.array([[[2, .5, .25], [.125, 1.5, .75], [.0625, .3125, 1]]])
+    detJ, K = np.linalg.det(J), np.linalg.inv(J)
+    U = np.array([[[1., 2, 3]]])
+    got = e.push_forward(U, J, detJ, K)
+    assert np.allclose(got, [[[0.38140267927502, 0.7123719464145, 2.37037037037037]]], rtol=0, atol=1e-14)
+    assert np.allclose(e.pull_back(U, J, detJ, K), [[[2.4375, 4.4375, 4.75]]], rtol=0, atol=1e-14)
+    nc = 5000
+    Jb, db, Kb = jacobians(nc, 3, 3)
+    Ub = np.random.default_rng(3).standard_normal((nc, 45, 3))
+    t = [torch.from_numpy(a).cuda() for a in (Ub, Jb, db, Kb)]
+    got = e.push_forward(*t)
+    assert got.is_cuda and np.array_equal(got.cpu().numpy(), r.push_forward(Ub, Jb, db, Kb))
+
+
+# ---- DOF transformations -----------------------------------------------------------------------------------
+def cell_infos(nc, seed=11):
+    rng = np.random.default_rng(seed)
+    ci = rng.integers(0, 2 ** 30, nc).astype(np.uint32)
+    ci[:4] = [0, 1, 0x2ABCD, 0x3FFFFFFF]
+    return ci
+
+
+PERM_ELEMENTS = [(P, TRI, 3, GLL), (P, TET, 5, GLL), (P, TET, 3, EQ), (P, HEX, 3, GLL), (P, QUAD, 4, GLL),
+                 (P, HEX, 4, GLL)]
+ALL_OPS = ["T_apply", "Tt_apply", "Tt_inv_apply", "Tinv_apply", "Tt_apply_right", "Tinv_apply_right",
+           "T_apply_right", "Tt_inv_apply_right"]
+
+
+@pytest.mark.parametrize("family,cell,degree,variant", PERM_ELEMENTS)
+def test_permute_bit_exact(ref, family, cell, degree, variant):
+    r, e = make_pair(ref, family, cell, degree, variant)
+    nc = 2049
+    ci = cell_infos(nc)
+    d = np.tile(np.arange(r.dim, dtype=np.int32), (nc, 1)) + 1000 * np.arange(nc, dtype=np.int32)[:, None]
+    for inverse in (False, True):
+        want = r.permute_batch(d.copy(), ci, inverse=inverse)
+        got = d.copy()
+        e.permute_batch(got, ci, inverse=inverse)
+        assert np.array_equal(got, want)
+    # round trip
+    rt = d.copy()
+    e.permute_batch(rt, ci)
+    e.permute_batch(rt, ci, inverse=True)
+    assert np.array_equal(rt, d)
+
+
+def test_permute_golden_p5_tet(ref):
+    """SURVEY 8c anchors for P5 tetrahedron."""
+    r, e = make_pair(ref, P, TET, 5, GLL)
+    d = np.arange(56, dtype=np.int32)
+    e.permute(d, 0x2ABCD)
+    want = [0, 1, 2, 3, 4, 5, 6, 7, 11, 10, 9, 8, 12, 13, 14, 15, 19, 18, 17, 16, 20, 21, 22, 23, 27, 26, 25, 24, 33,
+            32, 30, 31, 29, 28, 34, 37, 39, 35, 38, 36, 40, 43, 45, 41, 44, 42, 51, 50, 48, 49, 47, 46, 52, 53, 54, 55]
+    assert d.tolist() == want
+    d = np.arange(56, dtype=np.int32)
+    e.permute(d, 0x1000)
+    assert d[4:8].tolist() == [7, 6, 5, 4]
+    d = np.arange(56, dtype=np.int32)
+    e.permute(d, 0x1)
+    assert d[28:34].tolist() == [28, 31, 33, 29, 32, 30]
+
+
+@pytest.mark.parametrize("family,cell,degree,variant", PERM_ELEMENTS[:4])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.int32])
+@pytest.mark.parametrize("bs", [1, 3])
+def test_T_apply_permutation_elements_bit_exact(ref, family, cell, degree, variant, dtype, bs):
+    r, e = make_pair(ref, family, cell, degree, variant)
+    nc = 515
+    ci = cell_infos(nc)
+    rng = np.random.default_rng(5)
+    data = (rng.standard_normal((nc, r.dim * bs)) * 100).astype(dtype)
+    ops = ALL_OPS if dtype != np.int32 else ALL_OPS[:4]
+    for op in ops:
+        want = r.T_apply_batch(op, data.copy(), bs, ci)
+        got = data.copy()
+        e.T_apply_batch(got, bs, ci, op=op)
+        assert np.array_equal(got, want), op
+
+
+MATRIX_ELEMENTS = [(RT, TET, 4, LEG), (N1E, TET, 3, LEG), (RT, TET, 2, LEG), (N1E, TRI, 3, LEG), (N1E, HEX, 2, LEG)]
+
+
+@pytest.mark.parametrize("family,cell,degree,variant", MATRIX_ELEMENTS)
+@pytest.mark.parametrize("bs", [1, 3, 16])
+def test_T_apply_matrix_elements(ref, family, cell, degree, variant, bs):
+    r, e = make_pair(ref, family, cell, degree, variant)
+    nc = 300
+    ci = cell_infos(nc)
+    data = np.random.default_rng(6).standard_normal((nc, r.dim * bs))
+    for op in ALL_OPS:
+        want = r.T_apply_batch(op, data.copy(), bs, ci)
+        got = data.copy()
+        e.T_apply_batch(got, bs, ci, op=op)
+        assert np.max(np.abs(got - want)) <= 1e-12 * np.max(np.abs(want)), op
+
+
+def test_T_apply_single_cell_reference_signature(ref):
+    """The reference API: one cell per call (finite_element.py:153-166)."""
+    r, e = make_pair(ref, RT, TET, 2, LEG)
+    for ci in (0x1, 0x2, 0x4, 0x5A7):
+        want = r.T_apply(np.arange(1, 16, dtype=np.float64), 1, ci)
+        got = np.arange(1, 16, dtype=np.float64)
+        e.T_apply(got, 1, ci)
+        assert np.allclose(got, want, rtol=0, atol=1e-13)
+
+
+def test_T_apply_inverse_pairs(ref):
+    """T^-1 T = I and (T^t)^-1 T^t = I on random data (reference test_dof_transformations.py:45-66 style)."""
+    import torch
+
+    r, e = make_pair(ref, RT, TET, 4, LEG)
+    nc = 20000
+    ci = torch.from_numpy(cell_infos(nc).astype(np.int64)).cuda().to(torch.uint32)
+    data = torch.randn(nc, 70 * 2, dtype=torch.float64, device="cuda")
+    for a, b in (("T_apply", "Tinv_apply"), ("Tt_apply", "Tt_inv_apply"), ("Tt_apply_right", "Tt_inv_apply_right")):
+        w = data.clone()
+        e.T_apply_batch(w, 2, ci, op=a)
+        assert not torch.equal(w, data)
+        e.T_apply_batch(w, 2, ci, op=b)
+        assert float((w - data).abs().max()) < 1e-11
+
+
+def test_errors(ref):
+    r, e = make_pair(ref, RT, TET, 2, LEG)
+    with pytest.raises(RuntimeError, match="not permutations"):
+        e.permute(np.arange(15, dtype=np.int32), 1)
+    with pytest.raises(RuntimeError):
+        e.T_apply_batch(np.zeros((2, 14)), 1, np.zeros(2, dtype=np.uint32))
