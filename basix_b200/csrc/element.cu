@@ -7,6 +7,7 @@
 //                                           cpp/basix/finite-element.cpp:1349-1445
 //   order of application per cell_info      cpp/basix/finite-element.h:1703-1837
 #include "element.cuh"
+#include "jets.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -64,6 +65,39 @@ T* upload(const std::vector<T>& v)
 
 int num_states(int mask) { return mask + 1; }
 } // namespace
+
+// seq -> (basis slot, norm) in the order jets.cuh emits basis functions
+void jets::production_order(int tdim, int n, int* slot, double* norm)
+{
+  int s = 0;
+  if (tdim == 1)
+  {
+    for (int p = 0; p <= n; ++p, ++s)
+    {
+      slot[s] = p;
+      norm[s] = std::sqrt(double(2 * p + 1));
+    }
+  }
+  else if (tdim == 2)
+  {
+    for (int p = 0; p <= n; ++p)
+      for (int q = 0; q <= n - p; ++q, ++s)
+      {
+        slot[s] = idx2(q, p);
+        norm[s] = std::sqrt((p + 0.5) * (p + q + 1)) * 2;
+      }
+  }
+  else
+  {
+    for (int p = 0; p <= n; ++p)
+      for (int q = 0; q <= n - p; ++q)
+        for (int r = 0; r <= n - p - q; ++r, ++s)
+        {
+          slot[s] = idx3(r, q, p);
+          norm[s] = std::sqrt(2 * (p + 0.5) * (p + q + 1.0) * (p + q + r + 1.5)) * 2;
+        }
+  }
+}
 
 bx_element* element_from_desc(const bx_element_desc& d)
 {
@@ -127,6 +161,29 @@ bx_element* element_from_desc(const bx_element_desc& d)
   }
   if (e->on_device)
     e->d_Cp = upload(e->Cp);
+
+  // ---- fused simplex kernel operand (tabulate_fused.cuh): Cs[Npad8][KS], column s = production-order
+  //      position of the basis function, scaled by its norm; only when all output columns fit ----
+  if (e->polyset_type == BX_POLYSET_STANDARD
+      and (e->cell_type == BX_CELL_INTERVAL or e->cell_type == BX_CELL_TRIANGLE or e->cell_type == BX_CELL_TETRAHEDRON))
+  {
+    const int K = e->K;
+    const int npad = int(ceil_div(K, 8) * 8);
+    const int kpad = e->Kpad;
+    const int ks = kpad + ((4 - kpad % 16) + 16) % 16;
+    if (e->N <= npad)
+    {
+      std::vector<int> slot(K);
+      std::vector<double> norm(K);
+      jets::production_order(e->tdim, e->superdegree, slot.data(), norm.data());
+      e->Cs.assign(size_t(npad) * ks, 0.0);
+      for (int n = 0; n < e->N; ++n)
+        for (int s = 0; s < K; ++s)
+          e->Cs[size_t(n) * ks + s] = e->Cp[size_t(n) * e->Kpad + slot[s]] * norm[s];
+      if (e->on_device)
+        e->d_Cs = upload(e->Cs);
+    }
+  }
 
   // ---- entity dofs -----------------------------------------------------------------------------------
   if (!d.entity_dof_offsets or !d.entity_dofs)
@@ -482,6 +539,7 @@ bx_element::~bx_element()
 {
   // best effort; errors at teardown are ignored
   cudaFree(d_Cp);
+  cudaFree(d_Cs);
   cudaFree(d_dof_slot);
   cudaFree(d_dof_loc);
   cudaFree(d_slot_info);

@@ -34,7 +34,9 @@ struct bx_element
   // Cp[Npad][Kpad]: row (dof_ordering[dof]*vs + j) = coeffs[dof][j*psize .. (j+1)*psize), zero padded
   int N = 0, K = 0, Npad = 0, Kpad = 0;
   std::vector<double> Cp;
+  std::vector<double> Cs; // fused-kernel operand (host copy), empty when not applicable
   double* d_Cp = nullptr;
+  double* d_Cs = nullptr; // fused-kernel operand (norm-scaled, production order, padded) or null
 
   // ---- DOF transformations ----------------------------------------------------------------------
   // "slots" = transformable sub-entities in the reference's processing order (edges, then faces)

@@ -11,6 +11,9 @@
 // [d][pt][dof*vs] layout -- the reference's separate transpose pass does not exist here because the
 // MMA accumulator fragment already has (point, dof) orientation.
 #include "element.cuh"
+#include "fused_menu.cuh"
+
+#include <algorithm>
 
 namespace bx
 {
@@ -133,13 +136,38 @@ void tabulate_generic_device(const bx_element& e, int nd, const double* x, size_
 
 namespace bx
 {
+namespace
+{
+// Fused simplex kernel (tabulate_fused.cuh) when the element has the operand and (degree, nd) is on the menu.
+bool try_fused(const bx_element& e, int nd, const double* x, size_t npts, double* basis, cudaStream_t s, bool dry_run)
+{
+  if (e.Cs.empty() or (!dry_run and !e.d_Cs))
+    return false;
+  switch (e.cell_type)
+  {
+  case BX_CELL_INTERVAL: return fused::launch_interval(e, nd, x, npts, basis, s, dry_run);
+  case BX_CELL_TRIANGLE: return fused::launch_triangle(e, nd, x, npts, basis, s, dry_run);
+  case BX_CELL_TETRAHEDRON: return fused::launch_tetrahedron(e, nd, x, npts, basis, s, dry_run);
+  default: return false;
+  }
+}
+} // namespace
+
 // Which device path tabulate() takes: 0 generic, 1 fused simplex, 2 tensor product.
-int tabulate_path(const bx_element&, int) { return 0; }
+int tabulate_path(const bx_element& e, int nd)
+{
+  if (try_fused(e, nd, nullptr, 0, nullptr, nullptr, true))
+    return 1;
+  return 0;
+}
 
 void tabulate_device(const bx_element& e, int nd, const double* x, size_t npts, double* basis, size_t out_pts,
                      cudaStream_t s)
 {
   require_device(e);
+  // the fused kernels write a dense [nder][npts][N] table; a chunk of a larger table takes the generic path
+  if (out_pts == npts and try_fused(e, nd, x, npts, basis, s, false))
+    return;
   tabulate_generic_device(e, nd, x, npts, basis, out_pts, s);
 }
 } // namespace bx

@@ -316,3 +316,31 @@ def test_errors(ref):
         e.permute(np.arange(15, dtype=np.int32), 1)
     with pytest.raises(RuntimeError):
         e.T_apply_batch(np.zeros((2, 14)), 1, np.zeros(2, dtype=np.uint32))
+
+
+# ---- fused simplex kernel (tabulate_fused.cuh) ------------------------------------------------------------
+FUSED = [(TET, 2, 3), (TET, 3, 3), (TET, 4, 2), (TET, 5, 2), (TET, 5, 1), (TET, 5, 0), (TET, 6, 1), (TET, 6, 0),
+         (TRI, 3, 3), (TRI, 5, 2), (TRI, 8, 2), (TRI, 7, 1), (TRI, 6, 0), (INTERVAL, 7, 2), (INTERVAL, 8, 0)]
+
+
+@pytest.mark.parametrize("cell,degree,nd", FUSED)
+def test_tabulate_fused_path(ref, cell, degree, nd):
+    r, e = make_pair(ref, P, cell, degree, GLL)
+    assert e.tabulate_path(nd) == "fused"
+    # more tiles than CTAs (ring wraps many times), ragged tail
+    for npts in (5, 32, 20011):
+        x = random_points(cell, npts, seed=npts + degree)
+        slab_close(e.tabulate(nd, x), r.tabulate(nd, x, chunk=4096, nthreads=8), 1e-12)
+
+
+def test_tabulate_fused_dof_ordering_and_device(ref):
+    import torch
+
+    order = list(np.random.default_rng(0).permutation(35))
+    r, e = make_pair(ref, P, TET, 4, GLL, dof_ordering=[int(v) for v in order])
+    assert e.tabulate_path(1) == "fused"
+    x = random_points(TET, 3333, seed=9)
+    want = r.tabulate(1, x)
+    slab_close(e.tabulate(1, x), want, 1e-12)
+    got = e.tabulate(1, torch.from_numpy(x).cuda())
+    slab_close(got.cpu().numpy(), want, 1e-12)
