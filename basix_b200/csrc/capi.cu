@@ -293,8 +293,9 @@ void tabulate_any(const bx_element& e, int nd, const double* x, size_t npts, int
     BX_CUDA(cudaMemcpyAsync(dx[b].p, x + p0 * e.tdim, np * e.tdim * sizeof(double), cudaMemcpyHostToDevice, st.s[b]));
     tabulate_device(e, nd, dx[b].as<double>(), np, dout[b].as<double>(), np, st.s[b]);
     // each derivative slab of the chunk is one contiguous run of np * N values on both sides
-    BX_CUDA(cudaMemcpy2DAsync(basis + p0 * e.N, npts * e.N * sizeof(double), dout[b].p, np * e.N * sizeof(double),
-                              np * e.N * sizeof(double), nder, cudaMemcpyDeviceToHost, st.s[b]));
+    for (int d = 0; d < nder; ++d)
+      BX_CUDA(cudaMemcpyAsync(basis + (size_t(d) * npts + p0) * e.N, dout[b].as<double>() + size_t(d) * np * e.N,
+                              np * e.N * sizeof(double), cudaMemcpyDeviceToHost, st.s[b]));
   }
   st.sync();
 }

@@ -66,7 +66,8 @@ struct Cfg
   static constexpr int stages(int smem_budget)
   {
     int s = (smem_budget - CS_DOUBLES * 8 - 256) / (CHUNK_DOUBLES * 8);
-    return s > 2 * NCHUNK ? 2 * NCHUNK : (s > 15 ? 15 : s);
+    s = s > 2 * NCHUNK ? 2 * NCHUNK : s;
+    return s > 16 ? 16 : s; // the barrier block holds 2 x 16 mbarriers
   }
 };
 

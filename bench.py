@@ -228,7 +228,7 @@ def run_ours(args, w, rank, local_rank, world):
     while e2e_pts * (out_bytes / npts) > 0.4 * avail and e2e_pts > 100_000:
         e2e_pts //= 2
     e2e_shape = e.tabulate_shape(nd, e2e_pts)
-    out_host = torch.empty(e2e_shape, dtype=torch.float64).pin_memory()
+    out_host = None if args.no_e2e else torch.empty(e2e_shape, dtype=torch.float64).pin_memory()
     xh = x_host[:e2e_pts]
     del out
     torch.cuda.empty_cache()
@@ -238,17 +238,20 @@ def run_ours(args, w, rank, local_rank, world):
         _capi.check(lib.bx_tabulate_f64(e._h, nd, xh.data_ptr(), e2e_pts, xh.shape[1], out_host.data_ptr(),
                                         _capi.BX_MEM_HOST, None))
 
-    e2e_step()
-    barrier()
     e2e_steps = max(1, min(args.steps, 3))
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    if args.no_e2e:
+        e2e_value = None
+    else:
         e2e_step()
-    torch.cuda.synchronize()
-    dt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e_value = int(np.prod(e2e_shape)) * world / float(dt.item())
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e_value = int(np.prod(e2e_shape)) * world / float(dt.item())
 
     # ---- roofline of the dominant kernel ----
     hbm_peak, peak_src = measured_peaks()
@@ -300,6 +303,7 @@ def main():
     ap.add_argument("--workload", default="tabulate_p5_tet_nd2_10M", choices=sorted(WORKLOADS))
     ap.add_argument("--fp64-peak", type=float, default=37.0, help="FP64 peak in TFLOP/s used for roofline.frac")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
