@@ -66,6 +66,114 @@ T* upload(const std::vector<T>& v)
 int num_states(int mask) { return mask + 1; }
 } // namespace
 
+namespace
+{
+void factor_tensor_product(bx_element& e)
+{
+  const int tdim = e.tdim, n1 = e.superdegree + 1, N = e.N;
+  constexpr int kMaxFun = 16;
+  if (n1 > 9)
+    return;
+  auto& tp = e.tp;
+  std::vector<std::vector<double>> funs[3];
+  tp.ijk.assign(N, 0);
+  tp.scale.assign(N, 0.0);
+  double cmax = 0;
+  for (double v : e.Cp)
+    cmax = std::max(cmax, std::abs(v));
+  const double tol = 1e-13 * cmax;
+  const int stride[3] = {tdim == 2 ? n1 : n1 * n1, tdim == 2 ? 1 : n1, 1};
+  for (int n = 0; n < N; ++n)
+  {
+    const double* T = e.Cp.data() + size_t(n) * e.Kpad;
+    int kmax = 0;
+    for (int k = 1; k < e.K; ++k)
+      if (std::abs(T[k]) > std::abs(T[kmax]))
+        kmax = k;
+    const double T0 = T[kmax];
+    if (std::abs(T0) <= tol)
+      continue; // zero row: scale 0
+    int p0[3] = {0, 0, 0};
+    {
+      int rem = kmax;
+      for (int a = 0; a < tdim; ++a)
+      {
+        p0[a] = rem / stride[a];
+        rem -= p0[a] * stride[a];
+      }
+    }
+    // fibres through the pivot, normalised by the pivot
+    std::vector<double> f[3];
+    for (int a = 0; a < tdim; ++a)
+    {
+      f[a].resize(n1);
+      for (int q = 0; q < n1; ++q)
+      {
+        int k = 0;
+        for (int b = 0; b < tdim; ++b)
+          k += (b == a ? q : p0[b]) * stride[b];
+        f[a][q] = T[k] / T0;
+      }
+    }
+    // rank-1 check
+    for (int k = 0; k < e.K; ++k)
+    {
+      int rem = k;
+      double r = T0;
+      for (int a = 0; a < tdim; ++a)
+      {
+        const int q = rem / stride[a];
+        rem -= q * stride[a];
+        r *= f[a][q];
+      }
+      if (std::abs(r - T[k]) > tol)
+        return; // not a tensor product
+    }
+    int id[3] = {0, 0, 0};
+    for (int a = 0; a < tdim; ++a)
+    {
+      int found = -1;
+      for (size_t j = 0; j < funs[a].size() and found < 0; ++j)
+      {
+        double dmax = 0;
+        for (int q = 0; q < n1; ++q)
+          dmax = std::max(dmax, std::abs(funs[a][j][q] - f[a][q]));
+        if (dmax <= 1e-10)
+          found = int(j);
+      }
+      if (found < 0)
+      {
+        if (int(funs[a].size()) >= kMaxFun)
+          return;
+        funs[a].push_back(f[a]);
+        found = int(funs[a].size()) - 1;
+      }
+      id[a] = found;
+    }
+    tp.ijk[n] = id[0] | (id[1] << 8) | (id[2] << 16);
+    tp.scale[n] = T0;
+  }
+  tp.fstride = 1;
+  for (int a = 0; a < tdim; ++a)
+  {
+    tp.nfun[a] = int(funs[a].size());
+    tp.fstride = std::max(tp.fstride, tp.nfun[a]);
+  }
+  tp.A.assign(size_t(tdim) * tp.fstride * n1, 0.0);
+  for (int a = 0; a < tdim; ++a)
+    for (int j = 0; j < tp.nfun[a]; ++j)
+      for (int q = 0; q < n1; ++q)
+        tp.A[(size_t(a) * tp.fstride + j) * n1 + q] = funs[a][j][q] * std::sqrt(double(2 * q + 1));
+  tp.valid = true;
+  if (e.on_device)
+  {
+    tp.d_A = upload(tp.A);
+    tp.d_ijk = upload(tp.ijk);
+    tp.d_scale = upload(tp.scale);
+  }
+}
+} // namespace
+
 // seq -> (basis slot, norm) in the order jets.cuh emits basis functions
 void jets::production_order(int tdim, int n, int* slot, double* norm)
 {
@@ -184,6 +292,11 @@ bx_element* element_from_desc(const bx_element_desc& d)
         e->d_Cs = upload(e->Cs);
     }
   }
+
+  // ---- tensor-product factorisation of the rows of Cp (quad / hex): Cp[n][(px,py,pz)] =
+  //      s_n a_i[px] b_j[py] c_k[pz].  Detected numerically; any row that is not rank-1 disables the path.
+  if (e->polyset_type == BX_POLYSET_STANDARD and (e->cell_type == BX_CELL_QUADRILATERAL or e->cell_type == BX_CELL_HEXAHEDRON))
+    factor_tensor_product(*e);
 
   // ---- entity dofs -----------------------------------------------------------------------------------
   if (!d.entity_dof_offsets or !d.entity_dofs)
@@ -540,6 +653,9 @@ bx_element::~bx_element()
   // best effort; errors at teardown are ignored
   cudaFree(d_Cp);
   cudaFree(d_Cs);
+  cudaFree(tp.d_A);
+  cudaFree(tp.d_ijk);
+  cudaFree(tp.d_scale);
   cudaFree(d_dof_slot);
   cudaFree(d_dof_loc);
   cudaFree(d_slot_info);

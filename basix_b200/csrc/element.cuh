@@ -38,6 +38,20 @@ struct bx_element
   double* d_Cp = nullptr;
   double* d_Cs = nullptr; // fused-kernel operand (norm-scaled, production order, padded) or null
 
+  // ---- tabulate: tensor-product factorisation (quad / hex), see tabulate_tp.cu -------------------------
+  struct TensorProduct
+  {
+    bool valid = false;
+    int nfun[3] = {0, 0, 0};     // distinct 1-D functions per axis
+    int fstride = 0;             // max(nfun)
+    std::vector<double> A;       // [tdim][fstride][n1] 1-D coefficients (w.r.t. un-normalised Legendre)
+    std::vector<int32_t> ijk;    // [N] packed i | j << 8 | k << 16
+    std::vector<double> scale;   // [N]
+    double* d_A = nullptr;
+    int32_t* d_ijk = nullptr;
+    double* d_scale = nullptr;
+  } tp;
+
   // ---- DOF transformations ----------------------------------------------------------------------
   // "slots" = transformable sub-entities in the reference's processing order (edges, then faces)
   struct Slot

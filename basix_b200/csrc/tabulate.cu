@@ -136,6 +136,8 @@ void tabulate_generic_device(const bx_element& e, int nd, const double* x, size_
 
 namespace bx
 {
+bool tabulate_tp_device(const bx_element& e, int nd, const double* x, size_t npts, double* basis, cudaStream_t s,
+                        bool dry_run);
 namespace
 {
 // Fused simplex kernel (tabulate_fused.cuh) when the element has the operand and (degree, nd) is on the menu.
@@ -158,6 +160,8 @@ int tabulate_path(const bx_element& e, int nd)
 {
   if (try_fused(e, nd, nullptr, 0, nullptr, nullptr, true))
     return 1;
+  if (tabulate_tp_device(e, nd, nullptr, 0, nullptr, nullptr, true))
+    return 2;
   return 0;
 }
 
@@ -167,6 +171,8 @@ void tabulate_device(const bx_element& e, int nd, const double* x, size_t npts, 
   require_device(e);
   // the fused kernels write a dense [nder][npts][N] table; a chunk of a larger table takes the generic path
   if (out_pts == npts and try_fused(e, nd, x, npts, basis, s, false))
+    return;
+  if (out_pts == npts and tabulate_tp_device(e, nd, x, npts, basis, s, false))
     return;
   tabulate_generic_device(e, nd, x, npts, basis, out_pts, s);
 }

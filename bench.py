@@ -1,18 +1,22 @@
 #!/usr/bin/env python
-"""Benchmark of the basix hot path on B200 (contract: see the task statement / DESIGN.md "Measurement").
+"""Benchmark of the basix hot path on B200.
 
   python bench.py --gpus N --steps K --warmup W [--impl ours|reference] [--workload NAME]
 
-A "step" is one pass of the hot path over one batch of synthetic input.  The headline workload is
-BASELINE.json configs[1]: P5 Lagrange on the tetrahedron, tabulate(nd=2) at 10M points per GPU
-(weak scaling: every rank tabulates its own 10M-point slice, no data-path collective).
+A "step" is one pass of the hot path over one batch of synthetic input.  The headline workload (default) is
+BASELINE.json configs[1]: P5 Lagrange on the tetrahedron, tabulate(nd=2) at 10M points per GPU.  Multi-GPU is
+weak scaling: every rank processes its own slice of points / cells, no data-path collective.
 
-`value`   whole-job throughput, inputs resident in HBM, timed with CUDA events on the launch stream.
-`e2e`     the same metric through the C ABI with HOST buffers (H2D of x and D2H of the table inside the
-          timed region, pinned memory).
-`roofline`      the dominant kernel against the measured peak.
-`cpu_baseline`  the compiled reference (oracle/_ref) on this box's host cores, bounded sample (rank 0, N=1).
-`--impl reference` times only that CPU reference, same metric/config.
+JSON line keys (contract):
+  value         whole-job throughput, inputs resident in HBM, CUDA events on the launch stream, max over ranks
+  e2e           same metric through the C ABI with HOST (pinned) buffers: H2D of the inputs and D2H of the
+                result inside the timed region
+  roofline      the dominant kernel: algorithmic bytes (or flops) per launch / its measured duration, against
+                the measured peak (MEASURED_PEAKS.json for HBM; FP64 tensor peak measured by tools/peaks.cu,
+                profiles/r01_peaks_fp64_hbm_pcie.json, since the driver file has no FP64 figure)
+  cpu_baseline  the compiled reference (oracle/_ref) on this box's host cores, bounded sample (rank 0, N=1)
+  --impl reference   times only that CPU reference: same metric / config / unit
+Other workloads (--workload) are the remaining BASELINE.json configs; they print the same line.
 """
 
 from __future__ import annotations
@@ -31,29 +35,46 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden", "elements")
-
-# workload -> description
-WORKLOADS = {
-    # name: (element fixture, kind, params)
-    "tabulate_p5_tet_nd2_10M": dict(element="P5_tetrahedron_gll", kind="tabulate", cell=3, nd=2, units=10_000_000,
-                                    ref_args=(1, 3, 5, 2), unit="values/s",
-                                    desc="P5 Lagrange (gll_warped) tetrahedron, tabulate(nd=2), 10M points per GPU"),
-    "tabulate_p1_tri_nd1_1M": dict(element="P1_triangle_gll", kind="tabulate", cell=2, nd=1, units=1_000_000,
-                                   ref_args=(1, 2, 1, 2), unit="values/s",
-                                   desc="P1 Lagrange triangle, tabulate(nd=1), 1M points per GPU"),
-}
-METRIC = "tabulated basis values/sec (pts x dofs x derivs)"
+FP64_TENSOR_PEAK_TFLOPS = 37.0  # measured: DMMA m8n8k4 microbenchmark, profiles/r01_peaks_fp64_hbm_pcie.json
+METRIC_VALUES = "tabulated basis values/sec (pts x dofs x derivs)"
+METRIC_CELLS = "cells/sec"
 
 
+# ---- synthetic inputs ---------------------------------------------------------------------------
 def random_points(cell, n, seed):
     rng = np.random.default_rng(seed)
     if cell == 3:
         s = np.sort(rng.random((n, 3)), axis=1)
         return np.ascontiguousarray(np.stack([s[:, 0], s[:, 1] - s[:, 0], s[:, 2] - s[:, 1]], axis=1))
-    u = rng.random((n, 2))
-    flip = u.sum(axis=1) > 1
-    u[flip] = 1 - u[flip]
-    return np.ascontiguousarray(u)
+    if cell == 2:
+        u = rng.random((n, 2))
+        flip = u.sum(axis=1) > 1
+        u[flip] = 1 - u[flip]
+        return np.ascontiguousarray(u)
+    return np.ascontiguousarray(rng.random((n, {1: 1, 4: 2, 5: 3}[cell])))
+
+
+def random_jacobians(nc, seed):
+    """J = I + 0.3 N(0,1), rejecting |det| < 0.1; detJ and K = J^-1 in float64."""
+    rng = np.random.default_rng(seed)
+    J = np.eye(3)[None] + 0.3 * rng.standard_normal((nc, 3, 3))
+    det = np.linalg.det(J)
+    bad = np.abs(det) < 0.1
+    while bad.any():
+        J[bad] = np.eye(3)[None] + 0.3 * rng.standard_normal((int(bad.sum()), 3, 3))
+        det = np.linalg.det(J)
+        bad = np.abs(det) < 0.1
+    return np.ascontiguousarray(J), np.ascontiguousarray(det), np.ascontiguousarray(np.linalg.inv(J))
+
+
+def random_cell_info(nc, seed):
+    """Realistic tetrahedron cell_info: per face reflect in {0,1}, rotations in {0,1,2}; 6 edge bits."""
+    rng = np.random.default_rng(seed)
+    ci = np.zeros(nc, dtype=np.uint32)
+    for f in range(4):
+        ci |= (rng.integers(0, 2, nc).astype(np.uint32) | (rng.integers(0, 3, nc).astype(np.uint32) << 1)) << (3 * f)
+    ci |= rng.integers(0, 64, nc).astype(np.uint32) << 12
+    return ci
 
 
 class ClockSampler(threading.Thread):
@@ -93,7 +114,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.02)
 
     def stop(self):
         self._stop_evt.set()
@@ -102,75 +123,310 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def measured_peaks():
+def measured_hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         with open(p) as f:
-            d = json.load(f)
-        return float(d.get("hbm_gbs", 6650.0)), "MEASURED_PEAKS.json"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+            return float(json.load(f).get("hbm_gbs", 6650.0)), "MEASURED_PEAKS.json hbm_gbs"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def load_element(name):
+    import basix_b200 as bx
+
+    return bx.FiniteElement.from_arrays(np.load(os.path.join(GOLDEN, name + ".npz")))
 
 
 # ======================================================================================================
-def cpu_reference_run(w, steps, warmup, sample_pts=None):
-    """Times the compiled reference (oracle/_ref) on all host threads over a bounded sample."""
+# Workloads.  Each provides setup / step (device-resident), e2e_setup / e2e_step (host buffers through the
+# C ABI) and cpu_setup / cpu_step (the compiled reference), plus algorithmic bytes and flops PER LAUNCH.
+class Tabulate:
+    metric, unit = METRIC_VALUES, "values/s"
+
+    def __init__(self, element, ref_args, cell, nd, npts, chunks, desc, bound):
+        self.element_name, self.ref_args, self.cell, self.nd = element, ref_args, cell, nd
+        self.npts, self.chunks, self.desc, self.bound = npts, chunks, desc, bound
+
+    def setup(self, rank):
+        import torch
+
+        self.e = load_element(self.element_name)
+        e = self.e
+        self.cnp = self.npts // self.chunks  # points per launch (the table of one launch stays resident)
+        self.shape = e.tabulate_shape(self.nd, self.cnp)
+        self.values_per_step = int(np.prod(self.shape)) * self.chunks
+        self.units_per_step = self.values_per_step
+        self.x_host = torch.from_numpy(random_points(self.cell, self.npts, 42 + rank)).pin_memory()
+        self.x = self.x_host.cuda()
+        self.out = torch.empty(self.shape, dtype=torch.float64, device="cuda")
+        self.path = e.tabulate_path(self.nd)
+        self.launches_per_step = self.chunks
+        self.alg_bytes = self.cnp * e._tdim * 8 + int(np.prod(self.shape)) * 8
+        self.flops = 2.0 * e.dim * e.value_size * e._psize * self.shape[0] * self.cnp
+        self.config = {"workload": self.desc, "points_per_gpu": self.npts, "nd": self.nd, "tabulate_path": self.path,
+                       "points_per_launch": self.cnp,
+                       "l2": "table of one launch is %.2f GB (>> 126 MB L2)" % (int(np.prod(self.shape)) * 8 / 1e9)}
+
+    def step(self):
+        for c in range(self.chunks):
+            self.e.tabulate(self.nd, self.x[c * self.cnp:(c + 1) * self.cnp], out=self.out)
+
+    def e2e_setup(self, avail_bytes):
+        import torch
+
+        per_pt = self.values_per_step // self.npts * 8
+        pts = self.npts
+        while pts * per_pt > 0.4 * avail_bytes and pts > 100_000:
+            pts //= 2
+        self.e2e_pts = pts
+        self.e2e_shape = self.e.tabulate_shape(self.nd, pts)
+        del self.out
+        torch.cuda.empty_cache()
+        self.out_host = torch.empty(self.e2e_shape, dtype=torch.float64).pin_memory()
+        self.e2e_units = int(np.prod(self.e2e_shape))
+        self.h2d, self.d2h = pts * self.e._tdim * 8, self.e2e_units * 8
+        return {"points_per_gpu": pts}
+
+    def e2e_step(self):
+        from basix_b200 import _capi
+
+        _capi.check(_capi.lib().bx_tabulate_f64(self.e._h, self.nd, self.x_host.data_ptr(), self.e2e_pts,
+                                                self.x_host.shape[1], self.out_host.data_ptr(), _capi.BX_MEM_HOST,
+                                                None))
+
+    def cpu_setup(self, cores):
+        from oracle import ref
+
+        r = ref.RefElement(*self.ref_args)
+        per_pt = r.dim * r.value_size * ref.polyset_nderivs(r.cell_type, self.nd)
+        n = int(min(self.npts, 2_000_000, max(20_000, 6e7 * cores / per_pt)))
+        x = random_points(self.cell, n, 42)
+        out = np.empty((ref.polyset_nderivs(r.cell_type, self.nd), n, r.dim, r.value_size))
+        chunk = max(1024, min(65536, n // (cores * 4) or 1024))
+        self._cpu = (r, x, out, chunk, cores, n)
+        return per_pt * n, (f"{n} points per step, {chunk}-point chunks over {cores} std::threads, oracle/_ref "
+                            f"(unmodified reference, g++ -O2, scipy OpenBLAS, 1 BLAS thread per chunk)")
+
+    def cpu_step(self):
+        from oracle.ref import _check, _ptr, lib
+
+        r, x, out, chunk, cores, n = self._cpu
+        _check(lib().bxref_tabulate(r._h, self.nd, _ptr(x), n, x.shape[1], _ptr(out), chunk, cores))
+
+
+class PushForward:
+    metric, unit = METRIC_CELLS, "cells/s"
+    bound = "hbm"
+
+    def __init__(self, element, ref_args, nc, rows, pull, desc):
+        self.element_name, self.ref_args, self.nc, self.rows, self.pull, self.desc = element, ref_args, nc, rows, pull, desc
+
+    def setup(self, rank):
+        import torch
+
+        self.e = load_element(self.element_name)
+        nc, rows = self.nc, self.rows
+        J, detJ, K = random_jacobians(nc, 7 + rank)
+        U = np.random.default_rng(8 + rank).standard_normal((nc, rows, 3))
+        self.host = [torch.from_numpy(a).pin_memory() for a in (U, J, detJ, K)]
+        self.dev = [t.cuda() for t in self.host]
+        self.units_per_step = nc
+        self.launches_per_step = 1
+        # covariant push reads U and K, pull reads u and J; contravariant also reads detJ
+        contra = int(self.e.map_type) == 3
+        self.alg_bytes = nc * (2 * rows * 3 * 8 + 72 + (8 if contra else 0))
+        self.flops = 18.0 * rows * nc
+        self.config = {"workload": self.desc, "cells_per_gpu": nc, "rows": rows,
+                       "l2": "arrays are %.2f GB per step (>> 126 MB L2)" % (self.alg_bytes / 1e9)}
+
+    def step(self):
+        f = self.e.pull_back if self.pull else self.e.push_forward
+        self.result = f(*self.dev)
+
+    def e2e_setup(self, avail_bytes):
+        import torch
+
+        self.out_host = torch.empty((self.nc, self.rows, 3), dtype=torch.float64).pin_memory()
+        self.e2e_units = self.nc
+        self.h2d = sum(t.numel() * 8 for t in self.host)
+        self.d2h = self.out_host.numel() * 8
+        return {"cells_per_gpu": self.nc}
+
+    def e2e_step(self):
+        from basix_b200 import _capi
+
+        U, J, d, K = self.host
+        fn = _capi.lib().bx_pull_back_f64 if self.pull else _capi.lib().bx_push_forward_f64
+        _capi.check(fn(self.e._h, U.data_ptr(), J.data_ptr(), d.data_ptr(), K.data_ptr(), self.nc, self.rows, 3, 3, 3,
+                       self.out_host.data_ptr(), _capi.BX_MEM_HOST, None))
+
+    def cpu_setup(self, cores):
+        from oracle import ref
+
+        r = ref.RefElement(*self.ref_args)
+        n = int(min(self.nc, max(100_000, 4e7 * cores / self.rows)))
+        J, detJ, K = random_jacobians(n, 7)
+        U = np.random.default_rng(8).standard_normal((n, self.rows, 3))
+        self._cpu = (r, U, J, detJ, K, cores)
+        return n, f"{n} cells per step over {cores} std::threads, oracle/_ref (unmodified reference, g++ -O2)"
+
+    def cpu_step(self):
+        r, U, J, detJ, K, cores = self._cpu
+        (r.pull_back if self.pull else r.push_forward)(U, J, detJ, K, nthreads=cores)
+
+
+class TApply:
+    metric, unit = METRIC_CELLS, "cells/s"
+    bound = "hbm"
+
+    def __init__(self, element, ref_args, nc, bs, permute, desc):
+        self.element_name, self.ref_args, self.nc, self.bs, self.permute, self.desc = element, ref_args, nc, bs, permute, desc
+
+    def setup(self, rank):
+        import torch
+
+        self.e = load_element(self.element_name)
+        e, nc = self.e, self.nc
+        ci = random_cell_info(nc, 11 + rank)
+        self.ci_host = torch.from_numpy(ci.view(np.int32)).pin_memory()
+        self.ci = self.ci_host.cuda()
+        if self.permute:
+            d = np.tile(np.arange(e.dim, dtype=np.int32), (nc, 1))
+            esize = 4
+        else:
+            d = np.random.default_rng(12 + rank).standard_normal((nc, e.dim * self.bs))
+            esize = 8
+        self.data_host = torch.from_numpy(d).pin_memory()
+        self.data = self.data_host.cuda()
+        self.units_per_step = nc
+        self.launches_per_step = 1
+        # only the movable dofs need to be read and written (+ 4 B of cell_info)
+        if self.permute:
+            movable = int((np.asarray(e.net_permutation(0xFFFFFFFF)) != np.arange(e.dim)).sum())
+        else:
+            A = e.net_operator(0xFFFFFFFF)
+            movable = int((np.abs(A - np.eye(e.dim)).sum(axis=1) > 0).sum())
+        self.alg_bytes = nc * (2 * movable * esize * self.bs + 4)
+        self.flops = 0.0
+        self.config = {"workload": self.desc, "cells_per_gpu": nc, "block_size": self.bs, "movable_dofs": movable,
+                       "whole_array_bytes_per_cell": 2 * e.dim * esize * self.bs + 4,
+                       "l2": "data is %.2f GB per step (>> 126 MB L2)" % (nc * e.dim * esize * self.bs / 1e9)}
+
+    def step(self):
+        if self.permute:
+            self.e.permute_batch(self.data, self.ci)
+        else:
+            self.e.T_apply_batch(self.data, self.bs, self.ci)
+
+    def e2e_setup(self, avail_bytes):
+        self.e2e_units = self.nc
+        self.h2d = self.data_host.numel() * self.data_host.element_size() + self.nc * 4
+        self.d2h = self.data_host.numel() * self.data_host.element_size()
+        return {"cells_per_gpu": self.nc}
+
+    def e2e_step(self):
+        from basix_b200 import _capi
+
+        L = _capi.lib()
+        if self.permute:
+            _capi.check(L.bx_permute_i32(self.e._h, 0, self.data_host.data_ptr(), self.nc, self.ci_host.data_ptr(),
+                                         _capi.BX_MEM_HOST, None))
+        else:
+            _capi.check(L.bx_T_apply_f64(self.e._h, 0, self.data_host.data_ptr(), self.nc, self.e.dim * self.bs,
+                                         self.bs, self.ci_host.data_ptr(), _capi.BX_MEM_HOST, None))
+
+    def cpu_setup(self, cores):
+        from oracle import ref
+
+        r = ref.RefElement(*self.ref_args)
+        n = int(min(self.nc, max(100_000, (4e6 if self.permute else 1e6) * cores)))
+        ci = random_cell_info(n, 11)
+        if self.permute:
+            d = np.tile(np.arange(r.dim, dtype=np.int32), (n, 1))
+        else:
+            d = np.random.default_rng(12).standard_normal((n, r.dim * self.bs))
+        self._cpu = (r, d, ci, cores)
+        return n, f"{n} cells per step over {cores} std::threads, oracle/_ref (unmodified reference, g++ -O2)"
+
+    def cpu_step(self):
+        r, d, ci, cores = self._cpu
+        if self.permute:
+            r.permute_batch(d, ci, nthreads=cores)
+        else:
+            r.T_apply_batch("T_apply", d, self.bs, ci, nthreads=cores)
+
+
+WORKLOADS = {
+    "tabulate_p5_tet": lambda: Tabulate(
+        "P5_tetrahedron_gll", (1, 3, 5, 2), 3, 2, 10_000_000, 1,
+        "P5 Lagrange (gll_warped) tetrahedron, tabulate(nd=2), 10M points per GPU", "tensor"),
+    "tabulate_p1_tri": lambda: Tabulate(
+        "P1_triangle_gll", (1, 2, 1, 2), 2, 1, 1_000_000, 1,
+        "P1 Lagrange triangle, tabulate(nd=1), 1M points per GPU", "hbm"),
+    "tabulate_q4_hex": lambda: Tabulate(
+        "Q4_hexahedron_gll", (1, 5, 4, 2), 5, 1, 50_000_000, 5,
+        "Q4 Lagrange (gll_warped) hexahedron, tabulate(nd=1), 50M points per GPU streamed as 5 launches of 10M "
+        "through one resident 40 GB table", "hbm"),
+    "push_forward_n1curl3": lambda: PushForward(
+        "N1curl3_tetrahedron_legendre", (3, 3, 3, 11), 20_000_000, 1, False,
+        "N1curl degree 3 tetrahedron, covariant Piola push_forward, 20M cells x 1 row"),
+    "pull_back_n1curl3": lambda: PushForward(
+        "N1curl3_tetrahedron_legendre", (3, 3, 3, 11), 20_000_000, 1, True,
+        "N1curl degree 3 tetrahedron, covariant Piola pull_back, 20M cells x 1 row"),
+    "push_forward_n1curl3_rows45": lambda: PushForward(
+        "N1curl3_tetrahedron_legendre", (3, 3, 3, 11), 4_000_000, 45, False,
+        "N1curl degree 3 tetrahedron, covariant Piola push_forward, 4M cells x 45 rows"),
+    "t_apply_rt4": lambda: TApply(
+        "RT4_tetrahedron_legendre", (2, 3, 4, 11), 50_000_000, 1, False,
+        "RT degree 4 tetrahedron, T_apply(block 1) over 50M cells, random cell_info"),
+    "permute_p5_tet": lambda: TApply(
+        "P5_tetrahedron_gll", (1, 3, 5, 2), 50_000_000, 1, True,
+        "P5 Lagrange tetrahedron, permute (int32) over 50M cells, random cell_info"),
+}
+DEFAULT = "tabulate_p5_tet"
+
+
+# ======================================================================================================
+def cpu_reference(w, steps, warmup):
     from oracle import ref
 
     if not ref.available():
         return None
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
     cores = os.cpu_count() or 1
-    r = ref.RefElement(*w["ref_args"])
-    nd = w["nd"]
-    per_pt = r.dim * r.value_size * ref.polyset_nderivs(r.cell_type, nd)
-    # ~1.5 s of work per core per step at ~4e7 values/s/core
-    if sample_pts is None:
-        sample_pts = int(min(w["units"], 2_000_000, max(20_000, 6e7 * cores / per_pt)))
-    x = random_points(w["cell"], sample_pts, 42)
-    chunk = max(1024, min(65536, sample_pts // (cores * 4) or 1024))
-    out = np.empty((ref.polyset_nderivs(r.cell_type, nd), sample_pts, r.dim, r.value_size))
-    from oracle.ref import _check, _ptr, lib
-
-    def step():
-        _check(lib().bxref_tabulate(r._h, nd, _ptr(x), sample_pts, x.shape[1], _ptr(out), chunk, cores))
-
+    units, sample = w.cpu_setup(cores)
     for _ in range(warmup):
-        step()
+        w.cpu_step()
     t0 = time.perf_counter()
     for _ in range(steps):
-        step()
+        w.cpu_step()
     dt = (time.perf_counter() - t0) / steps
-    return dict(value=per_pt * sample_pts / dt, unit=w["unit"], cores=cores, kind="reference",
-                sample=f"{sample_pts} points per step, {chunk}-point chunks over {cores} std::threads, "
-                       f"oracle/_ref (unmodified reference, g++ -O2, scipy OpenBLAS 1 thread per chunk)",
-                ms_per_step=dt * 1e3)
+    return dict(value=units / dt, unit=w.unit, cores=cores, kind="reference", sample=sample, ms_per_step=dt * 1e3)
 
 
-def run_reference(args, w, rank, world):
+def run_reference(args, w, rank):
     if rank != 0:
         return
-    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
-    res = cpu_reference_run(w, max(1, args.steps), max(0, min(args.warmup, 1)))
+    res = cpu_reference(w, max(1, args.steps), max(0, min(args.warmup, 1)))
     if res is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libbasix_ref.so missing"}))
         return
-    line = {
-        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": w["unit"], "n_gpus": args.gpus,
+    print(json.dumps({
+        "impl": "reference", "metric": w.metric, "value": res["value"], "unit": w.unit, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w["desc"], "sample": res["sample"]},
+        "config": {"workload": w.desc, "sample": res["sample"]},
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
-        "e2e": {"value": res["value"], "unit": w["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": res["value"], "unit": w.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }
-    print(json.dumps(line))
+    }))
 
 
-# ======================================================================================================
 def run_ours(args, w, rank, local_rank, world):
+    import psutil
     import torch
 
     import basix_b200 as bx
-    from basix_b200 import _capi
 
     if bx.device_count() < 1:
         raise RuntimeError("bench.py: no CUDA device; the hot path has no CPU fallback")
@@ -187,109 +443,80 @@ def run_ours(args, w, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    e = bx.FiniteElement.from_arrays(np.load(os.path.join(GOLDEN, w["element"] + ".npz")))
-    nd, npts = w["nd"], w["units"]
-    shape = e.tabulate_shape(nd, npts)
-    values_per_step = int(np.prod(shape))
-    x_host = torch.from_numpy(random_points(w["cell"], npts, 42 + rank)).pin_memory()
-    x = x_host.cuda()
-    out = torch.empty(shape, dtype=torch.float64, device="cuda")
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    def step():
-        e.tabulate(nd, x, out=out)
-
-    for _ in range(args.warmup):
-        step()
+    w.setup(rank)
+    warmup = max(args.warmup, 3)
+    for _ in range(warmup):
+        w.step()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     n0 = bx.kernel_launch_count()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    ev[0].record()
-    for i in range(args.steps):
-        step()
-        ev[i + 1].record()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        w.step()
+    ev1.record()
     barrier()
     launches = bx.kernel_launch_count() - n0
     clocks = sampler.stop()
-    ms_total = ev[0].elapsed_time(ev[-1])
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
-    value = values_per_step * world / (ms_step * 1e-3)
+    ms_step = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+    value = w.units_per_step * world / (ms_step * 1e-3)
 
-    # ---- end to end through the C ABI with host buffers (pinned), H2D + D2H inside the timed region ----
-    import psutil
-
-    out_bytes = values_per_step * 8
-    avail = psutil.virtual_memory().available / max(1, world)
-    e2e_pts = npts
-    while e2e_pts * (out_bytes / npts) > 0.4 * avail and e2e_pts > 100_000:
-        e2e_pts //= 2
-    e2e_shape = e.tabulate_shape(nd, e2e_pts)
-    out_host = None if args.no_e2e else torch.empty(e2e_shape, dtype=torch.float64).pin_memory()
-    xh = x_host[:e2e_pts]
-    del out
-    torch.cuda.empty_cache()
-    lib = _capi.lib()
-
-    def e2e_step():
-        _capi.check(lib.bx_tabulate_f64(e._h, nd, xh.data_ptr(), e2e_pts, xh.shape[1], out_host.data_ptr(),
-                                        _capi.BX_MEM_HOST, None))
-
-    e2e_steps = max(1, min(args.steps, 3))
-    if args.no_e2e:
-        e2e_value = None
+    # ---- roofline of the dominant kernel (a step is `launches_per_step` launches of that one kernel) ----
+    ms_launch = ms_step / w.launches_per_step
+    hbm_peak, hbm_src = measured_hbm_peak()
+    hbm = {"achieved": w.alg_bytes / (ms_launch * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src}
+    hbm["frac"] = hbm["achieved"] / hbm_peak
+    if w.bound == "tensor":
+        ach = w.flops / (ms_launch * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "achieved": ach, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
+                    "frac": ach / FP64_TENSOR_PEAK_TFLOPS, "traffic": None,
+                    "peak_source": "FP64 tensor (DMMA m8n8k4) peak measured by tools/peaks.cu on this pool's B200 "
+                                   "(profiles/r01_peaks_fp64_hbm_pcie.json); MEASURED_PEAKS.json has no FP64 figure",
+                    "hbm": hbm}
     else:
-        e2e_step()
+        roofline = dict(bound="hbm", traffic=None, **hbm)
+    roofline["ms_per_launch"] = ms_launch
+    roofline["launches_per_step"] = w.launches_per_step
+
+    # ---- end to end through the C ABI with host (pinned) buffers ----
+    e2e = None
+    if not args.no_e2e:
+        extra = w.e2e_setup(psutil.virtual_memory().available / max(1, world))
+        w.e2e_step()
         barrier()
+        e2e_steps = max(1, min(args.steps, 3))
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            e2e_step()
+            w.e2e_step()
         torch.cuda.synchronize()
-        dt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device="cuda")
-        if dist is not None:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e_value = int(np.prod(e2e_shape)) * world / float(dt.item())
-
-    # ---- roofline of the dominant kernel ----
-    hbm_peak, peak_src = measured_peaks()
-    path = e.tabulate_path(nd)
-    flops = 2.0 * e.dim * e.value_size * e._psize * shape[0] * npts
-    bytes_alg = npts * (e._tdim * 8 + values_per_step / npts * 8)
-    roofline = {
-        "kernel": f"tabulate ({path} path)", "bound": "tensor", "achieved": flops / (ms_step * 1e-3) / 1e12,
-        "peak": args.fp64_peak, "unit": "TFLOP/s", "frac": flops / (ms_step * 1e-3) / 1e12 / args.fp64_peak,
-        "traffic": None, "peak_source": "nominal B200 FP64 (tensor = vector) 37 TFLOP/s; not in MEASURED_PEAKS.json",
-        "hbm": {"achieved": bytes_alg / (ms_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                "frac": bytes_alg / (ms_step * 1e-3) / 1e9 / hbm_peak, "peak_source": peak_src},
-    }
+        dt = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+        e2e = {"value": w.e2e_units * world / dt, "unit": w.unit, "h2d_bytes_per_step": int(w.h2d),
+               "d2h_bytes_per_step": int(w.d2h), "steps": e2e_steps, "ms_per_step": dt * 1e3}
+        e2e.update(extra)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
-        cpu = cpu_reference_run(w, 2, 1)
+        cpu = cpu_reference(w, 2, 1)
         if cpu is not None:
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": w["unit"], "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w["desc"], "points_per_gpu": npts, "nd": nd, "tabulate_path": path,
-                       "l2": "inputs+outputs larger than L2 (table is %.1f GB per step)" % (out_bytes / 1e9),
-                       "parallelism": f"points sharded over {world} GPU(s), no collective"},
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": w["unit"], "h2d_bytes_per_step": int(e2e_pts * e._tdim * 8),
-                    "d2h_bytes_per_step": int(np.prod(e2e_shape)) * 8, "points_per_gpu": e2e_pts,
-                    "steps": e2e_steps},
-            "gpu_launches": int(launches),
-            "roofline": roofline,
+        cfg = dict(w.config)
+        cfg["parallelism"] = f"independent slices over {world} GPU(s), no collective"
+        print(json.dumps({
+            "metric": w.metric, "value": value, "unit": w.unit, "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32" if getattr(w, "permute", False) else "f64", "data": "synthetic",
+            "config": cfg, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu,
-        }
-        print(json.dumps(line))
+        }))
     if dist is not None:
         dist.destroy_process_group()
 
@@ -300,17 +527,16 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="tabulate_p5_tet_nd2_10M", choices=sorted(WORKLOADS))
-    ap.add_argument("--fp64-peak", type=float, default=37.0, help="FP64 peak in TFLOP/s used for roofline.frac")
+    ap.add_argument("--workload", default=DEFAULT, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    w = WORKLOADS[args.workload]
+    w = WORKLOADS[args.workload]()
     if args.impl == "reference":
-        run_reference(args, w, rank, world)
+        run_reference(args, w, rank)
     else:
         run_ours(args, w, rank, local_rank, world)
 

@@ -344,3 +344,35 @@ def test_tabulate_fused_dof_ordering_and_device(ref):
     slab_close(e.tabulate(1, x), want, 1e-12)
     got = e.tabulate(1, torch.from_numpy(x).cuda())
     slab_close(got.cpu().numpy(), want, 1e-12)
+
+
+# ---- tensor-product kernel (tabulate_tp.cu) -----------------------------------------------------------------
+TP = [(P, QUAD, 1, GLL), (P, QUAD, 3, GLL), (P, QUAD, 5, EQ), (P, HEX, 1, GLL), (P, HEX, 2, GLL), (P, HEX, 3, EQ),
+      (P, HEX, 4, GLL), (P, HEX, 6, GLL)]
+
+
+@pytest.mark.parametrize("family,cell,degree,variant", TP)
+@pytest.mark.parametrize("nd", [0, 1, 2])
+def test_tabulate_tensor_product_path(ref, family, cell, degree, variant, nd):
+    """Q elements on quad/hex (reference test_tensor_products.py:60-200 checks the same structure)."""
+    r, e = make_pair(ref, family, cell, degree, variant)
+    assert e.tabulate_path(nd) == "tensor-product"
+    for npts in (1, 33, 4099):
+        x = random_points(cell, npts, seed=npts + degree)
+        slab_close(e.tabulate(nd, x), r.tabulate(nd, x), 1e-12)
+
+
+def test_tabulate_non_tensor_product_elements_take_generic_path(ref):
+    """Serendipity on a quadrilateral is not a tensor product: the rank-1 test must reject it."""
+    r, e = make_pair(ref, 10, QUAD, 3, LEG, 7)
+    assert e.tabulate_path(1) == "generic"
+    x = random_points(QUAD, 500)
+    slab_close(e.tabulate(1, x), r.tabulate(1, x), 1e-12)
+
+
+def test_tabulate_tp_dof_ordering(ref):
+    order = [int(v) for v in np.random.default_rng(1).permutation(27)]
+    r, e = make_pair(ref, P, HEX, 2, GLL, dof_ordering=order)
+    assert e.tabulate_path(1) == "tensor-product"
+    x = random_points(HEX, 1000)
+    slab_close(e.tabulate(1, x), r.tabulate(1, x), 1e-12)
