@@ -5,14 +5,20 @@
 // precompute::apply_* kernels (precompute.h:136-374), plus permute / permute_inv
 // (finite-element.h:800-843).
 //
-// B200 design (HBM-bound, integer-indexed): a CTA stages a tile of whole cells into shared memory
-// with fully coalesced loads, then every thread produces ONE output entry from the staged tile:
-//   * permutation elements: out[dof] = tile[src] with src from a gather table indexed by the
-//     owning sub-entity's cell_info bit-field (bit-exact for any data type);
-//   * matrix elements: out[dof] = sum_i A[state][loc][i] * tile[first + i] with the dense net
-//     operator of that bit-field composed on the host.
-// Each global byte is read once and written at most once; entries that cannot change are not
-// written back.
+// B200 design (HBM-bound, integer-indexed).  A persistent CTA walks tiles of whole cells:
+//   1. stage   the smallest contiguous range of each cell that holds every movable dof is copied to shared
+//              memory with coalesced loads (entries that can never move are not read at all); cells are laid
+//              out with an ODD pitch, so that 32 lanes working on 32 consecutive cells never share a bank;
+//   2. apply   one thread owns one (cell, sub-entity, block) item, lanes <-> consecutive cells.  It reads the
+//              entity's `dim` values into registers, then
+//                * permutation elements: writes them back through the gather table of the entity's cell_info
+//                  bit-field (bit-exact for any data type);
+//                * matrix elements: multiplies them by the dense net operator of that bit-field, composed on the
+//                  host (element.cu).  All states of all entity classes sit in shared memory, `mat_state_stride`
+//                  apart, so lanes in the same state broadcast and lanes in different states hit different
+//                  banks: one conflict-free 16-byte shared load feeds two FMAs;
+//   3. store   the range goes back with coalesced stores.
+// Each global byte of the movable range is read once and written once; nothing else is touched.
 #include "element.cuh"
 
 #include <algorithm>
@@ -23,128 +29,218 @@ namespace bx
 namespace
 {
 constexpr int kThreads = 256;
+constexpr int kMaxRegDim = 32; // largest entity dimension held in registers
 
 struct FastDiv
 {
-  unsigned long long m;
-  unsigned d;
-  __host__ explicit FastDiv(unsigned d_ = 1) : m((1ull << 32) / d_ + 1), d(d_) {}
-  // exact for q < 2^16 and d < 2^16
-  __device__ __forceinline__ unsigned div(unsigned q) const { return unsigned((q * m) >> 32); }
+  unsigned m = 0, d = 1;
+  FastDiv() = default;
+  // multiply-high form: exact whenever q * d < 2^32; `qmax` is the largest dividend the caller will pass.
+  // Outside that range (huge block sizes) m stays 0 and div() falls back to a hardware division.
+  __host__ FastDiv(unsigned d_, unsigned long long qmax)
+      : m(d_ > 1 and qmax * d_ < (1ull << 32) ? unsigned((1ull << 32) / d_ + 1) : 0), d(d_)
+  {
+  }
+  __device__ __forceinline__ unsigned div(unsigned q) const { return d > 1 ? (m ? __umulhi(q, m) : q / d) : q; }
 };
 
 struct TransformParams
 {
   size_t nc;
-  int cell_size, n, ndofs, cells_per_tile;
-  FastDiv by_cell, by_n, by_ndofs;
+  int cell_size, n, ndofs;
+  int cpt_log2;       // cells per tile = 1 << cpt_log2
+  int r0, len, pitch; // staged range [r0, r0 + len) of each cell (in entries), shared-memory pitch (odd)
+  int nslots, table_size;
+  FastDiv by_len, by_n;
   const uint32_t* cell_info;
-  const int16_t* dof_slot;
-  const int16_t* dof_loc;
-  const int4* slot_info;
-  const int16_t* gather; // op offset applied
-  const int2* slot_mat;
-  const double* mats; // op offset applied
+  const int4* slot_info;  // {shift, mask, dim, gather base}
+  const int2* slot_mat;   // {first dof, matrix base of the slot's class}
+  const int16_t* gather;  // op offset applied (permutation elements)
+  const double* mats;     // op offset applied (matrix elements)
 };
 
-template <typename T, bool RIGHT, bool MATRIX>
-__global__ void __launch_bounds__(kThreads) dof_transform_kernel(T* __restrict__ data, TransformParams p)
+// Entry index (within a cell) of (dof, block b): the left operators see u[ndofs][n], the right ones
+// n contiguous blocks of ndofs entries (finite-element.h:1904-1998).
+template <bool RIGHT>
+__device__ __forceinline__ int entry(int dof, int b, int n, int ndofs)
+{
+  return RIGHT ? b * ndofs + dof : dof * n + b;
+}
+
+// REG = number of entity values held in registers (>= the largest entity dimension), 0 = any dimension:
+// results then go straight to global memory and the staged tile stays read-only.
+template <typename T, bool RIGHT, bool MATRIX, int REG>
+__global__ void __launch_bounds__(kThreads) dof_transform_kernel(T* __restrict__ data, const TransformParams p)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* tile = reinterpret_cast<T*>(smem_raw);
-  const int cs = p.cell_size;
-  const size_t ntiles = ceil_div(p.nc, size_t(p.cells_per_tile));
+  // ---- carve shared memory: operator tables, slot descriptors, cell_info, tile --------------------------
+  const int table_bytes = (MATRIX ? p.table_size * 8 : p.table_size * 2 + 15) & ~15;
+  double* s_mats = reinterpret_cast<double*>(smem_raw);
+  int16_t* s_gather = reinterpret_cast<int16_t*>(smem_raw);
+  int4* s_info = reinterpret_cast<int4*>(smem_raw + table_bytes);
+  int2* s_mat = reinterpret_cast<int2*>(s_info + p.nslots);
+  const int cpt = 1 << p.cpt_log2;
+  uint32_t* s_ci = reinterpret_cast<uint32_t*>(s_mat + p.nslots + (p.nslots & 1));
+  T* tile = reinterpret_cast<T*>(s_ci + ((cpt + 3) & ~3));
+
+  if constexpr (MATRIX)
+    for (int i = threadIdx.x; i < p.table_size; i += kThreads)
+      s_mats[i] = p.mats[i];
+  else
+    for (int i = threadIdx.x; i < p.table_size; i += kThreads)
+      s_gather[i] = p.gather[i];
+  for (int i = threadIdx.x; i < p.nslots; i += kThreads)
+  {
+    s_info[i] = p.slot_info[i];
+    s_mat[i] = p.slot_mat[i];
+  }
+
+  const int cs = p.cell_size, n = p.n, ndofs = p.ndofs, pitch = p.pitch, r0 = p.r0, len = p.len;
+  const size_t ntiles = (p.nc + cpt - 1) >> p.cpt_log2;
+  const unsigned nitems = unsigned(p.nslots * n) << p.cpt_log2;
   for (size_t tl = blockIdx.x; tl < ntiles; tl += gridDim.x)
   {
-    const size_t c0 = tl * p.cells_per_tile;
-    const unsigned ncell = unsigned(min(size_t(p.cells_per_tile), p.nc - c0));
-    const unsigned total = ncell * cs;
-    T* g = data + c0 * cs;
-    // ---- stage the tile (coalesced; 16-byte vectors when the tile base is aligned) ----
-    if ((reinterpret_cast<uintptr_t>(g) & 15) == 0)
+    const size_t c0 = tl << p.cpt_log2;
+    const unsigned ncell = unsigned(min(size_t(cpt), p.nc - c0));
+    T* g = data + c0 * cs + r0;
+    __syncthreads(); // previous tile fully stored (and, first time, tables loaded)
+    // ---- 1. stage -------------------------------------------------------------------------------------
+    for (unsigned q = threadIdx.x; q < ncell * len; q += kThreads)
     {
-      constexpr unsigned V = 16 / sizeof(T);
-      const unsigned nv = total / V;
-      const uint4* g4 = reinterpret_cast<const uint4*>(g);
-      uint4* t4 = reinterpret_cast<uint4*>(tile);
-      for (unsigned q = threadIdx.x; q < nv; q += kThreads)
-        t4[q] = g4[q];
-      for (unsigned q = nv * V + threadIdx.x; q < total; q += kThreads)
-        tile[q] = g[q];
+      const unsigned c = p.by_len.div(q), k = q - c * len;
+      tile[c * pitch + k] = g[size_t(c) * cs + k];
     }
-    else
-    {
-      for (unsigned q = threadIdx.x; q < total; q += kThreads)
-        tile[q] = g[q];
-    }
+    for (unsigned c = threadIdx.x; c < ncell; c += kThreads)
+      s_ci[c] = p.cell_info[c0 + c];
     __syncthreads();
-    // ---- one output entry per thread-iteration ----
-    for (unsigned q = threadIdx.x; q < total; q += kThreads)
+    // ---- 2. apply: item = (slot, block, cell), cell fastest -----------------------------------------------
+    for (unsigned it = threadIdx.x; it < nitems; it += kThreads)
     {
-      const unsigned c = p.by_cell.div(q);
-      const unsigned r = q - c * cs;
-      unsigned dof, b;
-      if constexpr (RIGHT)
-      {
-        b = p.by_ndofs.div(r);
-        dof = r - b * p.ndofs;
-      }
-      else
-      {
-        dof = p.by_n.div(r);
-        b = r - dof * p.n;
-      }
-      const int slot = __ldg(p.dof_slot + dof);
-      if (slot < 0)
+      const unsigned c = it & (cpt - 1), sb = it >> p.cpt_log2;
+      if (c >= ncell)
         continue;
-      const int4 si = __ldg(p.slot_info + slot);
-      const unsigned state = (__ldg(p.cell_info + c0 + c) >> si.x) & unsigned(si.y);
+      const unsigned s = p.by_n.div(sb), b = sb - s * n;
+      const int4 si = s_info[s];
+      const unsigned state = (s_ci[c] >> si.x) & unsigned(si.y);
       if (state == 0)
         continue;
-      const int loc = __ldg(p.dof_loc + dof);
-      const T* cell = tile + c * cs;
+      const int dim = si.z;
+      T* cell = tile + c * pitch - r0;
       if constexpr (!MATRIX)
       {
-        const unsigned sd = unsigned(__ldg(p.gather + si.w + state * si.z + loc));
-        const unsigned src = RIGHT ? b * p.ndofs + sd : sd * p.n + b;
-        g[q] = cell[src];
-      }
-      else
-      {
-        const int2 sm = __ldg(p.slot_mat + slot);
-        const int dim = si.z;
-        const double* row = p.mats + sm.y + (size_t(state) * dim + loc) * dim;
-        double acc = 0.0;
-        if constexpr (RIGHT)
+        const int16_t* src = s_gather + si.w + state * dim; // source dofs of this state
+        const int16_t* dst = s_gather + si.w;               // state 0 is the identity: the entity's own dofs
+        if constexpr (REG > 0)
         {
-          const T* v = cell + b * p.ndofs + sm.x;
-          for (int i = 0; i < dim; ++i)
-            acc += __ldg(row + i) * static_cast<double>(v[i]);
+          T v[REG];
+#pragma unroll
+          for (int l = 0; l < REG; ++l)
+            if (l < dim)
+              v[l] = cell[entry<RIGHT>(src[l], b, n, ndofs)];
+#pragma unroll
+          for (int l = 0; l < REG; ++l)
+            if (l < dim)
+              cell[entry<RIGHT>(dst[l], b, n, ndofs)] = v[l];
         }
         else
         {
-          const T* v = cell + size_t(sm.x) * p.n + b;
-          for (int i = 0; i < dim; ++i)
-            acc += __ldg(row + i) * static_cast<double>(v[size_t(i) * p.n]);
+          T* gc = data + (c0 + c) * cs;
+          for (int l = 0; l < dim; ++l)
+            gc[entry<RIGHT>(dst[l], b, n, ndofs)] = cell[entry<RIGHT>(src[l], b, n, ndofs)];
         }
-        g[q] = static_cast<T>(acc);
+      }
+      else
+      {
+        const int2 sm = s_mat[s];
+        const int rs = mat_row_stride(dim);
+        const double* M = s_mats + sm.y + state * mat_state_stride(dim);
+        if constexpr (REG > 0)
+        {
+          double v[REG];
+#pragma unroll
+          for (int j = 0; j < REG; ++j)
+            v[j] = j < dim ? static_cast<double>(cell[entry<RIGHT>(sm.x + j, b, n, ndofs)]) : 0.0;
+          for (int i = 0; i < dim; ++i)
+          {
+            const double2* row = reinterpret_cast<const double2*>(M + i * rs);
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int jj = 0; jj < REG / 2; ++jj)
+              if (2 * jj < dim)
+              {
+                const double2 m = row[jj];
+                a0 = fma(m.x, v[2 * jj], a0);
+                a1 = fma(m.y, v[2 * jj + 1], a1);
+              }
+            cell[entry<RIGHT>(sm.x + i, b, n, ndofs)] = static_cast<T>(a0 + a1);
+          }
+        }
+        else
+        {
+          T* gc = data + (c0 + c) * cs;
+          for (int i = 0; i < dim; ++i)
+          {
+            double a = 0.0;
+            for (int j = 0; j < dim; ++j)
+              a = fma(M[i * rs + j], static_cast<double>(cell[entry<RIGHT>(sm.x + j, b, n, ndofs)]), a);
+            gc[entry<RIGHT>(sm.x + i, b, n, ndofs)] = static_cast<T>(a);
+          }
+        }
       }
     }
-    __syncthreads();
+    // ---- 3. store ---------------------------------------------------------------------------------------
+    if constexpr (REG > 0)
+    {
+      __syncthreads();
+      for (unsigned q = threadIdx.x; q < ncell * len; q += kThreads)
+      {
+        const unsigned c = p.by_len.div(q), k = q - c * len;
+        g[size_t(c) * cs + k] = tile[c * pitch + k];
+      }
+    }
   }
 }
 
-template <typename T, bool RIGHT, bool MATRIX>
-void launch(T* data, const TransformParams& p, size_t smem, cudaStream_t s)
+size_t smem_bytes(const TransformParams& p, bool matrix, size_t elem)
 {
-  auto kern = dof_transform_kernel<T, RIGHT, MATRIX>;
+  const size_t table = (matrix ? size_t(p.table_size) * 8 : size_t(p.table_size) * 2 + 15) & ~size_t(15);
+  const size_t cpt = size_t(1) << p.cpt_log2;
+  return table + size_t(p.nslots) * 16 + size_t(p.nslots + (p.nslots & 1)) * 8 + ((cpt + 3) & ~size_t(3)) * 4
+         + cpt * p.pitch * elem;
+}
+
+template <typename T, bool RIGHT, bool MATRIX, int REG>
+void launch(T* data, const TransformParams& p, cudaStream_t s)
+{
+  auto kern = dof_transform_kernel<T, RIGHT, MATRIX, REG>;
+  const size_t smem = smem_bytes(p, MATRIX, sizeof(T));
   if (smem > 48 * 1024)
     BX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  const size_t ntiles = ceil_div(p.nc, size_t(p.cells_per_tile));
-  const size_t cap = size_t(sm_count()) * 8;
-  const int grid = int(ntiles < cap ? ntiles : cap);
-  kern<<<grid, kThreads, smem, s>>>(data, p);
+  int per_sm = 0;
+  BX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+  const size_t ntiles = (p.nc + (size_t(1) << p.cpt_log2) - 1) >> p.cpt_log2;
+  const size_t cap = size_t(sm_count()) * std::max(per_sm, 1);
+  kern<<<unsigned(std::min(ntiles, cap)), kThreads, smem, s>>>(data, p);
   BX_LAUNCHED();
+}
+
+template <typename T, bool RIGHT, bool MATRIX>
+void launch_by_dim(T* data, const TransformParams& p, int maxdim, cudaStream_t s)
+{
+  if (maxdim <= 4)
+    launch<T, RIGHT, MATRIX, 4>(data, p, s);
+  else if (maxdim <= 8)
+    launch<T, RIGHT, MATRIX, 8>(data, p, s);
+  else if (maxdim <= 12)
+    launch<T, RIGHT, MATRIX, 12>(data, p, s);
+  else if (maxdim <= 16)
+    launch<T, RIGHT, MATRIX, 16>(data, p, s);
+  else if (maxdim <= 24)
+    launch<T, RIGHT, MATRIX, 24>(data, p, s);
+  else if (maxdim <= kMaxRegDim)
+    launch<T, RIGHT, MATRIX, kMaxRegDim>(data, p, s);
+  else
+    launch<T, RIGHT, MATRIX, 0>(data, p, s);
 }
 } // namespace
 
@@ -169,39 +265,51 @@ void dof_transform_device(const bx_element& e, int op, T* data, size_t nc, size_
   static const int kind_of[8] = {0, 1, 2, 3, 0, 2, 1, 3};
   const bool right = op >= 4;
   const int kind = kind_of[op];
-  if (cell_size >= 65536)
-    fail(BX_ERR_UNSUPPORTED, "T_apply: more than 65535 entries per cell");
 
   TransformParams p;
   p.nc = nc;
   p.cell_size = int(cell_size);
   p.n = n;
   p.ndofs = e.ndofs;
-  const size_t bytes_per_cell = cell_size * sizeof(T);
-  size_t cpt = std::max<size_t>(1, (32 * 1024) / bytes_per_cell);
-  cpt = std::min<size_t>(cpt, 65535 / cell_size);
-  cpt = std::min<size_t>(cpt, nc);
-  p.cells_per_tile = int(cpt);
-  const size_t smem = cpt * bytes_per_cell;
-  if (smem > 200 * 1024)
-    fail(BX_ERR_UNSUPPORTED, "T_apply: a single cell does not fit in shared memory");
-  p.by_cell = FastDiv(unsigned(cell_size));
-  p.by_n = FastDiv(unsigned(n));
-  p.by_ndofs = FastDiv(unsigned(e.ndofs));
+  // staged range: left layout u[dof][b] -> [lo*n, hi*n); right layout u[b][dof] -> [lo, (n-1)*ndofs + hi)
+  p.r0 = right ? e.lo_dof : e.lo_dof * n;
+  p.len = right ? (n - 1) * e.ndofs + e.hi_dof - e.lo_dof : (e.hi_dof - e.lo_dof) * n;
+  p.pitch = p.len | 1;
+  if (p.len >= 65536 or n >= 65536)
+    fail(BX_ERR_UNSUPPORTED, "T_apply: more than 65535 entries per cell");
+  p.nslots = int(e.slots.size());
+  p.table_size = e.perms ? e.gather_size : e.mats_size;
   p.cell_info = cell_info;
-  p.dof_slot = e.d_dof_slot;
-  p.dof_loc = e.d_dof_loc;
   p.slot_info = e.d_slot_info;
-  p.gather = e.d_gather ? e.d_gather + size_t(kind) * e.gather_size : nullptr;
   p.slot_mat = e.d_slot_mat;
+  p.gather = e.d_gather ? e.d_gather + size_t(kind) * e.gather_size : nullptr;
   p.mats = e.d_mats ? e.d_mats + size_t(kind) * e.mats_size : nullptr;
+
+  // cells per tile: a power of two, tile <= ~40 KB (several CTAs per SM hide the stage/apply/store phases
+  // of one another), at least one cell, fast-division range respected, no larger than the batch
+  const size_t cell_bytes = size_t(p.pitch) * sizeof(T);
+  int lg = 8;
+  while (lg > 0 and ((size_t(1) << lg) * cell_bytes > 40 * 1024 or (size_t(p.len) << lg) >= 65536
+                     or (size_t(p.nslots) * n << lg) >= (size_t(1) << 31)))
+    --lg;
+  while (lg > 0 and (size_t(1) << (lg - 1)) >= nc)
+    --lg;
+  p.cpt_log2 = lg;
+  p.by_len = FastDiv(unsigned(p.len), (unsigned long long)(p.len) << lg);
+  p.by_n = FastDiv(unsigned(n), (unsigned long long)(p.nslots) * n);
+  if (smem_bytes(p, !e.perms, sizeof(T)) > 200 * 1024)
+    fail(BX_ERR_UNSUPPORTED, "T_apply: a single cell does not fit in shared memory");
+
+  int maxdim = 0;
+  for (const auto& sl : e.slots)
+    maxdim = std::max(maxdim, sl.dim);
 
   if (e.perms)
   {
     if (right)
-      launch<T, true, false>(data, p, smem, s);
+      launch_by_dim<T, true, false>(data, p, maxdim, s);
     else
-      launch<T, false, false>(data, p, smem, s);
+      launch_by_dim<T, false, false>(data, p, maxdim, s);
   }
   else
   {
@@ -210,9 +318,9 @@ void dof_transform_device(const bx_element& e, int op, T* data, size_t nc, size_
     else
     {
       if (right)
-        launch<T, true, true>(data, p, smem, s);
+        launch_by_dim<T, true, true>(data, p, maxdim, s);
       else
-        launch<T, false, true>(data, p, smem, s);
+        launch_by_dim<T, false, true>(data, p, maxdim, s);
     }
   }
 }

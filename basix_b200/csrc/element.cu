@@ -492,7 +492,7 @@ bx_element* element_from_desc(const bx_element_desc& d)
       const int n = e->etrans_dim[cls];
       cls_base[cls] = msize;
       if (n > 0)
-        msize += (cls == BX_CELL_INTERVAL ? 2 : 8) * n * n;
+        msize += (cls == BX_CELL_INTERVAL ? 2 : 8) * mat_state_stride(n);
     }
   for (size_t s = 0; s < e->slots.size(); ++s)
     slot_mat[s] = make_int2(e->slots[s].first, cls_base[e->slots[s].cls]);
@@ -567,7 +567,9 @@ bx_element* element_from_desc(const bx_element_desc& d)
             if (post and refl)
               A = mat_mul(steps[cls][1], A, n);
           }
-          std::copy(A.begin(), A.end(), mats.begin() + size_t(op) * msize + cls_base[cls] + size_t(state) * n * n);
+          double* dst = mats.data() + size_t(op) * msize + cls_base[cls] + size_t(state) * mat_state_stride(n);
+          for (int row = 0; row < n; ++row)
+            std::copy(A.begin() + size_t(row) * n, A.begin() + size_t(row + 1) * n, dst + size_t(row) * mat_row_stride(n));
         }
       }
     }
@@ -639,7 +641,8 @@ void element_net_operator(const bx_element& e, int kind, uint32_t cell_info, int
       else if (A)
       {
         const double* row
-            = e.h_mats.data() + size_t(kind) * e.mats_size + e.h_slot_mat[s].y + (size_t(state) * sl.dim + l) * sl.dim;
+            = e.h_mats.data() + size_t(kind) * e.mats_size + e.h_slot_mat[s].y + size_t(state) * mat_state_stride(sl.dim)
+              + size_t(l) * mat_row_stride(sl.dim);
         for (int i = 0; i < sl.dim; ++i)
           A[size_t(dof) * n + sl.first + i] = row[i];
       }

@@ -92,6 +92,17 @@ struct bx_element
 
 namespace bx
 {
+// Layout of the dense net operators of one entity class: [state][row][mat_row_stride(dim)], states
+// mat_state_stride(dim) doubles apart.  Rows are padded to an even length (zero fill) so a thread can fetch
+// two entries with one 16-byte shared-memory load; the state stride is rounded up to == 2 (mod 16) doubles,
+// so lanes whose cells are in different states hit different banks when they read the same entry, while
+// lanes in the same state broadcast (dof_transform.cu).
+__host__ __device__ constexpr int mat_row_stride(int dim) { return dim + (dim & 1); }
+__host__ __device__ constexpr int mat_state_stride(int dim)
+{
+  const int n = dim * mat_row_stride(dim);
+  return n + ((2 - n % 16) + 16) % 16;
+}
 // Build host tables and upload the device mirror (current device).  Without a usable device the
 // host tables are still built (so they can be inspected) and every compute call fails.
 bx_element* element_from_desc(const bx_element_desc& d);
