@@ -5,7 +5,11 @@
 // precompute::apply_* kernels (precompute.h:136-374), plus permute / permute_inv
 // (finite-element.h:800-843).
 //
-// B200 design (HBM-bound, integer-indexed).  A persistent CTA walks tiles of whole cells:
+// Two implementations (HBM-bound, integer-indexed):
+//   * dof_transform_tma.cuh   pipelined kernels fed by bulk-async (TMA) copies; taken whenever the per-cell
+//                             ranges are 16-byte aligned -- the case for every BASELINE.json configuration;
+//   * dof_transform_kernel    (this file) the general fallback for any alignment, block size and entity
+//                             dimension.  A persistent CTA walks tiles of whole cells:
 //   1. stage   the smallest contiguous range of each cell that holds every movable dof is copied to shared
 //              memory with coalesced loads (entries that can never move are not read at all); cells are laid
 //              out with an ODD pitch, so that 32 lanes working on 32 consecutive cells never share a bank;
@@ -16,9 +20,10 @@
 //                * matrix elements: multiplies them by the dense net operator of that bit-field, composed on the
 //                  host (element.cu).  All states of all entity classes sit in shared memory, `mat_state_stride`
 //                  apart, so lanes in the same state broadcast and lanes in different states hit different
-//                  banks: one conflict-free 16-byte shared load feeds two FMAs;
+//                  banks: one 16-byte shared load feeds two FMAs;
 //   3. store   the range goes back with coalesced stores.
 // Each global byte of the movable range is read once and written once; nothing else is touched.
+#include "dof_transform_tma.cuh"
 #include "element.cuh"
 
 #include <algorithm>
@@ -227,20 +232,144 @@ void launch(T* data, const TransformParams& p, cudaStream_t s)
 template <typename T, bool RIGHT, bool MATRIX>
 void launch_by_dim(T* data, const TransformParams& p, int maxdim, cudaStream_t s)
 {
-  if (maxdim <= 4)
-    launch<T, RIGHT, MATRIX, 4>(data, p, s);
-  else if (maxdim <= 8)
+  if (maxdim <= 8)
     launch<T, RIGHT, MATRIX, 8>(data, p, s);
-  else if (maxdim <= 12)
-    launch<T, RIGHT, MATRIX, 12>(data, p, s);
   else if (maxdim <= 16)
     launch<T, RIGHT, MATRIX, 16>(data, p, s);
-  else if (maxdim <= 24)
-    launch<T, RIGHT, MATRIX, 24>(data, p, s);
   else if (maxdim <= kMaxRegDim)
     launch<T, RIGHT, MATRIX, kMaxRegDim>(data, p, s);
   else
     launch<T, RIGHT, MATRIX, 0>(data, p, s);
+}
+
+// ---- pipelined (TMA) path --------------------------------------------------------------------------------
+template <typename K>
+void launch_tma(K kern, void* data, const tma::Params& p, size_t smem, cudaStream_t s)
+{
+  if (smem > 48 * 1024)
+    BX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  int per_sm = 0;
+  BX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, tma::kThreads, smem));
+  const size_t ntiles = (p.nc + p.cpt - 1) / p.cpt;
+  const size_t cap = size_t(sm_count()) * std::max(per_sm, 1);
+  void* args[] = {&data, const_cast<tma::Params*>(&p)};
+  BX_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(kern), dim3(unsigned(std::min(ntiles, cap))),
+                           dim3(tma::kThreads), args, smem, s));
+  BX_LAUNCHED();
+}
+
+template <typename T, bool RIGHT, bool PAIRS>
+void launch_matrix_tma(T* data, const tma::Params& p, int maxdim, size_t smem, cudaStream_t s)
+{
+  if (maxdim <= 4)
+    launch_tma(tma::dof_matrix_tma_kernel<T, RIGHT, 4, PAIRS>, data, p, smem, s);
+  else if (maxdim <= 8)
+    launch_tma(tma::dof_matrix_tma_kernel<T, RIGHT, 8, PAIRS>, data, p, smem, s);
+  else if (maxdim <= 12)
+    launch_tma(tma::dof_matrix_tma_kernel<T, RIGHT, 12, PAIRS>, data, p, smem, s);
+  else if (maxdim <= 16)
+    launch_tma(tma::dof_matrix_tma_kernel<T, RIGHT, 16, PAIRS>, data, p, smem, s);
+  else if (maxdim <= 24)
+    launch_tma(tma::dof_matrix_tma_kernel<T, RIGHT, 24, PAIRS>, data, p, smem, s);
+  else
+    launch_tma(tma::dof_matrix_tma_kernel<T, RIGHT, 32, PAIRS>, data, p, smem, s);
+}
+
+// Returns false when the layout does not meet the bulk-copy alignment rules (the caller then takes the
+// register-staged kernel).
+template <typename T>
+bool try_tma(const bx_element& e, int kind, bool right, T* data, size_t nc, size_t cell_size, int n, int r0, int len,
+             int maxdim, const uint32_t* cell_info, cudaStream_t s)
+{
+  constexpr size_t sz = sizeof(T);
+  constexpr int per16 = int(16 / sz);
+  if (reinterpret_cast<uintptr_t>(data) % 16 != 0 or (cell_size * sz) % 16 != 0)
+    return false;
+  if (maxdim > kMaxRegDim or maxdim > 255 or e.gather_size >= 65536 or cell_size >= (size_t(1) << 20))
+    return false;
+  tma::Params p;
+  p.nc = nc;
+  p.cell_size = int(cell_size);
+  p.n = n;
+  p.ndofs = e.ndofs;
+  p.r0 = r0 / per16 * per16;
+  p.len = (r0 + len + per16 - 1) / per16 * per16 - p.r0;
+  const size_t len_bytes = size_t(p.len) * sz;
+  const size_t pitch_bytes = (len_bytes / 16) % 2 == 1 ? len_bytes : len_bytes + 16;
+  p.pitch = int(pitch_bytes / sz);
+  p.nslots = int(e.slots.size());
+  p.table_size = e.perms ? e.gather_size : e.mats_size;
+  p.band_size = e.band_size;
+  const size_t tables = e.perms ? ((size_t(e.ndofs) * 4 + size_t(e.gather_size) * 2 + 15) & ~size_t(15))
+                                : size_t(e.mats_size) * 8 + size_t(e.band_size + (e.band_size & 1)) * 8
+                                      + size_t(p.nslots) * 32;
+  // cells per tile: ~20 KB per buffer (three buffers per CTA, several CTAs per SM), whole warps of cells
+  size_t cpt = std::min<size_t>(256, (20 * 1024) / pitch_bytes);
+  if (cpt >= 32)
+    cpt = cpt / 32 * 32;
+  auto total = [&](size_t c) { return tables + 2 * tma::kBuffers * 8 + tma::kBuffers * (((c + 3) & ~size_t(3)) * 4 + c * pitch_bytes); };
+  while (cpt > 1 and total(cpt) > 100 * 1024)
+    cpt /= 2;
+  if (cpt < 8 or total(cpt) > 200 * 1024)
+    return false;
+  p.cpt = int(cpt);
+  const unsigned long long nitems = (unsigned long long)(p.nslots) * n * cpt;
+  if (nitems >= (1ull << 31) or (unsigned long long)(p.len) * cpt >= (1ull << 31))
+    return false;
+  p.by_cpt = tma::FastDiv(unsigned(cpt), nitems);
+  p.by_len = tma::FastDiv(unsigned(p.len), (unsigned long long)(p.len) * cpt);
+  p.by_n = tma::FastDiv(unsigned(n), std::max<unsigned long long>((unsigned long long)(p.nslots) * n, cell_size));
+  p.by_ndofs = tma::FastDiv(unsigned(e.ndofs), cell_size);
+  p.cell_info = cell_info;
+  p.slot_info = e.d_slot_info;
+  p.slot_mat = e.d_slot_mat;
+  p.slot_band = e.d_slot_band;
+  p.band = e.d_band;
+  p.mats = e.d_mats ? e.d_mats + size_t(kind) * e.mats_size : nullptr;
+  p.gather = e.d_gather ? e.d_gather + size_t(kind) * e.gather_size : nullptr;
+  p.dinfo = e.d_dinfo;
+  const size_t smem = total(cpt);
+
+  if (e.perms)
+  {
+    if (!e.d_dinfo)
+      return false;
+    if constexpr (sz == 4)
+    {
+      if (right)
+        launch_tma(tma::dof_perm_tma_kernel<uint32_t, true>, data, p, smem, s);
+      else
+        launch_tma(tma::dof_perm_tma_kernel<uint32_t, false>, data, p, smem, s);
+    }
+    else
+    {
+      if (right)
+        launch_tma(tma::dof_perm_tma_kernel<unsigned long long, true>, data, p, smem, s);
+      else
+        launch_tma(tma::dof_perm_tma_kernel<unsigned long long, false>, data, p, smem, s);
+    }
+    return true;
+  }
+  if constexpr (std::is_integral<T>::value)
+    return false;
+  else
+  {
+    bool pairs = std::is_same<T, double>::value and !right and n == 1;
+    for (const auto& sl : e.slots)
+      pairs = pairs and sl.first % 2 == 0;
+    if (right)
+      launch_matrix_tma<T, true, false>(data, p, maxdim, smem, s);
+    else if constexpr (std::is_same<T, double>::value)
+    {
+      if (pairs)
+        launch_matrix_tma<T, false, true>(data, p, maxdim, smem, s);
+      else
+        launch_matrix_tma<T, false, false>(data, p, maxdim, smem, s);
+    }
+    else
+      launch_matrix_tma<T, false, false>(data, p, maxdim, smem, s);
+    return true;
+  }
 }
 } // namespace
 
@@ -277,6 +406,12 @@ void dof_transform_device(const bx_element& e, int op, T* data, size_t nc, size_
   p.pitch = p.len | 1;
   if (p.len >= 65536 or n >= 65536)
     fail(BX_ERR_UNSUPPORTED, "T_apply: more than 65535 entries per cell");
+  int maxdim = 0;
+  for (const auto& sl : e.slots)
+    maxdim = std::max(maxdim, sl.dim);
+  if (try_tma<T>(e, kind, right, data, nc, cell_size, n, p.r0, p.len, maxdim, cell_info, s))
+    return;
+
   p.nslots = int(e.slots.size());
   p.table_size = e.perms ? e.gather_size : e.mats_size;
   p.cell_info = cell_info;
@@ -299,10 +434,6 @@ void dof_transform_device(const bx_element& e, int op, T* data, size_t nc, size_
   p.by_n = FastDiv(unsigned(n), (unsigned long long)(p.nslots) * n);
   if (smem_bytes(p, !e.perms, sizeof(T)) > 200 * 1024)
     fail(BX_ERR_UNSUPPORTED, "T_apply: a single cell does not fit in shared memory");
-
-  int maxdim = 0;
-  for (const auto& sl : e.slots)
-    maxdim = std::max(maxdim, sl.dim);
 
   if (e.perms)
   {

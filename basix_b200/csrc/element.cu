@@ -574,6 +574,51 @@ bx_element* element_from_desc(const bx_element_desc& d)
       }
     }
   }
+  // ---- column band of every operator row (matrix elements) -----------------------------------------------
+  // Legendre-variant moment dofs transform block-diagonally (one block per polynomial degree), so most of a
+  // dense dim x dim operator is zero; the kernel only walks [first, last) of each row.  The band is the union
+  // over the four operator kinds and all states, so one table serves every T-flavour.
+  std::vector<int2> band;
+  std::vector<int> slot_band(e->slots.size(), 0);
+  if (!e->perms)
+  {
+    std::array<int, 8> cls_band{};
+    for (int cls : {BX_CELL_INTERVAL, BX_CELL_TRIANGLE, BX_CELL_QUADRILATERAL})
+    {
+      const int n = e->etrans_dim[cls];
+      if (n <= 0)
+        continue;
+      cls_band[cls] = int(band.size());
+      const int nst = cls == BX_CELL_INTERVAL ? 2 : 8;
+      double amax = 0.0;
+      for (int op = 0; op < 4; ++op)
+        for (int state = 0; state < nst; ++state)
+          for (int k = 0; k < n * mat_row_stride(n); ++k)
+            amax = std::max(amax, std::abs(mats[size_t(op) * msize + cls_base[cls] + size_t(state) * mat_state_stride(n) + k]));
+      for (int row = 0; row < n; ++row)
+      {
+        int lo = n, hi = 0;
+        for (int op = 0; op < 4; ++op)
+          for (int state = 0; state < nst; ++state)
+          {
+            const double* r = mats.data() + size_t(op) * msize + cls_base[cls] + size_t(state) * mat_state_stride(n)
+                              + size_t(row) * mat_row_stride(n);
+            for (int j = 0; j < n; ++j)
+              if (std::abs(r[j]) > 1e-14 * amax)
+              {
+                lo = std::min(lo, j);
+                hi = std::max(hi, j + 1);
+              }
+          }
+        band.push_back(lo < hi ? make_int2(lo, hi) : make_int2(0, 0));
+      }
+    }
+    for (size_t s = 0; s < e->slots.size(); ++s)
+      slot_band[s] = cls_band[e->slots[s].cls];
+  }
+  e->h_band = band;
+  e->h_slot_band = slot_band;
+  e->band_size = int(band.size());
   e->gather_size = gsize;
   e->mats_size = msize;
   e->h_slot_info = slot_info;
@@ -588,6 +633,24 @@ bx_element* element_from_desc(const bx_element_desc& d)
     e->d_slot_mat = upload(slot_mat);
     e->d_gather = upload(gather);
     e->d_mats = upload(mats);
+    e->d_band = upload(band);
+    if (e->perms and gsize < 65536)
+    {
+      // packed per-dof descriptor of the permutation kernel (dof_transform_tma.cuh); mask 0 = never moves
+      std::vector<uint32_t> dinfo(ndofs, 0u);
+      bool ok = true;
+      for (size_t s = 0; s < e->slots.size(); ++s)
+      {
+        const auto& sl = e->slots[s];
+        ok = ok and sl.dim < 256 and sl.shift < 32;
+        for (int l = 0; l < sl.dim; ++l)
+          dinfo[sl.dofs[l]] = uint32_t(sl.shift) | uint32_t(sl.mask) << 5 | uint32_t(sl.dim) << 8
+                              | uint32_t(slot_info[s].w + l) << 16;
+      }
+      if (ok)
+        e->d_dinfo = upload(dinfo);
+    }
+    e->d_slot_band = upload(slot_band);
   }
   return e.release();
 }
@@ -665,4 +728,7 @@ bx_element::~bx_element()
   cudaFree(d_gather);
   cudaFree(d_slot_mat);
   cudaFree(d_mats);
+  cudaFree(d_band);
+  cudaFree(d_dinfo);
+  cudaFree(d_slot_band);
 }

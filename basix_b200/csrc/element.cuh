@@ -72,6 +72,9 @@ struct bx_element
   std::vector<int2> h_slot_mat;   // [nslots] {first dof, matrix base of the slot's class}
   std::vector<int16_t> h_gather;  // [4][gather_size]
   std::vector<double> h_mats;     // [4][mats_size]
+  std::vector<int2> h_band;       // per (class, row): [first, last) column of the non-zero band, union over all
+                                  // operator kinds and states (entries below 1e-14 * max|M| count as zero)
+  std::vector<int> h_slot_band;   // [nslots] index of the slot's class in h_band
   bool on_device = false;         // false when the element was built without a usable CUDA device
 
   // Device tables (all ops packed).  See dof_transform.cu for the layout.
@@ -83,6 +86,10 @@ struct bx_element
   int2* d_slot_mat = nullptr;     // [nslots] {first dof, matrix base of its class}
   double* d_mats = nullptr;       // [4 ops][mats_size]: dense [state][dim][dim] per class
   int mats_size = 0;
+  int2* d_band = nullptr;         // [band_size]
+  int* d_slot_band = nullptr;     // [nslots]
+  int band_size = 0;
+  uint32_t* d_dinfo = nullptr;    // [ndofs] shift | mask << 5 | dim << 8 | (gather base + loc) << 16, or null
 
   ~bx_element();
   bx_element() = default;

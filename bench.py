@@ -530,11 +530,20 @@ def main():
     ap.add_argument("--workload", default=DEFAULT, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--units", type=int, default=0,
+                    help="override the workload's points / cells per GPU (profiling runs only; the judged line "
+                         "uses the BASELINE.json size)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     w = WORKLOADS[args.workload]()
+    if args.units > 0:
+        if hasattr(w, "npts"):
+            w.npts = args.units
+        else:
+            w.nc = args.units
+        w.desc += f" [size overridden to {args.units} per GPU]"
     if args.impl == "reference":
         run_reference(args, w, rank)
     else:

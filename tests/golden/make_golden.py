@@ -41,6 +41,7 @@ CONFIG_ELEMENTS = {
     "P2_tetrahedron_eq": (P, TET, 2, EQ),
     "Q2_quadrilateral_gll": (P, QUAD, 2, GLL),
     "RT2_tetrahedron_legendre": (RT, TET, 2, LEG),
+    "RT2_tetrahedron_unset": (RT, TET, 2, 0),  # the element of the SURVEY 8c T_apply anchors
 }
 
 
