@@ -243,49 +243,116 @@ void launch_by_dim(T* data, const TransformParams& p, int maxdim, cudaStream_t s
 }
 
 // ---- pipelined (TMA) path --------------------------------------------------------------------------------
+using EncodeTiled = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
+EncodeTiled encode_tiled()
+{
+  static EncodeTiled fn = []() -> EncodeTiled
+  {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess
+        or q != cudaDriverEntryPointSuccess)
+    {
+      cudaGetLastError();
+      return nullptr;
+    }
+    return reinterpret_cast<EncodeTiled>(f);
+  }();
+  return fn;
+}
+
+// data[nc][cell_size] as a 2-D tensor, box = [cpt cells][box_w entries]
+bool make_tensor_map(CUtensorMap& map, void* data, size_t nc, size_t cell_size, size_t elem, int box_w, int cpt)
+{
+  EncodeTiled enc = encode_tiled();
+  if (!enc)
+    return false;
+  const cuuint64_t gdim[2] = {cuuint64_t(cell_size), cuuint64_t(nc)};
+  const cuuint64_t gstride[1] = {cuuint64_t(cell_size * elem)};
+  const cuuint32_t box[2] = {cuuint32_t(box_w), cuuint32_t(cpt)};
+  const cuuint32_t estride[2] = {1, 1};
+  const CUtensorMapDataType dt = elem == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32;
+  return enc(&map, dt, 2, data, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
+         == CUDA_SUCCESS;
+}
+
 template <typename K>
-void launch_tma(K kern, void* data, const tma::Params& p, size_t smem, cudaStream_t s)
+unsigned tma_grid(K kern, const tma::Params& p, size_t smem)
 {
   if (smem > 48 * 1024)
     BX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   int per_sm = 0;
   BX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, tma::kThreads, smem));
   const size_t ntiles = (p.nc + p.cpt - 1) / p.cpt;
-  const size_t cap = size_t(sm_count()) * std::max(per_sm, 1);
-  void* args[] = {&data, const_cast<tma::Params*>(&p)};
-  BX_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(kern), dim3(unsigned(std::min(ntiles, cap))),
-                           dim3(tma::kThreads), args, smem, s));
+  return unsigned(std::min(ntiles, size_t(sm_count()) * std::max(per_sm, 1)));
+}
+
+template <typename T, bool RIGHT, bool PAIRS, int REG>
+void launch_matrix_tma_reg(const CUtensorMap& map, const tma::Params& p, size_t smem, cudaStream_t s)
+{
+  auto kern = tma::dof_matrix_tma_kernel<T, RIGHT, REG, PAIRS>;
+  kern<<<tma_grid(kern, p, smem), tma::kThreads, smem, s>>>(map, p);
   BX_LAUNCHED();
 }
 
 template <typename T, bool RIGHT, bool PAIRS>
-void launch_matrix_tma(T* data, const tma::Params& p, int maxdim, size_t smem, cudaStream_t s)
+void launch_matrix_tma(const CUtensorMap& map, const tma::Params& p, int maxdim, size_t smem, cudaStream_t s)
 {
   if (maxdim <= 4)
-    launch_tma(tma::dof_matrix_tma_kernel<T, RIGHT, 4, PAIRS>, data, p, smem, s);
+    launch_matrix_tma_reg<T, RIGHT, PAIRS, 4>(map, p, smem, s);
   else if (maxdim <= 8)
-    launch_tma(tma::dof_matrix_tma_kernel<T, RIGHT, 8, PAIRS>, data, p, smem, s);
+    launch_matrix_tma_reg<T, RIGHT, PAIRS, 8>(map, p, smem, s);
   else if (maxdim <= 12)
-    launch_tma(tma::dof_matrix_tma_kernel<T, RIGHT, 12, PAIRS>, data, p, smem, s);
+    launch_matrix_tma_reg<T, RIGHT, PAIRS, 12>(map, p, smem, s);
   else if (maxdim <= 16)
-    launch_tma(tma::dof_matrix_tma_kernel<T, RIGHT, 16, PAIRS>, data, p, smem, s);
+    launch_matrix_tma_reg<T, RIGHT, PAIRS, 16>(map, p, smem, s);
   else if (maxdim <= 24)
-    launch_tma(tma::dof_matrix_tma_kernel<T, RIGHT, 24, PAIRS>, data, p, smem, s);
+    launch_matrix_tma_reg<T, RIGHT, PAIRS, 24>(map, p, smem, s);
   else
-    launch_tma(tma::dof_matrix_tma_kernel<T, RIGHT, 32, PAIRS>, data, p, smem, s);
+    launch_matrix_tma_reg<T, RIGHT, PAIRS, 32>(map, p, smem, s);
 }
 
-// Returns false when the layout does not meet the bulk-copy alignment rules (the caller then takes the
-// register-staged kernel).
+template <typename U, bool RIGHT, int EPL>
+void launch_perm_tma(const CUtensorMap& map, void* data, const tma::Params& p, size_t smem, cudaStream_t s)
+{
+  auto kern = tma::dof_perm_tma_kernel<U, RIGHT, EPL>;
+  kern<<<tma_grid(kern, p, smem), tma::kThreads, smem, s>>>(map, static_cast<U*>(data), p);
+  BX_LAUNCHED();
+}
+
+template <typename U>
+void launch_perm_tma_any(const CUtensorMap& map, void* data, const tma::Params& p, bool right, size_t smem,
+                         cudaStream_t s)
+{
+  if (right)
+    launch_perm_tma<U, true, 0>(map, data, p, smem, s);
+  else if (p.n == 1 and p.len <= 32)
+    launch_perm_tma<U, false, 1>(map, data, p, smem, s);
+  else if (p.n == 1 and p.len <= 64)
+    launch_perm_tma<U, false, 2>(map, data, p, smem, s);
+  else if (p.n == 1 and p.len <= 128)
+    launch_perm_tma<U, false, 4>(map, data, p, smem, s);
+  else
+    launch_perm_tma<U, false, 0>(map, data, p, smem, s);
+}
+
+// Returns false when the layout does not meet the TMA rules (the caller then takes the register-staged kernel).
 template <typename T>
 bool try_tma(const bx_element& e, int kind, bool right, T* data, size_t nc, size_t cell_size, int n, int r0, int len,
              int maxdim, const uint32_t* cell_info, cudaStream_t s)
 {
   constexpr size_t sz = sizeof(T);
   constexpr int per16 = int(16 / sz);
-  if (reinterpret_cast<uintptr_t>(data) % 16 != 0 or (cell_size * sz) % 16 != 0)
+  if (reinterpret_cast<uintptr_t>(data) % 16 != 0 or (cell_size * sz) % 16 != 0 or nc >= (size_t(1) << 31))
     return false;
-  if (maxdim > kMaxRegDim or maxdim > 255 or e.gather_size >= 65536 or cell_size >= (size_t(1) << 20))
+  if (maxdim > kMaxRegDim or e.gather_size >= 65536 or cell_size >= (size_t(1) << 20))
+    return false;
+  if (e.perms and !e.d_dinfo)
     return false;
   tma::Params p;
   p.nc = nc;
@@ -293,21 +360,32 @@ bool try_tma(const bx_element& e, int kind, bool right, T* data, size_t nc, size
   p.n = n;
   p.ndofs = e.ndofs;
   p.r0 = r0 / per16 * per16;
-  p.len = (r0 + len + per16 - 1) / per16 * per16 - p.r0;
-  const size_t len_bytes = size_t(p.len) * sz;
-  const size_t pitch_bytes = (len_bytes / 16) % 2 == 1 ? len_bytes : len_bytes + 16;
+  p.len = r0 + len - p.r0;
+  // box width: whole 16-byte units; matrix kernel: an ODD number of them, so that 8 lanes on 8 consecutive
+  // cells hit 8 different 16-byte bank groups
+  size_t units = (size_t(p.len) * sz + 15) / 16;
+  if (!e.perms and units % 2 == 0)
+    ++units;
+  const size_t pitch_bytes = units * 16;
   p.pitch = int(pitch_bytes / sz);
+  if (p.pitch > 256)
+    return false;
+  p.epl = 0;
   p.nslots = int(e.slots.size());
   p.table_size = e.perms ? e.gather_size : e.mats_size;
   p.band_size = e.band_size;
   const size_t tables = e.perms ? ((size_t(e.ndofs) * 4 + size_t(e.gather_size) * 2 + 15) & ~size_t(15))
                                 : size_t(e.mats_size) * 8 + size_t(e.band_size + (e.band_size & 1)) * 8
                                       + size_t(p.nslots) * 32;
-  // cells per tile: ~20 KB per buffer (three buffers per CTA, several CTAs per SM), whole warps of cells
-  size_t cpt = std::min<size_t>(256, (20 * 1024) / pitch_bytes);
+  // cells per tile: ~24 KB per buffer (three buffers per CTA, several CTAs per SM), whole warps of cells
+  size_t cpt = std::min<size_t>(256, (24 * 1024) / pitch_bytes);
   if (cpt >= 32)
     cpt = cpt / 32 * 32;
-  auto total = [&](size_t c) { return tables + 2 * tma::kBuffers * 8 + tma::kBuffers * (((c + 3) & ~size_t(3)) * 4 + c * pitch_bytes); };
+  auto total = [&](size_t c)
+  {
+    return tables + 2 * tma::kBuffers * 8 + tma::kBuffers * ((c + 3) & ~size_t(3)) * 4 + 128
+           + tma::kBuffers * size_t(tma::tile_stride_bytes(int(c), p.pitch, int(sz)));
+  };
   while (cpt > 1 and total(cpt) > 100 * 1024)
     cpt /= 2;
   if (cpt < 8 or total(cpt) > 200 * 1024)
@@ -329,25 +407,16 @@ bool try_tma(const bx_element& e, int kind, bool right, T* data, size_t nc, size
   p.gather = e.d_gather ? e.d_gather + size_t(kind) * e.gather_size : nullptr;
   p.dinfo = e.d_dinfo;
   const size_t smem = total(cpt);
+  CUtensorMap map;
+  if (!make_tensor_map(map, data, nc, cell_size, sz, p.pitch, p.cpt))
+    return false;
 
   if (e.perms)
   {
-    if (!e.d_dinfo)
-      return false;
     if constexpr (sz == 4)
-    {
-      if (right)
-        launch_tma(tma::dof_perm_tma_kernel<uint32_t, true>, data, p, smem, s);
-      else
-        launch_tma(tma::dof_perm_tma_kernel<uint32_t, false>, data, p, smem, s);
-    }
+      launch_perm_tma_any<uint32_t>(map, data, p, right, smem, s);
     else
-    {
-      if (right)
-        launch_tma(tma::dof_perm_tma_kernel<unsigned long long, true>, data, p, smem, s);
-      else
-        launch_tma(tma::dof_perm_tma_kernel<unsigned long long, false>, data, p, smem, s);
-    }
+      launch_perm_tma_any<unsigned long long>(map, data, p, right, smem, s);
     return true;
   }
   if constexpr (std::is_integral<T>::value)
@@ -358,16 +427,16 @@ bool try_tma(const bx_element& e, int kind, bool right, T* data, size_t nc, size
     for (const auto& sl : e.slots)
       pairs = pairs and sl.first % 2 == 0;
     if (right)
-      launch_matrix_tma<T, true, false>(data, p, maxdim, smem, s);
+      launch_matrix_tma<T, true, false>(map, p, maxdim, smem, s);
     else if constexpr (std::is_same<T, double>::value)
     {
       if (pairs)
-        launch_matrix_tma<T, false, true>(data, p, maxdim, smem, s);
+        launch_matrix_tma<T, false, true>(map, p, maxdim, smem, s);
       else
-        launch_matrix_tma<T, false, false>(data, p, maxdim, smem, s);
+        launch_matrix_tma<T, false, false>(map, p, maxdim, smem, s);
     }
     else
-      launch_matrix_tma<T, false, false>(data, p, maxdim, smem, s);
+      launch_matrix_tma<T, false, false>(map, p, maxdim, smem, s);
     return true;
   }
 }

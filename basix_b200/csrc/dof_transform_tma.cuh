@@ -1,21 +1,29 @@
-// Pipelined DOF-transformation kernels: the movable range of every cell travels between HBM and shared
-// memory as one bulk-async (TMA) copy per cell, issued by a dedicated DMA warp and tracked with mbarriers, so
-// the seven compute warps never execute a global load and the HBM stream of tile i+1 / i-1 overlaps the
-// arithmetic of tile i.  Used whenever the per-cell ranges are 16-byte aligned (dof_transform.cu decides);
-// the register-staged kernel in dof_transform.cu is the general fallback.
+// Pipelined DOF-transformation kernels.  data[nc][cell_size] is described to the TMA unit as a 2-D tensor
+// (cuTensorMapEncodeTiled, built per call in dof_transform.cu); ONE cp.async.bulk.tensor instruction moves the
+// movable column range of a whole tile of cells between HBM and shared memory, issued by a dedicated DMA warp
+// and tracked with mbarriers.  The seven compute warps never execute a global load, entries that can never move
+// are never read, and the HBM stream of tiles i+1 / i-1 overlaps the arithmetic of tile i (three buffers).
+// Used whenever the cell pitch is a multiple of 16 bytes and the range fits a TMA box (dof_transform.cu
+// decides); the register-staged kernel in dof_transform.cu is the general fallback.
 //
 //   dof_matrix_tma_kernel   matrix elements (transform_data, finite-element.h:1762-1837): one thread per
 //                           (cell, sub-entity, block) item, lanes <-> consecutive cells; the entity's values sit
 //                           in registers, the dense net operator of the item's cell_info state is read from
 //                           shared memory, two entries per 16-byte load, and only inside the non-zero column
-//                           band of each row; results go back in place and leave as per-cell bulk stores.
-//   dof_perm_tma_kernel     permutation elements (permute_data, finite-element.h:1703-1760): one thread per
-//                           entry of the movable range, lanes <-> consecutive entries of a cell; a packed per-dof
-//                           descriptor + the gather table give the source entry, the value is read from the
-//                           staged tile and stored straight to global memory (coalesced), bit for bit.
+//                           band of each row; results go back in place and leave as one tensor store per tile.
+//                           The box is an odd number of 16-byte units wide, so 8 lanes on 8 consecutive cells
+//                           hit 8 different bank groups.
+//   dof_perm_tma_kernel     permutation elements (permute_data, finite-element.h:1703-1760): a warp walks the
+//                           cells of the tile, lanes <-> entries of the movable range, each lane keeping the
+//                           packed descriptor of its entries in registers; the gather table gives the source
+//                           entry, the value is read from the staged tile and stored straight to global memory
+//                           (coalesced), bit for bit.  (General block sizes / right layout: one thread per
+//                           entry with the descriptor looked up in shared memory.)
 #pragma once
 
 #include "element.cuh"
+
+#include <cuda.h>
 
 namespace bx
 {
@@ -50,17 +58,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity)
                  : "memory");
   } while (!ok);
 }
-// global -> shared, completion counted in bytes on an mbarrier
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+// 2-D tensor tile, global -> shared; completion counted in bytes on an mbarrier.  (x, y) = (entry, cell)
+__device__ __forceinline__ void tensor_load(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar)
 {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(map), "r"(x), "r"(y), "r"(bar)
                : "memory");
 }
-// shared -> global, completion tracked per thread in bulk groups
-__device__ __forceinline__ void bulk_store(void* dst, uint32_t src, uint32_t bytes)
+// 2-D tensor tile, shared -> global (rows past the end of the tensor are clipped); tracked in bulk groups
+__device__ __forceinline__ void tensor_store(const CUtensorMap* map, int x, int y, uint32_t src)
 {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(x), "r"(y),
+               "r"(src)
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -89,8 +98,9 @@ struct Params
   size_t nc;
   int cell_size, n, ndofs;
   int cpt;              // cells per tile
-  int r0, len;          // staged range [r0, r0 + len) of each cell, in entries; 16-byte aligned at both ends
-  int pitch;            // shared-memory distance between cells, in entries (pitch bytes = odd multiple of 16)
+  int r0, len;          // movable range [r0, r0 + len) of each cell, in entries; r0 is 16-byte aligned
+  int pitch;            // TMA box width = shared-memory distance between cells, in entries (>= len)
+  int epl;              // permutation kernel: entries per lane of the warp-per-cell form (0: per-entry form)
   int nslots, table_size, band_size;
   FastDiv by_cpt, by_len, by_n, by_ndofs;
   const uint32_t* cell_info;
@@ -110,33 +120,37 @@ __device__ __forceinline__ int entry(int dof, int b, int n, int ndofs)
 }
 
 // ---- the DMA warp ---------------------------------------------------------------------------------------
-// Loads tile `tl` into buffer b: cell_info by plain loads, each cell's range by one bulk copy.  The `full`
-// barrier (count 32) completes when every lane has arrived and all bytes have landed.
-template <typename T>
-__device__ __forceinline__ void dma_load(const Params& p, const T* data, size_t tl, int lane, uint32_t* s_ci,
-                                         uint32_t tile_addr, uint32_t full_bar)
+// Loads tile `tl` into a buffer: cell_info by plain loads (all lanes), the data by one tensor copy (lane 0).
+// The `full` barrier (count 32) completes when every lane has arrived and all bytes of the box have landed.
+__device__ __forceinline__ void dma_load(const Params& p, const CUtensorMap* map, size_t tl, int lane, uint32_t* s_ci,
+                                         uint32_t tile_addr, uint32_t box_bytes, uint32_t full_bar)
 {
   const size_t c0 = tl * p.cpt;
   const unsigned ncell = unsigned(min(size_t(p.cpt), p.nc - c0));
   for (unsigned c = lane; c < ncell; c += 32)
     s_ci[c] = p.cell_info[c0 + c];
-  const uint32_t len_bytes = uint32_t(p.len) * sizeof(T);
   if (lane == 0)
-    mbar_arrive_expect_tx(full_bar, ncell * len_bytes);
+  {
+    mbar_arrive_expect_tx(full_bar, box_bytes);
+    tensor_load(tile_addr, map, p.r0, int(c0), full_bar);
+  }
   else
     mbar_arrive(full_bar);
-  __syncwarp();
-  const T* src = data + c0 * p.cell_size + p.r0;
-  for (unsigned c = lane; c < ncell; c += 32)
-    bulk_load(tile_addr + c * uint32_t(p.pitch) * sizeof(T), src + size_t(c) * p.cell_size, len_bytes, full_bar);
 }
 
 // =====================================================================================================
+// Shared-memory carve-up helper: tiles start on a 128-byte boundary (TMA), one tile every `tile_stride` bytes.
+__host__ __device__ inline uint32_t tile_stride_bytes(int cpt, int pitch, int elem)
+{
+  return (uint32_t(cpt) * uint32_t(pitch) * uint32_t(elem) + 127u) & ~127u;
+}
+
 template <typename T, bool RIGHT, int REG, bool PAIRS>
-__global__ void __launch_bounds__(kThreads) dof_matrix_tma_kernel(T* __restrict__ data, const Params p)
+__global__ void __launch_bounds__(kThreads)
+    dof_matrix_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params p)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  // ---- carve: mats | band | slot tables | barriers | cell_info[kBuffers] | tiles[kBuffers] ----------------
+  // ---- carve: mats | band | slot tables | barriers | cell_info[kBuffers] | (128 B aligned) tiles[kBuffers] ----
   double* s_mats = reinterpret_cast<double*>(smem_raw);
   int2* s_band = reinterpret_cast<int2*>(s_mats + p.table_size);
   int4* s_info = reinterpret_cast<int4*>(s_band + p.band_size + (p.band_size & 1));
@@ -144,8 +158,10 @@ __global__ void __launch_bounds__(kThreads) dof_matrix_tma_kernel(T* __restrict_
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_slot + p.nslots);
   uint32_t* s_ci = reinterpret_cast<uint32_t*>(s_bar + 2 * kBuffers);
   const int ci_stride = (p.cpt + 3) & ~3;
-  unsigned char* tiles = reinterpret_cast<unsigned char*>(s_ci + kBuffers * ci_stride);
-  const uint32_t tile_bytes = uint32_t(p.cpt) * p.pitch * sizeof(T);
+  const uint32_t head = (uint32_t(reinterpret_cast<unsigned char*>(s_ci + kBuffers * ci_stride) - smem_raw) + 127u) & ~127u;
+  unsigned char* tiles = smem_raw + head;
+  const uint32_t tile_bytes = tile_stride_bytes(p.cpt, p.pitch, sizeof(T));
+  const uint32_t box_bytes = uint32_t(p.cpt) * uint32_t(p.pitch) * sizeof(T);
   const uint32_t bar0 = smem_u32(s_bar);
 
   for (int i = threadIdx.x; i < p.table_size; i += kThreads)
@@ -172,38 +188,39 @@ __global__ void __launch_bounds__(kThreads) dof_matrix_tma_kernel(T* __restrict_
   const size_t ntiles = (p.nc + p.cpt - 1) / p.cpt;
   const size_t mine = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t len_bytes = uint32_t(p.len) * sizeof(T);
 
   if (warp == kThreads / 32 - 1)
   {
     // ---- DMA warp: loads run kBuffers-1 tiles ahead; stores follow the compute warps ----------------------
     for (size_t i = 0; i < mine and i < size_t(kBuffers - 1); ++i)
-      dma_load<T>(p, data, blockIdx.x + i * gridDim.x, lane, s_ci + int(i) * ci_stride,
-                  smem_u32(tiles) + uint32_t(i) * tile_bytes, bar0 + 8 * uint32_t(i));
+      dma_load(p, &tmap, blockIdx.x + i * gridDim.x, lane, s_ci + int(i) * ci_stride,
+               smem_u32(tiles) + uint32_t(i) * tile_bytes, box_bytes, bar0 + 8 * uint32_t(i));
     for (size_t i = 0; i < mine; ++i)
     {
-      // tile j = i + kBuffers - 1 reuses the buffer of tile i - 1, whose stores were committed one iteration
-      // ago: once they have read shared memory, refill it -- before waiting for tile i, so that the loads stay
-      // kBuffers - 1 tiles ahead of the compute warps
+      // tile j = i + kBuffers - 1 reuses the buffer of tile i - 1, whose store was committed one iteration
+      // ago: once it has read shared memory, refill the buffer -- before waiting for tile i, so that the loads
+      // stay kBuffers - 1 tiles ahead of the compute warps
       const size_t j = i + kBuffers - 1;
       if (j < mine)
       {
-        bulk_wait_read<0>();
+        if (lane == 0)
+          bulk_wait_read<0>();
+        __syncwarp();
         const int bj = int(j % kBuffers);
-        dma_load<T>(p, data, blockIdx.x + j * gridDim.x, lane, s_ci + bj * ci_stride,
-                    smem_u32(tiles) + uint32_t(bj) * tile_bytes, bar0 + 8 * uint32_t(bj));
+        dma_load(p, &tmap, blockIdx.x + j * gridDim.x, lane, s_ci + bj * ci_stride,
+                 smem_u32(tiles) + uint32_t(bj) * tile_bytes, box_bytes, bar0 + 8 * uint32_t(bj));
       }
       const int b = int(i % kBuffers);
-      const size_t tl = blockIdx.x + i * gridDim.x, c0 = tl * p.cpt;
-      const unsigned ncell = unsigned(min(size_t(p.cpt), p.nc - c0));
+      const size_t c0 = (blockIdx.x + i * gridDim.x) * size_t(p.cpt);
       mbar_wait(bar0 + 8 * (kBuffers + b), uint32_t(i / kBuffers) & 1); // compute warps are done with tile i
-      T* dst = data + c0 * p.cell_size + p.r0;
-      const uint32_t tile_addr = smem_u32(tiles) + uint32_t(b) * tile_bytes;
-      for (unsigned c = lane; c < ncell; c += 32)
-        bulk_store(dst + size_t(c) * p.cell_size, tile_addr + c * uint32_t(p.pitch) * sizeof(T), len_bytes);
-      bulk_commit();
+      if (lane == 0)
+      {
+        tensor_store(&tmap, p.r0, int(c0), smem_u32(tiles) + uint32_t(b) * tile_bytes);
+        bulk_commit();
+      }
     }
-    bulk_wait_all();
+    if (lane == 0)
+      bulk_wait_all();
     return;
   }
 
@@ -307,19 +324,24 @@ __global__ void __launch_bounds__(kThreads) dof_matrix_tma_kernel(T* __restrict_
 
 // =====================================================================================================
 // U is the unsigned integer type of the entry size (bit-exact moves for any 4- or 8-byte data type).
-template <typename U, bool RIGHT>
-__global__ void __launch_bounds__(kThreads) dof_perm_tma_kernel(U* __restrict__ data, const Params p)
+// EPL > 0: warp-per-cell form for block size 1 / left layout, EPL entries per lane (len <= 32 * EPL);
+// EPL == 0: one thread per entry, any block size and layout.
+template <typename U, bool RIGHT, int EPL>
+__global__ void __launch_bounds__(kThreads)
+    dof_perm_tma_kernel(const __grid_constant__ CUtensorMap tmap, U* __restrict__ data, const Params p)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // ---- carve: per-dof descriptors | gather table | barriers | cell_info[kBuffers] | tiles[kBuffers] --------
   uint32_t* s_dinfo = reinterpret_cast<uint32_t*>(smem_raw);
   int16_t* s_gather = reinterpret_cast<int16_t*>(s_dinfo + p.ndofs);
-  const size_t head = (size_t(p.ndofs) * 4 + size_t(p.table_size) * 2 + 15) & ~size_t(15);
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_raw + head);
+  const size_t tables = (size_t(p.ndofs) * 4 + size_t(p.table_size) * 2 + 15) & ~size_t(15);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_raw + tables);
   uint32_t* s_ci = reinterpret_cast<uint32_t*>(s_bar + 2 * kBuffers);
   const int ci_stride = (p.cpt + 3) & ~3;
-  unsigned char* tiles = reinterpret_cast<unsigned char*>(s_ci + kBuffers * ci_stride);
-  const uint32_t tile_bytes = uint32_t(p.cpt) * p.pitch * sizeof(U);
+  const uint32_t head = (uint32_t(reinterpret_cast<unsigned char*>(s_ci + kBuffers * ci_stride) - smem_raw) + 127u) & ~127u;
+  unsigned char* tiles = smem_raw + head;
+  const uint32_t tile_bytes = tile_stride_bytes(p.cpt, p.pitch, sizeof(U));
+  const uint32_t box_bytes = uint32_t(p.cpt) * uint32_t(p.pitch) * sizeof(U);
   const uint32_t bar0 = smem_u32(s_bar);
 
   for (int i = threadIdx.x; i < p.ndofs; i += kThreads)
@@ -348,13 +370,29 @@ __global__ void __launch_bounds__(kThreads) dof_perm_tma_kernel(U* __restrict__ 
       const int b = int(i % kBuffers);
       if (i >= size_t(kBuffers))
         mbar_wait(bar0 + 8 * (kBuffers + b), uint32_t(i / kBuffers - 1) & 1); // tile i - kBuffers has been read
-      dma_load<U>(p, data, blockIdx.x + i * gridDim.x, lane, s_ci + b * ci_stride,
-                  smem_u32(tiles) + uint32_t(b) * tile_bytes, bar0 + 8 * uint32_t(b));
+      dma_load(p, &tmap, blockIdx.x + i * gridDim.x, lane, s_ci + b * ci_stride,
+               smem_u32(tiles) + uint32_t(b) * tile_bytes, box_bytes, bar0 + 8 * uint32_t(b));
     }
     return;
   }
 
   const int n = p.n, ndofs = p.ndofs, pitch = p.pitch, r0 = p.r0, len = p.len, cs = p.cell_size;
+  // warp-per-cell form: the descriptors of this lane's entries never change -> registers
+  [[maybe_unused]] uint32_t shift[EPL > 0 ? EPL : 1], mask[EPL > 0 ? EPL : 1], gbase[EPL > 0 ? EPL : 1],
+      gdim[EPL > 0 ? EPL : 1];
+  if constexpr (EPL > 0)
+  {
+#pragma unroll
+    for (int k = 0; k < EPL; ++k)
+    {
+      const int e = lane + 32 * k;
+      const uint32_t info = e < len ? s_dinfo[r0 + e] : 0u;
+      shift[k] = info & 31u;
+      mask[k] = (info >> 5) & 7u;
+      gdim[k] = (info >> 8) & 0xFFu;
+      gbase[k] = info >> 16;
+    }
+  }
   for (size_t i = 0; i < mine; ++i)
   {
     const int b = int(i % kBuffers);
@@ -362,29 +400,47 @@ __global__ void __launch_bounds__(kThreads) dof_perm_tma_kernel(U* __restrict__ 
     const unsigned ncell = unsigned(min(size_t(p.cpt), p.nc - c0));
     const U* tile = reinterpret_cast<const U*>(tiles + size_t(b) * tile_bytes);
     const uint32_t* ci = s_ci + b * ci_stride;
-    U* g = data + c0 * cs;
     mbar_wait(bar0 + 8 * b, uint32_t(i / kBuffers) & 1);
-    for (unsigned q = threadIdx.x; q < ncell * len; q += kComputeThreads)
+    if constexpr (EPL > 0)
     {
-      const unsigned c = p.by_len.div(q), e = r0 + (q - c * len);
-      unsigned dof, bl;
-      if constexpr (RIGHT)
+      U* g = data + c0 * cs + r0 + lane;
+      for (unsigned c = warp; c < ncell; c += kComputeThreads / 32)
       {
-        bl = p.by_ndofs.div(e);
-        dof = e - bl * ndofs;
+        const uint32_t info = ci[c];
+        const U* row = tile + c * pitch - r0;
+#pragma unroll
+        for (int k = 0; k < EPL; ++k)
+        {
+          const unsigned state = (info >> shift[k]) & mask[k];
+          if (state != 0)
+            g[size_t(c) * cs + 32 * k] = row[s_gather[gbase[k] + state * gdim[k]]];
+        }
       }
-      else
+    }
+    else
+    {
+      U* g = data + c0 * cs;
+      for (unsigned q = threadIdx.x; q < ncell * len; q += kComputeThreads)
       {
-        dof = p.by_n.div(e);
-        bl = e - dof * n;
+        const unsigned c = p.by_len.div(q), e = r0 + (q - c * len);
+        unsigned dof, bl;
+        if constexpr (RIGHT)
+        {
+          bl = p.by_ndofs.div(e);
+          dof = e - bl * ndofs;
+        }
+        else
+        {
+          dof = p.by_n.div(e);
+          bl = e - dof * n;
+        }
+        const uint32_t info = s_dinfo[dof];
+        const unsigned state = (ci[c] >> (info & 31u)) & ((info >> 5) & 7u);
+        if (state == 0) // also every dof that never moves (mask 0)
+          continue;
+        const unsigned src = unsigned(s_gather[(info >> 16) + state * ((info >> 8) & 0xFFu)]);
+        g[size_t(c) * cs + e] = tile[c * pitch + entry<RIGHT>(src, bl, n, ndofs) - r0];
       }
-      const uint32_t info = s_dinfo[dof];
-      const unsigned mask = (info >> 5) & 7u;
-      const unsigned state = (ci[c] >> (info & 31u)) & mask;
-      if (state == 0) // also every dof that never moves (mask 0)
-        continue;
-      const unsigned src = unsigned(s_gather[(info >> 16) + state * ((info >> 8) & 0xFFu)]);
-      g[size_t(c) * cs + e] = tile[c * pitch + entry<RIGHT>(src, bl, n, ndofs) - r0];
     }
     mbar_arrive(bar0 + 8 * (kBuffers + b));
   }
