@@ -27,6 +27,9 @@
 #include "element.cuh"
 
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <string>
 #include <type_traits>
 
 namespace bx
@@ -266,6 +269,36 @@ EncodeTiled encode_tiled()
 }
 
 // data[nc][cell_size] as a 2-D tensor, box = [cpt cells][box_w entries]
+// Tuning aid (development only): BX_DOF_TUNE="cpt=64,nbuf=3,promo=0,skip=0" overrides the tile shape, the
+// number of tile buffers, the L2 promotion of the tensor map, and can skip the arithmetic (data movement only).
+struct Tune
+{
+  int cpt = 0, nbuf = 0, promo = -1, skip = 0;
+};
+const Tune& tune()
+{
+  static Tune t = []()
+  {
+    Tune v;
+    if (const char* e = std::getenv("BX_DOF_TUNE"))
+    {
+      std::string str(e);
+      auto get = [&](const char* key, int& out)
+      {
+        const size_t k = str.find(key);
+        if (k != std::string::npos)
+          out = std::atoi(str.c_str() + k + std::strlen(key));
+      };
+      get("cpt=", v.cpt);
+      get("nbuf=", v.nbuf);
+      get("promo=", v.promo);
+      get("skip=", v.skip);
+    }
+    return v;
+  }();
+  return t;
+}
+
 bool make_tensor_map(CUtensorMap& map, void* data, size_t nc, size_t cell_size, size_t elem, int box_w, int cpt)
 {
   EncodeTiled enc = encode_tiled();
@@ -277,7 +310,8 @@ bool make_tensor_map(CUtensorMap& map, void* data, size_t nc, size_t cell_size, 
   const cuuint32_t estride[2] = {1, 1};
   const CUtensorMapDataType dt = elem == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32;
   return enc(&map, dt, 2, data, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
+             tune().promo >= 0 ? CUtensorMapL2promotion(tune().promo) : CU_TENSOR_MAP_L2_PROMOTION_NONE,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
          == CUDA_SUCCESS;
 }
 
@@ -361,16 +395,14 @@ bool try_tma(const bx_element& e, int kind, bool right, T* data, size_t nc, size
   p.ndofs = e.ndofs;
   p.r0 = r0 / per16 * per16;
   p.len = r0 + len - p.r0;
-  // box width: whole 16-byte units; matrix kernel: an ODD number of them, so that 8 lanes on 8 consecutive
-  // cells hit 8 different 16-byte bank groups
-  size_t units = (size_t(p.len) * sz + 15) / 16;
-  if (!e.perms and units % 2 == 0)
-    ++units;
+  // box width: whole 16-byte units, nothing more -- the kernels are bound by the HBM stream, so the box is
+  // not padded to an odd number of units (that would remove the 2-way bank conflict of 8 lanes on 8 consecutive
+  // cells when the width is even, at the price of 16 more bytes read and written per cell)
+  const size_t units = (size_t(p.len) * sz + 15) / 16;
   const size_t pitch_bytes = units * 16;
   p.pitch = int(pitch_bytes / sz);
   if (p.pitch > 256)
     return false;
-  p.epl = 0;
   p.nslots = int(e.slots.size());
   p.table_size = e.perms ? e.gather_size : e.mats_size;
   p.band_size = e.band_size;
@@ -378,16 +410,22 @@ bool try_tma(const bx_element& e, int kind, bool right, T* data, size_t nc, size
                                 : size_t(e.mats_size) * 8 + size_t(e.band_size + (e.band_size & 1)) * 8
                                       + size_t(p.nslots) * 32;
   // cells per tile: ~24 KB per buffer (three buffers per CTA, several CTAs per SM), whole warps of cells
+  // buffers: measured on B200 (tools/sweep_dof.sh): 2 is best for the matrix kernel (4 CTAs per SM), 3 for the
+  // permutation kernel
+  p.nbuf = tune().nbuf >= 2 and tune().nbuf <= tma::kMaxBuffers ? tune().nbuf : (e.perms ? 3 : 2);
+  p.skip_apply = tune().skip;
   size_t cpt = std::min<size_t>(256, (24 * 1024) / pitch_bytes);
   if (cpt >= 32)
     cpt = cpt / 32 * 32;
   auto total = [&](size_t c)
   {
-    return tables + 2 * tma::kBuffers * 8 + tma::kBuffers * ((c + 3) & ~size_t(3)) * 4 + 128
-           + tma::kBuffers * size_t(tma::tile_stride_bytes(int(c), p.pitch, int(sz)));
+    return tables + 2 * tma::kMaxBuffers * 8 + tma::kMaxBuffers * ((c + 3) & ~size_t(3)) * 4 + 128
+           + p.nbuf * size_t(tma::tile_stride_bytes(int(c), p.pitch, int(sz)));
   };
   while (cpt > 1 and total(cpt) > 100 * 1024)
     cpt /= 2;
+  if (tune().cpt > 0 and tune().cpt <= 256)
+    cpt = size_t(tune().cpt);
   if (cpt < 8 or total(cpt) > 200 * 1024)
     return false;
   p.cpt = int(cpt);

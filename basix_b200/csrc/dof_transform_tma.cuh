@@ -11,8 +11,6 @@
 //                           in registers, the dense net operator of the item's cell_info state is read from
 //                           shared memory, two entries per 16-byte load, and only inside the non-zero column
 //                           band of each row; results go back in place and leave as one tensor store per tile.
-//                           The box is an odd number of 16-byte units wide, so 8 lanes on 8 consecutive cells
-//                           hit 8 different bank groups.
 //   dof_perm_tma_kernel     permutation elements (permute_data, finite-element.h:1703-1760): a warp walks the
 //                           cells of the tile, lanes <-> entries of the movable range, each lane keeping the
 //                           packed descriptor of its entries in registers; the gather table gives the source
@@ -29,9 +27,9 @@ namespace bx
 {
 namespace tma
 {
-constexpr int kThreads = 256;
-constexpr int kComputeThreads = kThreads - 32; // warps 0..6 compute, warp 7 is the DMA warp
-constexpr int kBuffers = 3;
+constexpr int kComputeThreads = 256;            // warps 0..7 compute
+constexpr int kThreads = kComputeThreads + 32;  // warp 8 is the DMA warp
+constexpr int kMaxBuffers = 4;                  // tile buffers per CTA (Params::nbuf <= kMaxBuffers)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint32_t a, uint32_t count)
@@ -100,7 +98,8 @@ struct Params
   int cpt;              // cells per tile
   int r0, len;          // movable range [r0, r0 + len) of each cell, in entries; r0 is 16-byte aligned
   int pitch;            // TMA box width = shared-memory distance between cells, in entries (>= len)
-  int epl;              // permutation kernel: entries per lane of the warp-per-cell form (0: per-entry form)
+  int nbuf;             // tile buffers in flight per CTA (2..kMaxBuffers)
+  int skip_apply;       // tuning aid: move the data only (BX_DOF_TUNE)
   int nslots, table_size, band_size;
   FastDiv by_cpt, by_len, by_n, by_ndofs;
   const uint32_t* cell_info;
@@ -156,9 +155,9 @@ __global__ void __launch_bounds__(kThreads)
   int4* s_info = reinterpret_cast<int4*>(s_band + p.band_size + (p.band_size & 1));
   int4* s_slot = s_info + p.nslots; // {first, matrix base, band base, 0}
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_slot + p.nslots);
-  uint32_t* s_ci = reinterpret_cast<uint32_t*>(s_bar + 2 * kBuffers);
+  uint32_t* s_ci = reinterpret_cast<uint32_t*>(s_bar + 2 * kMaxBuffers);
   const int ci_stride = (p.cpt + 3) & ~3;
-  const uint32_t head = (uint32_t(reinterpret_cast<unsigned char*>(s_ci + kBuffers * ci_stride) - smem_raw) + 127u) & ~127u;
+  const uint32_t head = (uint32_t(reinterpret_cast<unsigned char*>(s_ci + kMaxBuffers * ci_stride) - smem_raw) + 127u) & ~127u;
   unsigned char* tiles = smem_raw + head;
   const uint32_t tile_bytes = tile_stride_bytes(p.cpt, p.pitch, sizeof(T));
   const uint32_t box_bytes = uint32_t(p.cpt) * uint32_t(p.pitch) * sizeof(T);
@@ -176,10 +175,10 @@ __global__ void __launch_bounds__(kThreads)
   }
   if (threadIdx.x == 0)
   {
-    for (int b = 0; b < kBuffers; ++b)
+    for (int b = 0; b < kMaxBuffers; ++b)
     {
-      mbar_init(bar0 + 8 * b, 32);                          // full: the DMA lanes
-      mbar_init(bar0 + 8 * (kBuffers + b), kComputeThreads); // done: every compute thread
+      mbar_init(bar0 + 8 * b, 32);                             // full: the DMA lanes
+      mbar_init(bar0 + 8 * (kMaxBuffers + b), kComputeThreads); // done: every compute thread
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -191,32 +190,39 @@ __global__ void __launch_bounds__(kThreads)
 
   if (warp == kThreads / 32 - 1)
   {
-    // ---- DMA warp: loads run kBuffers-1 tiles ahead; stores follow the compute warps ----------------------
-    for (size_t i = 0; i < mine and i < size_t(kBuffers - 1); ++i)
-      dma_load(p, &tmap, blockIdx.x + i * gridDim.x, lane, s_ci + int(i) * ci_stride,
+    // ---- DMA warp: loads run nbuf-1 tiles ahead; stores follow the compute warps --------------------------
+    const int nbuf = p.nbuf;
+    for (int i = 0; size_t(i) < mine and i < nbuf - 1; ++i)
+      dma_load(p, &tmap, blockIdx.x + size_t(i) * gridDim.x, lane, s_ci + i * ci_stride,
                smem_u32(tiles) + uint32_t(i) * tile_bytes, box_bytes, bar0 + 8 * uint32_t(i));
+    int b = 0, bj = nbuf - 1; // buffer of tile i, buffer of tile j = i + nbuf - 1
+    uint32_t phase = 0;
     for (size_t i = 0; i < mine; ++i)
     {
-      // tile j = i + kBuffers - 1 reuses the buffer of tile i - 1, whose store was committed one iteration
-      // ago: once it has read shared memory, refill the buffer -- before waiting for tile i, so that the loads
-      // stay kBuffers - 1 tiles ahead of the compute warps
-      const size_t j = i + kBuffers - 1;
+      // tile j reuses the buffer of tile i - 1, whose store was committed one iteration ago: once it has read
+      // shared memory, refill the buffer -- before waiting for tile i, so that the loads stay nbuf - 1 tiles
+      // ahead of the compute warps
+      const size_t j = i + nbuf - 1;
       if (j < mine)
       {
         if (lane == 0)
           bulk_wait_read<0>();
         __syncwarp();
-        const int bj = int(j % kBuffers);
         dma_load(p, &tmap, blockIdx.x + j * gridDim.x, lane, s_ci + bj * ci_stride,
                  smem_u32(tiles) + uint32_t(bj) * tile_bytes, box_bytes, bar0 + 8 * uint32_t(bj));
       }
-      const int b = int(i % kBuffers);
       const size_t c0 = (blockIdx.x + i * gridDim.x) * size_t(p.cpt);
-      mbar_wait(bar0 + 8 * (kBuffers + b), uint32_t(i / kBuffers) & 1); // compute warps are done with tile i
+      mbar_wait(bar0 + 8 * (kMaxBuffers + b), phase); // compute warps are done with tile i
       if (lane == 0)
       {
         tensor_store(&tmap, p.r0, int(c0), smem_u32(tiles) + uint32_t(b) * tile_bytes);
         bulk_commit();
+      }
+      bj = bj + 1 == nbuf ? 0 : bj + 1;
+      if (++b == nbuf)
+      {
+        b = 0;
+        phase ^= 1;
       }
     }
     if (lane == 0)
@@ -226,15 +232,16 @@ __global__ void __launch_bounds__(kThreads)
 
   // ---- compute warps ---------------------------------------------------------------------------------------
   const int n = p.n, ndofs = p.ndofs, pitch = p.pitch, r0 = p.r0;
-  const unsigned nitems = unsigned(p.nslots * n) * unsigned(p.cpt);
+  const unsigned nitems = p.skip_apply ? 0u : unsigned(p.nslots * n) * unsigned(p.cpt);
+  int b = 0;
+  uint32_t phase = 0;
   for (size_t i = 0; i < mine; ++i)
   {
-    const int b = int(i % kBuffers);
     const size_t c0 = (blockIdx.x + i * gridDim.x) * size_t(p.cpt);
     const unsigned ncell = unsigned(min(size_t(p.cpt), p.nc - c0));
     T* tile = reinterpret_cast<T*>(tiles + size_t(b) * tile_bytes);
     const uint32_t* ci = s_ci + b * ci_stride;
-    mbar_wait(bar0 + 8 * b, uint32_t(i / kBuffers) & 1);
+    mbar_wait(bar0 + 8 * b, phase);
     for (unsigned it = threadIdx.x; it < nitems; it += kComputeThreads)
     {
       const unsigned sb = p.by_cpt.div(it), c = it - sb * p.cpt;
@@ -317,8 +324,13 @@ __global__ void __launch_bounds__(kThreads)
         }
       }
     }
-    fence_async_smem(); // generic-proxy writes of this thread -> visible to the bulk stores
-    mbar_arrive(bar0 + 8 * (kBuffers + b));
+    fence_async_smem(); // generic-proxy writes of this thread -> visible to the tensor store
+    mbar_arrive(bar0 + 8 * (kMaxBuffers + b));
+    if (++b == p.nbuf)
+    {
+      b = 0;
+      phase ^= 1;
+    }
   }
 }
 
@@ -336,9 +348,9 @@ __global__ void __launch_bounds__(kThreads)
   int16_t* s_gather = reinterpret_cast<int16_t*>(s_dinfo + p.ndofs);
   const size_t tables = (size_t(p.ndofs) * 4 + size_t(p.table_size) * 2 + 15) & ~size_t(15);
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_raw + tables);
-  uint32_t* s_ci = reinterpret_cast<uint32_t*>(s_bar + 2 * kBuffers);
+  uint32_t* s_ci = reinterpret_cast<uint32_t*>(s_bar + 2 * kMaxBuffers);
   const int ci_stride = (p.cpt + 3) & ~3;
-  const uint32_t head = (uint32_t(reinterpret_cast<unsigned char*>(s_ci + kBuffers * ci_stride) - smem_raw) + 127u) & ~127u;
+  const uint32_t head = (uint32_t(reinterpret_cast<unsigned char*>(s_ci + kMaxBuffers * ci_stride) - smem_raw) + 127u) & ~127u;
   unsigned char* tiles = smem_raw + head;
   const uint32_t tile_bytes = tile_stride_bytes(p.cpt, p.pitch, sizeof(U));
   const uint32_t box_bytes = uint32_t(p.cpt) * uint32_t(p.pitch) * sizeof(U);
@@ -350,10 +362,10 @@ __global__ void __launch_bounds__(kThreads)
     s_gather[i] = p.gather[i];
   if (threadIdx.x == 0)
   {
-    for (int b = 0; b < kBuffers; ++b)
+    for (int b = 0; b < kMaxBuffers; ++b)
     {
-      mbar_init(bar0 + 8 * b, 32);                          // full
-      mbar_init(bar0 + 8 * (kBuffers + b), kComputeThreads); // empty
+      mbar_init(bar0 + 8 * b, 32);                             // full
+      mbar_init(bar0 + 8 * (kMaxBuffers + b), kComputeThreads); // empty
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -365,13 +377,19 @@ __global__ void __launch_bounds__(kThreads)
 
   if (warp == kThreads / 32 - 1)
   {
+    int b = 0;
+    uint32_t phase = 1; // parity of the previous use of the buffer
     for (size_t i = 0; i < mine; ++i)
     {
-      const int b = int(i % kBuffers);
-      if (i >= size_t(kBuffers))
-        mbar_wait(bar0 + 8 * (kBuffers + b), uint32_t(i / kBuffers - 1) & 1); // tile i - kBuffers has been read
+      if (i >= size_t(p.nbuf))
+        mbar_wait(bar0 + 8 * (kMaxBuffers + b), phase); // tile i - nbuf has been read
       dma_load(p, &tmap, blockIdx.x + i * gridDim.x, lane, s_ci + b * ci_stride,
                smem_u32(tiles) + uint32_t(b) * tile_bytes, box_bytes, bar0 + 8 * uint32_t(b));
+      if (++b == p.nbuf)
+      {
+        b = 0;
+        phase ^= 1;
+      }
     }
     return;
   }
@@ -393,14 +411,15 @@ __global__ void __launch_bounds__(kThreads)
       gbase[k] = info >> 16;
     }
   }
+  int b = 0;
+  uint32_t phase = 0;
   for (size_t i = 0; i < mine; ++i)
   {
-    const int b = int(i % kBuffers);
     const size_t c0 = (blockIdx.x + i * gridDim.x) * size_t(p.cpt);
-    const unsigned ncell = unsigned(min(size_t(p.cpt), p.nc - c0));
+    const unsigned ncell = p.skip_apply ? 0u : unsigned(min(size_t(p.cpt), p.nc - c0));
     const U* tile = reinterpret_cast<const U*>(tiles + size_t(b) * tile_bytes);
     const uint32_t* ci = s_ci + b * ci_stride;
-    mbar_wait(bar0 + 8 * b, uint32_t(i / kBuffers) & 1);
+    mbar_wait(bar0 + 8 * b, phase);
     if constexpr (EPL > 0)
     {
       U* g = data + c0 * cs + r0 + lane;
@@ -442,7 +461,12 @@ __global__ void __launch_bounds__(kThreads)
         g[size_t(c) * cs + e] = tile[c * pitch + entry<RIGHT>(src, bl, n, ndofs) - r0];
       }
     }
-    mbar_arrive(bar0 + 8 * (kBuffers + b));
+    mbar_arrive(bar0 + 8 * (kMaxBuffers + b));
+    if (++b == p.nbuf)
+    {
+      b = 0;
+      phase ^= 1;
+    }
   }
 }
 } // namespace tma

@@ -279,11 +279,21 @@ bx_element* element_from_desc(const bx_element_desc& d)
     const int npad = int(ceil_div(K, 8) * 8);
     const int kpad = e->Kpad;
     const int ks = kpad + ((4 - kpad % 16) + 16) % 16;
+    std::vector<int> slot(K);
+    std::vector<double> norm(K);
+    jets::production_order(e->tdim, e->superdegree, slot.data(), norm.data());
+    if (K <= 10 and size_t(e->N) * K <= 4096)
+    {
+      // register-path operand (tabulate_small.cu): any number of output columns
+      e->Cq.assign(size_t(e->N) * K, 0.0);
+      for (int n = 0; n < e->N; ++n)
+        for (int s = 0; s < K; ++s)
+          e->Cq[size_t(n) * K + s] = e->Cp[size_t(n) * e->Kpad + slot[s]] * norm[s];
+      if (e->on_device)
+        e->d_Cq = upload(e->Cq);
+    }
     if (e->N <= npad)
     {
-      std::vector<int> slot(K);
-      std::vector<double> norm(K);
-      jets::production_order(e->tdim, e->superdegree, slot.data(), norm.data());
       e->Cs.assign(size_t(npad) * ks, 0.0);
       for (int n = 0; n < e->N; ++n)
         for (int s = 0; s < K; ++s)
@@ -719,6 +729,7 @@ bx_element::~bx_element()
   // best effort; errors at teardown are ignored
   cudaFree(d_Cp);
   cudaFree(d_Cs);
+  cudaFree(d_Cq);
   cudaFree(tp.d_A);
   cudaFree(tp.d_ijk);
   cudaFree(tp.d_scale);

@@ -37,6 +37,8 @@ struct bx_element
   std::vector<double> Cs; // fused-kernel operand (host copy), empty when not applicable
   double* d_Cp = nullptr;
   double* d_Cs = nullptr; // fused-kernel operand (norm-scaled, production order, padded) or null
+  std::vector<double> Cq; // register-path operand [N][K] (norm-scaled, production order), low-degree simplices
+  double* d_Cq = nullptr;
 
   // ---- tabulate: tensor-product factorisation (quad / hex), see tabulate_tp.cu -------------------------
   struct TensorProduct

@@ -138,6 +138,10 @@ namespace bx
 {
 bool tabulate_tp_device(const bx_element& e, int nd, const double* x, size_t npts, double* basis, cudaStream_t s,
                         bool dry_run);
+namespace small
+{
+bool launch_any(const bx_element& e, int nd, const double* x, size_t npts, double* basis, cudaStream_t s, bool dry_run);
+}
 namespace
 {
 // Fused simplex kernel (tabulate_fused.cuh) when the element has the operand and (degree, nd) is on the menu.
@@ -155,9 +159,11 @@ bool try_fused(const bx_element& e, int nd, const double* x, size_t npts, double
 }
 } // namespace
 
-// Which device path tabulate() takes: 0 generic, 1 fused simplex, 2 tensor product.
+// Which device path tabulate() takes: 0 generic, 1 fused simplex, 2 tensor product, 3 register path.
 int tabulate_path(const bx_element& e, int nd)
 {
+  if (small::launch_any(e, nd, nullptr, 0, nullptr, nullptr, true))
+    return 3;
   if (try_fused(e, nd, nullptr, 0, nullptr, nullptr, true))
     return 1;
   if (tabulate_tp_device(e, nd, nullptr, 0, nullptr, nullptr, true))
@@ -170,6 +176,8 @@ void tabulate_device(const bx_element& e, int nd, const double* x, size_t npts, 
 {
   require_device(e);
   // the fused kernels write a dense [nder][npts][N] table; a chunk of a larger table takes the generic path
+  if (out_pts == npts and small::launch_any(e, nd, x, npts, basis, s, false))
+    return;
   if (out_pts == npts and try_fused(e, nd, x, npts, basis, s, false))
     return;
   if (out_pts == npts and tabulate_tp_device(e, nd, x, npts, basis, s, false))

@@ -300,12 +300,10 @@ class TApply:
         self.data = self.data_host.cuda()
         self.units_per_step = nc
         self.launches_per_step = 1
-        # only the movable dofs need to be read and written (+ 4 B of cell_info)
-        if self.permute:
-            movable = int((np.asarray(e.net_permutation(0xFFFFFFFF)) != np.arange(e.dim)).sum())
-        else:
-            A = e.net_operator(0xFFFFFFFF)
-            movable = int((np.abs(A - np.eye(e.dim)).sum(axis=1) > 0).sum())
+        # only the dofs that CAN move (those on edges, and on faces of 3-D cells) need to be read
+        # and written (+ 4 B of cell_info); which of them actually move depends on each cell's cell_info
+        ed = e.entity_dofs
+        movable = sum(len(d) for dim in range(1, e._tdim) for d in ed[dim])
         self.alg_bytes = nc * (2 * movable * esize * self.bs + 4)
         self.flops = 0.0
         self.config = {"workload": self.desc, "cells_per_gpu": nc, "block_size": self.bs, "movable_dofs": movable,

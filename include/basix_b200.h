@@ -170,7 +170,7 @@ extern "C"
   int bx_element_net_operator(const bx_element* e, int op, uint32_t cell_info, int32_t* src, double* A);
   /* Which device path tabulate() will take for derivative order nd:
      0 generic (polyset kernel + DMMA contraction), 1 fused simplex kernel,
-     2 tensor-product kernel. */
+     2 tensor-product kernel, 3 register path (low-degree simplex elements). */
   int bx_element_tabulate_path(const bx_element* e, int nd);
 
   /* ---- FiniteElement::tabulate ------------------------------------------------------------

@@ -376,3 +376,76 @@ def test_tabulate_tp_dof_ordering(ref):
     assert e.tabulate_path(1) == "tensor-product"
     x = random_points(HEX, 1000)
     slab_close(e.tabulate(1, x), r.tabulate(1, x), 1e-12)
+
+
+# ---- register path for low-degree simplex elements (tabulate_small.cu) --------------------------------------
+SMALL = [(P, TRI, 1, GLL, 1), (P, TRI, 1, GLL, 3), (P, TRI, 2, GLL, 2), (P, TET, 1, GLL, 2), (P, TET, 2, EQ, 1),
+         (P, INTERVAL, 2, GLL, 3), (N1E, TRI, 1, LEG, 1), (N1E, TET, 1, LEG, 1), (RT, TRI, 2, LEG, 1), (RT, TET, 1, LEG, 0)]
+
+
+@pytest.mark.parametrize("family,cell,degree,variant,nd", SMALL)
+def test_tabulate_register_path(ref, family, cell, degree, variant, nd):
+    r, e = make_pair(ref, family, cell, degree, variant)
+    assert e.tabulate_path(nd) == "register"
+    for npts in (1, 127, 128, 129, 50021):  # one ragged tile, exact tile, tile + 1, many tiles per CTA
+        x = random_points(cell, npts, seed=npts + degree)
+        got = e.tabulate(nd, x)
+        slab_close(got, r.tabulate(nd, x), 1e-12)
+
+
+def test_tabulate_register_path_dof_ordering_and_device(ref):
+    import torch
+
+    order = [int(v) for v in np.random.default_rng(2).permutation(6)]
+    r, e = make_pair(ref, P, TRI, 2, GLL, dof_ordering=order)
+    assert e.tabulate_path(1) == "register"
+    x = random_points(TRI, 7777, seed=3)
+    want = r.tabulate(1, x)
+    slab_close(e.tabulate(1, x), want, 1e-12)
+    slab_close(e.tabulate(1, torch.from_numpy(x).cuda()).cpu().numpy(), want, 1e-12)
+
+
+# ---- DOF transformations: both device implementations -----------------------------------------------------
+@pytest.mark.parametrize("family,cell,degree,variant", [(P, TET, 5, GLL), (RT, TET, 4, LEG), (N1E, TET, 3, LEG),
+                                                         (P, HEX, 4, GLL), (N1E, HEX, 2, LEG)])
+@pytest.mark.parametrize("offset", [0, 1])
+def test_T_apply_aligned_and_unaligned_buffers(ref, family, cell, degree, variant, offset):
+    """offset 0: 16-byte aligned rows -> the TMA kernels (when the cell pitch allows); offset 1: the same data one
+    double further into the allocation -> the register-staged fallback.  Both must match the reference."""
+    import torch
+
+    r, e = make_pair(ref, family, cell, degree, variant)
+    nc = 3001  # several tiles, ragged last tile
+    ci = cell_infos(nc, seed=degree)
+    for bs in (1, 2):
+        data = np.random.default_rng(bs).standard_normal((nc, r.dim * bs))
+        want = r.T_apply_batch("T_apply", data.copy(), bs, ci)
+        flat = torch.empty(data.size + 2, dtype=torch.float64, device="cuda")
+        view = flat[offset:offset + data.size].view(nc, r.dim * bs)
+        view.copy_(torch.from_numpy(data))
+        e.T_apply_batch(view, bs, torch.from_numpy(ci.view(np.int32)).cuda())
+        got = view.cpu().numpy()
+        if r.dof_transformations_are_permutations:
+            assert np.array_equal(got, want)
+        else:
+            assert np.max(np.abs(got - want)) <= 1e-12 * np.max(np.abs(want))
+        assert flat[0].item() == flat[0].item()  # no stray writes trip the allocator's guard in later tests
+
+
+@pytest.mark.parametrize("op", ["T_apply", "Tt_apply", "Tt_inv_apply", "Tinv_apply", "Tt_apply_right",
+                                "Tinv_apply_right", "T_apply_right", "Tt_inv_apply_right"])
+def test_all_eight_operators_large_batch(ref, op):
+    """Every T flavour (finite-element.h:1839-1998) over a batch large enough for many tiles per CTA."""
+    nc = 20011
+    ci = cell_infos(nc, seed=17)
+    for family, cell, degree, variant in [(RT, TET, 4, LEG), (P, TET, 5, GLL)]:
+        r, e = make_pair(ref, family, cell, degree, variant)
+        for bs in (1, 3):
+            data = np.random.default_rng(bs).standard_normal((nc, r.dim * bs))
+            want = r.T_apply_batch(op, data.copy(), bs, ci, nthreads=8)
+            got = data.copy()
+            e.T_apply_batch(got, bs, ci, op=op)
+            if r.dof_transformations_are_permutations:
+                assert np.array_equal(got, want)
+            else:
+                assert np.max(np.abs(got - want)) <= 1e-12 * np.max(np.abs(want))
