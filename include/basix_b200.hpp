@@ -1,0 +1,249 @@
+// basix_b200.hpp -- C++ host mirror of the hot-path subset of basix::FiniteElement<F> over the C ABI
+// (include/basix_b200.h).  Header-only, C++17; link with basix_b200/libbasix_b200.so.
+//
+// Same method names, argument meaning and error behaviour as the reference class
+// (cpp/basix/finite-element.h): failures surface as std::runtime_error carrying the library's message,
+// exactly like the reference's `throw std::runtime_error` (finite-element.cpp:1838-1843,
+// finite-element.h:802-806, 653-654).  Shapes are passed explicitly instead of std::mdspan so the header has no
+// dependency on the vendored mdspan; every array is row-major and contiguous as in the reference.
+//
+//   reference                                                     here
+//   FiniteElement::tabulate_shape        finite-element.h:364-376      tabulate_shape(nd, npts)
+//   FiniteElement::tabulate              finite-element.h:399-483      tabulate(nd, x, npts[, out])
+//   FiniteElement::push_forward          finite-element.h:577-579      push_forward(U, J, detJ, K, nc, rows, ...)
+//   FiniteElement::pull_back             finite-element.h:592-594      pull_back(...)
+//   FiniteElement::T_apply (+7 siblings) finite-element.h:1067-1159    T_apply(u, n, cell_info) ...
+//   FiniteElement::permute{,_inv}        finite-element.h:800-843      permute(d, cell_info) ...
+//   polyset::tabulate                    polyset.h:181-183             polyset::tabulate(...)
+// plus the batched forms the reference cannot express (one cell_info per cell): *_batch.
+//
+// Memory kinds: every call takes `mem` (BX_MEM_HOST: host pointers, the library stages through the GPU and
+// returns when the result is in host memory -- the drop-in behaviour; BX_MEM_DEVICE: device pointers, work is
+// enqueued on `stream` and the call returns without synchronising).  There is no CPU fallback.
+#pragma once
+
+#include "basix_b200.h"
+
+#include <array>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+namespace basix_b200
+{
+inline void check(int status)
+{
+  if (status != BX_OK)
+    throw std::runtime_error(bx_last_error());
+}
+
+namespace polyset
+{
+inline int dim(int cell_type, int polyset_type, int degree) { return bx_polyset_dim(cell_type, polyset_type, degree); }
+inline int nderivs(int cell_type, int nderiv) { return bx_polyset_nderivs(cell_type, nderiv); }
+/// P[nderivs][psize][npts] (polyset.cpp:2914-2992).  x[npts][tdim].
+inline std::vector<double> tabulate(int cell_type, int polyset_type, int degree, int nderiv, const double* x,
+                                    std::size_t npts)
+{
+  std::vector<double> P(std::size_t(nderivs(cell_type, nderiv)) * dim(cell_type, polyset_type, degree) * npts);
+  check(bx_polyset_tabulate_f64(cell_type, polyset_type, degree, nderiv, x, npts, P.data(), BX_MEM_HOST, nullptr));
+  return P;
+}
+} // namespace polyset
+
+/// Arrays that define an element for the hot path: what basix::FiniteElement exposes through
+/// coefficient_matrix(), entity_dofs(), entity_transformations(), dof_ordering(), value_shape(), map_type() ...
+struct ElementData
+{
+  int cell_type = 0, polyset_type = 0, degree = 0, embedded_superdegree = 0, map_type = 0;
+  std::vector<std::size_t> value_shape;
+  std::vector<double> coefficient_matrix;                  // [ndofs][value_size * psize]
+  std::vector<std::vector<std::vector<int>>> entity_dofs;  // [dim][entity][k]
+  std::vector<int> dof_ordering;                           // empty or [ndofs]
+  // entity_transformations(): [ntrans][n][n] per sub-entity type; n = 0 when the type is present without dofs,
+  // n = -1 when the cell has no such sub-entity
+  std::vector<double> etrans_interval, etrans_triangle, etrans_quadrilateral;
+  int etrans_interval_dim = -1, etrans_triangle_dim = -1, etrans_quadrilateral_dim = -1;
+};
+
+class FiniteElement
+{
+public:
+  explicit FiniteElement(const ElementData& d)
+  {
+    std::size_t vs = 1;
+    for (std::size_t s : d.value_shape)
+      vs *= s;
+    const int psize = polyset::dim(d.cell_type, d.polyset_type, d.embedded_superdegree);
+    if (psize <= 0 or d.coefficient_matrix.size() % (vs * std::size_t(psize)) != 0)
+      throw std::runtime_error("coefficient_matrix has the wrong number of columns for this polyset");
+    std::vector<std::int32_t> offs{0}, flat;
+    for (const auto& row : d.entity_dofs)
+      for (const auto& e : row)
+      {
+        flat.insert(flat.end(), e.begin(), e.end());
+        offs.push_back(std::int32_t(flat.size()));
+      }
+    if (flat.empty())
+      flat.push_back(0);
+    static const double none = 0.0;
+    bx_element_desc desc{};
+    desc.cell_type = d.cell_type;
+    desc.polyset_type = d.polyset_type;
+    desc.degree = d.degree;
+    desc.embedded_superdegree = d.embedded_superdegree;
+    desc.map_type = d.map_type;
+    desc.ndofs = int(d.coefficient_matrix.size() / (vs * std::size_t(psize)));
+    desc.value_size = int(vs);
+    desc.coeffs = d.coefficient_matrix.data();
+    desc.dof_ordering = d.dof_ordering.empty() ? nullptr : d.dof_ordering.data();
+    desc.n_dof_ordering = int(d.dof_ordering.size());
+    desc.entity_dof_offsets = offs.data();
+    desc.entity_dofs = flat.data();
+    auto set = [](const std::vector<double>& m, int n, const double*& p, int& dim)
+    {
+      dim = n < 0 ? 0 : n;
+      p = n < 0 ? nullptr : (m.empty() ? &none : m.data());
+    };
+    set(d.etrans_interval, d.etrans_interval_dim, desc.etrans_interval, desc.etrans_interval_dim);
+    set(d.etrans_triangle, d.etrans_triangle_dim, desc.etrans_triangle, desc.etrans_triangle_dim);
+    set(d.etrans_quadrilateral, d.etrans_quadrilateral_dim, desc.etrans_quadrilateral, desc.etrans_quadrilateral_dim);
+    check(bx_element_create_from_arrays(&desc, &_h));
+    std::int32_t info[10];
+    check(bx_element_info(_h, info));
+    _tdim = info[2];
+    _ndofs = info[3];
+    _vs = info[4];
+    _map = info[5];
+    _perms = info[7] != 0;
+    _identity = info[8] != 0;
+    _value_shape = d.value_shape;
+  }
+  ~FiniteElement() { bx_element_destroy(_h); }
+  FiniteElement(const FiniteElement&) = delete;
+  FiniteElement& operator=(const FiniteElement&) = delete;
+  FiniteElement(FiniteElement&& o) noexcept { *this = std::move(o); }
+  FiniteElement& operator=(FiniteElement&& o) noexcept
+  {
+    std::swap(_h, o._h);
+    _tdim = o._tdim, _ndofs = o._ndofs, _vs = o._vs, _map = o._map, _perms = o._perms, _identity = o._identity;
+    _value_shape = o._value_shape;
+    return *this;
+  }
+
+  // ---- accessors (finite-element.h:487-561) ---------------------------------------------------------------
+  int dim() const { return _ndofs; }
+  int value_size() const { return _vs; }
+  const std::vector<std::size_t>& value_shape() const { return _value_shape; }
+  int map_type() const { return _map; }
+  bool dof_transformations_are_permutations() const { return _perms; }
+  bool dof_transformations_are_identity() const { return _identity; }
+  const bx_element* handle() const { return _h; }
+
+  /// {nderivs, npts, ndofs, value_size}  (finite-element.h:364-376)
+  std::array<std::size_t, 4> tabulate_shape(int nd, std::size_t npts) const
+  {
+    std::array<std::size_t, 4> s;
+    check(bx_element_tabulate_shape(_h, nd, npts, s.data()));
+    return s;
+  }
+
+  /// basis[nderivs][npts][ndofs][value_size]; x[npts][tdim_x]  (finite-element.h:454-455)
+  void tabulate(int nd, const double* x, std::size_t npts, int tdim_x, double* basis, int mem = BX_MEM_HOST,
+                bx_stream_t stream = nullptr) const
+  {
+    check(bx_tabulate_f64(_h, nd, x, npts, tdim_x, basis, mem, stream));
+  }
+  /// Allocating overload (finite-element.h:399-401), host memory.
+  std::pair<std::vector<double>, std::array<std::size_t, 4>> tabulate(int nd, const double* x, std::size_t npts,
+                                                                      int tdim_x) const
+  {
+    auto shape = tabulate_shape(nd, npts);
+    std::vector<double> out(shape[0] * shape[1] * shape[2] * shape[3]);
+    tabulate(nd, x, npts, tdim_x, out.data());
+    return {std::move(out), shape};
+  }
+
+  /// u[nc][rows][physical value size] = map(U[nc][rows][in_vs]; J[nc][gdim][tdim], detJ[nc], K[nc][tdim][gdim])
+  /// (finite-element.h:577-579).  Returns the physical value size.
+  int push_forward(const double* U, const double* J, const double* detJ, const double* K, std::size_t nc,
+                   std::size_t rows, int in_vs, int gdim, int tdim, double* u, int mem = BX_MEM_HOST,
+                   bx_stream_t stream = nullptr) const
+  {
+    check(bx_push_forward_f64(_h, U, J, detJ, K, nc, rows, in_vs, gdim, tdim, u, mem, stream));
+    return bx_map_value_size(_map, 0, in_vs, gdim, tdim);
+  }
+  /// (finite-element.h:592-594)
+  int pull_back(const double* u, const double* J, const double* detJ, const double* K, std::size_t nc,
+                std::size_t rows, int in_vs, int gdim, int tdim, double* U, int mem = BX_MEM_HOST,
+                bx_stream_t stream = nullptr) const
+  {
+    check(bx_pull_back_f64(_h, u, J, detJ, K, nc, rows, in_vs, gdim, tdim, U, mem, stream));
+    return bx_map_value_size(_map, 1, in_vs, gdim, tdim);
+  }
+
+  // ---- DOF transformations: single cell, reference signatures (finite-element.h:1067-1159) -----------------
+#define BASIX_B200_T_OP(NAME, OP)                                                                          \
+  template <typename T>                                                                                    \
+  void NAME(T* u, std::size_t size, int n, std::uint32_t cell_info) const                                  \
+  {                                                                                                        \
+    transform(OP, u, 1, size, n, &cell_info, BX_MEM_HOST, nullptr);                                        \
+  }
+  BASIX_B200_T_OP(T_apply, BX_T_APPLY)
+  BASIX_B200_T_OP(Tt_apply, BX_TT_APPLY)
+  BASIX_B200_T_OP(Tt_inv_apply, BX_TT_INV_APPLY)
+  BASIX_B200_T_OP(Tinv_apply, BX_TINV_APPLY)
+  BASIX_B200_T_OP(Tt_apply_right, BX_TT_APPLY_RIGHT)
+  BASIX_B200_T_OP(Tinv_apply_right, BX_TINV_APPLY_RIGHT)
+  BASIX_B200_T_OP(T_apply_right, BX_T_APPLY_RIGHT)
+  BASIX_B200_T_OP(Tt_inv_apply_right, BX_TT_INV_APPLY_RIGHT)
+#undef BASIX_B200_T_OP
+
+  /// Batched: data[nc][cell_size] in place, cell c with cell_info[c]; op is a bx_top.
+  template <typename T>
+  void T_apply_batch(int op, T* data, std::size_t nc, std::size_t cell_size, int n, const std::uint32_t* cell_info,
+                     int mem = BX_MEM_HOST, bx_stream_t stream = nullptr) const
+  {
+    transform(op, data, nc, cell_size, n, cell_info, mem, stream);
+  }
+
+  /// (finite-element.h:800-812, 831-843)
+  void permute(std::int32_t* d, std::uint32_t cell_info) const
+  {
+    check(bx_permute_i32(_h, 0, d, 1, &cell_info, BX_MEM_HOST, nullptr));
+  }
+  void permute_inv(std::int32_t* d, std::uint32_t cell_info) const
+  {
+    check(bx_permute_i32(_h, 1, d, 1, &cell_info, BX_MEM_HOST, nullptr));
+  }
+  void permute_batch(std::int32_t* d, std::size_t nc, const std::uint32_t* cell_info, bool inverse = false,
+                     int mem = BX_MEM_HOST, bx_stream_t stream = nullptr) const
+  {
+    check(bx_permute_i32(_h, inverse ? 1 : 0, d, nc, cell_info, mem, stream));
+  }
+
+private:
+  void transform(int op, double* u, std::size_t nc, std::size_t cs, int n, const std::uint32_t* ci, int mem,
+                 bx_stream_t s) const
+  {
+    check(bx_T_apply_f64(_h, op, u, nc, cs, n, ci, mem, s));
+  }
+  void transform(int op, float* u, std::size_t nc, std::size_t cs, int n, const std::uint32_t* ci, int mem,
+                 bx_stream_t s) const
+  {
+    check(bx_T_apply_f32(_h, op, u, nc, cs, n, ci, mem, s));
+  }
+  void transform(int op, std::int32_t* u, std::size_t nc, std::size_t cs, int n, const std::uint32_t* ci, int mem,
+                 bx_stream_t s) const
+  {
+    check(bx_T_apply_i32(_h, op, u, nc, cs, n, ci, mem, s));
+  }
+
+  bx_element* _h = nullptr;
+  int _tdim = 0, _ndofs = 0, _vs = 1, _map = 0;
+  bool _perms = false, _identity = true;
+  std::vector<std::size_t> _value_shape;
+};
+} // namespace basix_b200
