@@ -10,6 +10,8 @@
 // contraction.
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace bx
 {
 namespace
@@ -123,23 +125,34 @@ __global__ void __launch_bounds__(kThreads) copy_kernel(const double* __restrict
     out[t] = in[t];
 }
 
-int grid_for(size_t n)
+// Persistent grid-stride launch: exactly the CTAs that are resident at once (no ragged last wave).
+template <typename K>
+int grid_for(K kern, size_t n)
 {
+  int per_sm = 1;
+  BX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0));
   const size_t want = ceil_div(n, size_t(kThreads));
-  const size_t cap = size_t(sm_count()) * 8;
+  const size_t cap = size_t(sm_count()) * std::max(per_sm, 1);
   return int(want < cap ? (want == 0 ? 1 : want) : cap);
+}
+
+template <int MAP, int RA, int CA>
+void launch_one(const double* in, const double* A, const double* detJ, int inv, size_t nc, size_t rows, double* out,
+                cudaStream_t s)
+{
+  auto kern = map_kernel<MAP, RA, CA>;
+  kern<<<grid_for(kern, nc * rows), kThreads, 0, s>>>(in, A, detJ, inv, nc, rows, out);
 }
 
 template <int MAP, int RA>
 void launch_ca(int ca, const double* in, const double* A, const double* detJ, int inv, size_t nc, size_t rows,
                double* out, cudaStream_t s)
 {
-  const int g = grid_for(nc * rows);
   switch (ca)
   {
-  case 1: map_kernel<MAP, RA, 1><<<g, kThreads, 0, s>>>(in, A, detJ, inv, nc, rows, out); break;
-  case 2: map_kernel<MAP, RA, 2><<<g, kThreads, 0, s>>>(in, A, detJ, inv, nc, rows, out); break;
-  case 3: map_kernel<MAP, RA, 3><<<g, kThreads, 0, s>>>(in, A, detJ, inv, nc, rows, out); break;
+  case 1: launch_one<MAP, RA, 1>(in, A, detJ, inv, nc, rows, out, s); break;
+  case 2: launch_one<MAP, RA, 2>(in, A, detJ, inv, nc, rows, out, s); break;
+  case 3: launch_one<MAP, RA, 3>(in, A, detJ, inv, nc, rows, out, s); break;
   default: fail(BX_ERR_INVALID_ARG, "map: Jacobian dimensions must be between 1 and 3");
   }
   BX_LAUNCHED();
@@ -200,7 +213,7 @@ void map_device(int map_type, int pull, const double* U, const double* J, const 
   case BX_MAP_IDENTITY:
     if (in_vs != out_vs)
       fail(BX_ERR_INVALID_ARG, "map: identity map needs matching value sizes");
-    copy_kernel<<<grid_for(nc * rows * in_vs), kThreads, 0, s>>>(U, nc * rows * in_vs, out);
+    copy_kernel<<<grid_for(copy_kernel, nc * rows * in_vs), kThreads, 0, s>>>(U, nc * rows * in_vs, out);
     BX_LAUNCHED();
     return;
   case BX_MAP_COVARIANT_PIOLA:

@@ -16,6 +16,8 @@
 #include "element.cuh"
 
 #include <algorithm>
+#include <cstdlib>
+#include <string>
 
 namespace bx
 {
@@ -35,6 +37,7 @@ struct TPParams
   const double* scale;   // [N]
   int n1, N, fstride;    // fstride = max number of 1-D functions over the axes
   int nfun[3];
+  int plain_stores; // tuning aid (BX_TP_TUNE=plain): default write-back stores instead of streaming stores
 };
 
 // Un-normalised shifted Legendre values and derivatives L[k][p] = d^k/dx^k P_p(2x - 1), p < n1
@@ -66,6 +69,17 @@ __device__ __forceinline__ void legendre_raw(double (&L)[NK][kMaxN1], int n1, do
   }
 }
 
+// Shared-memory row of one point: [axis][function][NKP] with NKP = derivative orders rounded up to even, so a
+// lane fetches the value and first derivative of a 1-D factor with ONE 16-byte load.  Row stride: even
+// (16-byte aligned rows) with an odd number of 16-byte units (8 lanes on 8 points hit 8 different bank groups).
+__host__ __device__ constexpr int tp_nkp(int nk) { return nk == 1 ? 1 : (nk + 1) / 2 * 2; }
+__host__ __device__ constexpr int tp_pstride(int tdim, int nk, int F)
+{
+  const int base = tdim * F * tp_nkp(nk);
+  const int even = base + (base & 1);
+  return (even / 2) % 2 == 1 ? even : even + 2;
+}
+
 template <int TDIM, int ND, int MD>
 __global__ void __launch_bounds__(kWarps * 32) tabulate_tp_kernel(TPParams p)
 {
@@ -73,9 +87,10 @@ __global__ void __launch_bounds__(kWarps * 32) tabulate_tp_kernel(TPParams p)
   constexpr int NDER = TDIM == 2 ? (ND + 1) * (ND + 2) / 2 : (ND + 1) * (ND + 2) * (ND + 3) / 6;
   extern __shared__ __align__(16) double smem[];
   const int F = p.fstride;
-  const int pstride = TDIM * NK * F + 1; // +1: odd stride keeps phase-1 stores conflict free
+  constexpr int NKP = tp_nkp(NK);
+  const int pstride = tp_pstride(TDIM, NK, F);
   double* As = smem;                              // [TDIM][F][n1]
-  double* Phi = As + TDIM * F * p.n1;             // [kWarps*32][pstride]
+  double* Phi = As + ((TDIM * F * p.n1 + 1) & ~1); // [kWarps*32][pstride], 16-byte aligned
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < TDIM * F * p.n1; i += blockDim.x)
     As[i] = p.A[i];
@@ -120,42 +135,81 @@ __global__ void __launch_bounds__(kWarps * 32) tabulate_tp_kernel(TPParams p)
             for (int q = 0; q < kMaxN1; ++q)
               if (q < p.n1)
                 acc += Af[q] * L[k][q];
-            out[(a * NK + k) * F + f] = acc;
+            out[(a * F + f) * NKP + k] = acc;
           }
         }
       }
     }
     __syncwarp();
     // ---- phase 2: lane = output column ----
+    // Point q outermost, column group m innermost, so the N columns of one table row are written back to back
+    // (rows complete in L2 before they are evicted; the other loop order halves the throughput).  Everything
+    // that depends only on the column group -- the shared-memory offsets of its three 1-D factors, its scale --
+    // is hoisted out of the point loop, and one running pointer per derivative slab replaces the 64-bit
+    // address arithmetic.
     const int npt = int(min(size_t(32), p.npts - tile * 32));
-    for (int q = 0; q < npt; ++q)
+    const bool plain = p.plain_stores != 0;
+    auto store = [plain](double* a, double v)
     {
-      const double* ph = myPhi + q * pstride;
-      const size_t pt = tile * 32 + q;
+      if (plain)
+        *a = v;
+      else
+        __stcs(a, v);
+    };
+    int ox[MD], oy[MD], oz[MD];
+#pragma unroll
+    for (int m = 0; m < MD; ++m)
+    {
+      ox[m] = ci[m] * NKP;
+      oy[m] = (F + cj[m]) * NKP;
+      oz[m] = (2 * F + ck[m]) * NKP;
+    }
+    double* os[NDER];
+#pragma unroll
+    for (int d = 0; d < NDER; ++d)
+      os[d] = p.basis + size_t(d) * p.npts * p.N + tile * 32 * p.N + lane;
+    const double* ph = myPhi;
+    for (int q = 0; q < npt; ++q, ph += pstride)
+    {
 #pragma unroll
       for (int m = 0; m < MD; ++m)
       {
-        const int n = lane + 32 * m;
-        if (n < p.N)
+        if (lane + 32 * m < p.N)
         {
-          double vx[NK], vy[NK], vz[NK];
+          double vx[NKP], vy[NKP], vz[NKP];
+          if constexpr (NKP == 1)
+          {
+            vx[0] = ph[ox[m]];
+            vy[0] = ph[oy[m]];
+            if constexpr (TDIM == 3)
+              vz[0] = ph[oz[m]];
+          }
+          else
+          {
+#pragma unroll
+            for (int k = 0; k < NKP; k += 2)
+            {
+              const double2 tx = *reinterpret_cast<const double2*>(ph + ox[m] + k);
+              const double2 ty = *reinterpret_cast<const double2*>(ph + oy[m] + k);
+              vx[k] = tx.x, vx[k + 1] = tx.y;
+              vy[k] = ty.x, vy[k + 1] = ty.y;
+              if constexpr (TDIM == 3)
+              {
+                const double2 tz = *reinterpret_cast<const double2*>(ph + oz[m] + k);
+                vz[k] = tz.x, vz[k + 1] = tz.y;
+              }
+            }
+          }
 #pragma unroll
           for (int k = 0; k < NK; ++k)
-          {
-            vx[k] = ph[(0 * NK + k) * F + ci[m]] * cs[m];
-            vy[k] = ph[(1 * NK + k) * F + cj[m]];
-            if constexpr (TDIM == 3)
-              vz[k] = ph[(2 * NK + k) * F + ck[m]];
-          }
-          double* o = p.basis + pt * p.N + n;
-          const size_t slab = p.npts * p.N;
+            vx[k] *= cs[m];
           if constexpr (TDIM == 2)
           {
 #pragma unroll
             for (int kx = 0; kx <= ND; ++kx)
 #pragma unroll
               for (int ky = 0; ky <= ND - kx; ++ky)
-                __stcs(o + size_t(idx2(kx, ky)) * slab, vx[kx] * vy[ky]);
+                store(os[idx2(kx, ky)] + 32 * m, vx[kx] * vy[ky]);
           }
           else
           {
@@ -167,11 +221,14 @@ __global__ void __launch_bounds__(kWarps * 32) tabulate_tp_kernel(TPParams p)
                 const double vxy = vx[kx] * vy[ky];
 #pragma unroll
                 for (int kz = 0; kz <= ND - kx - ky; ++kz)
-                  __stcs(o + size_t(idx3(kx, ky, kz)) * slab, vxy * vz[kz]);
+                  store(os[idx3(kx, ky, kz)] + 32 * m, vxy * vz[kz]);
               }
           }
         }
       }
+#pragma unroll
+      for (int d = 0; d < NDER; ++d)
+        os[d] += p.N;
     }
     __syncwarp();
   }
@@ -187,6 +244,10 @@ void launch_md(int md, const TPParams& p, size_t smem, int grid, cudaStream_t s)
     auto kern = tabulate_tp_kernel<TDIM, ND, MD>;                                                          \
     if (smem > 48 * 1024)                                                                                  \
       BX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));         \
+    /* persistent grid = exactly the resident CTAs, so the grid-stride loop has no ragged last wave */      \
+    int per_sm = 1;                                                                                        \
+    BX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarps * 32, smem));              \
+    grid = std::min(grid, sm_count() * std::max(per_sm, 1));                                               \
     kern<<<grid, kWarps * 32, smem, s>>>(p);                                                               \
     break;                                                                                                 \
   }
@@ -229,12 +290,16 @@ bool tabulate_tp_device(const bx_element& e, int nd, const double* x, size_t npt
   p.n1 = n1;
   p.N = e.N;
   p.fstride = e.tp.fstride;
+  {
+    static const bool plain = []() { const char* v = std::getenv("BX_TP_TUNE"); return v and std::string(v) == "plain"; }();
+    p.plain_stores = plain ? 1 : 0;
+  }
   for (int a = 0; a < 3; ++a)
     p.nfun[a] = a < tdim ? e.tp.nfun[a] : 0;
   const int per_lane = int(ceil_div(e.N, 32));
   const int md = per_lane <= 1 ? 1 : per_lane <= 2 ? 2 : per_lane <= 4 ? 4 : per_lane <= 8 ? 8 : per_lane <= 16 ? 16 : 24;
-  const int pstride = tdim * (nd + 1) * p.fstride + 1;
-  const size_t smem = (size_t(tdim) * p.fstride * n1 + size_t(kWarps) * 32 * pstride) * sizeof(double);
+  const int pstride = tp_pstride(tdim, nd + 1, p.fstride);
+  const size_t smem = (((size_t(tdim) * p.fstride * n1 + 1) & ~size_t(1)) + size_t(kWarps) * 32 * pstride) * sizeof(double);
   if (smem > 200 * 1024)
     return false;
   const size_t ntiles = ceil_div(npts, size_t(32));

@@ -407,9 +407,9 @@ def run_reference(args, w, rank):
         return
     res = cpu_reference(w, max(1, args.steps), max(0, min(args.warmup, 1)))
     if res is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libbasix_ref.so missing"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/libbasix_ref.so missing"})
         return
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": w.metric, "value": res["value"], "unit": w.unit, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -417,7 +417,7 @@ def run_reference(args, w, rank):
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": res["value"], "unit": w.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 def run_ours(args, w, rank, local_rank, world):
@@ -508,18 +508,31 @@ def run_ours(args, w, rank, local_rank, world):
     if rank == 0:
         cfg = dict(w.config)
         cfg["parallelism"] = f"independent slices over {world} GPU(s), no collective"
-        print(json.dumps({
+        emit({
             "metric": w.metric, "value": value, "unit": w.unit, "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32" if getattr(w, "permute", False) else "f64", "data": "synthetic",
             "config": cfg, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu,
-        }))
+        })
     if dist is not None:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def emit(line: dict):
+    """The one JSON line goes to the process's ORIGINAL stdout; everything else any library prints on fd 1
+    (e.g. NCCL's version banner) has been redirected to stderr by main()."""
+    os.write(_JSON_OUT, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
