@@ -131,6 +131,17 @@ def measured_hbm_peak():
     return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
+def measured_traffic(workload, units_per_launch):
+    """roofline.traffic: DRAM bytes of the dominant kernel per launch, from the committed ncu capture."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(p) as f:
+            ent = json.load(f).get(workload)
+        return float(ent["bytes_per_unit"]) * units_per_launch if ent else None
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def load_element(name):
     import basix_b200 as bx
 
@@ -161,6 +172,7 @@ class Tabulate:
         self.out = torch.empty(self.shape, dtype=torch.float64, device="cuda")
         self.path = e.tabulate_path(self.nd)
         self.launches_per_step = self.chunks
+        self.units_per_launch = self.cnp
         self.alg_bytes = self.cnp * e._tdim * 8 + int(np.prod(self.shape)) * 8
         self.flops = 2.0 * e.dim * e.value_size * e._psize * self.shape[0] * self.cnp
         self.config = {"workload": self.desc, "points_per_gpu": self.npts, "nd": self.nd, "tabulate_path": self.path,
@@ -232,6 +244,7 @@ class PushForward:
         self.dev = [t.cuda() for t in self.host]
         self.units_per_step = nc
         self.launches_per_step = 1
+        self.units_per_launch = nc
         # covariant push reads U and K, pull reads u and J; contravariant also reads detJ
         contra = int(self.e.map_type) == 3
         self.alg_bytes = nc * (2 * rows * 3 * 8 + 72 + (8 if contra else 0))
@@ -300,6 +313,7 @@ class TApply:
         self.data = self.data_host.cuda()
         self.units_per_step = nc
         self.launches_per_step = 1
+        self.units_per_launch = nc
         # only the dofs that CAN move (those on edges, and on faces of 3-D cells) need to be read
         # and written (+ 4 B of cell_info); which of them actually move depends on each cell's cell_info
         ed = e.entity_dofs
@@ -480,6 +494,8 @@ def run_ours(args, w, rank, local_rank, world):
                     "hbm": hbm}
     else:
         roofline = dict(bound="hbm", traffic=None, **hbm)
+    roofline["traffic"] = measured_traffic(args.workload, w.units_per_launch)
+    roofline["traffic_source"] = "ncu --set full capture, profiles/r01_traffic.json" if roofline["traffic"] else None
     roofline["ms_per_launch"] = ms_launch
     roofline["launches_per_step"] = w.launches_per_step
 

@@ -1,0 +1,16 @@
+#!/usr/bin/env bash
+# ncu --set full capture of the dominant kernel of every workload (one launch each, reduced sizes where the
+# full size only repeats tiles).  Reports land in gpurun_out/; condense with tools/ncu_summary.py.
+set -u
+cap() { # name workload kernel-regex units
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:$3 -s 2 -c 1 -o gpurun_out/r01_$1 -f \
+    python bench.py --workload $2 ${4:+--units $4} --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_$1.log 2>&1
+  tail -1 gpurun_out/ncu_$1.log
+}
+cap fused_p5tet tabulate_p5_tet tabulate_fused 2000000
+cap tp_q4hex tabulate_q4_hex tabulate_tp 10000000
+cap small_p1tri tabulate_p1_tri tabulate_small
+cap map_rows1 push_forward_n1curl3 map_kernel
+cap map_rows45 push_forward_n1curl3_rows45 map_kernel 1000000
+cap dof_matrix_rt4 t_apply_rt4 dof_ 4000000
+cap dof_perm_p5tet permute_p5_tet dof_ 4000000
