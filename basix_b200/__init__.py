@@ -16,6 +16,7 @@ from .finite_element import (
     LagrangeVariant,
     MapType,
     PolysetType,
+    create_element,
     polyset_dim,
     polyset_nderivs,
     tabulate_polynomial_set,
@@ -46,7 +47,7 @@ def index(p: int, q: int | None = None, r: int | None = None) -> int:
 
 
 __all__ = [
-    "CellType", "DPCVariant", "ElementFamily", "FiniteElement", "LagrangeVariant", "MapType", "PolysetType",
+    "CellType", "DPCVariant", "create_element", "ElementFamily", "FiniteElement", "LagrangeVariant", "MapType", "PolysetType",
     "device_count", "index", "kernel_launch_count", "polyset_dim", "polyset_nderivs", "set_device",
     "tabulate_polynomial_set",
 ]

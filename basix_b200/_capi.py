@@ -61,6 +61,11 @@ SIGNATURES = {
     "bx_polyset_tabulate_f32": (_I, [_I, _I, _I, _I, _P, _SIZE, _P, _I, _P]),
     "bx_element_create_from_arrays": (_I, [C.POINTER(ElementDesc), C.POINTER(_P)]),
     "bx_element_destroy": (None, [_P]),
+    "bx_create_element": (_I, [_I, _I, _I, _I, _I, _I, _P, _I, C.POINTER(_P)]),
+    "bx_element_coefficient_matrix": (_I, [_P, _P]),
+    "bx_element_entity_dofs": (_I, [_P, _I, _I, _P]),
+    "bx_element_entity_transformations": (_I, [_P, _I, _P, _P]),
+    "bx_element_dof_ordering": (_I, [_P, _P]),
     "bx_element_info": (_I, [_P, _P]),
     "bx_element_tabulate_shape": (_I, [_P, _I, _SIZE, _P]),
     "bx_element_tabulate_path": (_I, [_P, _I]),

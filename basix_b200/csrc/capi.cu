@@ -149,6 +149,8 @@ void map_device(int map_type, int pull, const double* U, const double* J, const 
 template <typename T>
 void dof_transform_device(const bx_element& e, int op, T* data, size_t nc, size_t cell_size, int n,
                           const uint32_t* cell_info, cudaStream_t s);
+bx_element* create_lagrange(int cell, int degree, int variant, bool discontinuous, const int32_t* dof_ordering,
+                            int n_dof_ordering);
 
 namespace
 {
@@ -447,6 +449,65 @@ extern "C"
   }
 
   void bx_element_destroy(bx_element* e) { delete e; }
+
+  int bx_create_element(int family, int cell_type, int degree, int lagrange_variant, int dpc_variant,
+                        int discontinuous, const int32_t* dof_ordering, int n_dof_ordering, bx_element** out)
+  {
+    return bx::guarded(
+        [&]()
+        {
+          bx::require(out != nullptr, "create_element: null argument");
+          *out = nullptr;
+          (void)dpc_variant;
+          if (family != 1) // element::family::P
+            bx::fail(BX_ERR_UNSUPPORTED,
+                     "create_element: only the P (Lagrange) family is built natively; describe other families "
+                     "with bx_element_create_from_arrays");
+          *out = bx::create_lagrange(cell_type, degree, lagrange_variant, discontinuous != 0, dof_ordering,
+                                     n_dof_ordering);
+        });
+  }
+
+  int bx_element_coefficient_matrix(const bx_element* e, double* out)
+  {
+    return bx::guarded(
+        [&]()
+        {
+          bx::require(e and out, "coefficient_matrix: null argument");
+          std::copy(e->coeffs.begin(), e->coeffs.end(), out);
+        });
+  }
+
+  int bx_element_entity_dofs(const bx_element* e, int dim, int index, int32_t* out)
+  {
+    if (!e or dim < 0 or dim >= int(e->edofs.size()) or index < 0 or index >= int(e->edofs[dim].size()))
+      return -1;
+    const auto& d = e->edofs[dim][index];
+    if (out)
+      std::copy(d.begin(), d.end(), out);
+    return int(d.size());
+  }
+
+  int bx_element_entity_transformations(const bx_element* e, int entity_cell_type, int32_t shape[3], double* out)
+  {
+    if (!e or !shape or entity_cell_type < 0 or entity_cell_type > 7 or e->etrans_dim[entity_cell_type] < 0)
+      return 0;
+    const int n = e->etrans_dim[entity_cell_type];
+    shape[0] = entity_cell_type == BX_CELL_INTERVAL ? 1 : 2;
+    shape[1] = shape[2] = n;
+    if (out)
+      std::copy(e->etrans[entity_cell_type].begin(), e->etrans[entity_cell_type].end(), out);
+    return 1;
+  }
+
+  int bx_element_dof_ordering(const bx_element* e, int32_t* out)
+  {
+    if (!e)
+      return -1;
+    if (out)
+      std::copy(e->dof_ordering.begin(), e->dof_ordering.end(), out);
+    return int(e->dof_ordering.size());
+  }
 
   int bx_element_info(const bx_element* e, int32_t info[10])
   {

@@ -25,12 +25,12 @@ struct PointView
   T* p;       // address of P[0][0][this point]
   size_t ld;  // distance between consecutive basis functions (= #points in the table)
   int psize;  // basis functions per derivative
-  __device__ __forceinline__ T& operator()(int d, int k) const { return p[(size_t(d) * psize + k) * ld]; }
+  __host__ __device__ __forceinline__ T& operator()(int d, int k) const { return p[(size_t(d) * psize + k) * ld]; }
 };
 
 // Jacobi recurrence coefficients, reference polyset.cpp:31-41 (jrc).
 template <typename T>
-__device__ __forceinline__ void jacobi_abc(int a, int n, T& an, T& bn, T& cn)
+__host__ __device__ __forceinline__ void jacobi_abc(int a, int n, T& an, T& bn, T& cn)
 {
   an = (a + 2 * n + 1) * (a + 2 * n + 2) / static_cast<T>(2 * (n + 1) * (a + n + 1));
   bn = a * a * (a + 2 * n + 1) / static_cast<T>(2 * (n + 1) * (a + n + 1) * (a + 2 * n));
@@ -39,7 +39,7 @@ __device__ __forceinline__ void jacobi_abc(int a, int n, T& an, T& bn, T& cn)
 
 // ---- interval: shifted Legendre on [0,1] --------------------------------------------------------
 template <typename T, typename View>
-__device__ void polyset_interval(View P, int n, int nd, T x0)
+__host__ __device__ void polyset_interval(View P, int n, int nd, T x0)
 {
   const T X = x0 * T(2.0) - T(1.0);
   P(0, 0) = T(1.0);
@@ -76,7 +76,7 @@ __device__ void polyset_interval(View P, int n, int nd, T x0)
 // ---- triangle: Dubiner / Sherwin-Karniadakis --------------------------------------------------
 // basis slot idx2(q, p); derivative slot idx2(kx, ky)
 template <typename T, typename View>
-__device__ void polyset_triangle(View P, int n, int nd, T x0, T x1)
+__host__ __device__ void polyset_triangle(View P, int n, int nd, T x0, T x1)
 {
   const int nder = (nd + 1) * (nd + 2) / 2;
   if (n == 0)
@@ -147,7 +147,7 @@ __device__ void polyset_triangle(View P, int n, int nd, T x0, T x1)
 // ---- tetrahedron ------------------------------------------------------------------------------
 // basis slot idx3(r, q, p); derivative slot idx3(kx, ky, kz)
 template <typename T, typename View>
-__device__ void polyset_tetrahedron(View P, int n, int nd, T x0, T x1, T x2)
+__host__ __device__ void polyset_tetrahedron(View P, int n, int nd, T x0, T x1, T x2)
 {
   const int nder = (nd + 1) * (nd + 2) * (nd + 3) / 6;
   if (n == 0)
@@ -269,13 +269,13 @@ __device__ void polyset_tetrahedron(View P, int n, int nd, T x0, T x1, T x2)
 // ---- 1-D normalised Legendre values and derivatives into a small local table -----------------
 // L[k * (n + 1) + p] = sqrt(2p+1) d^k/dx^k P_p(2x-1), k <= nd
 template <typename T>
-__device__ void legendre_table(T* L, int n, int nd, T x0)
+__host__ __device__ void legendre_table(T* L, int n, int nd, T x0)
 {
   struct LocalView
   {
     T* p;
     int n1;
-    __device__ __forceinline__ T& operator()(int k, int q) const { return p[k * n1 + q]; }
+    __host__ __device__ __forceinline__ T& operator()(int k, int q) const { return p[k * n1 + q]; }
   };
   polyset_interval<T>(LocalView{L, n + 1}, n, nd, x0);
 }

@@ -276,6 +276,46 @@ class FiniteElement:
         self._tdim, self._ndofs, self._vs = info[2], info[3], info[4]
         self._perms, self._identity, self._psize = bool(info[7]), bool(info[8]), info[9]
 
+    @classmethod
+    def _from_handle(cls, h, *, family, lagrange_variant, dpc_variant, discontinuous, degree):
+        """Wrap an element built inside the library (``bx_create_element``): read the defining arrays back."""
+        self = cls.__new__(cls)
+        self._h = h
+        L = lib()
+        info = (C.c_int32 * 10)()
+        check(L.bx_element_info(h, info))
+        self._cell_type, self._polyset_type = CellType(info[0]), PolysetType(info[1])
+        self._tdim, self._ndofs, self._vs = info[2], info[3], info[4]
+        self._map_type, self._embedded_superdegree = MapType(info[5]), info[6]
+        self._perms, self._identity, self._psize = bool(info[7]), bool(info[8]), info[9]
+        self._degree = int(degree)
+        self._family, self._lagrange_variant = ElementFamily(int(family)), LagrangeVariant(int(lagrange_variant))
+        self._dpc_variant, self._discontinuous = DPCVariant(int(dpc_variant)), bool(discontinuous)
+        self._value_shape = () if self._vs == 1 else (self._vs,)
+        self._coeffs = np.empty((self._ndofs, self._vs * self._psize), dtype=np.float64)
+        check(L.bx_element_coefficient_matrix(h, self._coeffs.ctypes.data))
+        self._entity_dofs = []
+        for dim, cnt in enumerate(_NUM_ENTITIES[int(self._cell_type)]):
+            row = []
+            for i in range(cnt):
+                n = L.bx_element_entity_dofs(h, dim, i, None)
+                buf = np.zeros(max(n, 1), dtype=np.int32)
+                L.bx_element_entity_dofs(h, dim, i, buf.ctypes.data)
+                row.append([int(v) for v in buf[:n]])
+            self._entity_dofs.append(row)
+        self._entity_transformations = {}
+        for ct in (1, 2, 4):
+            shape = (C.c_int32 * 3)()
+            if L.bx_element_entity_transformations(h, ct, shape, None):
+                m = np.empty(tuple(shape), dtype=np.float64)
+                L.bx_element_entity_transformations(h, ct, shape, m.ctypes.data if m.size else None)
+                self._entity_transformations[ct] = m
+        n = L.bx_element_dof_ordering(h, None)
+        self._dof_ordering = np.zeros(n, dtype=np.int32)
+        if n:
+            L.bx_element_dof_ordering(h, self._dof_ordering.ctypes.data)
+        return self
+
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
         if h:
@@ -563,3 +603,27 @@ class FiniteElement:
 
     def permute_batch(self, d, cell_info, inverse: bool = False) -> None:
         self._permute(int(bool(inverse)), d, cell_info, True)
+
+
+def create_element(family, celltype, degree: int, lagrange_variant=LagrangeVariant.unset,
+                   dpc_variant=DPCVariant.unset, discontinuous: bool = False, dof_ordering=None,
+                   dtype=np.float64) -> FiniteElement:
+    """``basix.create_element`` (python/basix/finite_element.py:595-634), same argument order.
+
+    Built natively by the library (host set-up code in csrc/create.cu): the P (Lagrange) family with the
+    ``equispaced`` / ``gll_warped`` variants on interval, triangle, tetrahedron, quadrilateral and hexahedron.
+    Other families raise ``RuntimeError``; build those with ``FiniteElement(...)`` / ``FiniteElement.from_arrays``
+    from the arrays of an element constructed elsewhere."""
+    if np.dtype(dtype) != np.float64:
+        raise RuntimeError("create_element: elements are described in float64 (float32 data is accepted by the "
+                           "T_apply family and tabulate_polynomial_set)")
+    order = np.ascontiguousarray(dof_ordering if dof_ordering is not None else [], dtype=np.int32)
+    h = C.c_void_p()
+    check(lib().bx_create_element(int(family), int(celltype), int(degree), int(lagrange_variant), int(dpc_variant),
+                                  int(bool(discontinuous)), order.ctypes.data if len(order) else None, len(order),
+                                  C.byref(h)))
+    lv = int(lagrange_variant)
+    if lv == 0 and int(family) == 1 and degree < 3:
+        lv = int(LagrangeVariant.gll_warped)  # the reference resolves "unset" the same way (e-lagrange.cpp:491-500)
+    return FiniteElement._from_handle(h, family=family, lagrange_variant=lv, dpc_variant=dpc_variant,
+                                      discontinuous=discontinuous, degree=degree)

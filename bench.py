@@ -142,9 +142,14 @@ def measured_traffic(workload, units_per_launch):
         return None
 
 
-def load_element(name):
+def load_element(name, ref_args=None):
+    """P-family elements are built natively (basix_b200.create_element); the N1curl / RT elements of configs 4
+    and 5, whose construction is outside the accelerated path, come from the committed arrays of the reference
+    element (tests/golden/elements, written by tests/golden/make_golden.py)."""
     import basix_b200 as bx
 
+    if ref_args is not None and ref_args[0] == 1:
+        return bx.create_element(*ref_args)
     return bx.FiniteElement.from_arrays(np.load(os.path.join(GOLDEN, name + ".npz")))
 
 
@@ -161,7 +166,7 @@ class Tabulate:
     def setup(self, rank):
         import torch
 
-        self.e = load_element(self.element_name)
+        self.e = load_element(self.element_name, self.ref_args)
         e = self.e
         self.cnp = self.npts // self.chunks  # points per launch (the table of one launch stays resident)
         self.shape = e.tabulate_shape(self.nd, self.cnp)
@@ -298,7 +303,7 @@ class TApply:
     def setup(self, rank):
         import torch
 
-        self.e = load_element(self.element_name)
+        self.e = load_element(self.element_name, self.ref_args)
         e, nc = self.e, self.nc
         ci = random_cell_info(nc, 11 + rank)
         self.ci_host = torch.from_numpy(ci.view(np.int32)).pin_memory()

@@ -156,6 +156,25 @@ extern "C"
   int bx_element_create_from_arrays(const bx_element_desc* desc, bx_element** out);
   void bx_element_destroy(bx_element* e);
 
+  /* Native basix::create_element (finite-element.cpp create_element<T>, python basix.create_element,
+     finite_element.py:595-634): same argument order and enum values.  Built natively: family P (Lagrange),
+     variants equispaced / gll_warped (unset allowed for degree < 3), on interval, triangle, tetrahedron,
+     quadrilateral and hexahedron, continuous or discontinuous, optional dof_ordering (NULL / 0 for none).
+     Anything else returns BX_ERR_UNSUPPORTED: describe such elements with bx_element_create_from_arrays.
+     Set-up runs on the host (as in the reference); only the resulting tables go to the device. */
+  int bx_create_element(int family, int cell_type, int degree, int lagrange_variant, int dpc_variant,
+                        int discontinuous, const int32_t* dof_ordering, int n_dof_ordering, bx_element** out);
+
+  /* Defining arrays of an element (reference accessors finite-element.h:665-668, 772-776, 1342-1346, 1397):
+     coefficient_matrix() [ndofs][value_size * psize]; entity_dofs()[dim][index] (returns the count, fills
+     out when non-NULL); entity_transformations() of one sub-entity cell type (shape {ntrans, n, n}; returns
+     1 when the cell has that sub-entity type, 0 otherwise; fills out when non-NULL); dof_ordering()
+     (returns the length, 0 when none). */
+  int bx_element_coefficient_matrix(const bx_element* e, double* out);
+  int bx_element_entity_dofs(const bx_element* e, int dim, int index, int32_t* out);
+  int bx_element_entity_transformations(const bx_element* e, int entity_cell_type, int32_t shape[3], double* out);
+  int bx_element_dof_ordering(const bx_element* e, int32_t* out);
+
   /* Accessors (reference: finite-element.h:487-561). info[0..9] = cell_type, polyset_type,
      tdim, ndofs, value_size, map_type, embedded_superdegree, dof_transformations_are_permutations,
      dof_transformations_are_identity, psize. */

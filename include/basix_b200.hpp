@@ -111,15 +111,31 @@ public:
     set(d.etrans_triangle, d.etrans_triangle_dim, desc.etrans_triangle, desc.etrans_triangle_dim);
     set(d.etrans_quadrilateral, d.etrans_quadrilateral_dim, desc.etrans_quadrilateral, desc.etrans_quadrilateral_dim);
     check(bx_element_create_from_arrays(&desc, &_h));
+    read_info();
+    _value_shape = d.value_shape;
+  }
+  /// basix::create_element (finite-element.h:1623-1628): built natively for the P family (equispaced /
+  /// gll_warped) on interval, triangle, tetrahedron, quadrilateral, hexahedron; throws otherwise.
+  static FiniteElement create(int family, int cell_type, int degree, int lagrange_variant = 0, int dpc_variant = 0,
+                              bool discontinuous = false, const std::vector<int>& dof_ordering = {})
+  {
+    bx_element* h = nullptr;
+    check(bx_create_element(family, cell_type, degree, lagrange_variant, dpc_variant, discontinuous ? 1 : 0,
+                            dof_ordering.empty() ? nullptr : dof_ordering.data(), int(dof_ordering.size()), &h));
+    FiniteElement e;
+    e._h = h;
+    e.read_info();
+    e._value_shape = e._vs == 1 ? std::vector<std::size_t>{} : std::vector<std::size_t>{std::size_t(e._vs)};
+    return e;
+  }
+  /// coefficient_matrix() (finite-element.h:1342-1346): [ndofs][value_size * psize]
+  std::vector<double> coefficient_matrix() const
+  {
     std::int32_t info[10];
     check(bx_element_info(_h, info));
-    _tdim = info[2];
-    _ndofs = info[3];
-    _vs = info[4];
-    _map = info[5];
-    _perms = info[7] != 0;
-    _identity = info[8] != 0;
-    _value_shape = d.value_shape;
+    std::vector<double> c(std::size_t(info[3]) * info[4] * info[9]);
+    check(bx_element_coefficient_matrix(_h, c.data()));
+    return c;
   }
   ~FiniteElement() { bx_element_destroy(_h); }
   FiniteElement(const FiniteElement&) = delete;
@@ -225,6 +241,18 @@ public:
   }
 
 private:
+  FiniteElement() = default;
+  void read_info()
+  {
+    std::int32_t info[10];
+    check(bx_element_info(_h, info));
+    _tdim = info[2];
+    _ndofs = info[3];
+    _vs = info[4];
+    _map = info[5];
+    _perms = info[7] != 0;
+    _identity = info[8] != 0;
+  }
   void transform(int op, double* u, std::size_t nc, std::size_t cs, int n, const std::uint32_t* ci, int mem,
                  bx_stream_t s) const
   {

@@ -3,6 +3,7 @@
 // golden .npz (cell, polyset, degree, superdegree, map, value_shape, coeffs, entity dofs, transformations).
 #include "basix_b200.hpp"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -84,6 +85,31 @@ int main(int argc, char** argv)
   const auto shape = e.tabulate_shape(2, 7);
   REQUIRE(shape[0] == 10 and shape[1] == 7 and shape[2] == 56 and shape[3] == 1);
   REQUIRE(basix_b200::polyset::dim(BX_CELL_TETRAHEDRON, BX_POLYSET_STANDARD, 5) == 56);
+
+  // native create_element: P5 tetrahedron (gll_warped = 2) reproduces the arrays the element was described with
+  {
+    FiniteElement n = FiniteElement::create(/*P*/ 1, BX_CELL_TETRAHEDRON, 5, /*gll_warped*/ 2);
+    REQUIRE(n.dim() == 56 and n.dof_transformations_are_permutations());
+    const auto a = n.coefficient_matrix(), b = e.coefficient_matrix();
+    REQUIRE(a.size() == b.size());
+    double err = 0, scale = 0;
+    for (std::size_t i = 0; i < a.size(); ++i)
+    {
+      err = std::max(err, std::abs(a[i] - b[i]));
+      scale = std::max(scale, std::abs(b[i]));
+    }
+    REQUIRE(err <= 1e-11 * scale);
+    bool threw = false;
+    try
+    {
+      FiniteElement::create(/*RT*/ 2, BX_CELL_TETRAHEDRON, 2);
+    }
+    catch (const std::runtime_error&)
+    {
+      threw = true;
+    }
+    REQUIRE(threw);
+  }
 
   // wrong point dimension: the reference's message (finite-element.cpp:1838-1843)
   const double x2[4] = {0.1, 0.2, 0.3, 0.4};

@@ -449,3 +449,21 @@ def test_all_eight_operators_large_batch(ref, op):
                 assert np.array_equal(got, want)
             else:
                 assert np.max(np.abs(got - want)) <= 1e-12 * np.max(np.abs(want))
+
+
+# ---- natively constructed elements (csrc/create.cu) through the whole device path ---------------------------
+@pytest.mark.parametrize("cell,degree,variant,nd", [(TRI, 1, GLL, 1), (TET, 5, GLL, 2), (HEX, 4, GLL, 1), (QUAD, 3, EQ, 2),
+                                                    (TET, 3, EQ, 1), (INTERVAL, 6, GLL, 2)])
+def test_native_create_element_tabulate_and_permute(ref, cell, degree, variant, nd):
+    import basix_b200 as bx
+
+    r = ref.RefElement(P, cell, degree, variant)
+    e = bx.create_element(bx.ElementFamily.P, cell, degree, variant)
+    x = random_points(cell, 2049, seed=degree)
+    slab_close(e.tabulate(nd, x), r.tabulate(nd, x), 1e-12)
+    if not r.dof_transformations_are_identity:
+        ci = cell_infos(257, seed=degree)
+        d = np.tile(np.arange(r.dim, dtype=np.int32), (len(ci), 1))
+        want = r.permute_batch(d.copy(), ci)
+        e.permute_batch(d, ci)
+        assert np.array_equal(d, want)
