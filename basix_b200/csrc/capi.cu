@@ -151,6 +151,8 @@ void dof_transform_device(const bx_element& e, int op, T* data, size_t nc, size_
                           const uint32_t* cell_info, cudaStream_t s);
 bx_element* create_lagrange(int cell, int degree, int variant, bool discontinuous, const int32_t* dof_ordering,
                             int n_dof_ordering);
+bx_element* create_rt(int cell, int degree, int lvariant, bool discontinuous);
+bx_element* create_nedelec(int cell, int degree, int lvariant, bool discontinuous);
 
 namespace
 {
@@ -459,12 +461,20 @@ extern "C"
           bx::require(out != nullptr, "create_element: null argument");
           *out = nullptr;
           (void)dpc_variant;
-          if (family != 1) // element::family::P
+          if (family == 1) // element::family::P
+            *out = bx::create_lagrange(cell_type, degree, lagrange_variant, discontinuous != 0, dof_ordering,
+                                       n_dof_ordering);
+          else if (family == 2 or family == 3) // RT, N1E
+          {
+            if (n_dof_ordering != 0)
+              bx::fail(BX_ERR_UNSUPPORTED, "create_element: dof_ordering is supported for the P family only");
+            *out = family == 2 ? bx::create_rt(cell_type, degree, lagrange_variant, discontinuous != 0)
+                               : bx::create_nedelec(cell_type, degree, lagrange_variant, discontinuous != 0);
+          }
+          else
             bx::fail(BX_ERR_UNSUPPORTED,
-                     "create_element: only the P (Lagrange) family is built natively; describe other families "
+                     "create_element: the P, RT and N1E families are built natively; describe other families "
                      "with bx_element_create_from_arrays");
-          *out = bx::create_lagrange(cell_type, degree, lagrange_variant, discontinuous != 0, dof_ordering,
-                                     n_dof_ordering);
         });
   }
 

@@ -1,5 +1,6 @@
 // Native element construction (host side, runs once per element): basix.create_element for the Lagrange (P)
-// family on interval / triangle / tetrahedron / quadrilateral / hexahedron.
+// family on interval / triangle / tetrahedron / quadrilateral / hexahedron, and for Raviart-Thomas and Nedelec
+// (first kind) on triangle / tetrahedron.
 //
 // This is set-up code, not the accelerated path: it produces the immutable arrays the hot path consumes
 // (coefficient matrix, entity dofs, entity transformations) and hands them to element_from_desc().  What is
@@ -8,13 +9,16 @@
 //                             218-280 (quad / hex), 282-350 (triangle), 503-535 + 583-633 (tetrahedron)
 //   GLL nodes                 cpp/basix/quadrature.cpp:470-510 (there: Golub-Welsch with fixed end nodes; here:
 //                             Newton on (1 - x^2) P'_n, the same nodes to rounding)
+//   Gauss-Jacobi quadrature   cpp/basix/quadrature.cpp:215-372 (collapsed rules on simplices)
 //   dof points per entity     cpp/basix/e-lagrange.cpp:457-666 (vertices, then edges, faces, interior; the
 //                             sub-entity lattice mapped by v0 + sum_k (v_{k+1} - v0) t_k)
-//   coefficient matrix        cpp/basix/finite-element.cpp:84-175, 1105-1119: C = (B D^T)^-1 B with B = I, i.e.
-//                             C P(x_dofs) = I
+//   RT / N1curl spaces        cpp/basix/e-raviart-thomas.cpp:20-173, e-nedelec.cpp:24-380; math.h:386-444
+//   integral moment dofs      cpp/basix/moments.cpp:100-190 (vector pad-out), 262-330 (tangent), 336-440 (normal)
+//   coefficient matrix        cpp/basix/finite-element.cpp:84-175, 1105-1119: C = (B D)^-1 B
 //   entity transformations    cpp/basix/dof-transformations.cpp:71-330 (the cell-level maps that reverse /
 //                             rotate / reflect the first sub-entity of each type), 340-470 (tabulate the
-//                             element basis at the mapped dof points of that entity)
+//                             element basis at the mapped dof points of that entity, push it forward with the
+//                             element's Piola map, interpolate with the entity's dofs)
 //   discontinuous variant     cpp/basix/finite-element.cpp make_discontinuous: every dof moves to the interior
 // The orthonormal polynomial sets are evaluated with the SAME recurrence code the device kernels use
 // (polyset.cuh, compiled for the host here).
@@ -24,6 +28,8 @@
 #include <algorithm>
 #include <cmath>
 #include <functional>
+#include <limits>
+#include <memory>
 #include <numeric>
 
 namespace bx
@@ -389,6 +395,441 @@ std::vector<EntityMap> entity_maps(int cell)
   default: return {};
   }
 }
+
+// ---- Gauss-Jacobi quadrature (quadrature.cpp:215-372; Karniadakis & Sherwin collapsed rules) ----------------
+// P_m^{(a,0)} and its derivative at x by the three-term recurrence
+void jacobi_a0(double a, int m, double x, double& p, double& dp)
+{
+  double p0 = 1.0, d0 = 0.0;
+  if (m == 0)
+  {
+    p = 1.0, dp = 0.0;
+    return;
+  }
+  double p1 = (x * (a + 2.0) + a) * 0.5, d1 = a * 0.5 + 1.0;
+  for (int j = 2; j <= m; ++j)
+  {
+    const double a1 = 2.0 * j * (j + a) * (2.0 * j + a - 2.0);
+    const double a2 = (2.0 * j + a - 1.0) * (a * a) / a1;
+    const double a3 = (2.0 * j + a - 1.0) * (2.0 * j + a) / (2.0 * j * (j + a));
+    const double a4 = 2.0 * (j + a - 1.0) * (j - 1.0) * (2.0 * j + a) / a1;
+    const double p2 = p1 * (x * a3 + a2) - p0 * a4;
+    const double d2 = d1 * (x * a3 + a2) - d0 * a4 + a3 * p1;
+    p0 = p1, p1 = p2, d0 = d1, d1 = d2;
+  }
+  p = p1, dp = d1;
+}
+
+// m-point Gauss-Jacobi rule for the weight (1 - x)^a on [-1, 1]: Newton with deflation from Chebyshev guesses
+void gauss_jacobi(double a, int m, Vec& pts, Vec& wts)
+{
+  pts.assign(m, 0.0);
+  wts.assign(m, 0.0);
+  for (int k = 0; k < m; ++k)
+  {
+    double x = -std::cos((2.0 * k + 1.0) * M_PI / (2.0 * m));
+    if (k > 0)
+      x = 0.5 * (x + pts[k - 1]);
+    for (int it = 0; it < 100; ++it)
+    {
+      double s = 0.0;
+      for (int i = 0; i < k; ++i)
+        s += 1.0 / (x - pts[i]);
+      double f, df;
+      jacobi_a0(a, m, x, f, df);
+      const double delta = f / (df - f * s);
+      x -= delta;
+      if (std::abs(delta) < 1e-15)
+        break;
+    }
+    pts[k] = x;
+  }
+  for (int k = 0; k < m; ++k)
+  {
+    double f, df;
+    jacobi_a0(a, m, pts[k], f, df);
+    wts[k] = std::pow(2.0, a + 1.0) / (1.0 - pts[k] * pts[k]) / (df * df);
+  }
+}
+
+// Quadrature exact for polynomials of degree q on interval / triangle / tetrahedron: x[n][tdim], w[n].  The
+// reference's default for these cells is a tabulated Xiao-Gimbutas rule below degree 30 (quadrature.cpp:4960-4990);
+// every integrand formed here is a polynomial within the exactness degree, so any exact rule yields the same
+// moments and the same element to rounding.
+void make_quadrature(int cell, int q, Vec& x, Vec& w)
+{
+  const int m = (q + 2) / 2;
+  Vec px, wx, py, wy, pz, wz;
+  gauss_jacobi(0.0, m, px, wx);
+  x.clear();
+  w.clear();
+  if (cell == BX_CELL_INTERVAL)
+  {
+    for (int i = 0; i < m; ++i)
+    {
+      x.push_back(0.5 * (px[i] + 1.0));
+      w.push_back(0.5 * wx[i]);
+    }
+    return;
+  }
+  gauss_jacobi(1.0, m, py, wy);
+  if (cell == BX_CELL_TRIANGLE)
+  {
+    for (int i = 0; i < m; ++i)
+      for (int j = 0; j < m; ++j)
+      {
+        x.push_back(0.25 * (1.0 + px[i]) * (1.0 - py[j]));
+        x.push_back(0.5 * (1.0 + py[j]));
+        w.push_back(wx[i] * wy[j] * 0.125);
+      }
+    return;
+  }
+  if (cell != BX_CELL_TETRAHEDRON)
+    fail(BX_ERR_UNSUPPORTED, "create_element: quadrature on this cell is not available in the native factory");
+  gauss_jacobi(2.0, m, pz, wz);
+  for (int i = 0; i < m; ++i)
+    for (int j = 0; j < m; ++j)
+      for (int k = 0; k < m; ++k)
+      {
+        x.push_back(0.125 * (1.0 + px[i]) * (1.0 - py[j]) * (1.0 - pz[k]));
+        x.push_back(0.25 * (1.0 + py[j]) * (1.0 - pz[k]));
+        x.push_back(0.5 * (1.0 + pz[k]));
+        w.push_back(wx[i] * wy[j] * wz[k] * 0.125 * 0.125);
+      }
+}
+
+// math::orthogonalise (math.h:386-444): Gram-Schmidt on the rows [start, n) of B[n][cols]
+void orthogonalise(Vec& B, int n, int cols, int start)
+{
+  for (int i = start; i < n; ++i)
+  {
+    double* ri = B.data() + size_t(i) * cols;
+    double norm = 0.0;
+    for (int k = 0; k < cols; ++k)
+      norm += ri[k] * ri[k];
+    norm = std::sqrt(norm);
+    if (norm < 2 * std::numeric_limits<double>::epsilon())
+      fail(BX_ERR_RUNTIME, "Cannot orthogonalise the rows of a matrix with incomplete row rank");
+    for (int k = 0; k < cols; ++k)
+      ri[k] /= norm;
+    for (int j = i + 1; j < n; ++j)
+    {
+      double* rj = B.data() + size_t(j) * cols;
+      double a = 0.0;
+      for (int k = 0; k < cols; ++k)
+        a += rj[k] * ri[k];
+      for (int k = 0; k < cols; ++k)
+        rj[k] -= a * ri[k];
+    }
+  }
+}
+
+// Dofs of one element: x[d][e] points [np][tdim]; M[d][e] interpolation weights [ndofs_e][vs][np]
+struct DofSet
+{
+  std::vector<std::vector<Vec>> x, M;
+  std::vector<std::vector<int>> ndofs;
+};
+
+// Values of the moment space (discontinuous Lagrange of `degree` on `cell`, variant `lvariant`) at points:
+// phi[i][q].  legendre variant: the orthonormal set itself (e-lagrange.cpp:211-259); equispaced / gll_warped:
+// the nodal basis built by create_lagrange.
+bx_element* create_lagrange_host(int cell, int degree, int variant, bool discontinuous);
+Vec moment_space(int cell, int degree, int lvariant, const Vec& pts, size_t npts)
+{
+  const Vec P = host_polyset(cell, degree, pts, npts);
+  if (lvariant == 11) // legendre
+    return P;
+  std::unique_ptr<bx_element> e(create_lagrange_host(cell, degree, lvariant, true));
+  const int n = e->ndofs, psize = e->psize;
+  Vec phi(size_t(n) * npts, 0.0);
+  for (int i = 0; i < n; ++i)
+    for (int k = 0; k < psize; ++k)
+    {
+      const double c = e->coeffs[size_t(i) * psize + k];
+      for (size_t q = 0; q < npts; ++q)
+        phi[size_t(i) * npts + q] += c * P[size_t(k) * npts + q];
+    }
+  return phi;
+}
+
+struct Entity
+{
+  Vec v0;                // first vertex
+  std::vector<Vec> axes; // v_{k+1} - v0 (simplex sub-entities)
+};
+Entity entity_frame(int cell, int dim, int index)
+{
+  const int tdim = cell_tdim(cell);
+  const Vec geom = cell_geometry(cell);
+  const auto topo = cell_topology(cell);
+  const auto& verts = topo[dim][index];
+  Entity f;
+  f.v0.assign(geom.begin() + verts[0] * tdim, geom.begin() + (verts[0] + 1) * tdim);
+  for (int k = 0; k < dim; ++k)
+  {
+    Vec a(tdim);
+    for (int q = 0; q < tdim; ++q)
+      a[q] = geom[verts[k + 1] * tdim + q] - f.v0[q];
+    f.axes.push_back(a);
+  }
+  return f;
+}
+
+// The three moment kinds of moments.cpp on the entities of dimension `edim` of a simplex cell:
+//   kind 0  make_integral_moments against a vector-valued pad-out of a scalar space (moments.cpp:100-190):
+//           dof i*edim + d integrates  phi_i  v . axis_d
+//   kind 1  make_tangent_integral_moments (moments.cpp:262-330), edges
+//   kind 2  make_normal_integral_moments (moments.cpp:336-440), facets
+void add_moments(DofSet& dofs, int cell, int edim, int kind, int mdegree, int lvariant, int qdeg)
+{
+  const int tdim = cell_tdim(cell);
+  const int ecell = edim == 1 ? BX_CELL_INTERVAL : edim == 2 ? BX_CELL_TRIANGLE : BX_CELL_TETRAHEDRON;
+  Vec qx, qw;
+  make_quadrature(ecell, qdeg, qx, qw);
+  const size_t nq = qw.size();
+  const Vec phi = moment_space(ecell, mdegree, lvariant, qx, nq);
+  const int nphi = int(phi.size() / nq);
+  const int nent = cell_num_entities(cell, edim);
+  for (int e = 0; e < nent; ++e)
+  {
+    const Entity f = entity_frame(cell, edim, e);
+    Vec pts(nq * tdim);
+    for (size_t p = 0; p < nq; ++p)
+      for (int q = 0; q < tdim; ++q)
+      {
+        double v = f.v0[q];
+        for (int k = 0; k < edim; ++k)
+          v += qx[p * edim + k] * f.axes[k][q];
+        pts[p * tdim + q] = v;
+      }
+    const int nd = kind == 0 ? nphi * edim : nphi;
+    Vec M(size_t(nd) * tdim * nq, 0.0);
+    Vec dir(tdim, 0.0);
+    if (kind == 1)
+      dir = f.axes[0];
+    else if (kind == 2)
+    {
+      if (tdim == 2)
+        dir = {-f.axes[0][1], f.axes[0][0]};
+      else
+      {
+        const Vec &a = f.axes[0], &b = f.axes[1];
+        dir = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+      }
+    }
+    for (int i = 0; i < nphi; ++i)
+      for (int d = 0; d < (kind == 0 ? edim : 1); ++d)
+      {
+        const int dof = kind == 0 ? i * edim + d : i;
+        const Vec& v = kind == 0 ? f.axes[d] : dir;
+        for (int j = 0; j < tdim; ++j)
+          for (size_t k = 0; k < nq; ++k)
+            M[(size_t(dof) * tdim + j) * nq + k] = phi[size_t(i) * nq + k] * qw[k] * v[j];
+      }
+    dofs.x[edim].push_back(std::move(pts));
+    dofs.M[edim].push_back(std::move(M));
+    dofs.ndofs[edim].push_back(nd);
+  }
+}
+
+void add_empty(DofSet& dofs, int cell, int dim)
+{
+  for (int e = 0; e < cell_num_entities(cell, dim); ++e)
+  {
+    dofs.x[dim].push_back({});
+    dofs.M[dim].push_back({});
+    dofs.ndofs[dim].push_back(0);
+  }
+}
+
+// cell-level Jacobians of the entity maps (dof-transformations.cpp:71-200): {J, detJ, K} per map, in the order
+// of entity_maps()
+struct MapJac
+{
+  Vec J;
+  double detJ;
+  Vec K;
+};
+std::vector<MapJac> entity_map_jacobians(int cell)
+{
+  switch (cell)
+  {
+  case BX_CELL_TRIANGLE: return {{{0, 1, 1, 0}, -1.0, {0, 1, 1, 0}}};
+  case BX_CELL_TETRAHEDRON:
+    return {{{1, 0, 0, 0, 0, 1, 0, 1, 0}, -1.0, {1, 0, 0, 0, 0, 1, 0, 1, 0}},
+            {{0, 1, 0, 0, 0, 1, 1, 0, 0}, 1.0, {0, 0, 1, 1, 0, 0, 0, 1, 0}},
+            {{1, 0, 0, 0, 0, 1, 0, 1, 0}, -1.0, {1, 0, 0, 0, 0, 1, 0, 1, 0}}};
+  default: fail(BX_ERR_UNSUPPORTED, "create_element: vector-valued elements are built natively on simplices only");
+  }
+}
+
+// The general construction of finite-element.cpp:84-175, 1105-1119 and dof-transformations.cpp:340-470 for a
+// vector-valued element on a simplex: B = wcoeffs [n][tdim*psize], dofs = integral moments, Piola map `map_type`.
+bx_element* build_vector_element(int cell, int degree, int map_type, Vec B, DofSet dofs, bool discontinuous)
+{
+  const int tdim = cell_tdim(cell), vs = tdim;
+  const int psize = polyset_dim(cell, BX_POLYSET_STANDARD, degree);
+  const auto topo = cell_topology(cell);
+  int ndofs = 0;
+  for (int d = 0; d <= tdim; ++d)
+    ndofs += std::accumulate(dofs.ndofs[d].begin(), dofs.ndofs[d].end(), 0);
+  if (size_t(ndofs) * vs * psize != B.size())
+    fail(BX_ERR_RUNTIME, "create_element: internal error, space and dof counts differ");
+
+  // D[(j, m)][dof] = sum_k M(dof, j, k) P_m(x_k)
+  Vec D(size_t(vs) * psize * ndofs, 0.0);
+  {
+    int dof0 = 0;
+    for (int d = 0; d <= tdim; ++d)
+      for (size_t e = 0; e < dofs.x[d].size(); ++e)
+      {
+        const int nd = dofs.ndofs[d][e];
+        if (nd == 0)
+          continue;
+        const size_t np = dofs.x[d][e].size() / tdim;
+        const Vec P = host_polyset(cell, degree, dofs.x[d][e], np);
+        const Vec& M = dofs.M[d][e];
+        for (int i = 0; i < nd; ++i)
+          for (int j = 0; j < vs; ++j)
+            for (int m = 0; m < psize; ++m)
+            {
+              double s = 0.0;
+              for (size_t k = 0; k < np; ++k)
+                s += M[(size_t(i) * vs + j) * np + k] * P[size_t(m) * np + k];
+              D[(size_t(j) * psize + m) * ndofs + dof0 + i] = s;
+            }
+        dof0 += nd;
+      }
+  }
+  // dual = B D, C = dual^-1 B
+  const int cols = vs * psize;
+  Vec dual(size_t(ndofs) * ndofs, 0.0);
+  for (int i = 0; i < ndofs; ++i)
+    for (int k = 0; k < cols; ++k)
+    {
+      const double b = B[size_t(i) * cols + k];
+      if (b == 0.0)
+        continue;
+      for (int j = 0; j < ndofs; ++j)
+        dual[size_t(i) * ndofs + j] += b * D[size_t(k) * ndofs + j];
+    }
+  const Vec C = lu_solve(dual, B, ndofs, cols); // [ndofs][vs*psize]
+
+  // entity transformations
+  std::array<Vec, 8> etrans;
+  std::array<int, 8> edim;
+  edim.fill(-1);
+  const auto maps = entity_maps(cell);
+  const auto jacs = entity_map_jacobians(cell);
+  for (size_t mi = 0; mi < maps.size(); ++mi)
+  {
+    const EntityMap& em = maps[mi];
+    const MapJac& mj = jacs[mi];
+    const int ed = cell_tdim(em.entity_type);
+    const int entity = 0; // every sub-entity of a simplex has the same type
+    const int n = discontinuous ? 0 : dofs.ndofs[ed][entity];
+    edim[em.entity_type] = n;
+    if (n == 0)
+      continue;
+    int dofstart = 0;
+    for (int d = 0; d < ed; ++d)
+      dofstart += std::accumulate(dofs.ndofs[d].begin(), dofs.ndofs[d].end(), 0);
+    const Vec& pts = dofs.x[ed][entity];
+    const size_t np = pts.size() / tdim;
+    Vec mapped(np * tdim);
+    for (size_t p = 0; p < np; ++p)
+    {
+      double pt[3] = {0, 0, 0};
+      for (int q = 0; q < tdim; ++q)
+        pt[q] = pts[p * tdim + q];
+      const auto mp = em.map(pt);
+      for (int q = 0; q < tdim; ++q)
+        mapped[p * tdim + q] = mp[q];
+    }
+    const Vec Pm = host_polyset(cell, degree, mapped, np);
+    // pushed(pt, dof k1, :) = Piola map of the reference values of basis function dofstart + k1 at the mapped point
+    const Vec& M = dofs.M[ed][entity];
+    Vec T(size_t(n) * n, 0.0);
+    for (int k1 = 0; k1 < n; ++k1)
+      for (size_t p = 0; p < np; ++p)
+      {
+        double U[3] = {0, 0, 0}, u[3] = {0, 0, 0};
+        for (int j = 0; j < vs; ++j)
+          for (int m = 0; m < psize; ++m)
+            U[j] += C[size_t(dofstart + k1) * cols + j * psize + m] * Pm[size_t(m) * np + p];
+        if (map_type == BX_MAP_COVARIANT_PIOLA) // u = K^T U  (maps.h:73-94)
+        {
+          for (int i = 0; i < tdim; ++i)
+            for (int k = 0; k < tdim; ++k)
+              u[i] += mj.K[k * tdim + i] * U[k];
+        }
+        else // contravariant: u = J U / detJ  (maps.h:100-124)
+        {
+          for (int i = 0; i < tdim; ++i)
+          {
+            for (int k = 0; k < tdim; ++k)
+              u[i] += mj.J[i * tdim + k] * U[k];
+            u[i] /= mj.detJ;
+          }
+        }
+        // T(k1, k0) += sum_i imat(k0, i, p) pushed(p, k1, i)
+        for (int k0 = 0; k0 < n; ++k0)
+        {
+          double s = 0.0;
+          for (int i = 0; i < vs; ++i)
+            s += M[(size_t(k0) * vs + i) * np + p] * u[i];
+          T[size_t(k1) * n + k0] += s;
+        }
+      }
+    etrans[em.entity_type].insert(etrans[em.entity_type].end(), T.begin(), T.end());
+  }
+
+  std::vector<int32_t> offs{0}, flat;
+  {
+    int dof = 0;
+    for (int d = 0; d <= tdim; ++d)
+      for (size_t ent = 0; ent < topo[d].size(); ++ent)
+      {
+        int cnt = dofs.ndofs[d][ent];
+        if (discontinuous)
+          cnt = (d == tdim) ? ndofs : 0;
+        for (int i = 0; i < cnt; ++i)
+          flat.push_back(dof++);
+        offs.push_back(int32_t(flat.size()));
+      }
+  }
+  if (flat.empty())
+    flat.push_back(0);
+  static const double none = 0.0;
+  bx_element_desc desc{};
+  desc.cell_type = cell;
+  desc.polyset_type = BX_POLYSET_STANDARD;
+  desc.degree = degree;
+  desc.embedded_superdegree = degree;
+  desc.map_type = map_type;
+  desc.ndofs = ndofs;
+  desc.value_size = vs;
+  desc.coeffs = C.data();
+  desc.entity_dof_offsets = offs.data();
+  desc.entity_dofs = flat.data();
+  auto set = [&](int cls, const double*& p, int& dim)
+  {
+    dim = edim[cls] < 0 ? 0 : edim[cls];
+    p = edim[cls] < 0 ? nullptr : (etrans[cls].empty() ? &none : etrans[cls].data());
+  };
+  set(BX_CELL_INTERVAL, desc.etrans_interval, desc.etrans_interval_dim);
+  set(BX_CELL_TRIANGLE, desc.etrans_triangle, desc.etrans_triangle_dim);
+  set(BX_CELL_QUADRILATERAL, desc.etrans_quadrilateral, desc.etrans_quadrilateral_dim);
+  return element_from_desc(desc);
+}
+
+void check_moment_variant(int lvariant)
+{
+  if (lvariant != 11 and lvariant != 1 and lvariant != 2)
+    fail(BX_ERR_UNSUPPORTED, "create_element: the native factory builds RT / N1curl with the legendre, equispaced "
+                             "or gll_warped variant of the moment spaces");
+}
 } // namespace
 
 // basix::element::create_lagrange for the point-evaluation variants (equispaced, gll_warped).
@@ -578,5 +1019,179 @@ bx_element* create_lagrange(int cell, int degree, int variant, bool discontinuou
   set(BX_CELL_TRIANGLE, desc.etrans_triangle, desc.etrans_triangle_dim);
   set(BX_CELL_QUADRILATERAL, desc.etrans_quadrilateral, desc.etrans_quadrilateral_dim);
   return element_from_desc(desc);
+}
+
+namespace
+{
+bx_element* create_lagrange_host(int cell, int degree, int variant, bool discontinuous)
+{
+  return create_lagrange(cell, degree, variant, discontinuous, nullptr, 0);
+}
+
+// "unset" moment-space variant: resolved per space as create_lagrange does (e-lagrange.cpp:491-500)
+int resolve_variant(int lvariant, int space_degree)
+{
+  if (lvariant != 0)
+    return lvariant;
+  if (space_degree < 3)
+    return 2; // gll_warped
+  fail(BX_ERR_RUNTIME, "Lagrange elements of degree > 2 need to be given a variant.");
+}
+
+// phi[k][q] of the orthonormal set of `degree` on `cell` at a quadrature exact to degree 2*degree, with weights
+void space_quadrature(int cell, int degree, Vec& pts, Vec& wts, Vec& phi)
+{
+  make_quadrature(cell, 2 * degree, pts, wts);
+  phi = host_polyset(cell, degree, pts, wts.size());
+}
+} // namespace
+
+// basix::element::create_rt (e-raviart-thomas.cpp:20-173), triangle / tetrahedron
+bx_element* create_rt(int cell, int degree, int lvariant, bool discontinuous)
+{
+  if (cell != BX_CELL_TRIANGLE and cell != BX_CELL_TETRAHEDRON)
+    fail(BX_ERR_RUNTIME, "Unsupported cell type");
+  if (degree < 1)
+    fail(BX_ERR_RUNTIME, "Degree must be at least 1");
+  const int tdim = cell_tdim(cell);
+  const int facet = tdim == 2 ? BX_CELL_INTERVAL : BX_CELL_TRIANGLE;
+  const int nv = polyset_dim(cell, BX_POLYSET_STANDARD, degree - 1);
+  const int ns0 = degree >= 2 ? polyset_dim(cell, BX_POLYSET_STANDARD, degree - 2) : 0;
+  const int ns = polyset_dim(facet, BX_POLYSET_STANDARD, degree - 1);
+  const int psize = polyset_dim(cell, BX_POLYSET_STANDARD, degree);
+  Vec pts, wts, phi;
+  space_quadrature(cell, degree, pts, wts, phi);
+  const size_t npts = wts.size();
+  const int rows = nv * tdim + ns, cols = psize * tdim;
+  Vec B(size_t(rows) * cols, 0.0);
+  for (int i = 0; i < tdim; ++i)
+    for (int j = 0; j < nv; ++j)
+      B[size_t(nv * i + j) * cols + psize * i + j] = 1.0;
+  // x_j * (homogeneous degree-1 part), expanded in the orthonormal set by quadrature
+  for (int j = 0; j < tdim; ++j)
+    for (int i = 0; i < ns; ++i)
+      for (int kc = 0; kc < psize - nv; ++kc)
+      {
+        double s = 0.0;
+        for (size_t k = 0; k < npts; ++k)
+          s += wts[k] * pts[k * tdim + j] * phi[size_t(ns0 + i) * npts + k] * phi[size_t(nv + kc) * npts + k];
+        B[size_t(nv * tdim + i) * cols + nv + kc + psize * j] = s;
+      }
+  orthogonalise(B, rows, cols, nv * tdim);
+
+  DofSet dofs;
+  dofs.x.resize(tdim + 1), dofs.M.resize(tdim + 1), dofs.ndofs.resize(tdim + 1);
+  for (int d = 0; d < tdim - 1; ++d)
+    add_empty(dofs, cell, d);
+  const int fv = resolve_variant(lvariant, degree - 1);
+  check_moment_variant(fv);
+  add_moments(dofs, cell, tdim - 1, 2, degree - 1, fv, 2 * degree - 1);
+  if (degree > 1)
+  {
+    const int iv = resolve_variant(lvariant, degree - 2);
+    check_moment_variant(iv);
+    add_moments(dofs, cell, tdim, 0, degree - 2, iv, 2 * degree - 2);
+  }
+  else
+    add_empty(dofs, cell, tdim);
+  return build_vector_element(cell, degree, BX_MAP_CONTRAVARIANT_PIOLA, std::move(B), std::move(dofs), discontinuous);
+}
+
+// basix::element::create_nedelec (e-nedelec.cpp:24-380), first kind, triangle / tetrahedron
+bx_element* create_nedelec(int cell, int degree, int lvariant, bool discontinuous)
+{
+  if (cell != BX_CELL_TRIANGLE and cell != BX_CELL_TETRAHEDRON)
+    fail(BX_ERR_RUNTIME, "Invalid celltype in Nedelec");
+  if (degree < 1)
+    fail(BX_ERR_RUNTIME, "Degree must be at least 1");
+  const int tdim = cell_tdim(cell);
+  const int psize = polyset_dim(cell, BX_POLYSET_STANDARD, degree);
+  const int nv = polyset_dim(cell, BX_POLYSET_STANDARD, degree - 1);
+  const int ns0 = degree >= 2 ? polyset_dim(cell, BX_POLYSET_STANDARD, degree - 2) : 0;
+  Vec pts, wts, phi;
+  space_quadrature(cell, degree, pts, wts, phi);
+  const size_t npts = wts.size();
+  const int ncols = psize - nv;
+  const int cols = psize * tdim;
+  // W[dim](i, jc) = int x_dim phi_{ns0+i} phi_{nv+jc}
+  auto moment = [&](int dim, int i, int jc)
+  {
+    double s = 0.0;
+    for (size_t k = 0; k < npts; ++k)
+      s += wts[k] * pts[k * tdim + dim] * phi[size_t(ns0 + i) * npts + k] * phi[size_t(nv + jc) * npts + k];
+    return s;
+  };
+  Vec B;
+  int rows = 0;
+  if (tdim == 2)
+  {
+    const int ns = degree;
+    rows = 2 * nv + ns;
+    B.assign(size_t(rows) * cols, 0.0);
+    for (int i = 0; i < nv; ++i)
+    {
+      B[size_t(i) * cols + i] = 1.0;
+      B[size_t(nv + i) * cols + psize + i] = 1.0;
+    }
+    for (int i = 0; i < ns; ++i)
+      for (int jc = 0; jc < ncols; ++jc)
+      {
+        B[size_t(2 * nv + i) * cols + nv + jc] = moment(1, i, jc);
+        B[size_t(2 * nv + i) * cols + nv + jc + psize] = -moment(0, i, jc);
+      }
+    orthogonalise(B, rows, cols, 2 * nv);
+  }
+  else
+  {
+    const int ns = degree * (degree + 1) / 2;
+    const int ns_remove = degree * (degree - 1) / 2;
+    rows = 6 * degree + 4 * degree * (degree - 1) + (degree - 2) * (degree - 1) * degree / 2;
+    B.assign(size_t(rows) * cols, 0.0);
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < nv; ++j)
+        B[size_t(i * nv + j) * cols + i * psize + j] = 1.0;
+    for (int i = 0; i < ns; ++i)
+      for (int jc = 0; jc < ncols; ++jc)
+      {
+        const int j = nv + jc;
+        const double w0 = moment(0, i, jc), w1 = moment(1, i, jc), w2 = moment(2, i, jc);
+        if (i >= ns_remove)
+          B[size_t(3 * nv + i - ns_remove) * cols + psize + j] = -w2;
+        B[size_t(3 * nv + i + ns - ns_remove) * cols + j] = w2;
+        B[size_t(3 * nv + i + 2 * ns - ns_remove) * cols + j] = -w1;
+        if (i >= ns_remove)
+          B[size_t(3 * nv + i - ns_remove) * cols + 2 * psize + j] = w1;
+        B[size_t(3 * nv + i + ns - ns_remove) * cols + 2 * psize + j] = -w0;
+        B[size_t(3 * nv + i + 2 * ns - ns_remove) * cols + psize + j] = w0;
+      }
+    orthogonalise(B, rows, cols, 3 * nv);
+  }
+
+  DofSet dofs;
+  dofs.x.resize(tdim + 1), dofs.M.resize(tdim + 1), dofs.ndofs.resize(tdim + 1);
+  add_empty(dofs, cell, 0);
+  const int ev = resolve_variant(lvariant, degree - 1);
+  check_moment_variant(ev);
+  add_moments(dofs, cell, 1, 1, degree - 1, ev, 2 * degree - 1);
+  if (degree > 1)
+  {
+    const int fv = resolve_variant(lvariant, degree - 2);
+    check_moment_variant(fv);
+    add_moments(dofs, cell, 2, 0, degree - 2, fv, 2 * degree - 2);
+  }
+  else
+    add_empty(dofs, cell, 2);
+  if (tdim == 3)
+  {
+    if (degree > 2)
+    {
+      const int iv = resolve_variant(lvariant, degree - 3);
+      check_moment_variant(iv);
+      add_moments(dofs, cell, 3, 0, degree - 3, iv, 2 * degree - 3);
+    }
+    else
+      add_empty(dofs, cell, 3);
+  }
+  return build_vector_element(cell, degree, BX_MAP_COVARIANT_PIOLA, std::move(B), std::move(dofs), discontinuous);
 }
 } // namespace bx

@@ -610,8 +610,13 @@ def create_element(family, celltype, degree: int, lagrange_variant=LagrangeVaria
                    dtype=np.float64) -> FiniteElement:
     """``basix.create_element`` (python/basix/finite_element.py:595-634), same argument order.
 
-    Built natively by the library (host set-up code in csrc/create.cu): the P (Lagrange) family with the
-    ``equispaced`` / ``gll_warped`` variants on interval, triangle, tetrahedron, quadrilateral and hexahedron.
+    Built natively by the library (host set-up code in csrc/create.cu):
+
+    * P (Lagrange), variants ``equispaced`` / ``gll_warped`` (``unset`` below degree 3), on interval, triangle,
+      tetrahedron, quadrilateral, hexahedron; continuous or discontinuous; optional ``dof_ordering``;
+    * RT (Raviart-Thomas) and N1E (Nedelec first kind) on triangle and tetrahedron, moment spaces of variant
+      ``legendre`` / ``equispaced`` / ``gll_warped`` (``unset`` resolves as in the reference).
+
     Other families raise ``RuntimeError``; build those with ``FiniteElement(...)`` / ``FiniteElement.from_arrays``
     from the arrays of an element constructed elsewhere."""
     if np.dtype(dtype) != np.float64:

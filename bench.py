@@ -143,12 +143,11 @@ def measured_traffic(workload, units_per_launch):
 
 
 def load_element(name, ref_args=None):
-    """P-family elements are built natively (basix_b200.create_element); the N1curl / RT elements of configs 4
-    and 5, whose construction is outside the accelerated path, come from the committed arrays of the reference
-    element (tests/golden/elements, written by tests/golden/make_golden.py)."""
+    """Elements are built natively by the library (basix_b200.create_element: P, RT, N1curl); `name` is the
+    committed array fixture of the same reference element, used only if a family is not built natively."""
     import basix_b200 as bx
 
-    if ref_args is not None and ref_args[0] == 1:
+    if ref_args is not None and ref_args[0] in (1, 2, 3):
         return bx.create_element(*ref_args)
     return bx.FiniteElement.from_arrays(np.load(os.path.join(GOLDEN, name + ".npz")))
 
@@ -241,7 +240,7 @@ class PushForward:
     def setup(self, rank):
         import torch
 
-        self.e = load_element(self.element_name)
+        self.e = load_element(self.element_name, self.ref_args)
         nc, rows = self.nc, self.rows
         J, detJ, K = random_jacobians(nc, 7 + rank)
         U = np.random.default_rng(8 + rank).standard_normal((nc, rows, 3))

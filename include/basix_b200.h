@@ -157,11 +157,16 @@ extern "C"
   void bx_element_destroy(bx_element* e);
 
   /* Native basix::create_element (finite-element.cpp create_element<T>, python basix.create_element,
-     finite_element.py:595-634): same argument order and enum values.  Built natively: family P (Lagrange),
-     variants equispaced / gll_warped (unset allowed for degree < 3), on interval, triangle, tetrahedron,
-     quadrilateral and hexahedron, continuous or discontinuous, optional dof_ordering (NULL / 0 for none).
-     Anything else returns BX_ERR_UNSUPPORTED: describe such elements with bx_element_create_from_arrays.
-     Set-up runs on the host (as in the reference); only the resulting tables go to the device. */
+     finite_element.py:595-634): same argument order and enum values.  Built natively (host set-up code, as in
+     the reference; only the resulting tables go to the device):
+       family P   (e-lagrange.cpp:457-666)       variants equispaced / gll_warped (unset allowed for degree < 3) on
+                                                  interval, triangle, tetrahedron, quadrilateral, hexahedron;
+                                                  continuous or discontinuous; optional dof_ordering
+       family RT  (e-raviart-thomas.cpp:20-173)   triangle, tetrahedron
+       family N1E (e-nedelec.cpp:24-380)          triangle, tetrahedron
+     RT / N1E take the variant of their moment spaces: legendre, equispaced or gll_warped (unset resolves per
+     moment space as the reference does).  Anything else returns BX_ERR_UNSUPPORTED: describe such elements
+     with bx_element_create_from_arrays. */
   int bx_create_element(int family, int cell_type, int degree, int lagrange_variant, int dpc_variant,
                         int discontinuous, const int32_t* dof_ordering, int n_dof_ordering, bx_element** out);
 

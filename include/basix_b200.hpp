@@ -115,7 +115,8 @@ public:
     _value_shape = d.value_shape;
   }
   /// basix::create_element (finite-element.h:1623-1628): built natively for the P family (equispaced /
-  /// gll_warped) on interval, triangle, tetrahedron, quadrilateral, hexahedron; throws otherwise.
+  /// gll_warped; interval, triangle, tetrahedron, quadrilateral, hexahedron) and for RT / N1E on triangle and
+  /// tetrahedron; throws otherwise (see bx_create_element in basix_b200.h).
   static FiniteElement create(int family, int cell_type, int degree, int lagrange_variant = 0, int dpc_variant = 0,
                               bool discontinuous = false, const std::vector<int>& dof_ordering = {})
   {

@@ -102,7 +102,7 @@ int main(int argc, char** argv)
     bool threw = false;
     try
     {
-      FiniteElement::create(/*RT*/ 2, BX_CELL_TETRAHEDRON, 2);
+      FiniteElement::create(/*BDM*/ 4, BX_CELL_TETRAHEDRON, 2);
     }
     catch (const std::runtime_error&)
     {

@@ -41,6 +41,55 @@ def test_lagrange_matches_reference(ref, cell, degree, variant):
             assert np.array_equal(np.arange(r.dim, dtype=np.int32)[src], want)
 
 
+RT, N1E, LEG = 2, 3, 11
+VECTOR_CASES = [(RT, TRI, 1, LEG), (RT, TRI, 2, LEG), (RT, TRI, 3, EQ), (RT, TET, 1, LEG), (RT, TET, 2, LEG),
+                (RT, TET, 2, 0), (RT, TET, 3, GLL), (RT, TET, 4, LEG), (N1E, TRI, 1, LEG), (N1E, TRI, 2, LEG),
+                (N1E, TRI, 3, LEG), (N1E, TET, 1, LEG), (N1E, TET, 2, GLL), (N1E, TET, 3, LEG), (N1E, TET, 4, LEG)]
+
+
+@pytest.mark.parametrize("family,cell,degree,variant", VECTOR_CASES)
+def test_rt_and_nedelec_match_reference(ref, family, cell, degree, variant):
+    """Native RT / N1curl (quadrature, moment dofs, orthogonalised spaces, Piola-mapped entity transformations)
+    against the reference: coefficient matrix, entity dofs, transformation matrices, and the composed net operator
+    of T_apply for random cell_info."""
+    import basix_b200 as bx
+
+    r = ref.RefElement(family, cell, degree, variant)
+    e = bx.create_element(family, cell, degree, variant)
+    assert e.dim == r.dim and e.value_size == r.value_size and int(e.map_type) == r.map_type
+    assert e.entity_dofs == r.entity_dofs
+    assert e.dof_transformations_are_permutations == r.dof_transformations_are_permutations
+    C, Cr = e.coefficient_matrix, r.coefficient_matrix
+    assert np.max(np.abs(C - Cr)) <= 1e-12 * np.max(np.abs(Cr))
+    names = {1: "interval", 2: "triangle", 4: "quadrilateral"}
+    et = e.entity_transformations()
+    assert sorted(et) == sorted(names[k] for k in r.entity_transformations)
+    for k, m in r.entity_transformations.items():
+        assert et[names[k]].shape == m.shape
+        assert np.max(np.abs(et[names[k]] - m), initial=0.0) <= 1e-12
+    rng = np.random.default_rng(degree)
+    for ci in rng.integers(0, 2 ** 30, 4):
+        u = rng.standard_normal((1, r.dim))
+        want = r.T_apply_batch("T_apply", u.copy(), 1, np.array([ci], dtype=np.uint32))[0]
+        got = e.net_operator(int(ci)) @ u[0]
+        assert np.max(np.abs(got - want)) <= 1e-12 * max(1.0, np.max(np.abs(want)))
+
+
+def test_vector_families_errors_and_discontinuous(ref):
+    import basix_b200 as bx
+
+    with pytest.raises(RuntimeError, match="need to be given a variant"):
+        bx.create_element(bx.ElementFamily.RT, TET, 4)  # moment space of degree 3 needs a variant (SURVEY 7.2-9)
+    with pytest.raises(RuntimeError):
+        bx.create_element(bx.ElementFamily.RT, QUAD, 1, LEG)
+    with pytest.raises(RuntimeError, match="built natively"):
+        bx.create_element(bx.ElementFamily.BDM, TRI, 1, LEG)
+    e = bx.create_element(bx.ElementFamily.N1E, TET, 2, LEG, discontinuous=True)
+    r = ref.RefElement(N1E, TET, 2, LEG, 0, True)
+    assert e.entity_dofs == r.entity_dofs and e.dof_transformations_are_identity
+    assert np.max(np.abs(e.coefficient_matrix - r.coefficient_matrix)) <= 1e-12 * np.max(np.abs(r.coefficient_matrix))
+
+
 def test_variants_discontinuous_and_ordering(ref):
     import basix_b200 as bx
 
@@ -52,8 +101,6 @@ def test_variants_discontinuous_and_ordering(ref):
         bx.create_element(bx.ElementFamily.P, TRI, 3)
     with pytest.raises(RuntimeError, match="continuous order 0"):
         bx.create_element(bx.ElementFamily.P, TRI, 0, EQ)
-    with pytest.raises(RuntimeError, match="only the P"):
-        bx.create_element(bx.ElementFamily.RT, TRI, 1)
     # discontinuous: all dofs interior, no transformations left
     e = bx.create_element(bx.ElementFamily.P, TET, 3, GLL, discontinuous=True)
     r = ref.RefElement(P, TET, 3, GLL, 0, True)
