@@ -71,6 +71,10 @@ SIGNATURES = {
     "bx_element_tabulate_path": (_I, [_P, _I]),
     "bx_element_net_operator": (_I, [_P, _I, C.c_uint32, _P, _P]),
     "bx_tabulate_f64": (_I, [_P, _I, _P, _SIZE, _I, _P, _I, _P]),
+    "bx_tabulate_f32": (_I, [_P, _I, _P, _SIZE, _I, _P, _I, _P]),
+    "bx_map_f32": (_I, [_I, _I, _P, _P, _P, _P, _SIZE, _SIZE, _I, _I, _I, _P, _I, _P]),
+    "bx_push_forward_f32": (_I, [_P, _P, _P, _P, _P, _SIZE, _SIZE, _I, _I, _I, _P, _I, _P]),
+    "bx_pull_back_f32": (_I, [_P, _P, _P, _P, _P, _SIZE, _SIZE, _I, _I, _I, _P, _I, _P]),
     "bx_map_value_size": (_I, [_I, _I, _I, _I, _I]),
     "bx_map_f64": (_I, [_I, _I, _P, _P, _P, _P, _SIZE, _SIZE, _I, _I, _I, _P, _I, _P]),
     "bx_push_forward_f64": (_I, [_P, _P, _P, _P, _P, _SIZE, _SIZE, _I, _I, _I, _P, _I, _P]),

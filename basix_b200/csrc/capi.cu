@@ -140,12 +140,13 @@ int polyset_nderivs(int c, int n)
 template <typename T>
 void polyset_tabulate_device(int cell, int ptype, int degree, int nd, const T* x, size_t npts, T* P,
                              cudaStream_t stream);
-void tabulate_device(const bx_element& e, int nd, const double* x, size_t npts, double* basis, size_t out_pts,
-                     cudaStream_t s);
+template <typename T>
+void tabulate_device(const bx_element& e, int nd, const T* x, size_t npts, T* basis, size_t out_pts, cudaStream_t s);
 int tabulate_path(const bx_element& e, int nd);
 int map_value_size(int map_type, int pull, int in_vs, int gdim, int tdim);
-void map_device(int map_type, int pull, const double* U, const double* J, const double* detJ, const double* K,
-                size_t nc, size_t rows, int in_vs, int gdim, int tdim, double* out, cudaStream_t s);
+template <typename T>
+void map_device(int map_type, int pull, const T* U, const T* J, const T* detJ, const T* K, size_t nc, size_t rows,
+                int in_vs, int gdim, int tdim, T* out, cudaStream_t s);
 template <typename T>
 void dof_transform_device(const bx_element& e, int op, T* data, size_t nc, size_t cell_size, int n,
                           const uint32_t* cell_info, cudaStream_t s);
@@ -263,8 +264,8 @@ void polyset_any(int cell, int ptype, int degree, int nd, const T* x, size_t npt
   st.sync();
 }
 
-void tabulate_any(const bx_element& e, int nd, const double* x, size_t npts, int tdim_x, double* basis, int mem,
-                  bx_stream_t stream)
+template <typename T>
+void tabulate_any(const bx_element& e, int nd, const T* x, size_t npts, int tdim_x, T* basis, int mem, bx_stream_t stream)
 {
   check_mem(mem);
   if (tdim_x != e.tdim)
@@ -276,17 +277,17 @@ void tabulate_any(const bx_element& e, int nd, const double* x, size_t npts, int
   require(x and basis, "tabulate: null pointer");
   if (mem == BX_MEM_DEVICE)
   {
-    tabulate_device(e, nd, x, npts, basis, npts, static_cast<cudaStream_t>(stream));
+    tabulate_device<T>(e, nd, x, npts, basis, npts, static_cast<cudaStream_t>(stream));
     return;
   }
   const int nder = polyset_nderivs(e.cell_type, nd);
-  const size_t per_pt = size_t(nder) * e.N * sizeof(double);
+  const size_t per_pt = size_t(nder) * e.N * sizeof(T);
   const size_t chunk = chunk_units(npts, per_pt, 32);
   TwoStreams st;
   DevBuf dx[2], dout[2];
   for (int b = 0; b < 2; ++b)
   {
-    dx[b].alloc(chunk * e.tdim * sizeof(double));
+    dx[b].alloc(chunk * e.tdim * sizeof(T));
     dout[b].alloc(chunk * per_pt);
   }
   size_t i = 0;
@@ -294,18 +295,19 @@ void tabulate_any(const bx_element& e, int nd, const double* x, size_t npts, int
   {
     const int b = int(i & 1);
     const size_t np = std::min(chunk, npts - p0);
-    BX_CUDA(cudaMemcpyAsync(dx[b].p, x + p0 * e.tdim, np * e.tdim * sizeof(double), cudaMemcpyHostToDevice, st.s[b]));
-    tabulate_device(e, nd, dx[b].as<double>(), np, dout[b].as<double>(), np, st.s[b]);
+    BX_CUDA(cudaMemcpyAsync(dx[b].p, x + p0 * e.tdim, np * e.tdim * sizeof(T), cudaMemcpyHostToDevice, st.s[b]));
+    tabulate_device<T>(e, nd, dx[b].as<T>(), np, dout[b].as<T>(), np, st.s[b]);
     // each derivative slab of the chunk is one contiguous run of np * N values on both sides
     for (int d = 0; d < nder; ++d)
-      BX_CUDA(cudaMemcpyAsync(basis + (size_t(d) * npts + p0) * e.N, dout[b].as<double>() + size_t(d) * np * e.N,
-                              np * e.N * sizeof(double), cudaMemcpyDeviceToHost, st.s[b]));
+      BX_CUDA(cudaMemcpyAsync(basis + (size_t(d) * npts + p0) * e.N, dout[b].as<T>() + size_t(d) * np * e.N,
+                              np * e.N * sizeof(T), cudaMemcpyDeviceToHost, st.s[b]));
   }
   st.sync();
 }
 
-void map_any(int map_type, int pull, const double* U, const double* J, const double* detJ, const double* K, size_t nc,
-             size_t rows, int in_vs, int gdim, int tdim, double* out, int mem, bx_stream_t stream)
+template <typename T>
+void map_any(int map_type, int pull, const T* U, const T* J, const T* detJ, const T* K, size_t nc, size_t rows, int in_vs,
+             int gdim, int tdim, T* out, int mem, bx_stream_t stream)
 {
   check_mem(mem);
   require(in_vs > 0 and gdim >= 1 and gdim <= 3 and tdim >= 1 and tdim <= 3, "map: bad value size or Jacobian shape");
@@ -315,21 +317,21 @@ void map_any(int map_type, int pull, const double* U, const double* J, const dou
   require(U and J and detJ and K and out, "map: null pointer");
   if (mem == BX_MEM_DEVICE)
   {
-    map_device(map_type, pull, U, J, detJ, K, nc, rows, in_vs, gdim, tdim, out, static_cast<cudaStream_t>(stream));
+    map_device<T>(map_type, pull, U, J, detJ, K, nc, rows, in_vs, gdim, tdim, out, static_cast<cudaStream_t>(stream));
     return;
   }
   const size_t jsz = size_t(gdim) * tdim;
-  const size_t per_cell = rows * std::max(in_vs, out_vs) * sizeof(double);
+  const size_t per_cell = rows * std::max(in_vs, out_vs) * sizeof(T);
   const size_t chunk = chunk_units(nc, per_cell, 1);
   TwoStreams st;
   DevBuf dU[2], dJ[2], dd[2], dK[2], dout[2];
   for (int b = 0; b < 2; ++b)
   {
-    dU[b].alloc(chunk * rows * in_vs * sizeof(double));
-    dJ[b].alloc(chunk * jsz * sizeof(double));
-    dd[b].alloc(chunk * sizeof(double));
-    dK[b].alloc(chunk * jsz * sizeof(double));
-    dout[b].alloc(chunk * rows * out_vs * sizeof(double));
+    dU[b].alloc(chunk * rows * in_vs * sizeof(T));
+    dJ[b].alloc(chunk * jsz * sizeof(T));
+    dd[b].alloc(chunk * sizeof(T));
+    dK[b].alloc(chunk * jsz * sizeof(T));
+    dout[b].alloc(chunk * rows * out_vs * sizeof(T));
   }
   size_t i = 0;
   for (size_t c0 = 0; c0 < nc; c0 += chunk, ++i)
@@ -337,13 +339,13 @@ void map_any(int map_type, int pull, const double* U, const double* J, const dou
     const int b = int(i & 1);
     const size_t n = std::min(chunk, nc - c0);
     cudaStream_t s = st.s[b];
-    BX_CUDA(cudaMemcpyAsync(dU[b].p, U + c0 * rows * in_vs, n * rows * in_vs * sizeof(double), cudaMemcpyHostToDevice, s));
-    BX_CUDA(cudaMemcpyAsync(dJ[b].p, J + c0 * jsz, n * jsz * sizeof(double), cudaMemcpyHostToDevice, s));
-    BX_CUDA(cudaMemcpyAsync(dd[b].p, detJ + c0, n * sizeof(double), cudaMemcpyHostToDevice, s));
-    BX_CUDA(cudaMemcpyAsync(dK[b].p, K + c0 * jsz, n * jsz * sizeof(double), cudaMemcpyHostToDevice, s));
-    map_device(map_type, pull, dU[b].as<double>(), dJ[b].as<double>(), dd[b].as<double>(), dK[b].as<double>(), n, rows,
-               in_vs, gdim, tdim, dout[b].as<double>(), s);
-    BX_CUDA(cudaMemcpyAsync(out + c0 * rows * out_vs, dout[b].p, n * rows * out_vs * sizeof(double),
+    BX_CUDA(cudaMemcpyAsync(dU[b].p, U + c0 * rows * in_vs, n * rows * in_vs * sizeof(T), cudaMemcpyHostToDevice, s));
+    BX_CUDA(cudaMemcpyAsync(dJ[b].p, J + c0 * jsz, n * jsz * sizeof(T), cudaMemcpyHostToDevice, s));
+    BX_CUDA(cudaMemcpyAsync(dd[b].p, detJ + c0, n * sizeof(T), cudaMemcpyHostToDevice, s));
+    BX_CUDA(cudaMemcpyAsync(dK[b].p, K + c0 * jsz, n * jsz * sizeof(T), cudaMemcpyHostToDevice, s));
+    map_device<T>(map_type, pull, dU[b].as<T>(), dJ[b].as<T>(), dd[b].as<T>(), dK[b].as<T>(), n, rows,
+               in_vs, gdim, tdim, dout[b].as<T>(), s);
+    BX_CUDA(cudaMemcpyAsync(out + c0 * rows * out_vs, dout[b].p, n * rows * out_vs * sizeof(T),
                             cudaMemcpyDeviceToHost, s));
   }
   st.sync();
@@ -572,7 +574,18 @@ extern "C"
         [&]()
         {
           bx::require(e != nullptr, "tabulate: null element");
-          bx::tabulate_any(*e, nd, x, npts, tdim_x, basis, mem, stream);
+          bx::tabulate_any<double>(*e, nd, x, npts, tdim_x, basis, mem, stream);
+        });
+  }
+
+  int bx_tabulate_f32(const bx_element* e, int nd, const float* x, size_t npts, int tdim_x, float* basis, int mem,
+                      bx_stream_t stream)
+  {
+    return bx::guarded(
+        [&]()
+        {
+          bx::require(e != nullptr, "tabulate: null element");
+          bx::tabulate_any<float>(*e, nd, x, npts, tdim_x, basis, mem, stream);
         });
   }
 
@@ -586,7 +599,7 @@ extern "C"
   int bx_map_f64(int map_type, int pull, const double* U, const double* J, const double* detJ, const double* K,
                  size_t nc, size_t rows, int in_vs, int gdim, int tdim, double* out, int mem, bx_stream_t stream)
   {
-    return bx::guarded([&]() { bx::map_any(map_type, pull, U, J, detJ, K, nc, rows, in_vs, gdim, tdim, out, mem, stream); });
+    return bx::guarded([&]() { bx::map_any<double>(map_type, pull, U, J, detJ, K, nc, rows, in_vs, gdim, tdim, out, mem, stream); });
   }
 
   int bx_push_forward_f64(const bx_element* e, const double* U, const double* J, const double* detJ, const double* K,
@@ -597,7 +610,7 @@ extern "C"
         [&]()
         {
           bx::require(e != nullptr, "push_forward: null element");
-          bx::map_any(e->map_type, 0, U, J, detJ, K, nc, rows, in_vs, gdim, tdim, out, mem, stream);
+          bx::map_any<double>(e->map_type, 0, U, J, detJ, K, nc, rows, in_vs, gdim, tdim, out, mem, stream);
         });
   }
 
@@ -608,7 +621,36 @@ extern "C"
         [&]()
         {
           bx::require(e != nullptr, "pull_back: null element");
-          bx::map_any(e->map_type, 1, u, J, detJ, K, nc, rows, in_vs, gdim, tdim, out, mem, stream);
+          bx::map_any<double>(e->map_type, 1, u, J, detJ, K, nc, rows, in_vs, gdim, tdim, out, mem, stream);
+        });
+  }
+
+  int bx_map_f32(int map_type, int pull, const float* U, const float* J, const float* detJ, const float* K, size_t nc,
+                 size_t rows, int in_vs, int gdim, int tdim, float* out, int mem, bx_stream_t stream)
+  {
+    return bx::guarded([&]() { bx::map_any<float>(map_type, pull, U, J, detJ, K, nc, rows, in_vs, gdim, tdim, out, mem, stream); });
+  }
+
+  int bx_push_forward_f32(const bx_element* e, const float* U, const float* J, const float* detJ, const float* K,
+                          size_t nc, size_t rows, int in_vs, int gdim, int tdim, float* out, int mem,
+                          bx_stream_t stream)
+  {
+    return bx::guarded(
+        [&]()
+        {
+          bx::require(e != nullptr, "push_forward: null element");
+          bx::map_any<float>(e->map_type, 0, U, J, detJ, K, nc, rows, in_vs, gdim, tdim, out, mem, stream);
+        });
+  }
+
+  int bx_pull_back_f32(const bx_element* e, const float* u, const float* J, const float* detJ, const float* K,
+                       size_t nc, size_t rows, int in_vs, int gdim, int tdim, float* out, int mem, bx_stream_t stream)
+  {
+    return bx::guarded(
+        [&]()
+        {
+          bx::require(e != nullptr, "pull_back: null element");
+          bx::map_any<float>(e->map_type, 1, u, J, detJ, K, nc, rows, in_vs, gdim, tdim, out, mem, stream);
         });
   }
 

@@ -23,10 +23,10 @@ constexpr int kThreads = 256;
 //   contravariant      A = "J" argument:  out[i] = (sum_k A[i][k] in[k]) / det         maps.h:100-124
 //   double covariant   A = "K" argument:  out = A^T in A                                maps.h:128-160
 //   double contravar.  A = "J" argument:  out = A in A^T / det^2                        maps.h:163-192
-template <int MAP, int RA, int CA>
+template <typename T, int MAP, int RA, int CA>
 __global__ void __launch_bounds__(kThreads)
-    map_kernel(const double* __restrict__ in, const double* __restrict__ A, const double* __restrict__ detJ,
-               int invert_det, size_t nc, size_t rows, double* __restrict__ out)
+    map_kernel(const T* __restrict__ in, const T* __restrict__ A, const T* __restrict__ detJ,
+               int invert_det, size_t nc, size_t rows, T* __restrict__ out)
 {
   constexpr int IN_VS = MAP == BX_MAP_COVARIANT_PIOLA            ? RA
                         : MAP == BX_MAP_CONTRAVARIANT_PIOLA      ? CA
@@ -41,23 +41,23 @@ __global__ void __launch_bounds__(kThreads)
   for (size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += stride)
   {
     const size_t c = t / rows;
-    double a[RA][CA];
+    T a[RA][CA];
 #pragma unroll
     for (int i = 0; i < RA; ++i)
 #pragma unroll
       for (int j = 0; j < CA; ++j)
         a[i][j] = A[c * (RA * CA) + i * CA + j];
-    double u[IN_VS];
+    T u[IN_VS];
 #pragma unroll
     for (int i = 0; i < IN_VS; ++i)
       u[i] = in[t * IN_VS + i];
-    double r[OUT_VS];
+    T r[OUT_VS];
     if constexpr (MAP == BX_MAP_COVARIANT_PIOLA)
     {
 #pragma unroll
       for (int i = 0; i < CA; ++i)
       {
-        double acc = 0;
+        T acc = 0;
 #pragma unroll
         for (int k = 0; k < RA; ++k)
           acc += a[k][i] * u[k];
@@ -66,11 +66,11 @@ __global__ void __launch_bounds__(kThreads)
     }
     else if constexpr (MAP == BX_MAP_CONTRAVARIANT_PIOLA)
     {
-      const double det = invert_det ? 1.0 / detJ[c] : detJ[c];
+      const T det = invert_det ? T(1.0) / detJ[c] : detJ[c];
 #pragma unroll
       for (int i = 0; i < RA; ++i)
       {
-        double acc = 0;
+        T acc = 0;
 #pragma unroll
         for (int k = 0; k < CA; ++k)
           acc += a[i][k] * u[k];
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
         for (int j = 0; j < CA; ++j)
         {
-          double acc = 0;
+          T acc = 0;
 #pragma unroll
           for (int k = 0; k < RA; ++k)
 #pragma unroll
@@ -95,14 +95,14 @@ __global__ void __launch_bounds__(kThreads)
     }
     else
     {
-      const double det = invert_det ? 1.0 / detJ[c] : detJ[c];
-      const double det2 = det * det;
+      const T det = invert_det ? T(1.0) / detJ[c] : detJ[c];
+      const T det2 = det * det;
 #pragma unroll
       for (int i = 0; i < RA; ++i)
 #pragma unroll
         for (int j = 0; j < RA; ++j)
         {
-          double acc = 0;
+          T acc = 0;
 #pragma unroll
           for (int k = 0; k < CA; ++k)
 #pragma unroll
@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(kThreads)
 }
 
 // identity map: u(i, j) = U(i, j)  (finite-element.h:632-640)
-__global__ void __launch_bounds__(kThreads) copy_kernel(const double* __restrict__ in, size_t n, double* __restrict__ out)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) copy_kernel(const T* __restrict__ in, size_t n, T* __restrict__ out)
 {
   const size_t stride = size_t(gridDim.x) * blockDim.x;
   for (size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += stride)
@@ -136,37 +137,35 @@ int grid_for(K kern, size_t n)
   return int(want < cap ? (want == 0 ? 1 : want) : cap);
 }
 
-template <int MAP, int RA, int CA>
-void launch_one(const double* in, const double* A, const double* detJ, int inv, size_t nc, size_t rows, double* out,
-                cudaStream_t s)
+template <typename T, int MAP, int RA, int CA>
+void launch_one(const T* in, const T* A, const T* detJ, int inv, size_t nc, size_t rows, T* out, cudaStream_t s)
 {
-  auto kern = map_kernel<MAP, RA, CA>;
+  auto kern = map_kernel<T, MAP, RA, CA>;
   kern<<<grid_for(kern, nc * rows), kThreads, 0, s>>>(in, A, detJ, inv, nc, rows, out);
 }
 
-template <int MAP, int RA>
-void launch_ca(int ca, const double* in, const double* A, const double* detJ, int inv, size_t nc, size_t rows,
-               double* out, cudaStream_t s)
+template <typename T, int MAP, int RA>
+void launch_ca(int ca, const T* in, const T* A, const T* detJ, int inv, size_t nc, size_t rows, T* out, cudaStream_t s)
 {
   switch (ca)
   {
-  case 1: launch_one<MAP, RA, 1>(in, A, detJ, inv, nc, rows, out, s); break;
-  case 2: launch_one<MAP, RA, 2>(in, A, detJ, inv, nc, rows, out, s); break;
-  case 3: launch_one<MAP, RA, 3>(in, A, detJ, inv, nc, rows, out, s); break;
+  case 1: launch_one<T, MAP, RA, 1>(in, A, detJ, inv, nc, rows, out, s); break;
+  case 2: launch_one<T, MAP, RA, 2>(in, A, detJ, inv, nc, rows, out, s); break;
+  case 3: launch_one<T, MAP, RA, 3>(in, A, detJ, inv, nc, rows, out, s); break;
   default: fail(BX_ERR_INVALID_ARG, "map: Jacobian dimensions must be between 1 and 3");
   }
   BX_LAUNCHED();
 }
 
-template <int MAP>
-void launch_ra(int ra, int ca, const double* in, const double* A, const double* detJ, int inv, size_t nc,
-               size_t rows, double* out, cudaStream_t s)
+template <typename T, int MAP>
+void launch_ra(int ra, int ca, const T* in, const T* A, const T* detJ, int inv, size_t nc, size_t rows, T* out,
+               cudaStream_t s)
 {
   switch (ra)
   {
-  case 1: launch_ca<MAP, 1>(ca, in, A, detJ, inv, nc, rows, out, s); break;
-  case 2: launch_ca<MAP, 2>(ca, in, A, detJ, inv, nc, rows, out, s); break;
-  case 3: launch_ca<MAP, 3>(ca, in, A, detJ, inv, nc, rows, out, s); break;
+  case 1: launch_ca<T, MAP, 1>(ca, in, A, detJ, inv, nc, rows, out, s); break;
+  case 2: launch_ca<T, MAP, 2>(ca, in, A, detJ, inv, nc, rows, out, s); break;
+  case 3: launch_ca<T, MAP, 3>(ca, in, A, detJ, inv, nc, rows, out, s); break;
   default: fail(BX_ERR_INVALID_ARG, "map: Jacobian dimensions must be between 1 and 3");
   }
 }
@@ -190,15 +189,16 @@ int map_value_size(int map_type, int pull, int in_vs, int gdim, int tdim)
 }
 
 // Device pointers.  U[nc][rows][in_vs], J[nc][gdim][tdim], detJ[nc], K[nc][tdim][gdim].
-void map_device(int map_type, int pull, const double* U, const double* J, const double* detJ, const double* K,
-                size_t nc, size_t rows, int in_vs, int gdim, int tdim, double* out, cudaStream_t s)
+template <typename T>
+void map_device(int map_type, int pull, const T* U, const T* J, const T* detJ, const T* K, size_t nc, size_t rows,
+                int in_vs, int gdim, int tdim, T* out, cudaStream_t s)
 {
   const int out_vs = map_value_size(map_type, pull, in_vs, gdim, tdim);
   if (nc == 0 or rows == 0)
     return;
   // The reference kernel's "J" and "K" arguments: push (J, K); pull (K, J).
-  const double* Jarg = pull ? K : J;
-  const double* Karg = pull ? J : K;
+  const T* Jarg = pull ? K : J;
+  const T* Karg = pull ? J : K;
   const int Jr = pull ? tdim : gdim, Jc = pull ? gdim : tdim; // shape of the "J" argument
   const int Kr = Jc, Kc = Jr;                                  // shape of the "K" argument
   const int dim_in = pull ? gdim : tdim;
@@ -213,26 +213,31 @@ void map_device(int map_type, int pull, const double* U, const double* J, const 
   case BX_MAP_IDENTITY:
     if (in_vs != out_vs)
       fail(BX_ERR_INVALID_ARG, "map: identity map needs matching value sizes");
-    copy_kernel<<<grid_for(copy_kernel, nc * rows * in_vs), kThreads, 0, s>>>(U, nc * rows * in_vs, out);
+    copy_kernel<T><<<grid_for(copy_kernel<T>, nc * rows * in_vs), kThreads, 0, s>>>(U, nc * rows * in_vs, out);
     BX_LAUNCHED();
     return;
   case BX_MAP_COVARIANT_PIOLA:
     need(dim_in);
-    launch_ra<BX_MAP_COVARIANT_PIOLA>(Kr, Kc, U, Karg, detJ, pull, nc, rows, out, s);
+    launch_ra<T, BX_MAP_COVARIANT_PIOLA>(Kr, Kc, U, Karg, detJ, pull, nc, rows, out, s);
     return;
   case BX_MAP_CONTRAVARIANT_PIOLA:
     need(dim_in);
-    launch_ra<BX_MAP_CONTRAVARIANT_PIOLA>(Jr, Jc, U, Jarg, detJ, pull, nc, rows, out, s);
+    launch_ra<T, BX_MAP_CONTRAVARIANT_PIOLA>(Jr, Jc, U, Jarg, detJ, pull, nc, rows, out, s);
     return;
   case BX_MAP_DOUBLE_COVARIANT_PIOLA:
     need(dim_in * dim_in);
-    launch_ra<BX_MAP_DOUBLE_COVARIANT_PIOLA>(Kr, Kc, U, Karg, detJ, pull, nc, rows, out, s);
+    launch_ra<T, BX_MAP_DOUBLE_COVARIANT_PIOLA>(Kr, Kc, U, Karg, detJ, pull, nc, rows, out, s);
     return;
   case BX_MAP_DOUBLE_CONTRAVARIANT_PIOLA:
     need(dim_in * dim_in);
-    launch_ra<BX_MAP_DOUBLE_CONTRAVARIANT_PIOLA>(Jr, Jc, U, Jarg, detJ, pull, nc, rows, out, s);
+    launch_ra<T, BX_MAP_DOUBLE_CONTRAVARIANT_PIOLA>(Jr, Jc, U, Jarg, detJ, pull, nc, rows, out, s);
     return;
   default: fail(BX_ERR_UNSUPPORTED, "Map not implemented");
   }
 }
+
+template void map_device<double>(int, int, const double*, const double*, const double*, const double*, size_t, size_t, int,
+                                 int, int, double*, cudaStream_t);
+template void map_device<float>(int, int, const float*, const float*, const float*, const float*, size_t, size_t, int, int,
+                                int, float*, cudaStream_t);
 } // namespace bx

@@ -21,6 +21,9 @@ template <typename T>
 void polyset_tabulate_device(int cell, int ptype, int degree, int nd, const T* x, size_t npts, T* P,
                              cudaStream_t stream);
 
+template <typename T>
+void tabulate_device(const bx_element& e, int nd, const T* x, size_t npts, T* basis, size_t out_pts, cudaStream_t s);
+
 namespace
 {
 constexpr int kWarps = 4;
@@ -136,11 +139,12 @@ void tabulate_generic_device(const bx_element& e, int nd, const double* x, size_
 
 namespace bx
 {
-bool tabulate_tp_device(const bx_element& e, int nd, const double* x, size_t npts, double* basis, cudaStream_t s,
-                        bool dry_run);
+template <typename T>
+bool tabulate_tp_device(const bx_element& e, int nd, const T* x, size_t npts, T* basis, cudaStream_t s, bool dry_run);
 namespace small
 {
-bool launch_any(const bx_element& e, int nd, const double* x, size_t npts, double* basis, cudaStream_t s, bool dry_run);
+template <typename T>
+bool launch_any(const bx_element& e, int nd, const T* x, size_t npts, T* basis, cudaStream_t s, bool dry_run);
 }
 namespace
 {
@@ -157,31 +161,91 @@ bool try_fused(const bx_element& e, int nd, const double* x, size_t npts, double
   default: return false;
   }
 }
+
+// float32 API on the paths that have no float instantiation (fused simplex, generic): widen the points, run the
+// float64 path on a bounded chunk, narrow the table.  All on the device, stream ordered.
+__global__ void widen_kernel(const float* __restrict__ in, size_t n, double* __restrict__ out)
+{
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = double(in[i]);
+}
+// in[nder][np * N] (dense chunk) -> out[(d * out_pts + p0) * N + i]
+__global__ void narrow_slabs_kernel(const double* __restrict__ in, size_t run, int nder, float* __restrict__ out,
+                                    size_t slab)
+{
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < run * nder; i += stride)
+  {
+    const size_t d = i / run, k = i - d * run;
+    out[d * slab + k] = float(in[i]);
+  }
+}
 } // namespace
 
 // Which device path tabulate() takes: 0 generic, 1 fused simplex, 2 tensor product, 3 register path.
 int tabulate_path(const bx_element& e, int nd)
 {
-  if (small::launch_any(e, nd, nullptr, 0, nullptr, nullptr, true))
+  if (small::launch_any<double>(e, nd, nullptr, 0, nullptr, nullptr, true))
     return 3;
   if (try_fused(e, nd, nullptr, 0, nullptr, nullptr, true))
     return 1;
-  if (tabulate_tp_device(e, nd, nullptr, 0, nullptr, nullptr, true))
+  if (tabulate_tp_device<double>(e, nd, nullptr, 0, nullptr, nullptr, true))
     return 2;
   return 0;
 }
 
-void tabulate_device(const bx_element& e, int nd, const double* x, size_t npts, double* basis, size_t out_pts,
-                     cudaStream_t s)
+template <>
+void tabulate_device<double>(const bx_element& e, int nd, const double* x, size_t npts, double* basis, size_t out_pts,
+                             cudaStream_t s)
 {
   require_device(e);
-  // the fused kernels write a dense [nder][npts][N] table; a chunk of a larger table takes the generic path
-  if (out_pts == npts and small::launch_any(e, nd, x, npts, basis, s, false))
+  // the single-kernel paths write a dense [nder][npts][N] table; a chunk of a larger table takes the generic path
+  if (out_pts == npts and small::launch_any<double>(e, nd, x, npts, basis, s, false))
     return;
   if (out_pts == npts and try_fused(e, nd, x, npts, basis, s, false))
     return;
-  if (out_pts == npts and tabulate_tp_device(e, nd, x, npts, basis, s, false))
+  if (out_pts == npts and tabulate_tp_device<double>(e, nd, x, npts, basis, s, false))
     return;
   tabulate_generic_device(e, nd, x, npts, basis, out_pts, s);
+}
+
+template <>
+void tabulate_device<float>(const bx_element& e, int nd, const float* x, size_t npts, float* basis, size_t out_pts,
+                            cudaStream_t s)
+{
+  require_device(e);
+  if (out_pts == npts and small::launch_any<float>(e, nd, x, npts, basis, s, false))
+    return;
+  if (out_pts == npts and tabulate_tp_device<float>(e, nd, x, npts, basis, s, false))
+    return;
+  const int nder = polyset_nderivs(e.cell_type, nd);
+  const size_t per_pt = (size_t(e.tdim) + size_t(nder) * e.N) * sizeof(double);
+  size_t chunk = std::max<size_t>(32, ((size_t(512) << 20) / per_pt) / 32 * 32);
+  chunk = std::min(chunk, npts);
+  double *x64 = nullptr, *b64 = nullptr;
+  BX_CUDA(cudaMallocAsync(&x64, chunk * e.tdim * sizeof(double), s));
+  BX_CUDA(cudaMallocAsync(&b64, chunk * size_t(nder) * e.N * sizeof(double), s));
+  try
+  {
+    const int grid = sm_count() * 8;
+    for (size_t p0 = 0; p0 < npts; p0 += chunk)
+    {
+      const size_t np = std::min(chunk, npts - p0);
+      widen_kernel<<<grid, 256, 0, s>>>(x + p0 * e.tdim, np * e.tdim, x64);
+      BX_LAUNCHED();
+      tabulate_device<double>(e, nd, x64, np, b64, np, s);
+      narrow_slabs_kernel<<<grid, 256, 0, s>>>(b64, np * e.N, nder, basis + p0 * e.N, out_pts * e.N);
+      BX_LAUNCHED();
+    }
+  }
+  catch (...)
+  {
+    cudaFreeAsync(x64, s);
+    cudaFreeAsync(b64, s);
+    throw;
+  }
+  BX_CUDA(cudaFreeAsync(x64, s));
+  BX_CUDA(cudaFreeAsync(b64, s));
 }
 } // namespace bx

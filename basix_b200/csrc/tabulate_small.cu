@@ -32,10 +32,12 @@ struct RegSink
   }
 };
 
-template <int TDIM, int DEG, int ND>
+// T = type of the points and of the table (double, or float for the float32 API: loads widen, stores narrow,
+// the arithmetic is double either way).
+template <int TDIM, int DEG, int ND, typename T>
 __global__ void __launch_bounds__(kThreads)
-    tabulate_small_kernel(const double* __restrict__ x, size_t npts, const double* __restrict__ Cq,
-                          double* __restrict__ basis, int N, int NP, unsigned inv_n)
+    tabulate_small_kernel(const T* __restrict__ x, size_t npts, const double* __restrict__ Cq,
+                          T* __restrict__ basis, int N, int NP, unsigned inv_n)
 {
   constexpr int NDER = jets::nder(TDIM, ND);
   constexpr int K = jets::psize(TDIM, DEG);
@@ -55,11 +57,11 @@ __global__ void __launch_bounds__(kThreads)
     double J[K][NDER];
     RegSink<K, NDER> sink{J};
     if constexpr (TDIM == 1)
-      jets::interval<DEG, ND>(x[pt], sink);
+      jets::interval<DEG, ND>(double(x[pt]), sink);
     else if constexpr (TDIM == 2)
-      jets::triangle<DEG, ND>(x[2 * pt], x[2 * pt + 1], sink);
+      jets::triangle<DEG, ND>(double(x[2 * pt]), double(x[2 * pt + 1]), sink);
     else
-      jets::tetrahedron<DEG, ND>(x[3 * pt], x[3 * pt + 1], x[3 * pt + 2], sink);
+      jets::tetrahedron<DEG, ND>(double(x[3 * pt]), double(x[3 * pt + 1]), double(x[3 * pt + 2]), sink);
 
     double* mine = tile + threadIdx.x * NP;
     for (int n = 0; n < N; ++n)
@@ -86,20 +88,20 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
     for (int d = 0; d < NDER; ++d)
     {
-      double* g = basis + (size_t(d) * npts + pt0) * N;
+      T* g = basis + (size_t(d) * npts + pt0) * N;
       const double* t = tile + d * (kThreads * NP);
       for (unsigned i = threadIdx.x; i < run; i += kThreads)
       {
         const unsigned p = __umulhi(i, inv_n), n = i - p * unsigned(N); // p = i / N (exact: i < 2^16)
-        g[i] = t[p * NP + n];
+        g[i] = static_cast<T>(t[p * NP + n]);
       }
     }
     __syncthreads();
   }
 }
 
-template <int TDIM, int DEG, int ND>
-bool launch(const bx_element& e, const double* x, size_t npts, double* basis, cudaStream_t s, bool dry_run)
+template <int TDIM, int DEG, int ND, typename T>
+bool launch(const bx_element& e, const T* x, size_t npts, T* basis, cudaStream_t s, bool dry_run)
 {
   constexpr int NDER = jets::nder(TDIM, ND);
   constexpr int K = jets::psize(TDIM, DEG);
@@ -112,7 +114,7 @@ bool launch(const bx_element& e, const double* x, size_t npts, double* basis, cu
     return true;
   if (!e.d_Cq)
     return false;
-  auto kern = tabulate_small_kernel<TDIM, DEG, ND>;
+  auto kern = tabulate_small_kernel<TDIM, DEG, ND, T>;
   if (smem > 48 * 1024)
     BX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   int per_sm = 0;
@@ -127,12 +129,13 @@ bool launch(const bx_element& e, const double* x, size_t npts, double* basis, cu
   return true;
 }
 
-#define BX_SMALL(T, DEG, ND)                                                                             \
-  if (e.tdim == T and e.superdegree == DEG and nd == ND)                                                   \
-    return launch<T, DEG, ND>(e, x, npts, basis, s, dry_run);
+#define BX_SMALL(TD, DEG, ND)                                                                            \
+  if (e.tdim == TD and e.superdegree == DEG and nd == ND)                                                   \
+    return launch<TD, DEG, ND, T>(e, x, npts, basis, s, dry_run);
 
 // Menu: every (cell, degree, nd) whose jet is at most 40 doubles.  Returns false when off the menu.
-bool launch_any(const bx_element& e, int nd, const double* x, size_t npts, double* basis, cudaStream_t s, bool dry_run)
+template <typename T>
+bool launch_any(const bx_element& e, int nd, const T* x, size_t npts, T* basis, cudaStream_t s, bool dry_run)
 {
   if (e.polyset_type != BX_POLYSET_STANDARD or e.N < 2)
     return false;
@@ -146,5 +149,7 @@ bool launch_any(const bx_element& e, int nd, const double* x, size_t npts, doubl
   BX_SMALL(3, 2, 0) BX_SMALL(3, 2, 1)
   return false;
 }
+template bool launch_any<double>(const bx_element&, int, const double*, size_t, double*, cudaStream_t, bool);
+template bool launch_any<float>(const bx_element&, int, const float*, size_t, float*, cudaStream_t, bool);
 } // namespace small
 } // namespace bx

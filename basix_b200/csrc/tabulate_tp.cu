@@ -27,11 +27,13 @@ constexpr int kWarps = 8;
 constexpr int kMaxN1 = 9;   // degree + 1
 constexpr int kMaxFun = 16; // distinct 1-D functions per axis
 
+// T = type of the points and of the table (double, or float for the float32 API; arithmetic is double)
+template <typename T>
 struct TPParams
 {
-  const double* x;
+  const T* x;
   size_t npts;
-  double* basis;
+  T* basis;
   const double* A;       // [TDIM][fstride][n1] 1-D expansion coefficients, sqrt(2q+1) norms folded in
   const int32_t* ijk;    // [N] packed i | j << 8 | k << 16
   const double* scale;   // [N]
@@ -80,8 +82,8 @@ __host__ __device__ constexpr int tp_pstride(int tdim, int nk, int F)
   return (even / 2) % 2 == 1 ? even : even + 2;
 }
 
-template <int TDIM, int ND, int MD>
-__global__ void __launch_bounds__(kWarps * 32) tabulate_tp_kernel(TPParams p)
+template <int TDIM, int ND, int MD, typename T>
+__global__ void __launch_bounds__(kWarps * 32) tabulate_tp_kernel(TPParams<T> p)
 {
   constexpr int NK = ND + 1;
   constexpr int NDER = TDIM == 2 ? (ND + 1) * (ND + 2) / 2 : (ND + 1) * (ND + 2) * (ND + 3) / 6;
@@ -123,7 +125,7 @@ __global__ void __launch_bounds__(kWarps * 32) tabulate_tp_kernel(TPParams p)
       for (int a = 0; a < TDIM; ++a)
       {
         double L[NK][kMaxN1];
-        legendre_raw<NK>(L, p.n1, p.x[pt * TDIM + a]);
+        legendre_raw<NK>(L, p.n1, double(p.x[pt * TDIM + a]));
         for (int f = 0; f < p.nfun[a]; ++f)
         {
           const double* Af = As + (a * F + f) * p.n1;
@@ -149,12 +151,12 @@ __global__ void __launch_bounds__(kWarps * 32) tabulate_tp_kernel(TPParams p)
     // address arithmetic.
     const int npt = int(min(size_t(32), p.npts - tile * 32));
     const bool plain = p.plain_stores != 0;
-    auto store = [plain](double* a, double v)
+    auto store = [plain](T* a, double v)
     {
       if (plain)
-        *a = v;
+        *a = static_cast<T>(v);
       else
-        __stcs(a, v);
+        __stcs(a, static_cast<T>(v));
     };
     int ox[MD], oy[MD], oz[MD];
 #pragma unroll
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(kWarps * 32) tabulate_tp_kernel(TPParams p)
       oy[m] = (F + cj[m]) * NKP;
       oz[m] = (2 * F + ck[m]) * NKP;
     }
-    double* os[NDER];
+    T* os[NDER];
 #pragma unroll
     for (int d = 0; d < NDER; ++d)
       os[d] = p.basis + size_t(d) * p.npts * p.N + tile * 32 * p.N + lane;
@@ -235,13 +237,13 @@ __global__ void __launch_bounds__(kWarps * 32) tabulate_tp_kernel(TPParams p)
   (void)NDER;
 }
 
-template <int TDIM, int ND>
-void launch_md(int md, const TPParams& p, size_t smem, int grid, cudaStream_t s)
+template <int TDIM, int ND, typename T>
+void launch_md(int md, const TPParams<T>& p, size_t smem, int grid, cudaStream_t s)
 {
 #define BX_TP_CASE(MD)                                                                                     \
   case MD:                                                                                                 \
   {                                                                                                        \
-    auto kern = tabulate_tp_kernel<TDIM, ND, MD>;                                                          \
+    auto kern = tabulate_tp_kernel<TDIM, ND, MD, T>;                                                          \
     if (smem > 48 * 1024)                                                                                  \
       BX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));         \
     /* persistent grid = exactly the resident CTAs, so the grid-stride loop has no ragged last wave */      \
@@ -267,8 +269,8 @@ void launch_md(int md, const TPParams& p, size_t smem, int grid, cudaStream_t s)
 } // namespace
 
 // Returns false when the element has no tensor-product factorisation or the shape is outside the menu.
-bool tabulate_tp_device(const bx_element& e, int nd, const double* x, size_t npts, double* basis, cudaStream_t s,
-                        bool dry_run)
+template <typename T>
+bool tabulate_tp_device(const bx_element& e, int nd, const T* x, size_t npts, T* basis, cudaStream_t s, bool dry_run)
 {
   if (!e.tp.valid or nd < 0 or nd > 2)
     return false;
@@ -280,7 +282,7 @@ bool tabulate_tp_device(const bx_element& e, int nd, const double* x, size_t npt
     return true;
   if (!e.tp.d_A)
     return false;
-  TPParams p;
+  TPParams<T> p;
   p.x = x;
   p.npts = npts;
   p.basis = basis;
@@ -309,21 +311,23 @@ bool tabulate_tp_device(const bx_element& e, int nd, const double* x, size_t npt
   if (tdim == 2)
   {
     if (nd == 0)
-      launch_md<2, 0>(md, p, smem, grid, s);
+      launch_md<2, 0, T>(md, p, smem, grid, s);
     else if (nd == 1)
-      launch_md<2, 1>(md, p, smem, grid, s);
+      launch_md<2, 1, T>(md, p, smem, grid, s);
     else
-      launch_md<2, 2>(md, p, smem, grid, s);
+      launch_md<2, 2, T>(md, p, smem, grid, s);
   }
   else
   {
     if (nd == 0)
-      launch_md<3, 0>(md, p, smem, grid, s);
+      launch_md<3, 0, T>(md, p, smem, grid, s);
     else if (nd == 1)
-      launch_md<3, 1>(md, p, smem, grid, s);
+      launch_md<3, 1, T>(md, p, smem, grid, s);
     else
-      launch_md<3, 2>(md, p, smem, grid, s);
+      launch_md<3, 2, T>(md, p, smem, grid, s);
   }
   return true;
 }
+template bool tabulate_tp_device<double>(const bx_element&, int, const double*, size_t, double*, cudaStream_t, bool);
+template bool tabulate_tp_device<float>(const bx_element&, int, const float*, size_t, float*, cudaStream_t, bool);
 } // namespace bx

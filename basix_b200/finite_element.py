@@ -178,6 +178,16 @@ def _stream_and_like(arg: _Arg):
     return None, lambda shape, dtype: np.empty(shape, dtype=dtype)
 
 
+def _float_dtype(a):
+    """np.float32 when ``a`` is a float32 numpy array / torch tensor, else np.float64 (everything else is
+    converted to float64, as numpy callers of the reference's float64 element expect)."""
+    if _is_torch(a):
+        import torch
+
+        return np.float32 if a.dtype == torch.float32 else np.float64
+    return np.float32 if getattr(a, "dtype", None) == np.float32 else np.float64
+
+
 def _ptr_of(a) -> int:
     return a.data_ptr() if _is_torch(a) else a.ctypes.data
 
@@ -463,9 +473,12 @@ class FiniteElement:
     def tabulate(self, n: int, x, out=None):
         """``FiniteElement.tabulate`` (finite_element.py:63-95): shape (nderivs, npts, ndofs, value_size).
 
-        ``out`` (optional, same kind as ``x``) mirrors the reference's C++ overload with the basis data as an
-        out argument (finite-element.h:454-455), avoiding the allocation on repeated calls."""
-        xa = _Arg(x, np.float64, "x")
+        float64 or float32 points (the dtype of ``x`` selects ``bx_tabulate_f64`` / ``_f32``, as the reference's
+        ``FiniteElement_float64`` / ``_float32`` classes do).  ``out`` (optional, same kind and dtype as ``x``)
+        mirrors the reference's C++ overload with the basis data as an out argument (finite-element.h:454-455),
+        avoiding the allocation on repeated calls."""
+        dt = _float_dtype(x)
+        xa = _Arg(x, dt, "x")
         if len(xa.shape) != 2:
             raise TypeError("x must be a 2-D array of shape (npts, tdim)")
         npts, xdim = xa.shape
@@ -474,17 +487,19 @@ class FiniteElement:
             raise RuntimeError(f"Point dim ({xdim}) does not match element dim ({self._tdim}).")
         shape = self.tabulate_shape(n, npts)
         if out is None:
-            out = alloc(shape, np.float64)
+            out = alloc(shape, dt)
         else:
-            oa = _Arg(out, np.float64, "out", writable=True)
+            oa = _Arg(out, dt, "out", writable=True)
             if oa.mem != xa.mem or tuple(oa.shape) != shape:
                 raise RuntimeError(f"out must have shape {shape} and live where x lives")
-        check(lib().bx_tabulate_f64(self._h, int(n), xa.ptr, npts, xdim, _ptr_of(out), xa.mem, stream))
+        fn = lib().bx_tabulate_f32 if dt is np.float32 else lib().bx_tabulate_f64
+        check(fn(self._h, int(n), xa.ptr, npts, xdim, _ptr_of(out), xa.mem, stream))
         return out
 
     def _map(self, pull: int, U, J, detJ, K):
-        Ua, Ja = _Arg(U, np.float64, "U"), _Arg(J, np.float64, "J")
-        da, Ka = _Arg(detJ, np.float64, "detJ"), _Arg(K, np.float64, "K")
+        dt = _float_dtype(U)
+        Ua, Ja = _Arg(U, dt, "U"), _Arg(J, dt, "J")
+        da, Ka = _Arg(detJ, dt, "detJ"), _Arg(K, dt, "K")
         mem = _same_mem(Ua, Ja, da, Ka)
         if len(Ua.shape) != 3 or len(Ja.shape) != 3 or len(Ka.shape) != 3 or len(da.shape) != 1:
             raise TypeError("expected U (nc, rows, vs), J (nc, gdim, tdim), detJ (nc,), K (nc, tdim, gdim)")
@@ -496,8 +511,12 @@ class FiniteElement:
         if out_vs < 0:
             check(1)
         stream, alloc = _stream_and_like(Ua)
-        out = alloc((nc, rows, out_vs), np.float64)
-        fn = lib().bx_pull_back_f64 if pull else lib().bx_push_forward_f64
+        out = alloc((nc, rows, out_vs), dt)
+        L = lib()
+        if dt is np.float32:
+            fn = L.bx_pull_back_f32 if pull else L.bx_push_forward_f32
+        else:
+            fn = L.bx_pull_back_f64 if pull else L.bx_push_forward_f64
         check(fn(self._h, Ua.ptr, Ja.ptr, da.ptr, Ka.ptr, nc, rows, in_vs, gdim, tdim, _ptr_of(out), mem, stream))
         return out
 

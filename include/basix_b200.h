@@ -204,6 +204,10 @@ extern "C"
    * validated against the element ("Point dim (..) does not match element dim (..)."). */
   int bx_tabulate_f64(const bx_element* e, int nd, const double* x, size_t npts, int tdim_x, double* basis,
                       int mem, bx_stream_t stream);
+  /* float32 points and table (the reference's FiniteElement<float>, finite-element.cpp:2051).  The element data
+     stays float64 and the arithmetic is float64; loads widen and stores narrow inside the kernels. */
+  int bx_tabulate_f32(const bx_element* e, int nd, const float* x, size_t npts, int tdim_x, float* basis,
+                      int mem, bx_stream_t stream);
 
   /* ---- push_forward / pull_back -----------------------------------------------------------
    * Replaces FiniteElement<F>::push_forward (finite-element.cpp:1971-2005), pull_back
@@ -221,6 +225,15 @@ extern "C"
   int bx_pull_back_f64(const bx_element* e, const double* u, const double* J, const double* detJ,
                        const double* K, size_t nc, size_t rows, int in_vs, int gdim, int tdim, double* out,
                        int mem, bx_stream_t stream);
+  /* float32 instantiations (float arithmetic in the reference's operation order, as FiniteElement<float>). */
+  int bx_map_f32(int map_type, int pull, const float* U, const float* J, const float* detJ, const float* K,
+                 size_t nc, size_t rows, int in_vs, int gdim, int tdim, float* out, int mem, bx_stream_t stream);
+  int bx_push_forward_f32(const bx_element* e, const float* U, const float* J, const float* detJ, const float* K,
+                          size_t nc, size_t rows, int in_vs, int gdim, int tdim, float* out, int mem,
+                          bx_stream_t stream);
+  int bx_pull_back_f32(const bx_element* e, const float* u, const float* J, const float* detJ, const float* K,
+                       size_t nc, size_t rows, int in_vs, int gdim, int tdim, float* out, int mem,
+                       bx_stream_t stream);
 
   /* ---- DOF transformations ----------------------------------------------------------------
    * Replaces T_apply and its 7 siblings (finite-element.h:1839-1998), i.e. permute_data

@@ -467,3 +467,45 @@ def test_native_create_element_tabulate_and_permute(ref, cell, degree, variant, 
         want = r.permute_batch(d.copy(), ci)
         e.permute_batch(d, ci)
         assert np.array_equal(d, want)
+
+
+# ---- float32 API (the reference's FiniteElement<float>, finite-element.cpp:2051) ----------------------------
+F32_TAB = [(P, TRI, 1, GLL, 1), (P, TET, 2, EQ, 1), (P, TET, 5, GLL, 2), (P, HEX, 4, GLL, 1), (P, QUAD, 3, GLL, 2),
+           (N1E, TET, 3, LEG, 1), (RT, TET, 2, LEG, 0)]
+
+
+@pytest.mark.parametrize("family,cell,degree,variant,nd", F32_TAB)
+def test_tabulate_float32(ref, family, cell, degree, variant, nd):
+    """Every tabulate path with float32 points / table: compared with the float64 reference evaluated at the
+    same (float-representable) points, to a few float32 ulp of the slab maximum."""
+    import torch
+
+    r, e = make_pair(ref, family, cell, degree, variant)
+    for npts in (1, 129, 20011):
+        x32 = random_points(cell, npts, seed=npts).astype(np.float32)
+        want = r.tabulate(nd, x32.astype(np.float64))
+        got = e.tabulate(nd, x32)
+        assert got.dtype == np.float32 and got.shape == want.shape
+        slab_close(got.astype(np.float64), want, 1e-6)
+        got_dev = e.tabulate(nd, torch.from_numpy(x32).cuda())
+        assert got_dev.dtype == torch.float32 and np.array_equal(got_dev.cpu().numpy(), got)
+
+
+@pytest.mark.parametrize("family,cell,degree,variant,vs", MAP_ELEMENTS)
+def test_push_pull_float32(ref, family, cell, degree, variant, vs):
+    r, e = make_pair(ref, family, cell, degree, variant)
+    tdim = {TRI: 2, TET: 3, QUAD: 2, HEX: 3, INTERVAL: 1}[cell]
+    nc, rows = 513, 3
+    J, detJ, K = jacobians(nc, tdim, tdim)
+    U = np.random.default_rng(3).standard_normal((nc, rows, vs))
+    a32 = [a.astype(np.float32) for a in (U, J, detJ, K)]
+    a64 = [a.astype(np.float64) for a in a32]
+    u = e.push_forward(*a32)
+    want = r.push_forward(*a64)
+    assert u.dtype == np.float32 and u.shape == want.shape
+    assert np.max(np.abs(u - want)) <= 2e-5 * np.max(np.abs(want))
+    back = e.pull_back(u, *a32[1:])
+    want_back = r.pull_back(u.astype(np.float64), *a64[1:])
+    # float arithmetic through K^T (.) K / J (.) J^T: the double Piola maps square the conditioning of J
+    tol = 1e-3 if vs >= 4 else 1e-4
+    assert back.dtype == np.float32 and np.max(np.abs(back - want_back)) <= tol * np.max(np.abs(want_back))
