@@ -26,8 +26,12 @@ __global__ void __launch_bounds__(kThreads)
       polyset_interval<T>(v, n, nd, x[i]);
     else if (cell == BX_CELL_TRIANGLE)
       polyset_triangle<T>(v, n, nd, x[2 * i], x[2 * i + 1]);
-    else
+    else if (cell == BX_CELL_TETRAHEDRON)
       polyset_tetrahedron<T>(v, n, nd, x[3 * i], x[3 * i + 1], x[3 * i + 2]);
+    else if (cell == BX_CELL_PRISM)
+      polyset_prism<T>(v, n, nd, x[3 * i], x[3 * i + 1], x[3 * i + 2]);
+    else
+      polyset_pyramid<T>(v, n, nd, x[3 * i], x[3 * i + 1], x[3 * i + 2]);
   }
 }
 
@@ -120,6 +124,8 @@ void polyset_tabulate_device(int cell, int ptype, int degree, int nd, const T* x
   case BX_CELL_INTERVAL:
   case BX_CELL_TRIANGLE:
   case BX_CELL_TETRAHEDRON:
+  case BX_CELL_PRISM:
+  case BX_CELL_PYRAMID:
     polyset_simplex_kernel<T>
         <<<grid_for(npts, kThreads, 16), kThreads, 0, stream>>>(cell, degree, nd, psize, x, npts, P);
     BX_LAUNCHED();
@@ -134,9 +140,6 @@ void polyset_tabulate_device(int cell, int ptype, int degree, int nd, const T* x
       polyset_tp_kernel<T, 3><<<grid_for(npts, kThreads, 8), kThreads, 0, stream>>>(degree, nd, x, npts, P);
     BX_LAUNCHED();
     return;
-  case BX_CELL_PRISM:
-  case BX_CELL_PYRAMID:
-    fail(BX_ERR_UNSUPPORTED, "Polynomial set: prism/pyramid are not implemented on the device yet");
   default:
     fail(BX_ERR_INVALID_ARG, "Polynomial set: unsupported cell type");
   }

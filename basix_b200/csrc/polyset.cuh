@@ -5,6 +5,8 @@
 //   triangle     tabulate_polyset_triangle_derivs     polyset.cpp:1601-1743
 //   tetrahedron  tabulate_polyset_tetrahedron_derivs  polyset.cpp:1745-2020
 //   quad / hex   tensor products of the interval set  polyset.cpp:2241-2702
+//   prism        tabulate_polyset_prism_derivs        polyset.cpp:2704-2911
+//   pyramid      tabulate_polyset_pyramid_derivs      polyset.cpp:2022-2239
 // How it is computed is different: each thread owns one point and walks the three-term
 // recurrences through a strided view `P(d, k)` whose backing store is either global memory
 // (generic kernel: element stride = npts, so a warp's accesses are coalesced) or a shared
@@ -263,6 +265,190 @@ __host__ __device__ void polyset_tetrahedron(View P, int n, int nd, T x0, T x1, 
         const int j = idx3(r, q, p);
         for (int d = 0; d < nder; ++d)
           P(d, j) *= norm;
+      }
+}
+
+// ---- prism: triangle (x, y) set extended by the interval set in z ---------------------------------
+// reference tabulate_polyset_prism_derivs, polyset.cpp:2704-2911
+// basis slot (n+1) idx2(q, p) + r; derivative slot idx3(kx, ky, kz)
+template <typename T, typename View>
+__host__ __device__ void polyset_prism(View P, int n, int nd, T x0, T x1, T x2)
+{
+  const int nder = (nd + 1) * (nd + 2) * (nd + 3) / 6;
+  const int n1 = n + 1;
+  const int psize = n1 * n1 * (n + 2) / 2;
+  for (int d = 0; d < nder; ++d)
+    for (int k = 0; k < psize; ++k)
+      P(d, k) = T(0.0);
+  if (n == 0)
+  {
+    P(0, 0) = static_cast<T>(sqrt(2.0));
+    return;
+  }
+  P(0, 0) = T(1.0);
+  const T X = x0 * T(2.0) - T(1.0), Y = x1 * T(2.0) - T(1.0), Z = x2 * T(2.0) - T(1.0);
+  const T lin = X + T(0.5) * Y + T(0.5);
+  const T f2 = T(1.0) - x1;
+  auto slot = [n1](int p, int q, int r) { return n1 * idx2(q, p) + r; };
+  // triangle part (r = 0, kz = 0)
+  for (int kx = 0; kx <= nd; ++kx)
+    for (int ky = 0; ky <= nd - kx; ++ky)
+    {
+      const int d = idx3(kx, ky, 0);
+      for (int p = 1; p <= n; ++p)
+      {
+        const T a = static_cast<T>(2 * p - 1) / static_cast<T>(p);
+        T v = lin * P(d, slot(p - 1, 0, 0)) * a;
+        if (kx > 0)
+          v += static_cast<T>(2 * kx) * a * P(idx3(kx - 1, ky, 0), slot(p - 1, 0, 0));
+        if (ky > 0)
+          v += static_cast<T>(ky) * a * P(idx3(kx, ky - 1, 0), slot(p - 1, 0, 0));
+        if (p > 1)
+        {
+          v -= f2 * f2 * P(d, slot(p - 2, 0, 0)) * (a - T(1.0));
+          if (ky > 0)
+            v -= static_cast<T>(ky) * (Y - T(1.0)) * P(idx3(kx, ky - 1, 0), slot(p - 2, 0, 0)) * (a - T(1.0));
+          if (ky > 1)
+            v -= static_cast<T>(ky * (ky - 1)) * P(idx3(kx, ky - 2, 0), slot(p - 2, 0, 0)) * (a - T(1.0));
+        }
+        P(d, slot(p, 0, 0)) = v;
+      }
+      for (int p = 0; p < n; ++p)
+      {
+        T v = P(d, slot(p, 0, 0)) * (Y * (T(1.5) + p) + T(0.5) + p);
+        if (ky > 0)
+          v += static_cast<T>(2 * ky) * (T(1.5) + p) * P(idx3(kx, ky - 1, 0), slot(p, 0, 0));
+        P(d, slot(p, 1, 0)) = v;
+        for (int q = 1; q < n - p; ++q)
+        {
+          T a1, a2, a3;
+          jacobi_abc<T>(2 * p + 1, q, a1, a2, a3);
+          T w = P(d, slot(p, q, 0)) * (Y * a1 + a2) - P(d, slot(p, q - 1, 0)) * a3;
+          if (ky > 0)
+            w += static_cast<T>(2 * ky) * a1 * P(idx3(kx, ky - 1, 0), slot(p, q, 0));
+          P(d, slot(p, q + 1, 0)) = w;
+        }
+      }
+    }
+  // interval recurrence in z on top of every triangle function
+  for (int kz = 0; kz <= nd; ++kz)
+    for (int r = 1; r <= n; ++r)
+    {
+      const T a = T(1.0) - T(1.0) / static_cast<T>(r);
+      for (int kx = 0; kx <= nd - kz; ++kx)
+        for (int ky = 0; ky <= nd - kx - kz; ++ky)
+        {
+          const int d = idx3(kx, ky, kz);
+          for (int p = 0; p <= n; ++p)
+            for (int q = 0; q <= n - p; ++q)
+            {
+              T v = Z * P(d, slot(p, q, r - 1)) * (a + T(1.0));
+              if (kz > 0)
+                v += static_cast<T>(2 * kz) * P(idx3(kx, ky, kz - 1), slot(p, q, r - 1)) * (a + T(1.0));
+              if (r > 1)
+                v -= P(d, slot(p, q, r - 2)) * a;
+              P(d, slot(p, q, r)) = v;
+            }
+        }
+    }
+  for (int p = 0; p <= n; ++p)
+    for (int q = 0; q <= n - p; ++q)
+      for (int r = 0; r <= n; ++r)
+      {
+        const T norm = static_cast<T>(sqrt((p + 0.5) * (p + q + 1) * (2 * r + 1)) * 2);
+        for (int d = 0; d < nder; ++d)
+          P(d, slot(p, q, r)) *= norm;
+      }
+}
+
+// ---- pyramid: rational recurrences in x / (1 - z), y / (1 - z), Jacobi (2, 0) in z ---------------------------
+// reference tabulate_polyset_pyramid_derivs, polyset.cpp:2022-2239 (the apex z = 1 takes the same special
+// values as there); basis slot (n+1)^2 p + (n+1) q + r; derivative slot idx3(kx, ky, kz)
+template <typename T, typename View>
+__host__ __device__ void polyset_pyramid(View P, int n, int nd, T x0, T x1, T x2)
+{
+  const int nder = (nd + 1) * (nd + 2) * (nd + 3) / 6;
+  const int n1 = n + 1;
+  const int psize = n1 * n1 * n1;
+  for (int d = 0; d < nder; ++d)
+    for (int k = 0; k < psize; ++k)
+      P(d, k) = T(0.0);
+  if (n == 0)
+  {
+    P(0, 0) = static_cast<T>(sqrt(3.0));
+    return;
+  }
+  P(0, 0) = T(1.0);
+  auto slot = [n1](int p, int q, int r) { return n1 * n1 * p + n1 * q + r; };
+  const bool apex = x2 == T(1.0);
+  const T x0over = apex ? T(0.0) : x0 / (T(1.0) - x2);
+  const T x1over = apex ? T(0.0) : x1 / (T(1.0) - x2);
+  const T over_z = apex ? T(1.0) : T(1.0) / (T(1.0) - x2);
+  for (int kx = 0; kx <= nd; ++kx)
+    for (int ky = 0; ky <= nd - kx; ++ky)
+      for (int kz = 0; kz <= nd - kx - ky; ++kz)
+      {
+        const int d = idx3(kx, ky, kz);
+        for (int p = 0; p <= n; ++p)
+        {
+          if (p > 0)
+          {
+            const T a = static_cast<T>(p - 1) / static_cast<T>(p);
+            T v = (a + T(1.0)) * (T(2.0) * x0over - T(1.0)) * P(d, slot(p - 1, 0, 0));
+            if (kx > 0)
+              v += (a + T(1.0)) * T(2.0) * static_cast<T>(kx) * P(idx3(kx - 1, ky, kz), slot(p - 1, 0, 0)) * over_z;
+            if (kz > 0)
+              v += static_cast<T>(kz)
+                   * ((a + T(1.0)) * P(idx3(kx, ky, kz - 1), slot(p - 1, 0, 0)) + P(idx3(kx, ky, kz - 1), slot(p, 0, 0)))
+                   * over_z;
+            if (p > 1)
+            {
+              v -= a * P(d, slot(p - 2, 0, 0));
+              if (kz > 0)
+                v += a * static_cast<T>(kz) * P(idx3(kx, ky, kz - 1), slot(p - 2, 0, 0)) * over_z;
+            }
+            P(d, slot(p, 0, 0)) = v;
+          }
+          for (int q = 1; q <= n; ++q)
+          {
+            const T a = static_cast<T>(q - 1) / static_cast<T>(q);
+            T v = (a + T(1.0)) * (T(2.0) * x1over - T(1.0)) * P(d, slot(p, q - 1, 0));
+            if (ky > 0)
+              v += T(2.0) * (a + T(1.0)) * static_cast<T>(ky) * P(idx3(kx, ky - 1, kz), slot(p, q - 1, 0)) * over_z;
+            if (kz > 0)
+              v += static_cast<T>(kz)
+                   * ((a + T(1.0)) * P(idx3(kx, ky, kz - 1), slot(p, q - 1, 0)) + P(idx3(kx, ky, kz - 1), slot(p, q, 0)))
+                   * over_z;
+            if (q > 1)
+            {
+              v -= a * P(d, slot(p, q - 2, 0));
+              if (kz > 0)
+                v += a * static_cast<T>(kz) * P(idx3(kx, ky, kz - 1), slot(p, q - 2, 0)) * over_z;
+            }
+            P(d, slot(p, q, 0)) = v;
+          }
+        }
+        for (int p = 0; p <= n; ++p)
+          for (int q = 0; q <= n; ++q)
+            for (int r = 1; r <= n; ++r)
+            {
+              T ar, br, cr;
+              jacobi_abc<T>(2, r - 1, ar, br, cr);
+              T v = P(d, slot(p, q, r - 1)) * (T(2.0) * ar * x2 + br - ar);
+              if (r > 1)
+                v -= P(d, slot(p, q, r - 2)) * cr;
+              if (kz > 0)
+                v += static_cast<T>(2 * kz) * ar * P(idx3(kx, ky, kz - 1), slot(p, q, r - 1));
+              P(d, slot(p, q, r)) = v;
+            }
+      }
+  for (int p = 0; p <= n; ++p)
+    for (int q = 0; q <= n; ++q)
+      for (int r = 0; r <= n; ++r)
+      {
+        const T norm = static_cast<T>(sqrt(2 * (q + 0.5) * (p + 0.5) * (r + 1.5)) * 2);
+        for (int d = 0; d < nder; ++d)
+          P(d, slot(p, q, r)) *= norm;
       }
 }
 

@@ -112,7 +112,9 @@ extern "C"
    * Replaces polyset::dim (polyset.cpp:3003-3050), polyset::nderivs (polyset.cpp:3052-3075)
    * and polyset::tabulate (dispatch polyset.cpp:2914-2978; python binding
    * tabulate_polynomial_set_float64, basix_wrappers.h:467-475).
-   * x[npts][tdim] row-major; P[nderivs][psize][npts] (point index fastest). */
+   * x[npts][tdim] row-major; P[nderivs][psize][npts] (point index fastest).
+   * Standard polysets of every cell type (point, interval, triangle, tetrahedron, quadrilateral, hexahedron, prism,
+   * pyramid); the macroedge polysets return BX_ERR_UNSUPPORTED. */
   int bx_polyset_dim(int cell_type, int polyset_type, int degree);
   int bx_polyset_nderivs(int cell_type, int nderiv);
   int bx_polyset_tabulate_f64(int cell_type, int polyset_type, int degree, int nderiv, const double* x,

@@ -65,8 +65,14 @@ def make_pair(ref, family, cell, degree, lvariant=0, dvariant=0, discontinuous=F
 def random_points(cell, n, seed=42):
     """Uniform points in the reference cell."""
     rng = np.random.default_rng(seed)
-    tdim = {1: 1, 2: 2, 3: 3, 4: 2, 5: 3}[cell]
+    tdim = {1: 1, 2: 2, 3: 3, 4: 2, 5: 3, 6: 3, 7: 3}[cell]
     u = rng.random((n, tdim))
+    if cell == 6:  # prism: triangle x interval
+        flip = u[:, :2].sum(axis=1) > 1
+        u[flip, :2] = 1 - u[flip, :2]
+    elif cell == 7:  # pyramid: (x, y) in [0, 1 - z]^2
+        u[:, 2] = 1 - np.cbrt(u[:, 2])
+        u[:, :2] *= (1 - u[:, 2])[:, None]
     if cell == 2:
         flip = u.sum(axis=1) > 1
         u[flip] = 1 - u[flip]

@@ -85,8 +85,11 @@ def main():
 
     vec = {}
     # polyset::tabulate
-    for cell, deg, nd in [(INTERVAL, 5, 2), (TRI, 4, 2), (TET, 5, 2), (QUAD, 3, 1), (HEX, 4, 1), (TET, 0, 1)]:
+    for cell, deg, nd in [(INTERVAL, 5, 2), (TRI, 4, 2), (TET, 5, 2), (QUAD, 3, 1), (HEX, 4, 1), (TET, 0, 1),
+                          (6, 3, 2), (7, 3, 2), (7, 0, 1)]:  # 6 = prism, 7 = pyramid
         x = random_points(cell, 37, seed=100 + cell)
+        if cell == 7:
+            x[0] = [0.0, 0.0, 1.0]  # the apex takes special values (polyset.cpp:2070-2072)
         vec[f"polyset/{cell}_{deg}_{nd}/x"] = x
         vec[f"polyset/{cell}_{deg}_{nd}/P"] = ref.tabulate_polynomial_set(cell, 0, deg, nd, x)
     # FiniteElement::tabulate on the config elements

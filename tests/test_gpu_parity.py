@@ -23,16 +23,19 @@ GLL, EQ, LEG = 2, 1, 11
 @pytest.mark.parametrize("cell,degree,nd", [(INTERVAL, 0, 0), (INTERVAL, 1, 1), (INTERVAL, 7, 3), (TRI, 0, 2),
                                             (TRI, 1, 1), (TRI, 2, 1), (TRI, 6, 3), (TET, 0, 1), (TET, 1, 0),
                                             (TET, 3, 1), (TET, 5, 2), (TET, 4, 3), (QUAD, 0, 1), (QUAD, 3, 2),
-                                            (HEX, 1, 0), (HEX, 4, 1), (HEX, 2, 2)])
+                                            (HEX, 1, 0), (HEX, 4, 1), (HEX, 2, 2), (6, 0, 1), (6, 1, 0), (6, 3, 2),
+                                            (6, 5, 1), (7, 0, 1), (7, 1, 2), (7, 4, 1), (7, 3, 3)])  # 6 prism, 7 pyramid
 def test_polyset_tabulate(ref, cell, degree, nd):
     import basix_b200 as bx
 
     x = random_points(cell, 1003)
+    if cell == 7:
+        x[:2] = [[0.0, 0.0, 1.0], [0.25, 0.5, 0.5]]  # apex (special values) and a face point
     want = ref.tabulate_polynomial_set(cell, 0, degree, nd, x)
     got = bx.tabulate_polynomial_set(cell, 0, degree, nd, x)
     assert got.shape == want.shape
     slab_close(got, want, 1e-13)
-    if cell in (INTERVAL, TRI, TET):
+    if cell in (INTERVAL, TRI, TET, 6, 7):
         # same operation order, no FMA contraction -> identical bits
         assert np.array_equal(got, want)
 

@@ -114,7 +114,8 @@ def test_anchors():
 
 
 # ---- live against the compiled reference (skipped when oracle/_ref was not built) ---------------------------
-@pytest.mark.parametrize("cell,degree,nd", [(1, 6, 2), (2, 5, 2), (3, 4, 2), (3, 6, 1), (4, 4, 2), (5, 3, 2)])
+@pytest.mark.parametrize("cell,degree,nd", [(1, 6, 2), (2, 5, 2), (3, 4, 2), (3, 6, 1), (4, 4, 2), (5, 3, 2), (6, 4, 2),
+                                            (6, 1, 3), (7, 4, 2), (7, 2, 3)])
 def test_polyset_vs_compiled_reference(ref, cell, degree, nd):
     x = random_points(cell, 211, seed=degree)
     assert np.array_equal(R.tabulate_polyset(cell, degree, nd, x), ref.tabulate_polynomial_set(cell, 0, degree, nd, x))
