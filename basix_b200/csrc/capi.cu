@@ -160,55 +160,107 @@ namespace
 // ---- host-pointer staging -----------------------------------------------------------------------------
 // Two streams, each with its own device buffers; chunk i runs H2D -> kernels -> D2H in order on
 // stream i % 2, so the copies of one chunk overlap the kernels of the other.
-struct DevBuf
+// Per-thread staging resources, created on first use and kept: two streams and a set of grow-only device
+// buffers.  (Creating streams and cudaMalloc-ing per call costs more than a small call itself; the reference API
+// is one cell / a handful of points per call.)  The pool follows the calling thread's current device.
+struct StagePool
 {
-  void* p = nullptr;
-  DevBuf() = default;
-  DevBuf(const DevBuf&) = delete;
-  DevBuf& operator=(const DevBuf&) = delete;
-  void alloc(size_t bytes)
-  {
-    release();
-    if (bytes)
-      BX_CUDA(cudaMalloc(&p, bytes));
-  }
+  static constexpr int kSlots = 5;
+  int device = -1;
+  cudaStream_t s[2] = {nullptr, nullptr};
+  void* buf[kSlots][2] = {};
+  size_t cap[kSlots][2] = {};
+
   void release()
   {
-    if (p)
-      cudaFree(p);
-    p = nullptr;
+    for (auto& st : s)
+      if (st)
+      {
+        cudaStreamSynchronize(st);
+        cudaStreamDestroy(st);
+        st = nullptr;
+      }
+    for (int i = 0; i < kSlots; ++i)
+      for (int b = 0; b < 2; ++b)
+      {
+        if (buf[i][b])
+          cudaFree(buf[i][b]);
+        buf[i][b] = nullptr;
+        cap[i][b] = 0;
+      }
+    device = -1;
   }
-  ~DevBuf() { release(); }
-  template <typename T>
-  T* as() const
+  void attach()
   {
-    return static_cast<T*>(p);
-  }
-};
-
-struct TwoStreams
-{
-  cudaStream_t s[2] = {nullptr, nullptr};
-  TwoStreams()
-  {
+    int dev = 0;
+    BX_CUDA(cudaGetDevice(&dev));
+    if (dev == device)
+      return;
+    release();
     BX_CUDA(cudaStreamCreateWithFlags(&s[0], cudaStreamNonBlocking));
     BX_CUDA(cudaStreamCreateWithFlags(&s[1], cudaStreamNonBlocking));
+    device = dev;
+  }
+  // buffer `slot` of pipeline half b, at least `bytes` large; buffers above 1 GiB are not kept between calls
+  template <typename T>
+  T* get(int slot, int b, size_t bytes)
+  {
+    if (cap[slot][b] < bytes)
+    {
+      if (buf[slot][b])
+      {
+        BX_CUDA(cudaStreamSynchronize(s[b]));
+        BX_CUDA(cudaFree(buf[slot][b]));
+        buf[slot][b] = nullptr;
+        cap[slot][b] = 0;
+      }
+      if (bytes)
+      {
+        BX_CUDA(cudaMalloc(&buf[slot][b], bytes));
+        cap[slot][b] = bytes;
+      }
+    }
+    return static_cast<T*>(buf[slot][b]);
   }
   void sync()
   {
     BX_CUDA(cudaStreamSynchronize(s[0]));
     BX_CUDA(cudaStreamSynchronize(s[1]));
   }
-  ~TwoStreams()
+  // give large buffers back so an occasional huge call does not pin device memory for the thread's lifetime
+  void trim()
   {
-    for (auto st : s)
+    for (int i = 0; i < kSlots; ++i)
+      for (int b = 0; b < 2; ++b)
+        if (cap[i][b] > (size_t(1) << 30))
+        {
+          cudaFree(buf[i][b]);
+          buf[i][b] = nullptr;
+          cap[i][b] = 0;
+        }
+  }
+  ~StagePool() { release(); }
+};
+
+// Drains both staging streams when a host-pointer call leaves its scope, also on an exception: the caller may
+// free its host buffers as soon as the call returns.
+struct DrainOnExit
+{
+  StagePool& p;
+  ~DrainOnExit()
+  {
+    for (auto st : p.s)
       if (st)
-      {
         cudaStreamSynchronize(st);
-        cudaStreamDestroy(st);
-      }
   }
 };
+
+StagePool& stage_pool()
+{
+  static thread_local StagePool pool;
+  pool.attach();
+  return pool;
+}
 
 constexpr size_t kStageBytes = size_t(256) << 20; // target size of one staged chunk (largest array)
 
@@ -242,12 +294,13 @@ void polyset_any(int cell, int ptype, int degree, int nd, const T* x, size_t npt
   }
   const size_t rows = size_t(polyset_nderivs(cell, nd)) * polyset_dim(cell, ptype, degree);
   const size_t chunk = chunk_units(npts, rows * sizeof(T), 32);
-  TwoStreams st;
-  DevBuf dx[2], dP[2];
+  StagePool& st = stage_pool();
+  DrainOnExit drain{st};
+  T *dx[2], *dP[2];
   for (int b = 0; b < 2; ++b)
   {
-    dx[b].alloc(chunk * std::max(tdim, 1) * sizeof(T));
-    dP[b].alloc(chunk * rows * sizeof(T));
+    dx[b] = st.get<T>(0, b, chunk * std::max(tdim, 1) * sizeof(T));
+    dP[b] = st.get<T>(1, b, chunk * rows * sizeof(T));
   }
   size_t i = 0;
   for (size_t p0 = 0; p0 < npts; p0 += chunk, ++i)
@@ -255,13 +308,14 @@ void polyset_any(int cell, int ptype, int degree, int nd, const T* x, size_t npt
     const int b = int(i & 1);
     const size_t np = std::min(chunk, npts - p0);
     if (tdim > 0)
-      BX_CUDA(cudaMemcpyAsync(dx[b].p, x + p0 * tdim, np * tdim * sizeof(T), cudaMemcpyHostToDevice, st.s[b]));
-    polyset_tabulate_device<T>(cell, ptype, degree, nd, dx[b].as<T>(), np, dP[b].as<T>(), st.s[b]);
+      BX_CUDA(cudaMemcpyAsync(dx[b], x + p0 * tdim, np * tdim * sizeof(T), cudaMemcpyHostToDevice, st.s[b]));
+    polyset_tabulate_device<T>(cell, ptype, degree, nd, dx[b], np, dP[b], st.s[b]);
     // table rows are npts apart on the host, np apart on the device
-    BX_CUDA(cudaMemcpy2DAsync(P + p0, npts * sizeof(T), dP[b].p, np * sizeof(T), np * sizeof(T), rows,
+    BX_CUDA(cudaMemcpy2DAsync(P + p0, npts * sizeof(T), dP[b], np * sizeof(T), np * sizeof(T), rows,
                               cudaMemcpyDeviceToHost, st.s[b]));
   }
   st.sync();
+  st.trim();
 }
 
 template <typename T>
@@ -283,26 +337,28 @@ void tabulate_any(const bx_element& e, int nd, const T* x, size_t npts, int tdim
   const int nder = polyset_nderivs(e.cell_type, nd);
   const size_t per_pt = size_t(nder) * e.N * sizeof(T);
   const size_t chunk = chunk_units(npts, per_pt, 32);
-  TwoStreams st;
-  DevBuf dx[2], dout[2];
+  StagePool& st = stage_pool();
+  DrainOnExit drain{st};
+  T *dx[2], *dout[2];
   for (int b = 0; b < 2; ++b)
   {
-    dx[b].alloc(chunk * e.tdim * sizeof(T));
-    dout[b].alloc(chunk * per_pt);
+    dx[b] = st.get<T>(0, b, chunk * e.tdim * sizeof(T));
+    dout[b] = st.get<T>(1, b, chunk * per_pt);
   }
   size_t i = 0;
   for (size_t p0 = 0; p0 < npts; p0 += chunk, ++i)
   {
     const int b = int(i & 1);
     const size_t np = std::min(chunk, npts - p0);
-    BX_CUDA(cudaMemcpyAsync(dx[b].p, x + p0 * e.tdim, np * e.tdim * sizeof(T), cudaMemcpyHostToDevice, st.s[b]));
-    tabulate_device<T>(e, nd, dx[b].as<T>(), np, dout[b].as<T>(), np, st.s[b]);
+    BX_CUDA(cudaMemcpyAsync(dx[b], x + p0 * e.tdim, np * e.tdim * sizeof(T), cudaMemcpyHostToDevice, st.s[b]));
+    tabulate_device<T>(e, nd, dx[b], np, dout[b], np, st.s[b]);
     // each derivative slab of the chunk is one contiguous run of np * N values on both sides
     for (int d = 0; d < nder; ++d)
-      BX_CUDA(cudaMemcpyAsync(basis + (size_t(d) * npts + p0) * e.N, dout[b].as<T>() + size_t(d) * np * e.N,
+      BX_CUDA(cudaMemcpyAsync(basis + (size_t(d) * npts + p0) * e.N, dout[b] + size_t(d) * np * e.N,
                               np * e.N * sizeof(T), cudaMemcpyDeviceToHost, st.s[b]));
   }
   st.sync();
+  st.trim();
 }
 
 template <typename T>
@@ -321,17 +377,26 @@ void map_any(int map_type, int pull, const T* U, const T* J, const T* detJ, cons
     return;
   }
   const size_t jsz = size_t(gdim) * tdim;
+  // Only the arrays the map reads cross the PCIe bus: the covariant maps use the reference kernel's "K" argument
+  // alone, the contravariant maps its "J" argument and detJ (maps.h:73-192); pull_back swaps J and K
+  // (finite-element.cpp:2038).  For the covariant push of BASELINE config 4 that is 96 instead of 176 bytes per cell.
+  const bool uses_Karg = map_type == BX_MAP_COVARIANT_PIOLA or map_type == BX_MAP_DOUBLE_COVARIANT_PIOLA;
+  const bool uses_Jarg = map_type == BX_MAP_CONTRAVARIANT_PIOLA or map_type == BX_MAP_DOUBLE_CONTRAVARIANT_PIOLA;
+  const bool need_det = uses_Jarg;
+  const bool need_J = pull ? uses_Karg : uses_Jarg;
+  const bool need_K = pull ? uses_Jarg : uses_Karg;
   const size_t per_cell = rows * std::max(in_vs, out_vs) * sizeof(T);
   const size_t chunk = chunk_units(nc, per_cell, 1);
-  TwoStreams st;
-  DevBuf dU[2], dJ[2], dd[2], dK[2], dout[2];
+  StagePool& st = stage_pool();
+  DrainOnExit drain{st};
+  T *dU[2], *dJ[2], *dd[2], *dK[2], *dout[2];
   for (int b = 0; b < 2; ++b)
   {
-    dU[b].alloc(chunk * rows * in_vs * sizeof(T));
-    dJ[b].alloc(chunk * jsz * sizeof(T));
-    dd[b].alloc(chunk * sizeof(T));
-    dK[b].alloc(chunk * jsz * sizeof(T));
-    dout[b].alloc(chunk * rows * out_vs * sizeof(T));
+    dU[b] = st.get<T>(0, b, chunk * rows * in_vs * sizeof(T));
+    dJ[b] = st.get<T>(1, b, chunk * jsz * sizeof(T));
+    dd[b] = st.get<T>(2, b, chunk * sizeof(T));
+    dK[b] = st.get<T>(3, b, chunk * jsz * sizeof(T));
+    dout[b] = st.get<T>(4, b, chunk * rows * out_vs * sizeof(T));
   }
   size_t i = 0;
   for (size_t c0 = 0; c0 < nc; c0 += chunk, ++i)
@@ -339,16 +404,18 @@ void map_any(int map_type, int pull, const T* U, const T* J, const T* detJ, cons
     const int b = int(i & 1);
     const size_t n = std::min(chunk, nc - c0);
     cudaStream_t s = st.s[b];
-    BX_CUDA(cudaMemcpyAsync(dU[b].p, U + c0 * rows * in_vs, n * rows * in_vs * sizeof(T), cudaMemcpyHostToDevice, s));
-    BX_CUDA(cudaMemcpyAsync(dJ[b].p, J + c0 * jsz, n * jsz * sizeof(T), cudaMemcpyHostToDevice, s));
-    BX_CUDA(cudaMemcpyAsync(dd[b].p, detJ + c0, n * sizeof(T), cudaMemcpyHostToDevice, s));
-    BX_CUDA(cudaMemcpyAsync(dK[b].p, K + c0 * jsz, n * jsz * sizeof(T), cudaMemcpyHostToDevice, s));
-    map_device<T>(map_type, pull, dU[b].as<T>(), dJ[b].as<T>(), dd[b].as<T>(), dK[b].as<T>(), n, rows,
-               in_vs, gdim, tdim, dout[b].as<T>(), s);
-    BX_CUDA(cudaMemcpyAsync(out + c0 * rows * out_vs, dout[b].p, n * rows * out_vs * sizeof(T),
-                            cudaMemcpyDeviceToHost, s));
+    BX_CUDA(cudaMemcpyAsync(dU[b], U + c0 * rows * in_vs, n * rows * in_vs * sizeof(T), cudaMemcpyHostToDevice, s));
+    if (need_J)
+      BX_CUDA(cudaMemcpyAsync(dJ[b], J + c0 * jsz, n * jsz * sizeof(T), cudaMemcpyHostToDevice, s));
+    if (need_det)
+      BX_CUDA(cudaMemcpyAsync(dd[b], detJ + c0, n * sizeof(T), cudaMemcpyHostToDevice, s));
+    if (need_K)
+      BX_CUDA(cudaMemcpyAsync(dK[b], K + c0 * jsz, n * jsz * sizeof(T), cudaMemcpyHostToDevice, s));
+    map_device<T>(map_type, pull, dU[b], dJ[b], dd[b], dK[b], n, rows, in_vs, gdim, tdim, dout[b], s);
+    BX_CUDA(cudaMemcpyAsync(out + c0 * rows * out_vs, dout[b], n * rows * out_vs * sizeof(T), cudaMemcpyDeviceToHost, s));
   }
   st.sync();
+  st.trim();
 }
 
 template <typename T>
@@ -366,18 +433,30 @@ void transform_any(const bx_element* e, int op, T* data, size_t nc, size_t cell_
     return;
   }
   // validate once (throws on bad arguments) and return early for identity elements, before staging
+  dof_transform_device<T>(*e, op, static_cast<T*>(nullptr), 0, cell_size, n, nullptr, nullptr);
   if (e->identity or e->tdim < 2 or e->slots.empty())
-  {
-    dof_transform_device<T>(*e, op, static_cast<T*>(nullptr), 0, cell_size, n, nullptr, nullptr);
     return;
-  }
   const size_t chunk = chunk_units(nc, cell_size * sizeof(T), 1);
-  TwoStreams st;
-  DevBuf dd[2], dc[2];
+  // movable range of a cell (the kernels never touch anything else): left layout u[dof][b], right layout u[b][dof]
+  const bool right = op >= 4;
+  size_t r0 = right ? size_t(e->lo_dof) : size_t(e->lo_dof) * n;
+  size_t len = right ? size_t(n - 1) * e->ndofs + e->hi_dof - e->lo_dof : size_t(e->hi_dof - e->lo_dof) * n;
+  // Strided (2-D) PCIe copies pay off only for wide rows that skip a good part of the cell: measured on B200,
+  // 320-byte rows at a 560-byte pitch (RT4) move 1.5x more cells per second than whole cells, 192-byte rows at a
+  // 224-byte pitch (P5 permute) 15x fewer.  Otherwise ship whole cells as one contiguous copy.
+  if (len * sizeof(T) < 256 or 3 * len > 2 * cell_size)
+  {
+    r0 = 0;
+    len = cell_size;
+  }
+  StagePool& st = stage_pool();
+  DrainOnExit drain{st};
+  T* dd[2];
+  uint32_t* dc[2];
   for (int b = 0; b < 2; ++b)
   {
-    dd[b].alloc(chunk * cell_size * sizeof(T));
-    dc[b].alloc(chunk * sizeof(uint32_t));
+    dd[b] = st.get<T>(0, b, chunk * cell_size * sizeof(T));
+    dc[b] = st.get<uint32_t>(1, b, chunk * sizeof(uint32_t));
   }
   size_t i = 0;
   for (size_t c0 = 0; c0 < nc; c0 += chunk, ++i)
@@ -385,12 +464,22 @@ void transform_any(const bx_element* e, int op, T* data, size_t nc, size_t cell_
     const int b = int(i & 1);
     const size_t m = std::min(chunk, nc - c0);
     cudaStream_t s = st.s[b];
-    BX_CUDA(cudaMemcpyAsync(dd[b].p, data + c0 * cell_size, m * cell_size * sizeof(T), cudaMemcpyHostToDevice, s));
-    BX_CUDA(cudaMemcpyAsync(dc[b].p, cell_info + c0, m * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-    dof_transform_device<T>(*e, op, dd[b].as<T>(), m, cell_size, n, dc[b].as<uint32_t>(), s);
-    BX_CUDA(cudaMemcpyAsync(data + c0 * cell_size, dd[b].p, m * cell_size * sizeof(T), cudaMemcpyDeviceToHost, s));
+    // only the entries that can move travel: columns [r0, r0 + len) of every cell, same pitch on both sides
+    if (len == cell_size)
+      BX_CUDA(cudaMemcpyAsync(dd[b], data + c0 * cell_size, m * cell_size * sizeof(T), cudaMemcpyHostToDevice, s));
+    else
+      BX_CUDA(cudaMemcpy2DAsync(dd[b] + r0, cell_size * sizeof(T), data + c0 * cell_size + r0,
+                                cell_size * sizeof(T), len * sizeof(T), m, cudaMemcpyHostToDevice, s));
+    BX_CUDA(cudaMemcpyAsync(dc[b], cell_info + c0, m * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    dof_transform_device<T>(*e, op, dd[b], m, cell_size, n, dc[b], s);
+    if (len == cell_size)
+      BX_CUDA(cudaMemcpyAsync(data + c0 * cell_size, dd[b], m * cell_size * sizeof(T), cudaMemcpyDeviceToHost, s));
+    else
+      BX_CUDA(cudaMemcpy2DAsync(data + c0 * cell_size + r0, cell_size * sizeof(T), dd[b] + r0,
+                                cell_size * sizeof(T), len * sizeof(T), m, cudaMemcpyDeviceToHost, s));
   }
   st.sync();
+  st.trim();
 }
 } // namespace
 } // namespace bx

@@ -23,7 +23,11 @@ constexpr int kThreads = 256;
 //   contravariant      A = "J" argument:  out[i] = (sum_k A[i][k] in[k]) / det         maps.h:100-124
 //   double covariant   A = "K" argument:  out = A^T in A                                maps.h:128-160
 //   double contravar.  A = "J" argument:  out = A in A^T / det^2                        maps.h:163-192
-template <typename T, int MAP, int RA, int CA>
+// STAGE (used when every cell has several rows): the RA x CA matrices of the cells a CTA tile of kThreads rows
+// touches are first copied to shared memory with one coalesced pass, so each thread issues global loads for its
+// own row only -- with 45 rows per cell the per-thread matrix loads otherwise outnumber the row loads 3 : 1 and
+// the load/store unit, not HBM, sets the pace.
+template <typename T, int MAP, int RA, int CA, bool STAGE>
 __global__ void __launch_bounds__(kThreads)
     map_kernel(const T* __restrict__ in, const T* __restrict__ A, const T* __restrict__ detJ,
                int invert_det, size_t nc, size_t rows, T* __restrict__ out)
@@ -38,15 +42,32 @@ __global__ void __launch_bounds__(kThreads)
                                                                   : RA * RA;
   const size_t total = nc * rows;
   const size_t stride = size_t(gridDim.x) * blockDim.x;
-  for (size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += stride)
+  extern __shared__ __align__(16) unsigned char map_smem[];
+  T* sA = reinterpret_cast<T*>(map_smem); // STAGE: [cells of this tile][RA * CA]
+  // every thread of a CTA runs the same number of iterations (tiles), so the barriers below are uniform
+  for (size_t t0 = size_t(blockIdx.x) * blockDim.x; t0 < total; t0 += stride)
   {
+    const size_t t = t0 + threadIdx.x;
+    size_t c_first = 0;
+    if constexpr (STAGE)
+    {
+      c_first = t0 / rows;
+      const size_t t_last = min(t0 + blockDim.x, total) - 1;
+      const size_t nA = (t_last / rows - c_first + 1) * (RA * CA);
+      __syncthreads(); // the previous tile's matrices are no longer read
+      for (size_t i = threadIdx.x; i < nA; i += blockDim.x)
+        sA[i] = A[c_first * (RA * CA) + i];
+      __syncthreads();
+    }
+    if (t >= total)
+      continue;
     const size_t c = t / rows;
     T a[RA][CA];
 #pragma unroll
     for (int i = 0; i < RA; ++i)
 #pragma unroll
       for (int j = 0; j < CA; ++j)
-        a[i][j] = A[c * (RA * CA) + i * CA + j];
+        a[i][j] = STAGE ? sA[(c - c_first) * (RA * CA) + i * CA + j] : A[c * (RA * CA) + i * CA + j];
     T u[IN_VS];
 #pragma unroll
     for (int i = 0; i < IN_VS; ++i)
@@ -128,10 +149,10 @@ __global__ void __launch_bounds__(kThreads) copy_kernel(const T* __restrict__ in
 
 // Persistent grid-stride launch: exactly the CTAs that are resident at once (no ragged last wave).
 template <typename K>
-int grid_for(K kern, size_t n)
+int grid_for(K kern, size_t n, size_t smem)
 {
   int per_sm = 1;
-  BX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0));
+  BX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
   const size_t want = ceil_div(n, size_t(kThreads));
   const size_t cap = size_t(sm_count()) * std::max(per_sm, 1);
   return int(want < cap ? (want == 0 ? 1 : want) : cap);
@@ -140,8 +161,18 @@ int grid_for(K kern, size_t n)
 template <typename T, int MAP, int RA, int CA>
 void launch_one(const T* in, const T* A, const T* detJ, int inv, size_t nc, size_t rows, T* out, cudaStream_t s)
 {
-  auto kern = map_kernel<T, MAP, RA, CA>;
-  kern<<<grid_for(kern, nc * rows), kThreads, 0, s>>>(in, A, detJ, inv, nc, rows, out);
+  if (rows >= 2)
+  {
+    auto kern = map_kernel<T, MAP, RA, CA, true>;
+    // a tile of kThreads rows touches at most kThreads / rows + 2 cells
+    const size_t smem = (kThreads / rows + 2) * (RA * CA) * sizeof(T);
+    kern<<<grid_for(kern, nc * rows, smem), kThreads, smem, s>>>(in, A, detJ, inv, nc, rows, out);
+  }
+  else
+  {
+    auto kern = map_kernel<T, MAP, RA, CA, false>;
+    kern<<<grid_for(kern, nc * rows, 0), kThreads, 0, s>>>(in, A, detJ, inv, nc, rows, out);
+  }
 }
 
 template <typename T, int MAP, int RA>
@@ -213,7 +244,7 @@ void map_device(int map_type, int pull, const T* U, const T* J, const T* detJ, c
   case BX_MAP_IDENTITY:
     if (in_vs != out_vs)
       fail(BX_ERR_INVALID_ARG, "map: identity map needs matching value sizes");
-    copy_kernel<T><<<grid_for(copy_kernel<T>, nc * rows * in_vs), kThreads, 0, s>>>(U, nc * rows * in_vs, out);
+    copy_kernel<T><<<grid_for(copy_kernel<T>, nc * rows * in_vs, 0), kThreads, 0, s>>>(U, nc * rows * in_vs, out);
     BX_LAUNCHED();
     return;
   case BX_MAP_COVARIANT_PIOLA:
