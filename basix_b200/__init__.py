@@ -37,6 +37,27 @@ def kernel_launch_count() -> int:
     return int(_capi.lib().bx_kernel_launch_count())
 
 
+class tabulate_paths:
+    """Context manager narrowing which tabulate kernels may be used (tests / profiling): names from
+    ``FiniteElement.tabulate_path`` -- "fused", "tensor-product", "register", "derivative-operator"; the generic
+    path is always available."""
+
+    _BITS = {"generic": 0, "fused": 1, "tensor-product": 2, "register": 3, "derivative-operator": 4}
+
+    def __init__(self, *allowed: str):
+        self.mask = 1
+        for name in allowed:
+            self.mask |= 1 << self._BITS[name]
+
+    def __enter__(self):
+        self.prev = _capi.lib().bx_tabulate_path_mask(self.mask)
+        return self
+
+    def __exit__(self, *exc):
+        _capi.lib().bx_tabulate_path_mask(self.prev)
+        return False
+
+
 def index(p: int, q: int | None = None, r: int | None = None) -> int:
     """``basix.index`` (python/basix/utils.py; cpp/basix/indexing.h:13-34)."""
     if q is None:
@@ -48,6 +69,6 @@ def index(p: int, q: int | None = None, r: int | None = None) -> int:
 
 __all__ = [
     "CellType", "DPCVariant", "create_element", "ElementFamily", "FiniteElement", "LagrangeVariant", "MapType", "PolysetType",
-    "device_count", "index", "kernel_launch_count", "polyset_dim", "polyset_nderivs", "set_device",
+    "device_count", "index", "kernel_launch_count", "polyset_dim", "polyset_nderivs", "set_device", "tabulate_paths",
     "tabulate_polynomial_set",
 ]

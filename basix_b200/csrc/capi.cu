@@ -143,6 +143,7 @@ void polyset_tabulate_device(int cell, int ptype, int degree, int nd, const T* x
 template <typename T>
 void tabulate_device(const bx_element& e, int nd, const T* x, size_t npts, T* basis, size_t out_pts, cudaStream_t s);
 int tabulate_path(const bx_element& e, int nd);
+unsigned tabulate_path_mask(unsigned mask);
 int map_value_size(int map_type, int pull, int in_vs, int gdim, int tdim);
 template <typename T>
 void map_device(int map_type, int pull, const T* U, const T* J, const T* detJ, const T* K, size_t nc, size_t rows,
@@ -655,6 +656,7 @@ extern "C"
   }
 
   int bx_element_tabulate_path(const bx_element* e, int nd) { return e ? bx::tabulate_path(*e, nd) : -1; }
+  unsigned bx_tabulate_path_mask(unsigned mask) { return bx::tabulate_path_mask(mask); }
 
   int bx_tabulate_f64(const bx_element* e, int nd, const double* x, size_t npts, int tdim_x, double* basis, int mem,
                       bx_stream_t stream)

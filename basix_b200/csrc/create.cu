@@ -38,40 +38,50 @@ namespace
 {
 using Vec = std::vector<double>;
 
-// ---- host polyset tabulate, nd = 0: P[psize][npts] ---------------------------------------------------------
-Vec host_polyset(int cell, int degree, const Vec& x, size_t npts)
+// ---- host polyset tabulate: P[nder][psize][npts] (the device recurrences of polyset.cuh, run on the host) ----
+Vec host_polyset_nd(int cell, int degree, int nd, const Vec& x, size_t npts)
 {
   const int tdim = cell_tdim(cell);
   const int psize = polyset_dim(cell, BX_POLYSET_STANDARD, degree);
-  Vec P(size_t(psize) * npts, 0.0);
+  const int nder = polyset_nderivs(cell, nd);
+  Vec P(size_t(nder) * psize * npts, 0.0);
   const int n1 = degree + 1;
-  Vec L(size_t(3) * n1);
+  Vec L(size_t(3) * (nd + 1) * n1);
   for (size_t i = 0; i < npts; ++i)
   {
     PointView<double> v{P.data() + i, npts, psize};
     switch (cell)
     {
     case BX_CELL_POINT: P[i] = 1.0; break;
-    case BX_CELL_INTERVAL: polyset_interval<double>(v, degree, 0, x[i]); break;
-    case BX_CELL_TRIANGLE: polyset_triangle<double>(v, degree, 0, x[2 * i], x[2 * i + 1]); break;
-    case BX_CELL_TETRAHEDRON: polyset_tetrahedron<double>(v, degree, 0, x[3 * i], x[3 * i + 1], x[3 * i + 2]); break;
+    case BX_CELL_INTERVAL: polyset_interval<double>(v, degree, nd, x[i]); break;
+    case BX_CELL_TRIANGLE: polyset_triangle<double>(v, degree, nd, x[2 * i], x[2 * i + 1]); break;
+    case BX_CELL_TETRAHEDRON: polyset_tetrahedron<double>(v, degree, nd, x[3 * i], x[3 * i + 1], x[3 * i + 2]); break;
+    case BX_CELL_PRISM: polyset_prism<double>(v, degree, nd, x[3 * i], x[3 * i + 1], x[3 * i + 2]); break;
+    case BX_CELL_PYRAMID: polyset_pyramid<double>(v, degree, nd, x[3 * i], x[3 * i + 1], x[3 * i + 2]); break;
     case BX_CELL_QUADRILATERAL:
     case BX_CELL_HEXAHEDRON:
     {
+      const int tsz = (nd + 1) * n1; // per-axis table L[k][p]
       for (int a = 0; a < tdim; ++a)
-        legendre_table<double>(L.data() + size_t(a) * n1, degree, 0, x[tdim * i + a]);
+        legendre_table<double>(L.data() + size_t(a) * tsz, degree, nd, x[tdim * i + a]);
       if (tdim == 2)
       {
-        for (int px = 0; px < n1; ++px)
-          for (int py = 0; py < n1; ++py)
-            P[size_t(px * n1 + py) * npts + i] = L[px] * L[n1 + py];
+        for (int kx = 0; kx <= nd; ++kx)
+          for (int ky = 0; ky <= nd - kx; ++ky)
+            for (int px = 0; px < n1; ++px)
+              for (int py = 0; py < n1; ++py)
+                v(idx2(kx, ky), px * n1 + py) = L[kx * n1 + px] * L[tsz + ky * n1 + py];
       }
       else
       {
-        for (int px = 0; px < n1; ++px)
-          for (int py = 0; py < n1; ++py)
-            for (int pz = 0; pz < n1; ++pz)
-              P[size_t((px * n1 + py) * n1 + pz) * npts + i] = L[px] * L[n1 + py] * L[2 * n1 + pz];
+        for (int kx = 0; kx <= nd; ++kx)
+          for (int ky = 0; ky <= nd - kx; ++ky)
+            for (int kz = 0; kz <= nd - kx - ky; ++kz)
+              for (int px = 0; px < n1; ++px)
+                for (int py = 0; py < n1; ++py)
+                  for (int pz = 0; pz < n1; ++pz)
+                    v(idx3(kx, ky, kz), (px * n1 + py) * n1 + pz)
+                        = L[kx * n1 + px] * L[tsz + ky * n1 + py] * L[2 * tsz + kz * n1 + pz];
       }
       break;
     }
@@ -80,6 +90,8 @@ Vec host_polyset(int cell, int degree, const Vec& x, size_t npts)
   }
   return P;
 }
+
+Vec host_polyset(int cell, int degree, const Vec& x, size_t npts) { return host_polyset_nd(cell, degree, 0, x, npts); }
 
 // ---- dense LU solve with partial pivoting: returns X with A X = B (A n x n, B n x m, row-major) -------------
 Vec lu_solve(Vec A, Vec B, int n, int m)
@@ -1194,4 +1206,14 @@ bx_element* create_nedelec(int cell, int degree, int lvariant, bool discontinuou
   }
   return build_vector_element(cell, degree, BX_MAP_COVARIANT_PIOLA, std::move(B), std::move(dofs), discontinuous);
 }
+
+// ---- host helpers shared with other set-up code (hostmath.cuh) ------------------------------------------------
+namespace host
+{
+std::vector<double> polyset_tabulate(int cell, int degree, int nd, const std::vector<double>& x, size_t npts)
+{
+  return host_polyset_nd(cell, degree, nd, x, npts);
+}
+void quadrature(int cell, int q, std::vector<double>& x, std::vector<double>& w) { make_quadrature(cell, q, x, w); }
+} // namespace host
 } // namespace bx

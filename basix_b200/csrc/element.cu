@@ -269,6 +269,7 @@ bx_element* element_from_desc(const bx_element_desc& d)
   }
   if (e->on_device)
     e->d_Cp = upload(e->Cp);
+  e->dop_cache = dop_cache_create();
 
   // ---- fused simplex kernel operand (tabulate_fused.cuh): Cs[Npad8][KS], column s = production-order
   //      position of the basis function, scaled by its norm; only when all output columns fit ----
@@ -730,6 +731,7 @@ bx_element::~bx_element()
   cudaFree(d_Cp);
   cudaFree(d_Cs);
   cudaFree(d_Cq);
+  bx::dop_cache_destroy(dop_cache);
   cudaFree(tp.d_A);
   cudaFree(tp.d_ijk);
   cudaFree(tp.d_scale);

@@ -15,6 +15,14 @@
 #include <array>
 #include <vector>
 
+namespace bx
+{
+// Per-element cache of the derivative-operator tabulate operands, one per derivative order (tabulate_dop.cu).
+struct bx_element_dop;
+bx_element_dop* dop_cache_create();
+void dop_cache_destroy(bx_element_dop* c);
+} // namespace bx
+
 struct bx_element
 {
   // ---- scalar facts -------------------------------------------------------------------------
@@ -39,6 +47,7 @@ struct bx_element
   double* d_Cs = nullptr; // fused-kernel operand (norm-scaled, production order, padded) or null
   std::vector<double> Cq; // register-path operand [N][K] (norm-scaled, production order), low-degree simplices
   double* d_Cq = nullptr;
+  bx::bx_element_dop* dop_cache = nullptr; // derivative-operator path operands, built lazily per nd
 
   // ---- tabulate: tensor-product factorisation (quad / hex), see tabulate_tp.cu -------------------------
   struct TensorProduct

@@ -14,6 +14,7 @@
 #include "fused_menu.cuh"
 
 #include <algorithm>
+#include <atomic>
 
 namespace bx
 {
@@ -146,6 +147,10 @@ namespace small
 template <typename T>
 bool launch_any(const bx_element& e, int nd, const T* x, size_t npts, T* basis, cudaStream_t s, bool dry_run);
 }
+namespace dop
+{
+bool launch_any(const bx_element& e, int nd, const double* x, size_t npts, double* basis, cudaStream_t s, bool dry_run);
+}
 namespace
 {
 // Fused simplex kernel (tabulate_fused.cuh) when the element has the operand and (degree, nd) is on the menu.
@@ -183,14 +188,26 @@ __global__ void narrow_slabs_kernel(const double* __restrict__ in, size_t run, i
 }
 } // namespace
 
-// Which device path tabulate() takes: 0 generic, 1 fused simplex, 2 tensor product, 3 register path.
+// Which single-kernel paths tabulate() may take (bit i = path i below; the generic path is always available).
+// All enabled by default; tests and profiling runs narrow the mask to reach a specific kernel.
+std::atomic<unsigned> g_path_mask{~0u};
+unsigned tabulate_path_mask(unsigned mask) { return g_path_mask.exchange(mask); }
+namespace
+{
+bool allowed(int path) { return (g_path_mask.load(std::memory_order_relaxed) >> path) & 1u; }
+} // namespace
+
+// Which device path tabulate() takes: 0 generic, 1 fused simplex, 2 tensor product, 3 register path,
+// 4 derivative-operator path.
 int tabulate_path(const bx_element& e, int nd)
 {
-  if (small::launch_any<double>(e, nd, nullptr, 0, nullptr, nullptr, true))
+  if (allowed(3) and small::launch_any<double>(e, nd, nullptr, 0, nullptr, nullptr, true))
     return 3;
-  if (try_fused(e, nd, nullptr, 0, nullptr, nullptr, true))
+  if (allowed(4) and dop::launch_any(e, nd, nullptr, 0, nullptr, nullptr, true))
+    return 4;
+  if (allowed(1) and try_fused(e, nd, nullptr, 0, nullptr, nullptr, true))
     return 1;
-  if (tabulate_tp_device<double>(e, nd, nullptr, 0, nullptr, nullptr, true))
+  if (allowed(2) and tabulate_tp_device<double>(e, nd, nullptr, 0, nullptr, nullptr, true))
     return 2;
   return 0;
 }
@@ -201,11 +218,13 @@ void tabulate_device<double>(const bx_element& e, int nd, const double* x, size_
 {
   require_device(e);
   // the single-kernel paths write a dense [nder][npts][N] table; a chunk of a larger table takes the generic path
-  if (out_pts == npts and small::launch_any<double>(e, nd, x, npts, basis, s, false))
+  if (out_pts == npts and allowed(3) and small::launch_any<double>(e, nd, x, npts, basis, s, false))
     return;
-  if (out_pts == npts and try_fused(e, nd, x, npts, basis, s, false))
+  if (out_pts == npts and allowed(4) and dop::launch_any(e, nd, x, npts, basis, s, false))
     return;
-  if (out_pts == npts and tabulate_tp_device<double>(e, nd, x, npts, basis, s, false))
+  if (out_pts == npts and allowed(1) and try_fused(e, nd, x, npts, basis, s, false))
+    return;
+  if (out_pts == npts and allowed(2) and tabulate_tp_device<double>(e, nd, x, npts, basis, s, false))
     return;
   tabulate_generic_device(e, nd, x, npts, basis, out_pts, s);
 }
@@ -215,9 +234,9 @@ void tabulate_device<float>(const bx_element& e, int nd, const float* x, size_t 
                             cudaStream_t s)
 {
   require_device(e);
-  if (out_pts == npts and small::launch_any<float>(e, nd, x, npts, basis, s, false))
+  if (out_pts == npts and allowed(3) and small::launch_any<float>(e, nd, x, npts, basis, s, false))
     return;
-  if (out_pts == npts and tabulate_tp_device<float>(e, nd, x, npts, basis, s, false))
+  if (out_pts == npts and allowed(2) and tabulate_tp_device<float>(e, nd, x, npts, basis, s, false))
     return;
   const int nder = polyset_nderivs(e.cell_type, nd);
   const size_t per_pt = (size_t(e.tdim) + size_t(nder) * e.N) * sizeof(double);

@@ -467,7 +467,7 @@ class FiniteElement:
         return tuple(int(s) for s in shape)
 
     def tabulate_path(self, nd: int) -> str:
-        return {0: "generic", 1: "fused", 2: "tensor-product", 3: "register"}.get(lib().bx_element_tabulate_path(self._h, int(nd)), "?")
+        return {0: "generic", 1: "fused", 2: "tensor-product", 3: "register", 4: "derivative-operator"}.get(lib().bx_element_tabulate_path(self._h, int(nd)), "?")
 
     # ---- hot path ---------------------------------------------------------------------------------------
     def tabulate(self, n: int, x, out=None):

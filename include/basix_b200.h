@@ -196,8 +196,12 @@ extern "C"
   int bx_element_net_operator(const bx_element* e, int op, uint32_t cell_info, int32_t* src, double* A);
   /* Which device path tabulate() will take for derivative order nd:
      0 generic (polyset kernel + DMMA contraction), 1 fused simplex kernel,
-     2 tensor-product kernel, 3 register path (low-degree simplex elements). */
+     2 tensor-product kernel, 3 register path (low-degree simplex elements),
+     4 derivative-operator kernel (simplex elements: all slabs from the values of the orthonormal set). */
   int bx_element_tabulate_path(const bx_element* e, int nd);
+  /* Testing / profiling hook: bit i of `mask` allows path i above (the generic path 0 is always available).
+     Returns the previous mask; the default allows everything. */
+  unsigned bx_tabulate_path_mask(unsigned mask);
 
   /* ---- FiniteElement::tabulate ------------------------------------------------------------
    * Replaces FiniteElement<F>::tabulate (finite-element.cpp:1834-1888; python

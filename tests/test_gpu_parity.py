@@ -328,25 +328,68 @@ FUSED = [(TET, 2, 3), (TET, 3, 3), (TET, 4, 2), (TET, 5, 2), (TET, 5, 1), (TET, 
 
 @pytest.mark.parametrize("cell,degree,nd", FUSED)
 def test_tabulate_fused_path(ref, cell, degree, nd):
+    import basix_b200 as bx
+
     r, e = make_pair(ref, P, cell, degree, GLL)
-    assert e.tabulate_path(nd) == "fused"
-    # more tiles than CTAs (ring wraps many times), ragged tail
-    for npts in (5, 32, 20011):
-        x = random_points(cell, npts, seed=npts + degree)
-        slab_close(e.tabulate(nd, x), r.tabulate(nd, x, chunk=4096, nthreads=8), 1e-12)
+    with bx.tabulate_paths("fused"):
+        assert e.tabulate_path(nd) == "fused"
+        # more tiles than CTAs (ring wraps many times), ragged tail
+        for npts in (5, 32, 20011):
+            x = random_points(cell, npts, seed=npts + degree)
+            slab_close(e.tabulate(nd, x), r.tabulate(nd, x, chunk=4096, nthreads=8), 1e-12)
+
+
+DOP = [c for c in FUSED if c != (TET, 6, 1)] + [(TET, 1, 2), (TRI, 2, 3), (TRI, 8, 3), (TRI, 6, 4), (INTERVAL, 10, 4), (INTERVAL, 1, 2)]
+
+
+@pytest.mark.parametrize("cell,degree,nd", DOP)
+def test_tabulate_derivative_operator_path(ref, cell, degree, nd):
+    """Every slab from the values of the orthonormal set (tabulate_dop.cu); also nd above the degree (zero slabs)."""
+    import basix_b200 as bx
+
+    r, e = make_pair(ref, P, cell, degree, GLL)
+    with bx.tabulate_paths("derivative-operator"):
+        assert e.tabulate_path(nd) == "derivative-operator"
+        for npts in (1, 63, 64, 65, 20011):
+            x = random_points(cell, npts, seed=npts + degree)
+            slab_close(e.tabulate(nd, x), r.tabulate(nd, x, chunk=4096, nthreads=8), 1e-12)
+
+
+def test_tabulate_operands_too_large_for_shared_memory_fall_back(ref):
+    """P6 on the tetrahedron with derivatives: the resident operands exceed shared memory -> ring-streamed fused kernel."""
+    r, e = make_pair(ref, P, TET, 6, GLL)
+    assert e.tabulate_path(0) == "derivative-operator" and e.tabulate_path(1) == "fused"
+    x = random_points(TET, 4001, seed=1)
+    slab_close(e.tabulate(1, x), r.tabulate(1, x, chunk=4096, nthreads=8), 1e-12)
+
+
+@pytest.mark.parametrize("family,cell,degree,variant,nd", [(N1E, TET, 3, LEG, 1), (RT, TET, 4, LEG, 1), (N1E, TRI, 2, LEG, 2),
+                                                           (RT, TRI, 3, LEG, 0)])
+def test_tabulate_derivative_operator_vector_valued(ref, family, cell, degree, variant, nd):
+    import basix_b200 as bx
+
+    r, e = make_pair(ref, family, cell, degree, variant)
+    with bx.tabulate_paths("derivative-operator"):
+        assert e.tabulate_path(nd) == "derivative-operator"
+        x = random_points(cell, 5003, seed=degree)
+        slab_close(e.tabulate(nd, x), r.tabulate(nd, x), 1e-12)
 
 
 def test_tabulate_fused_dof_ordering_and_device(ref):
     import torch
 
     order = list(np.random.default_rng(0).permutation(35))
+    import basix_b200 as bx
+
     r, e = make_pair(ref, P, TET, 4, GLL, dof_ordering=[int(v) for v in order])
-    assert e.tabulate_path(1) == "fused"
     x = random_points(TET, 3333, seed=9)
     want = r.tabulate(1, x)
-    slab_close(e.tabulate(1, x), want, 1e-12)
-    got = e.tabulate(1, torch.from_numpy(x).cuda())
-    slab_close(got.cpu().numpy(), want, 1e-12)
+    for path in ("fused", "derivative-operator"):
+        with bx.tabulate_paths(path):
+            assert e.tabulate_path(1) == path
+            slab_close(e.tabulate(1, x), want, 1e-12)
+            got = e.tabulate(1, torch.from_numpy(x).cuda())
+            slab_close(got.cpu().numpy(), want, 1e-12)
 
 
 # ---- tensor-product kernel (tabulate_tp.cu) -----------------------------------------------------------------
