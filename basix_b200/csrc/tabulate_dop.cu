@@ -10,21 +10,34 @@
 //   d^alpha P_k = sum_{j < dim P_{n-m}} (prod_a D_a^{alpha_a})[k][j] P_j
 //   basis[d][pt][n] = sum_{j < dim P_{n-m}} B_d[n][j] P_j(x_pt),     B_d = C * prod_a D_a^{alpha_a}   (host, once).
 // Consequences on the device:
-//   * the producers evaluate only VALUES of the orthonormal set (no derivative jets: 10x less recurrence work
-//     for nd = 2), once per point tile, into shared memory;
+//   * only VALUES of the orthonormal set are evaluated (no derivative jets: 10x less recurrence work for nd = 2),
+//     once per point, into shared memory;
 //   * slab d contracts over dim P_{n-m} columns instead of K: for P5 on the tetrahedron with nd = 2 the k-extent
 //     summed over the 10 slabs is 56 + 3*35 + 6*20 = 281 instead of 560 -- half the FP64 tensor-core work;
 //   * all B_d stay resident in shared memory for the whole kernel; vector-valued elements (N > K) fit too.
-// Kernel: persistent, warp specialised.  2 producer warps (lane = point, register recurrences of jets.cuh) fill a
-// double-buffered 64-point tile P[k][pt]; 8 consumer warps each own 16 points (two m8 row tiles, so every
-// B-fragment load feeds two DMMAs) and half of the (slab, column-group) work items; accumulators live in
-// registers for one item at a time and the m8n8 fragment is stored straight as basis[d][pt][n].
+// Kernel: persistent, one CTA per SM, twelve INDEPENDENT warps (three per SM sub-partition; eight when the operands
+// leave less room).  Each warp walks its own 16-point chunks: lanes 0..15 evaluate the recurrences for one point each
+// (compile-time (p, q, r): literal coefficients, immediate store offsets) into the warp's private, XOR-swizzled
+// shared-memory slab P[k][16]; then the warp contracts its two m8 row tiles with every slab operand on the FP64 tensor
+// cores (each B-fragment load feeds two DMMAs) and stores each m8n8 accumulator fragment straight as
+// basis[d][pt][n].  The contraction is ONE flat loop over the k-steps of all slabs, driven by a step table in shared
+// memory, with the fragments of step s+1 loaded into a second register set before the DMMAs of step s: a slab
+// boundary costs only its stores, not a pipeline drain (a separate loop per slab reached 65 % of the DMMA peak for
+// one warp per sub-partition and 80 % for two, tools/dmma_loop.cu).  No block barrier and no mbarrier after set-up:
+// DFMA and DMMA share one execution pipe on B200 (tools/mixed_fp64.cu: 37 TFLOP/s alone or mixed), so dedicated
+// producer warps starve behind the DMMA stream and stall every consumer waiting on their tile (measured: 2 ms of
+// 12.5 ms per 10 M points); with independent warps a warp that is producing or storing simply leaves the pipe to
+// the other warps of its sub-partition.  Measured on P5 / nd = 2, 10 M points: 10.1 ms (84 % of the DMMA peak on
+// the flops this algorithm executes), against 20.9 ms for the dense fused kernel.
 // Parity: 2.8e-14 * max|ref| per slab against the reference on P5 / nd = 2 (bar: 1e-12).
 #include "element.cuh"
 #include "hostmath.cuh"
 #include "jets.cuh"
 
 #include <algorithm>
+#include <type_traits>
+#include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 
@@ -32,34 +45,9 @@ namespace bx
 {
 namespace dop
 {
-constexpr int kTilePts = 64;
-constexpr int kConsumers = 8;
-constexpr int kProducers = 2;
-constexpr int kThreads = 32 * (kConsumers + kProducers);
-constexpr int kPStride = 68; // doubles between consecutive basis rows of a point tile (== 4 mod 16: conflict free)
-constexpr int kMaxNT = 8;    // 8-column output tiles per work item
-constexpr int kMaxItems = 96;
+constexpr int kChunkPts = 16; // points per warp chunk: two m8 row tiles
+constexpr int kMaxNT = 7;     // 8-column output tiles per column group
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mbar_init(uint32_t a, uint32_t count)
-{
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t a)
-{
-  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(a) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity)
-{
-  uint32_t ok;
-  do
-  {
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok)
-                 : "r"(a), "r"(parity)
-                 : "memory");
-  } while (!ok);
-}
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
 {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -67,41 +55,189 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
       : "d"(a), "d"(b));
 }
 
-// One work item: NT column tiles of slab `slab`, contraction over 4 * ksteps rows of the point tile.
-struct Item
+// One k-step of the flat contraction loop: rows 4 ks .. 4 ks + 3 of the point slab against slab operand `slab`.
+struct __align__(16) Step
 {
-  int boff;    // offset (doubles) of B_slab row 0 inside the operand block
-  int ksteps;  // ceil(dim P_{n-m} / 4)
-  int kstride; // row stride of B_slab (>= 4 * ksteps, == 4 mod 16)
-  int n0;      // first output column
-  int nt;      // column tiles (<= kMaxNT)
-  int slab;    // derivative slab index
-  int pad0, pad1;
+  int boff;    // offset (doubles) of B_slab[0][4 ks] inside the operand block
+  int kstride; // row stride of B_slab (>= 4 * ksteps, == 4 mod 8: conflict-free fragment loads)
+  int aoff;    // offset (doubles) of slab row 4 ks: 64 ks
+  int last;    // 0, or 1 + derivative slab index when this is the last k-step of that slab
 };
 
 struct Params
 {
   const double* x;
   size_t npts;
-  const double* B;       // all slabs
-  const Item* items;     // half 0 first, then half 1
-  const int* rowmap;     // production order -> natural basis index
+  const double* B;   // all slab operands
+  const Step* steps; // nsteps + 1 entries (the last one repeats its predecessor: prefetch target)
   double* basis;
-  int N, K, kpad;        // output columns, basis functions, rows of the point tile (multiple of 4)
-  int b_doubles, nitems, split; // items [0, split) belong to half 0, [split, nitems) to half 1
+  int N, K, kpad;    // output columns, basis functions, rows of a point slab (multiple of 4)
+  int b_doubles, nsteps;
+  int debug;         // profiling only: bit 0 = no stores, bit 2 = record phase clocks into `timing`
+  unsigned long long* timing; // [warp][3]: produce, contract, chunks
 };
 
-template <int K>
-struct TileSink
+// Point slab: element (k, c), c = point 0..15, lives at 16 k + (c ^ 4 (k & 3)); both the producer's row writes
+// (16 lanes, fixed k) and the consumers' A-fragment reads (k = 4 ks + t, c = g or g + 8) are conflict free.
+struct SlabSink
 {
-  double* col;       // &P[0][this point]
-  const int* rowmap; // shared memory
-  __device__ __forceinline__ void operator()(int s, const double (&J)[1]) const { col[rowmap[s] * kPStride] = J[0]; }
+  double* base[4]; // slab + (c ^ 4 m), m = k & 3: row k is one store at a compile-time offset
+  template <int SLOT>
+  __device__ __forceinline__ void put(double v) const
+  {
+    base[SLOT & 3][16 * SLOT] = v;
+  }
 };
 
-template <int NT>
-__device__ __forceinline__ void run_item(const Item& it, const double* __restrict__ Pa, const double* __restrict__ Bs,
-                                         double* __restrict__ basis, size_t npts, int N, size_t pt, int g, int t)
+// ---- values of the orthonormal set, un-normalised (norms are folded into the operands) --------------------
+// The same three-term recurrences as jets.cuh with ND = 0 (reference polyset.cpp:66-120, 1601-1743, 1745-2020),
+// written with compile-time (p, q, r) so every recurrence coefficient is a literal and every value goes to its
+// natural basis slot (indexing.h:13-34) at an immediate shared-memory offset.
+template <int I, int E, typename F>
+__device__ __forceinline__ void static_for(F&& f)
+{
+  if constexpr (I < E)
+  {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, E>(f);
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void values_interval(double x0, const SlabSink& out)
+{
+  const double X = x0 * 2.0 - 1.0;
+  double J1 = 1.0, J2 = 0.0;
+  out.put<0>(J1);
+  static_for<1, N + 1>(
+      [&](auto P)
+      {
+        constexpr int p = decltype(P)::value;
+        constexpr double a = 1.0 - 1.0 / double(p);
+        double v = (X * (a + 1.0)) * J1;
+        if constexpr (p > 1)
+          v -= a * J2;
+        J2 = J1;
+        J1 = v;
+        out.put<p>(J1);
+      });
+}
+
+template <int N>
+__device__ __forceinline__ void values_triangle(double x0, double x1, const SlabSink& out)
+{
+  const double X = x0 * 2.0 - 1.0, Y = x1 * 2.0 - 1.0;
+  const double lin = X + 0.5 * Y + 0.5;
+  const double f3 = 1.0 - x1;
+  const double f3sq = f3 * f3;
+  double Jp = 1.0, Jpm = 0.0;
+  static_for<0, N + 1>(
+      [&](auto P)
+      {
+        constexpr int p = decltype(P)::value;
+        if constexpr (p > 0)
+        {
+          constexpr double a = double(2 * p - 1) / double(p);
+          double v = (lin * a) * Jp;
+          if constexpr (p > 1)
+            v -= (f3sq * (a - 1.0)) * Jpm;
+          Jpm = Jp;
+          Jp = v;
+        }
+        out.put<idx2(0, p)>(Jp);
+        double Jq = Jp, Jqm = 0.0;
+        static_for<1, N - p + 1>(
+            [&](auto Q)
+            {
+              constexpr int q = decltype(Q)::value;
+              double v;
+              if constexpr (q == 1)
+                v = (Y * (1.5 + p) + (0.5 + p)) * Jq;
+              else
+              {
+                constexpr double a1 = jets::jrc_a(2 * p + 1, q - 1), a2 = jets::jrc_b(2 * p + 1, q - 1),
+                                 a3 = jets::jrc_c(2 * p + 1, q - 1);
+                v = (Y * a1 + a2) * Jq - a3 * Jqm;
+              }
+              Jqm = Jq;
+              Jq = v;
+              out.put<idx2(q, p)>(Jq);
+            });
+      });
+}
+
+template <int N>
+__device__ __forceinline__ void values_tetrahedron(double x0, double x1, double x2, const SlabSink& out)
+{
+  const double X = x0 * 2.0 - 1.0, Y = x1 * 2.0 - 1.0, Z = x2 * 2.0 - 1.0;
+  const double lin = X + 0.5 * (Y + Z) + 1.0;
+  const double f2 = x1 + x2 - 1.0;
+  const double f2sq = f2 * f2;
+  const double f4 = 1.0 - x2;
+  const double f4sq = f4 * f4;
+  const double f3 = Y + x2;
+  double Jp = 1.0, Jpm = 0.0;
+  static_for<0, N + 1>(
+      [&](auto P)
+      {
+        constexpr int p = decltype(P)::value;
+        if constexpr (p > 0)
+        {
+          constexpr double a = double(2 * p - 1) / double(p);
+          double v = (lin * a) * Jp;
+          if constexpr (p > 1)
+            v -= (f2sq * (a - 1.0)) * Jpm;
+          Jpm = Jp;
+          Jp = v;
+        }
+        double Jq = Jp, Jqm = 0.0;
+        static_for<0, N - p + 1>(
+            [&](auto Q)
+            {
+              constexpr int q = decltype(Q)::value;
+              if constexpr (q == 1)
+              {
+                const double v = ((1.0 + Y) * p + (2.0 + Y * 3.0 + Z) * 0.5) * Jq;
+                Jqm = Jq;
+                Jq = v;
+              }
+              else if constexpr (q > 1)
+              {
+                constexpr double aq = jets::jrc_a(2 * p + 1, q - 1), bq = jets::jrc_b(2 * p + 1, q - 1),
+                                 cq = jets::jrc_c(2 * p + 1, q - 1);
+                const double v = (f3 * aq + f4 * bq) * Jq - (f4sq * cq) * Jqm;
+                Jqm = Jq;
+                Jq = v;
+              }
+              out.put<idx3(0, q, p)>(Jq);
+              double Jr = Jq, Jrm = 0.0;
+              static_for<1, N - p - q + 1>(
+                  [&](auto R)
+                  {
+                    constexpr int r = decltype(R)::value;
+                    double v;
+                    if constexpr (r == 1)
+                      v = ((1.0 + p + q) + Z * (2.0 + p + q)) * Jr;
+                    else
+                    {
+                      constexpr double ar = jets::jrc_a(2 * p + 2 * q + 2, r - 1), br = jets::jrc_b(2 * p + 2 * q + 2, r - 1),
+                                       cr = jets::jrc_c(2 * p + 2 * q + 2, r - 1);
+                      v = (Z * ar + br) * Jr - cr * Jrm;
+                    }
+                    Jrm = Jr;
+                    Jr = v;
+                    out.put<idx3(r, q, p)>(Jr);
+                  });
+            });
+      });
+}
+
+// All slabs for the column group [n0, n0 + 8 NT) of this warp's 16 points.
+template <int NT, bool LEAN>
+__device__ __forceinline__ void run_group(const Step* __restrict__ steps, int nsteps, const double* __restrict__ A0,
+                                          const double* __restrict__ A1, const double* __restrict__ Bgt, int n0,
+                                          int g, int t, double* __restrict__ basis, size_t npts, size_t npts_st, int N,
+                                          size_t pt)
 {
   double acc[2][NT][2];
 #pragma unroll
@@ -109,151 +245,198 @@ __device__ __forceinline__ void run_item(const Item& it, const double* __restric
 #pragma unroll
     for (int j = 0; j < NT; ++j)
       acc[m][j][0] = acc[m][j][1] = 0.0;
-  const double* Bp = Bs + it.boff + (it.n0 + g) * it.kstride + t;
-  const int tile_stride = 8 * it.kstride;
-#pragma unroll 2
-  for (int ks = 0; ks < it.ksteps; ++ks)
+  Step st = steps[0];
+  double a0, a1, b[NT];
   {
-    const double a0 = Pa[(ks * 4 + t) * kPStride];
-    const double a1 = Pa[(ks * 4 + t) * kPStride + 8];
+    const double* bp = Bgt + st.boff + (n0 + g) * st.kstride;
+    a0 = A0[st.aoff];
+    a1 = A1[st.aoff];
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+      b[j] = bp[j * 8 * st.kstride];
+  }
+#pragma unroll 1
+  for (int s = 0; s < nsteps; ++s)
+  {
+    // fragments of the next step (the table ends with a repeat of the last step)
+    const Step nx = steps[s + 1];
+    const double* bp = Bgt + nx.boff + (n0 + g) * nx.kstride;
+    const double an0 = A0[nx.aoff], an1 = A1[nx.aoff];
+    double bn[NT];
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+      bn[j] = bp[j * 8 * nx.kstride];
 #pragma unroll
     for (int j = 0; j < NT; ++j)
     {
-      const double b = Bp[j * tile_stride + ks * 4];
-      dmma(acc[0][j][0], acc[0][j][1], a0, b);
-      dmma(acc[1][j][0], acc[1][j][1], a1, b);
+      dmma(acc[0][j][0], acc[0][j][1], a0, b[j]);
+      dmma(acc[1][j][0], acc[1][j][1], a1, b[j]);
     }
-  }
-  // accumulator fragment: row g = point, columns 2t, 2t+1 of each 8-column tile
-#pragma unroll
-  for (int m = 0; m < 2; ++m)
-  {
-    const size_t p = pt + 8 * m;
-    if (p < npts)
+    if (st.last)
     {
-      double* row = basis + (size_t(it.slab) * npts + p) * N;
-#pragma unroll
-      for (int j = 0; j < NT; ++j)
+      // accumulator fragment: row g = point, columns 2t, 2t+1 of each 8-column tile
+      const size_t slab = size_t(st.last - 1);
+      if constexpr (LEAN)
       {
-        const int n = it.n0 + j * 8 + 2 * t;
-        if ((N & 1) == 0)
+        // whole chunk inside the table, N even: 16-byte stores at compile-time offsets from one row pointer;
+        // only the last column tile of the operand can run past N
+        double* row = basis + (slab * npts + pt) * N + n0 + 2 * t;
+        const bool last_ok = n0 + (NT - 1) * 8 + 2 * t < N;
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
         {
-          if (n < N)
-            __stcs(reinterpret_cast<double2*>(row + n), make_double2(acc[m][j][0], acc[m][j][1]));
-        }
-        else
-        {
-          if (n < N)
-            __stcs(row + n, acc[m][j][0]);
-          if (n + 1 < N)
-            __stcs(row + n + 1, acc[m][j][1]);
+#pragma unroll
+          for (int j = 0; j < NT - 1; ++j)
+            __stcs(reinterpret_cast<double2*>(row + j * 8), make_double2(acc[m][j][0], acc[m][j][1]));
+          if (last_ok)
+            __stcs(reinterpret_cast<double2*>(row + (NT - 1) * 8), make_double2(acc[m][NT - 1][0], acc[m][NT - 1][1]));
+          row += size_t(8) * N;
         }
       }
+      else
+      {
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+        {
+          const size_t q = pt + 8 * m;
+          if (q < npts_st)
+          {
+            double* row = basis + (slab * npts + q) * N;
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+            {
+              const int n = n0 + j * 8 + 2 * t;
+              if (n < N)
+                __stcs(row + n, acc[m][j][0]);
+              if (n + 1 < N)
+                __stcs(row + n + 1, acc[m][j][1]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+          acc[m][j][0] = acc[m][j][1] = 0.0;
+    }
+    st = nx;
+    a0 = an0;
+    a1 = an1;
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+      b[j] = bn[j];
+  }
+}
+
+template <bool LEAN>
+__device__ __forceinline__ void run_groups(const Step* steps, int nsteps, const double* A0, const double* A1,
+                                           const double* Bgt, int g, int t, double* basis, size_t npts, size_t npts_st,
+                                           int N, size_t pt)
+{
+  for (int n0 = 0; n0 < N; n0 += 8 * kMaxNT)
+  {
+    const int nt = min(kMaxNT, (N - n0 + 7) >> 3);
+    switch (nt)
+    {
+    case 1: run_group<1, LEAN>(steps, nsteps, A0, A1, Bgt, n0, g, t, basis, npts, npts_st, N, pt); break;
+    case 2: run_group<2, LEAN>(steps, nsteps, A0, A1, Bgt, n0, g, t, basis, npts, npts_st, N, pt); break;
+    case 3: run_group<3, LEAN>(steps, nsteps, A0, A1, Bgt, n0, g, t, basis, npts, npts_st, N, pt); break;
+    case 4: run_group<4, LEAN>(steps, nsteps, A0, A1, Bgt, n0, g, t, basis, npts, npts_st, N, pt); break;
+    case 5: run_group<5, LEAN>(steps, nsteps, A0, A1, Bgt, n0, g, t, basis, npts, npts_st, N, pt); break;
+    case 6: run_group<6, LEAN>(steps, nsteps, A0, A1, Bgt, n0, g, t, basis, npts, npts_st, N, pt); break;
+    default: run_group<7, LEAN>(steps, nsteps, A0, A1, Bgt, n0, g, t, basis, npts, npts_st, N, pt); break;
     }
   }
 }
 
-template <int TDIM, int DEG>
-__global__ void __launch_bounds__(kThreads, 1) tabulate_dop_kernel(const Params p)
+template <int TDIM, int DEG, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, 1) tabulate_dop_kernel(const Params p)
 {
   constexpr int K = jets::psize(TDIM, DEG);
+  constexpr int kThreads = 32 * WARPS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // [ barriers 64 B ][ items ][ rowmap ][ B ][ P tile 0 ][ P tile 1 ]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
-  Item* items = reinterpret_cast<Item*>(smem_raw + 64);
-  int* rowmap = reinterpret_cast<int*>(items + kMaxItems);
-  double* Bs = reinterpret_cast<double*>(rowmap + ((K + 3) & ~3));
-  double* Pt = Bs + p.b_doubles;
-  const int tile_doubles = p.kpad * kPStride;
-  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 16;
+  // [ steps ][ B ][ slab of warp 0 ] ... [ slab of warp WARPS-1 ]
+  Step* steps = reinterpret_cast<Step*>(smem_raw);
+  double* Bs = reinterpret_cast<double*>(steps + p.nsteps + 1);
+  const int slab_doubles = p.kpad * 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* slab = Bs + p.b_doubles + warp * slab_doubles;
 
   for (int i = threadIdx.x; i < p.b_doubles; i += kThreads)
     Bs[i] = p.B[i];
-  for (int i = threadIdx.x; i < p.nitems; i += kThreads)
-    items[i] = p.items[i];
-  for (int i = threadIdx.x; i < K; i += kThreads)
-    rowmap[i] = p.rowmap[i];
-  for (int i = threadIdx.x; i < 2 * tile_doubles; i += kThreads)
-    Pt[i] = 0.0; // rows K .. kpad-1 are read by the last k-step of the value slab and must stay finite
-  if (threadIdx.x == 0)
-  {
-    for (int b = 0; b < 2; ++b)
-    {
-      mbar_init(full0 + 8 * b, kProducers);
-      mbar_init(empty0 + 8 * b, kConsumers);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
+  for (int i = threadIdx.x; i <= p.nsteps; i += kThreads)
+    steps[i] = p.steps[i];
+  for (int i = threadIdx.x; i < WARPS * slab_doubles; i += kThreads)
+    Bs[p.b_doubles + i] = 0.0; // rows K .. kpad-1 are read by the last k-step of the value slab and must stay finite
   __syncthreads();
 
-  const size_t ntiles = ceil_div(p.npts, size_t(kTilePts));
-  if (warp >= kConsumers)
-  {
-    // ---- producers: values of the orthonormal set, lane = point ----
-    const int pw = warp - kConsumers;
-    uint32_t phase = 1; // parity of the previous use of the buffer
-    int b = 0;
-    size_t i = 0;
-    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i)
-    {
-      if (i >= 2)
-        mbar_wait(empty0 + 8 * b, phase);
-      size_t pt = tile * kTilePts + pw * 32 + lane;
-      pt = pt < p.npts ? pt : p.npts - 1; // ragged tail: recompute the last point, stores are predicated
-      TileSink<K> sink{Pt + b * tile_doubles + pw * 32 + lane, rowmap};
-      if constexpr (TDIM == 1)
-        jets::interval<DEG, 0>(p.x[pt], sink);
-      else if constexpr (TDIM == 2)
-        jets::triangle<DEG, 0>(p.x[2 * pt], p.x[2 * pt + 1], sink);
-      else
-        jets::tetrahedron<DEG, 0>(p.x[3 * pt], p.x[3 * pt + 1], p.x[3 * pt + 2], sink);
-      __syncwarp();
-      if (lane == 0)
-        mbar_arrive(full0 + 8 * b);
-      if (++b == 2)
-      {
-        b = 0;
-        phase ^= 1;
-      }
-    }
-    return;
-  }
-
-  // ---- consumers: FP64 tensor cores ----
+  // chunk c of this warp: points [16 c, 16 c + 16); consecutive warps / CTAs take consecutive chunks
+  const size_t nchunks = ceil_div(p.npts, size_t(kChunkPts));
+  const size_t stride = size_t(gridDim.x) * WARPS;
   const int g = lane >> 2, t = lane & 3;
-  const int mp = warp & 3, half = warp >> 2;
-  const int first = half == 0 ? 0 : p.split, last = half == 0 ? p.split : p.nitems;
-  uint32_t phase = 0;
-  int b = 0;
-  for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+  const bool n_even = (p.N & 1) == 0;
+  const double* A0 = slab + t * 16 + (g ^ (t << 2));
+  const double* A1 = slab + t * 16 + ((g + 8) ^ (t << 2));
+  const double* Bgt = Bs + t;
+  const int c = lane & 15;
+  const SlabSink sink{{slab + c, slab + (c ^ 4), slab + (c ^ 8), slab + (c ^ 12)}};
+
+  auto load_x = [&](size_t chunk, double (&xr)[TDIM])
   {
-    mbar_wait(full0 + 8 * b, phase);
-    const double* Pa = Pt + b * tile_doubles + mp * 16 + g;
-    const size_t pt = tile * kTilePts + mp * 16 + g;
-    for (int i = first; i < last; ++i)
+    size_t pt = chunk * kChunkPts + (lane & 15);
+    pt = pt < p.npts ? pt : p.npts - 1; // ragged tail: recompute the last point, stores are predicated
+#pragma unroll
+    for (int a = 0; a < TDIM; ++a)
+      xr[a] = __ldg(p.x + TDIM * pt + a);
+  };
+
+  size_t chunk = size_t(blockIdx.x) * WARPS + warp;
+  double xr[TDIM];
+  if (chunk < nchunks)
+    load_x(chunk, xr);
+  const bool timed = p.debug & 4;
+  long long t_prod = 0, t_con = 0, n_chunks = 0;
+  for (; chunk < nchunks; chunk += stride)
+  {
+    long long c0 = 0, c1 = 0;
+    if (timed)
+      c0 = clock64();
+    // ---- values of the orthonormal set: lane = point (lanes 16..31 idle) ----
+    if (lane < kChunkPts)
     {
-      const Item it = items[i];
-      switch (it.nt)
-      {
-      case 1: run_item<1>(it, Pa, Bs, p.basis, p.npts, p.N, pt, g, t); break;
-      case 2: run_item<2>(it, Pa, Bs, p.basis, p.npts, p.N, pt, g, t); break;
-      case 3: run_item<3>(it, Pa, Bs, p.basis, p.npts, p.N, pt, g, t); break;
-      case 4: run_item<4>(it, Pa, Bs, p.basis, p.npts, p.N, pt, g, t); break;
-      case 5: run_item<5>(it, Pa, Bs, p.basis, p.npts, p.N, pt, g, t); break;
-      case 6: run_item<6>(it, Pa, Bs, p.basis, p.npts, p.N, pt, g, t); break;
-      case 7: run_item<7>(it, Pa, Bs, p.basis, p.npts, p.N, pt, g, t); break;
-      default: run_item<8>(it, Pa, Bs, p.basis, p.npts, p.N, pt, g, t); break;
-      }
+      if constexpr (TDIM == 1)
+        values_interval<DEG>(xr[0], sink);
+      else if constexpr (TDIM == 2)
+        values_triangle<DEG>(xr[0], xr[1], sink);
+      else
+        values_tetrahedron<DEG>(xr[0], xr[1], xr[2], sink);
     }
     __syncwarp();
-    if (lane == 0)
-      mbar_arrive(empty0 + 8 * b);
-    if (++b == 2)
+    if (timed)
+      c1 = clock64();
+    if (chunk + stride < nchunks)
+      load_x(chunk + stride, xr); // in flight during the contraction
+
+    // ---- FP64 tensor cores: every slab on this warp's two row tiles ----
+    const size_t pt = chunk * kChunkPts + g;
+    const bool lean = n_even and (chunk + 1) * kChunkPts <= p.npts and !(p.debug & 1);
+    if (lean)
+      run_groups<true>(steps, p.nsteps, A0, A1, Bgt, g, t, p.basis, p.npts, p.npts, p.N, pt);
+    else
+      run_groups<false>(steps, p.nsteps, A0, A1, Bgt, g, t, p.basis, p.npts, (p.debug & 1) ? 0 : p.npts, p.N, pt);
+    __syncwarp(); // the slab is overwritten by the next chunk
+    if (timed)
     {
-      b = 0;
-      phase ^= 1;
+      t_prod += c1 - c0;
+      t_con += clock64() - c1;
+      ++n_chunks;
     }
+  }
+  if (timed and lane == 0)
+  {
+    unsigned long long* o = p.timing + (size_t(blockIdx.x) * WARPS + warp) * 3;
+    o[0] = t_prod, o[1] = t_con, o[2] = n_chunks;
   }
 }
 
@@ -261,9 +444,8 @@ __global__ void __launch_bounds__(kThreads, 1) tabulate_dop_kernel(const Params 
 struct Operand
 {
   double* d_B = nullptr;
-  Item* d_items = nullptr;
-  int* d_rowmap = nullptr;
-  int b_doubles = 0, nitems = 0, split = 0, kpad = 0;
+  Step* d_steps = nullptr;
+  int b_doubles = 0, nsteps = 0, kpad = 0, warps = 0;
   bool usable = false;
   size_t smem = 0;
 };
@@ -278,8 +460,7 @@ struct bx_element_dop
     for (auto& kv : by_nd)
     {
       cudaFree(kv.second.d_B);
-      cudaFree(kv.second.d_items);
-      cudaFree(kv.second.d_rowmap);
+      cudaFree(kv.second.d_steps);
     }
   }
 };
@@ -345,7 +526,7 @@ Operand build_operand(const bx_element& e, int nd, bool upload_to_device)
   const int npad = int(ceil_div(N, 8) * 8);
   op.kpad = int(ceil_div(K, 4) * 4);
   Vec B;
-  std::vector<Item> items;
+  std::vector<Step> steps;
   auto matmul = [K](const Vec& A, const Vec& Bm)
   {
     Vec Cm(size_t(K) * K, 0.0);
@@ -376,9 +557,9 @@ Operand build_operand(const bx_element& e, int nd, bool upload_to_device)
           for (int r = 0; r < cnt[a]; ++r)
             M = matmul(M, D[a]);
         const int Kd = simplex_dim(tdim, n - m);
-        const int ksteps = int(ceil_div(Kd, 4));
+        const int ksteps = std::max(1, int(ceil_div(Kd, 4))); // derivative order above the degree: one zero step
         const int kp = ksteps * 4;
-        const int kstride = kp + ((4 - kp % 16) + 16) % 16;
+        const int kstride = kp % 8 == 4 ? kp : kp + 4;
         const int boff = int(B.size());
         B.resize(B.size() + size_t(npad) * kstride, 0.0);
         for (int row = 0; row < N; ++row)
@@ -389,79 +570,84 @@ Operand build_operand(const bx_element& e, int nd, bool upload_to_device)
               s += e.Cp[size_t(row) * e.Kpad + k] * M[size_t(k) * K + j];
             B[size_t(boff) + size_t(row) * kstride + j] = s * norm[j];
           }
-        for (int n0 = 0; n0 < npad; n0 += 8 * kMaxNT)
-        {
-          Item it{};
-          it.boff = boff;
-          it.ksteps = ksteps;
-          it.kstride = kstride;
-          it.n0 = n0;
-          it.nt = std::min(kMaxNT, (npad - n0) / 8);
-          it.slab = d;
-          items.push_back(it);
-        }
+        for (int ks = 0; ks < ksteps; ++ks)
+          steps.push_back(Step{boff + 4 * ks, kstride, 64 * ks, ks + 1 == ksteps ? 1 + d : 0});
       }
-  if (int(items.size()) > kMaxItems)
-    return op;
-  // balance the items over the two consumer halves (largest first)
-  std::sort(items.begin(), items.end(),
-            [](const Item& a, const Item& b) { return a.ksteps * a.nt > b.ksteps * b.nt; });
-  std::vector<Item> h0, h1;
-  long c0 = 0, c1 = 0;
-  for (const Item& it : items)
-  {
-    const long cost = long(it.ksteps) * it.nt + 1;
-    if (c0 <= c1)
-    {
-      h0.push_back(it);
-      c0 += cost;
-    }
-    else
-    {
-      h1.push_back(it);
-      c1 += cost;
-    }
-  }
-  op.split = int(h0.size());
-  h0.insert(h0.end(), h1.begin(), h1.end());
-  op.nitems = int(h0.size());
+  op.nsteps = int(steps.size());
+  steps.push_back(steps.back()); // prefetch target of the last step
   op.b_doubles = int((B.size() + 1) & ~size_t(1));
   B.resize(op.b_doubles, 0.0);
-  op.smem = 64 + sizeof(Item) * kMaxItems + size_t((K + 3) & ~3) * sizeof(int) + size_t(op.b_doubles) * 8
-            + 2 * size_t(op.kpad) * kPStride * 8;
-  if (op.smem > 225 * 1024)
+  // three warps per SM sub-partition when their slabs fit beside the operands, else two
+  static const int warps_env = std::getenv("BX_DOP_WARPS") ? std::atoi(std::getenv("BX_DOP_WARPS")) : 0;
+  for (int warps : {12, 8})
+  {
+    if (warps_env and warps != warps_env)
+      continue;
+    const size_t smem = sizeof(Step) * steps.size() + size_t(op.b_doubles) * 8
+                        + size_t(warps) * op.kpad * 16 * 8;
+    if (smem <= 227 * 1024)
+    {
+      op.smem = smem;
+      op.warps = warps;
+      break;
+    }
+  }
+  if (op.warps == 0)
     return op;
   if (upload_to_device)
   {
     op.d_B = upload(B);
-    op.d_items = upload(h0);
-    op.d_rowmap = upload(slot);
+    op.d_steps = upload(steps);
   }
   op.usable = true;
   return op;
 }
 
-template <int TDIM, int DEG>
-void launch(const Operand& op, const bx_element& e, const double* x, size_t npts, double* basis, cudaStream_t s)
+template <int TDIM, int DEG, int WARPS>
+void launch_warps(const Operand& op, const bx_element& e, const double* x, size_t npts, double* basis, cudaStream_t s)
 {
-  auto kern = tabulate_dop_kernel<TDIM, DEG>;
+  auto kern = tabulate_dop_kernel<TDIM, DEG, WARPS>;
   BX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(op.smem)));
   Params p;
   p.x = x;
   p.npts = npts;
   p.B = op.d_B;
-  p.items = op.d_items;
-  p.rowmap = op.d_rowmap;
+  p.steps = op.d_steps;
   p.basis = basis;
   p.N = e.N;
   p.K = e.K;
   p.kpad = op.kpad;
   p.b_doubles = op.b_doubles;
-  p.nitems = op.nitems;
-  p.split = op.split;
-  const size_t ntiles = ceil_div(npts, size_t(kTilePts));
-  kern<<<unsigned(std::min<size_t>(ntiles, size_t(sm_count()))), kThreads, op.smem, s>>>(p);
+  p.nsteps = op.nsteps;
+  static const int debug = std::getenv("BX_DOP_DEBUG") ? std::atoi(std::getenv("BX_DOP_DEBUG")) : 0;
+  p.debug = debug;
+  const size_t nblocks = ceil_div(npts, size_t(kChunkPts) * WARPS);
+  const unsigned grid = unsigned(std::min<size_t>(nblocks, size_t(sm_count())));
+  p.timing = nullptr;
+  if (debug & 4)
+    BX_CUDA(cudaMalloc(&p.timing, size_t(grid) * WARPS * 3 * sizeof(unsigned long long)));
+  kern<<<grid, 32 * WARPS, op.smem, s>>>(p);
   BX_LAUNCHED();
+  if (debug & 4)
+  {
+    std::vector<unsigned long long> h(size_t(grid) * WARPS * 3);
+    BX_CUDA(cudaMemcpy(h.data(), p.timing, h.size() * 8, cudaMemcpyDeviceToHost));
+    BX_CUDA(cudaFree(p.timing));
+    double a[3] = {0, 0, 0};
+    for (size_t i = 0; i < h.size(); ++i)
+      a[i % 3] += double(h[i]);
+    fprintf(stderr, "dop timing: per chunk cycles produce %.0f contract+store %.0f (chunks/warp %.1f)\n", a[0] / a[2],
+            a[1] / a[2], a[2] / (double(grid) * WARPS));
+  }
+}
+
+template <int TDIM, int DEG>
+void launch(const Operand& op, const bx_element& e, const double* x, size_t npts, double* basis, cudaStream_t s)
+{
+  if (op.warps == 12)
+    launch_warps<TDIM, DEG, 12>(op, e, x, npts, basis, s);
+  else
+    launch_warps<TDIM, DEG, 8>(op, e, x, npts, basis, s);
 }
 
 #define BX_DOP(T, DEG)                                                                                     \

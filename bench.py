@@ -77,6 +77,15 @@ def random_cell_info(nc, seed):
     return ci
 
 
+def _multi_indices(tdim, nd):
+    """Derivative multi-indices of total order <= nd (one per slab of tabulate's output)."""
+    if tdim == 1:
+        return [(k,) for k in range(nd + 1)]
+    if tdim == 2:
+        return [(kx, ky) for kx in range(nd + 1) for ky in range(nd + 1 - kx)]
+    return [(kx, ky, kz) for kx in range(nd + 1) for ky in range(nd + 1 - kx) for kz in range(nd + 1 - kx - ky)]
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons through NVML while the timed region runs."""
 
@@ -178,9 +187,21 @@ class Tabulate:
         self.launches_per_step = self.chunks
         self.units_per_launch = self.cnp
         self.alg_bytes = self.cnp * e._tdim * 8 + int(np.prod(self.shape)) * 8
-        self.flops = 2.0 * e.dim * e.value_size * e._psize * self.shape[0] * self.cnp
+        # FP64 flops per point: the reference contracts every derivative slab with the full psize-column
+        # coefficient matrix; the derivative-operator kernel contracts slab d with dim P_{n-|alpha_d|} columns
+        # (csrc/tabulate_dop.cu).  roofline.achieved counts the flops of the algorithm that runs.
+        dense = 2.0 * e.dim * e.value_size * e._psize * self.shape[0]
+        self.flops_per_point = dense
+        if self.path == "derivative-operator":
+            from math import comb
+
+            tdim, n = e._tdim, e.embedded_superdegree
+            orders = [sum(a) for a in _multi_indices(tdim, self.nd)]
+            self.flops_per_point = 2.0 * e.dim * e.value_size * sum(comb(n - m + tdim, tdim) if m <= n else 0 for m in orders)
+        self.flops = self.flops_per_point * self.cnp
         self.config = {"workload": self.desc, "points_per_gpu": self.npts, "nd": self.nd, "tabulate_path": self.path,
-                       "points_per_launch": self.cnp,
+                       "points_per_launch": self.cnp, "fp64_flops_per_point": self.flops_per_point,
+                       "fp64_flops_per_point_reference_algorithm": dense,
                        "l2": "table of one launch is %.2f GB (>> 126 MB L2)" % (int(np.prod(self.shape)) * 8 / 1e9)}
 
     def step(self):

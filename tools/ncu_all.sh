@@ -7,7 +7,7 @@ cap() { # name workload kernel-regex units
     python bench.py --workload $2 ${4:+--units $4} --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_$1.log 2>&1
   tail -1 gpurun_out/ncu_$1.log
 }
-cap fused_p5tet tabulate_p5_tet tabulate_fused 2000000
+cap dop_p5tet tabulate_p5_tet tabulate_dop 2000000
 cap tp_q4hex tabulate_q4_hex tabulate_tp 10000000
 cap small_p1tri tabulate_p1_tri tabulate_small
 cap map_rows1 push_forward_n1curl3 map_kernel
