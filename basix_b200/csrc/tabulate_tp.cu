@@ -25,7 +25,6 @@ namespace
 {
 constexpr int kWarps = 8;
 constexpr int kMaxN1 = 9;   // degree + 1
-constexpr int kMaxFun = 16; // distinct 1-D functions per axis
 
 // T = type of the points and of the table (double, or float for the float32 API; arithmetic is double)
 template <typename T>
