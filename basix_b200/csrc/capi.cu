@@ -3,6 +3,7 @@
 // kernel of this library (there is no CPU fallback).
 #include "element.cuh"
 
+#include <cstdlib>
 #include <algorithm>
 #include <memory>
 #include <mutex>
@@ -27,6 +28,8 @@ int sm_count()
   {
     BX_CUDA(cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev));
     cached_dev = dev;
+    if (const char* v = std::getenv("BX_L2_FETCH")) // tuning aid: L2 -> DRAM fetch granularity hint (32 / 64 / 128)
+      cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, size_t(std::atoi(v)));
   }
   return cached;
 }
@@ -263,11 +266,21 @@ StagePool& stage_pool()
   return pool;
 }
 
-constexpr size_t kStageBytes = size_t(256) << 20; // target size of one staged chunk (largest array)
+// Target size of one staged chunk (all arrays of the chunk that cross the bus).  BX_STAGE_MB overrides (tuning).
+size_t stage_bytes()
+{
+  static const size_t v = []
+  {
+    const char* e = std::getenv("BX_STAGE_MB");
+    const long mb = e ? std::atol(e) : 0;
+    return size_t(mb > 0 ? mb : 256) << 20;
+  }();
+  return v;
+}
 
 size_t chunk_units(size_t nunits, size_t bytes_per_unit, size_t align)
 {
-  size_t c = std::max<size_t>(1, kStageBytes / std::max<size_t>(1, bytes_per_unit));
+  size_t c = std::max<size_t>(1, stage_bytes() / std::max<size_t>(1, bytes_per_unit));
   c = std::max(align, c / align * align);
   return std::min(c, nunits);
 }
@@ -386,7 +399,7 @@ void map_any(int map_type, int pull, const T* U, const T* J, const T* detJ, cons
   const bool need_det = uses_Jarg;
   const bool need_J = pull ? uses_Karg : uses_Jarg;
   const bool need_K = pull ? uses_Jarg : uses_Karg;
-  const size_t per_cell = rows * std::max(in_vs, out_vs) * sizeof(T);
+  const size_t per_cell = (rows * (in_vs + out_vs) + (need_J ? jsz : 0) + (need_K ? jsz : 0) + (need_det ? 1 : 0)) * sizeof(T);
   const size_t chunk = chunk_units(nc, per_cell, 1);
   StagePool& st = stage_pool();
   DrainOnExit drain{st};
