@@ -84,6 +84,9 @@ SIGNATURES = {
     "bx_T_apply_f32": (_I, [_P, _I, _P, _SIZE, _SIZE, _I, _P, _I, _P]),
     "bx_T_apply_i32": (_I, [_P, _I, _P, _SIZE, _SIZE, _I, _P, _I, _P]),
     "bx_permute_i32": (_I, [_P, _I, _P, _SIZE, _P, _I, _P]),
+    "bx_permute_subentity_closure_i32": (_I, [_P, _I, _P, _SIZE, _SIZE, _P, _I, _I, _I, _P]),
+    "bx_element_subentity_closure_size": (_I, [_P, _I]),
+    "bx_element_subentity_closure_map": (_I, [_P, _I, _I, C.c_uint32, _P]),
 }
 
 _lib = None

@@ -28,8 +28,6 @@ int sm_count()
   {
     BX_CUDA(cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev));
     cached_dev = dev;
-    if (const char* v = std::getenv("BX_L2_FETCH")) // tuning aid: L2 -> DRAM fetch granularity hint (32 / 64 / 128)
-      cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, size_t(std::atoi(v)));
   }
   return cached;
 }
@@ -146,6 +144,8 @@ void polyset_tabulate_device(int cell, int ptype, int degree, int nd, const T* x
 template <typename T>
 void tabulate_device(const bx_element& e, int nd, const T* x, size_t npts, T* basis, size_t out_pts, cudaStream_t s);
 int tabulate_path(const bx_element& e, int nd);
+void closure_permute_device(const bx_element& e, int inverse, int32_t* d, size_t nc, size_t m, const uint32_t* info,
+                            int entity_type, int entity_index, cudaStream_t s);
 unsigned tabulate_path_mask(unsigned mask);
 int map_value_size(int map_type, int pull, int in_vs, int gdim, int tdim);
 template <typename T>
@@ -495,6 +495,45 @@ void transform_any(const bx_element* e, int op, T* data, size_t nc, size_t cell_
   st.sync();
   st.trim();
 }
+void closure_permute_any(const bx_element* e, int inverse, int32_t* d, size_t nc, size_t m, const uint32_t* info,
+                         int entity_type, int entity_index, int mem, bx_stream_t stream)
+{
+  check_mem(mem);
+  require(e != nullptr, "permute_subentity_closure: null element");
+  require(nc == 0 or (d and info), "permute_subentity_closure: null pointer");
+  if (mem == BX_MEM_DEVICE)
+  {
+    closure_permute_device(*e, inverse, d, nc, m, info, entity_type, entity_index, static_cast<cudaStream_t>(stream));
+    return;
+  }
+  // validate once (throws on bad arguments / returns for vertices) before staging
+  closure_permute_device(*e, inverse, nullptr, 0, m, nullptr, entity_type, entity_index, nullptr);
+  if (nc == 0 or entity_type == BX_CELL_POINT)
+    return;
+  const size_t chunk = chunk_units(nc, 2 * m * sizeof(int32_t) + sizeof(uint32_t), 1);
+  StagePool& st = stage_pool();
+  DrainOnExit drain{st};
+  int32_t* dd[2];
+  uint32_t* dc[2];
+  for (int b = 0; b < 2; ++b)
+  {
+    dd[b] = st.get<int32_t>(0, b, chunk * m * sizeof(int32_t));
+    dc[b] = st.get<uint32_t>(1, b, chunk * sizeof(uint32_t));
+  }
+  size_t i = 0;
+  for (size_t c0 = 0; c0 < nc; c0 += chunk, ++i)
+  {
+    const int b = int(i & 1);
+    const size_t k = std::min(chunk, nc - c0);
+    cudaStream_t s = st.s[b];
+    BX_CUDA(cudaMemcpyAsync(dd[b], d + c0 * m, k * m * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    BX_CUDA(cudaMemcpyAsync(dc[b], info + c0, k * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    closure_permute_device(*e, inverse, dd[b], k, m, dc[b], entity_type, entity_index, s);
+    BX_CUDA(cudaMemcpyAsync(d + c0 * m, dd[b], k * m * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  }
+  st.sync();
+  st.trim();
+}
 } // namespace
 } // namespace bx
 
@@ -772,6 +811,36 @@ extern "C"
                      const uint32_t* cell_info, int mem, bx_stream_t stream)
   {
     return bx::guarded([&]() { bx::transform_any<int32_t>(e, op, data, nc, cell_size, n, cell_info, mem, stream); });
+  }
+
+  int bx_element_subentity_closure_size(const bx_element* e, int entity_type)
+  {
+    if (!e or entity_type < 0 or entity_type >= 8)
+      return -1;
+    return e->closure[entity_type].size;
+  }
+
+  int bx_element_subentity_closure_map(const bx_element* e, int entity_type, int inverse, uint32_t entity_info, int32_t* src)
+  {
+    return bx::guarded(
+        [&]()
+        {
+          bx::require(e != nullptr and src != nullptr, "subentity_closure_map: null pointer");
+          bx::require(entity_type >= 0 and entity_type < 8 and e->closure[entity_type].size > 0,
+                      "subentity_closure_map: the element has no closure permutation for this sub-entity type");
+          const auto& cl = e->closure[entity_type];
+          const uint32_t st = entity_info & uint32_t(cl.states - 1);
+          for (int k = 0; k < cl.size; ++k)
+            src[k] = cl.src[(size_t(inverse ? 1 : 0) * cl.states + st) * cl.size + k];
+        });
+  }
+
+  int bx_permute_subentity_closure_i32(const bx_element* e, int inverse, int32_t* d, size_t nc, size_t m,
+                                       const uint32_t* info, int entity_type, int entity_index, int mem,
+                                       bx_stream_t stream)
+  {
+    return bx::guarded(
+        [&]() { bx::closure_permute_any(e, inverse, d, nc, m, info, entity_type, entity_index, mem, stream); });
   }
 
   int bx_permute_i32(const bx_element* e, int inverse, int32_t* d, size_t nc, const uint32_t* cell_info, int mem,

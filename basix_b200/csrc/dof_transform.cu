@@ -563,6 +563,97 @@ void dof_transform_device(const bx_element& e, int op, T* data, size_t nc, size_
   }
 }
 
+// ---- permute_subentity_closure{,_inv} (finite-element.h:860-1035), batched over cells ----------------------
+// d[nc][m]: the dofs on the closure of one sub-entity per cell; info[c] is the entity's own bits (shift < 0) or
+// the cell's cell_info, from which the entity's bits are (info >> shift) & mask.  The net gather of every state
+// was composed on the host (element.cu); a CTA stages `cpb` cells through shared memory so the in-place gather
+// reads every entry before any is overwritten, global accesses are coalesced runs of cpb * m entries.
+namespace
+{
+constexpr int kClosureThreads = 256;
+__global__ void __launch_bounds__(kClosureThreads)
+    closure_permute_kernel(int32_t* __restrict__ d, size_t nc, int m, int cpb, const uint32_t* __restrict__ info,
+                           int shift, uint32_t mask, const int16_t* __restrict__ src, int states, unsigned inv_m)
+{
+  extern __shared__ int32_t closure_smem[];
+  int16_t* s_src = reinterpret_cast<int16_t*>(closure_smem);                     // [states][m]
+  int32_t* tile = closure_smem + ((states * m + 1) / 2 + 3) / 4 * 4;              // [cpb][m]
+  uint32_t* s_state = reinterpret_cast<uint32_t*>(tile + size_t(cpb) * m);       // [cpb]
+  for (int i = threadIdx.x; i < states * m; i += kClosureThreads)
+    s_src[i] = src[i];
+  const size_t ntiles = (nc + cpb - 1) / cpb;
+  for (size_t tl = blockIdx.x; tl < ntiles; tl += gridDim.x)
+  {
+    const size_t c0 = tl * cpb;
+    const unsigned ncell = unsigned(min(size_t(cpb), nc - c0));
+    __syncthreads(); // previous tile fully written back (and s_src ready on the first pass)
+    for (unsigned c = threadIdx.x; c < ncell; c += kClosureThreads)
+    {
+      const uint32_t v = info[c0 + c];
+      s_state[c] = (shift < 0 ? v : (v >> shift)) & mask;
+    }
+    int32_t* g = d + c0 * m;
+    const unsigned run = ncell * unsigned(m);
+    for (unsigned q = threadIdx.x; q < run; q += kClosureThreads)
+      tile[q] = g[q];
+    __syncthreads();
+    for (unsigned q = threadIdx.x; q < run; q += kClosureThreads)
+    {
+      const unsigned c = inv_m ? __umulhi(q, inv_m) : q, k = q - c * unsigned(m); // c = q / m (exact: q < 2^16)
+      const unsigned st = s_state[c];
+      if (st != 0)
+        g[q] = tile[c * m + s_src[st * m + k]];
+    }
+  }
+}
+} // namespace
+
+void closure_permute_device(const bx_element& e, int inverse, int32_t* d, size_t nc, size_t m, const uint32_t* info,
+                            int entity_type, int entity_index, cudaStream_t s)
+{
+  // entity_dim == 0: nothing moves; the cell_info overload returns before looking at the element
+  // (finite-element.h:871-875), the entity_info overload after the permutation check (950-960)
+  if (entity_index >= 0 and entity_type == BX_CELL_POINT)
+    return;
+  if (!e.perms)
+    fail(BX_ERR_RUNTIME, "The DOF transformations for this element are not permutations");
+  if (entity_type == BX_CELL_POINT)
+    return;
+  if (entity_type != BX_CELL_INTERVAL and entity_type != BX_CELL_TRIANGLE and entity_type != BX_CELL_QUADRILATERAL)
+    fail(BX_ERR_RUNTIME, entity_index < 0 ? "Invalid dimension for permute_subentity_closure" : "Unsupported cell dimension");
+  const bx_element::Closure& cl = e.closure[entity_type];
+  if (cl.size == 0)
+    fail(BX_ERR_RUNTIME, "permute_subentity_closure: the cell has no sub-entity of this type");
+  if (m != size_t(cl.size))
+    fail(BX_ERR_INVALID_ARG, "permute_subentity_closure: row length does not match the closure of the sub-entity");
+  int shift = -1;
+  if (entity_index >= 0)
+  {
+    const int edim = entity_type == BX_CELL_INTERVAL ? 1 : 2;
+    if (edim >= int(e.edofs.size()) or entity_index >= int(e.edofs[edim].size()))
+      fail(BX_ERR_INVALID_ARG, "permute_subentity_closure: entity index out of range");
+    const int face_start = e.tdim == 3 ? 3 * int(e.edofs[2].size()) : 0;
+    shift = edim == 1 ? face_start + entity_index : 3 * entity_index;
+  }
+  if (nc == 0)
+    return;
+  require_device(e);
+  const int cpb = std::max(1, std::min(256, 16384 / cl.size)); // cpb * m < 2^16 entries per tile
+  const size_t smem = (size_t((cl.states * cl.size + 1) / 2 + 3) / 4 * 4 + size_t(cpb) * cl.size + cpb) * 4;
+  if (smem > 96 * 1024)
+    fail(BX_ERR_UNSUPPORTED, "permute_subentity_closure: closure too large");
+  if (smem > 48 * 1024)
+    BX_CUDA(cudaFuncSetAttribute(closure_permute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  const size_t ntiles = (nc + cpb - 1) / cpb;
+  const unsigned grid = unsigned(std::min(ntiles, size_t(sm_count()) * 4));
+  const unsigned inv_m = cl.size > 1 ? unsigned((1ull << 32) / unsigned(cl.size) + 1) : 0u;
+  closure_permute_kernel<<<grid, kClosureThreads, smem, s>>>(d, nc, cl.size, cpb, info, shift,
+                                                             entity_type == BX_CELL_INTERVAL ? 1u : 7u,
+                                                             cl.d_src + size_t(inverse ? 1 : 0) * cl.states * cl.size,
+                                                             cl.states, inv_m);
+  BX_LAUNCHED();
+}
+
 template void dof_transform_device<double>(const bx_element&, int, double*, size_t, size_t, int, const uint32_t*,
                                            cudaStream_t);
 template void dof_transform_device<float>(const bx_element&, int, float*, size_t, size_t, int, const uint32_t*,

@@ -207,6 +207,158 @@ void jets::production_order(int tdim, int n, int* slot, double* norm)
   }
 }
 
+// ---- sub-entity closure permutations ------------------------------------------------------------------
+using StepMaps = std::array<std::array<std::vector<int>, 2>, 8>; // [sub-entity type][i]: new[r] = old[map[r]]
+void build_closure_tables(bx_element& e, const StepMaps& fwd, const StepMaps& inv)
+{
+  // finite-element.cpp:1449-1705 builds, for edge 0 and for one face of each face type, the permutation of the dofs
+  // on the entity's CLOSURE (vertex blocks, edge blocks, interior) under a rotation / reflection of the entity,
+  // and finite-element.h:942-1035 applies them per entity_info: forward = rotate x r then reflect, inverse =
+  // reflect then inverse-rotate x r.  Here the three generators are built the same way as index maps and the net
+  // gather of every state is composed once.
+  if (e.perms)
+  {
+    struct Conn
+    {
+      int cell, sub;
+      std::vector<int> v, ed, f;
+    };
+    // cell.cpp:143-292 sub_entity_connectivity of edge 0 / the face used by the reference (face_n)
+    static const Conn conns[] = {
+        {BX_CELL_TRIANGLE, BX_CELL_INTERVAL, {1, 2}, {0}, {}},
+        {BX_CELL_QUADRILATERAL, BX_CELL_INTERVAL, {0, 1}, {0}, {}},
+        {BX_CELL_TETRAHEDRON, BX_CELL_INTERVAL, {2, 3}, {0}, {}},
+        {BX_CELL_HEXAHEDRON, BX_CELL_INTERVAL, {0, 1}, {0}, {}},
+        {BX_CELL_PRISM, BX_CELL_INTERVAL, {0, 1}, {0}, {}},
+        {BX_CELL_PYRAMID, BX_CELL_INTERVAL, {0, 1}, {0}, {}},
+        {BX_CELL_TETRAHEDRON, BX_CELL_TRIANGLE, {1, 2, 3}, {0, 1, 2}, {0}},
+        {BX_CELL_PRISM, BX_CELL_TRIANGLE, {0, 1, 2}, {0, 1, 3}, {0}},
+        {BX_CELL_PYRAMID, BX_CELL_TRIANGLE, {0, 1, 4}, {0, 2, 4}, {1}},
+        {BX_CELL_HEXAHEDRON, BX_CELL_QUADRILATERAL, {0, 1, 2, 3}, {0, 1, 3, 5}, {0}},
+        {BX_CELL_PRISM, BX_CELL_QUADRILATERAL, {0, 1, 3, 4}, {0, 2, 4, 6}, {1}},
+        {BX_CELL_PYRAMID, BX_CELL_QUADRILATERAL, {0, 1, 2, 3}, {0, 1, 3, 5}, {0}},
+    };
+    using Idx = std::vector<int>;
+    // data[offset + i] <- data[offset + map[i]] (the effect of precompute::apply_permutation with the prepared map)
+    auto apply_at = [](const Idx& map, Idx& data, int offset)
+    {
+      Idx tmp(map.size());
+      for (size_t i = 0; i < map.size(); ++i)
+        tmp[i] = data[offset + map[i]];
+      std::copy(tmp.begin(), tmp.end(), data.begin() + offset);
+    };
+    auto apply_all = [&](const Idx& map, Idx& data) { apply_at(map, data, 0); };
+    for (const Conn& cn : conns)
+    {
+      if (cn.cell != e.cell_type)
+        continue;
+      std::vector<std::vector<Idx>> dofs(3);
+      int n = 0;
+      const std::vector<int>* ents[3] = {&cn.v, &cn.ed, &cn.f};
+      for (int dim = 0; dim < 3; ++dim)
+        for (int ent : *ents[dim])
+        {
+          Idx blk(e.edofs[dim][ent].size());
+          for (int& b : blk)
+            b = n++;
+          dofs[dim].push_back(blk);
+        }
+      auto cat = [](std::initializer_list<const Idx*> blocks)
+      {
+        Idx out;
+        for (const Idx* b : blocks)
+          out.insert(out.end(), b->begin(), b->end());
+        return out;
+      };
+      const auto &V = dofs[0], &E = dofs[1], &F = dofs[2];
+      const bool move = !e.identity;
+      const Idx& t1 = fwd[BX_CELL_INTERVAL][0];
+      Idx rot, rot_inv, ref;
+      if (cn.sub == BX_CELL_INTERVAL)
+      {
+        ref = cat({&V[1], &V[0], &E[0]});
+        if (move and !E[0].empty())
+          apply_at(t1, ref, E[0][0]);
+      }
+      else if (cn.sub == BX_CELL_TRIANGLE)
+      {
+        rot = cat({&V[1], &V[2], &V[0], &E[1], &E[2], &E[0], &F[0]});
+        rot_inv = cat({&V[2], &V[0], &V[1], &E[2], &E[0], &E[1], &F[0]});
+        ref = cat({&V[0], &V[2], &V[1], &E[0], &E[2], &E[1], &F[0]});
+        if (move and !E[0].empty())
+        {
+          apply_at(t1, rot, E[0][0]);
+          apply_at(t1, rot, E[1][0]);
+          apply_at(t1, ref, E[0][0]);
+          apply_at(t1, rot_inv, E[1][0]);
+          apply_at(t1, rot_inv, E[2][0]);
+        }
+        if (move and !F[0].empty())
+        {
+          apply_at(fwd[BX_CELL_TRIANGLE][0], rot_inv, F[0][0]);
+          apply_at(fwd[BX_CELL_TRIANGLE][1], ref, F[0][0]);
+          apply_at(inv[BX_CELL_TRIANGLE][0], rot, F[0][0]);
+        }
+      }
+      else
+      {
+        rot = cat({&V[1], &V[3], &V[0], &V[2], &E[2], &E[0], &E[3], &E[1], &F[0]});
+        rot_inv = cat({&V[2], &V[0], &V[3], &V[1], &E[1], &E[3], &E[0], &E[2], &F[0]});
+        ref = cat({&V[0], &V[2], &V[1], &V[3], &E[1], &E[0], &E[3], &E[2], &F[0]});
+        if (move and !E[0].empty())
+        {
+          apply_at(t1, rot, E[1][0]);
+          apply_at(t1, rot, E[2][0]);
+          apply_at(t1, rot_inv, E[0][0]);
+          apply_at(t1, rot_inv, E[3][0]);
+        }
+        if (move and !F[0].empty())
+        {
+          apply_at(fwd[BX_CELL_QUADRILATERAL][0], rot_inv, F[0][0]);
+          apply_at(fwd[BX_CELL_QUADRILATERAL][1], ref, F[0][0]);
+          apply_at(inv[BX_CELL_QUADRILATERAL][0], rot, F[0][0]);
+        }
+      }
+      bx_element::Closure& cl = e.closure[cn.sub];
+      cl.size = n;
+      cl.states = cn.sub == BX_CELL_INTERVAL ? 2 : 8;
+      cl.src.assign(size_t(2) * cl.states * n, 0);
+      for (int dir = 0; dir < 2; ++dir)
+        for (int st = 0; st < cl.states; ++st)
+        {
+          Idx net(n);
+          for (int i = 0; i < n; ++i)
+            net[i] = i;
+          if (cn.sub == BX_CELL_INTERVAL)
+          {
+            if (st & 1)
+              apply_all(ref, net);
+          }
+          else if (dir == 0)
+          {
+            for (int r = 0; r < ((st >> 1) & 3); ++r)
+              apply_all(rot, net);
+            if (st & 1)
+              apply_all(ref, net);
+          }
+          else
+          {
+            if (st & 1)
+              apply_all(ref, net);
+            for (int r = 0; r < ((st >> 1) & 3); ++r)
+              apply_all(rot_inv, net);
+          }
+          for (int i = 0; i < n; ++i)
+            cl.src[(size_t(dir) * cl.states + st) * n + i] = int16_t(net[i]);
+        }
+    }
+  }
+  if (e.on_device)
+    for (auto& cl : e.closure)
+      if (cl.size > 0)
+        cl.d_src = upload(cl.src);
+}
+
 bx_element* element_from_desc(const bx_element_desc& d)
 {
   if (d.cell_type < BX_CELL_POINT or d.cell_type > BX_CELL_PYRAMID)
@@ -390,7 +542,11 @@ bx_element* element_from_desc(const bx_element_desc& d)
   e->dof_loc.assign(ndofs, 0);
   e->lo_dof = e->hi_dof = 0;
   if (e->identity or e->tdim < 2)
+  {
+    if (e->tdim >= 2)
+      build_closure_tables(*e, {}, {}); // vertex and edge blocks still move with the entity
     return e.release();
+  }
 
   // ---- slots in the reference's processing order ------------------------------------------------------
   const int nfaces = e->tdim == 3 ? int(e->edofs[2].size()) : 0;
@@ -443,7 +599,7 @@ bx_element* element_from_desc(const bx_element_desc& d)
 
   // ---- per-class step operators -----------------------------------------------------------------------
   // index maps (permutation elements): new[r] = old[map[r]]
-  std::array<std::array<std::vector<int>, 2>, 8> fwd, inv;
+  StepMaps fwd, inv;
   // matrices (general elements): new = M old ; [cls][i] for the four stored flavours
   std::array<std::array<Mat, 2>, 8> M_, MT_, Minv_, MinvT_;
   for (int cls : {BX_CELL_INTERVAL, BX_CELL_TRIANGLE, BX_CELL_QUADRILATERAL})
@@ -484,6 +640,8 @@ bx_element* element_from_desc(const bx_element_desc& d)
       }
     }
   }
+
+  build_closure_tables(*e, fwd, inv);
 
   // ---- compose net operator per (op, slot/class, state) --------------------------------------------
   // op kinds: 0 T, 1 Tt, 2 Tt_inv, 3 Tinv.  `post` (reflect after rotate) for 1 and 3.
@@ -744,4 +902,6 @@ bx_element::~bx_element()
   cudaFree(d_band);
   cudaFree(d_dinfo);
   cudaFree(d_slot_band);
+  for (auto& cl : closure)
+    cudaFree(cl.d_src);
 }

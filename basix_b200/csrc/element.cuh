@@ -102,6 +102,16 @@ struct bx_element
   int band_size = 0;
   uint32_t* d_dinfo = nullptr;    // [ndofs] shift | mask << 5 | dim << 8 | (gather base + loc) << 16, or null
 
+  // ---- sub-entity closure permutations (permutation elements; finite-element.cpp:1449-1705) -----------
+  struct Closure
+  {
+    int size = 0;             // dofs on the closure of a sub-entity of this type; 0: the cell has none
+    int states = 0;           // 2 (interval: reversed?) or 8 (faces: reflect | rotations << 1)
+    std::vector<int16_t> src; // [2 directions][states][size] net gather: out[k] = in[src[k]]
+    int16_t* d_src = nullptr;
+  };
+  std::array<Closure, 8> closure; // by sub-entity cell type (interval, triangle, quadrilateral)
+
   ~bx_element();
   bx_element() = default;
   bx_element(const bx_element&) = delete;

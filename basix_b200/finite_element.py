@@ -623,6 +623,51 @@ class FiniteElement:
     def permute_batch(self, d, cell_info, inverse: bool = False) -> None:
         self._permute(int(bool(inverse)), d, cell_info, True)
 
+    # ---- sub-entity closure permutations ---------------------------------------------------------------
+    def subentity_closure_size(self, entity_type) -> int:
+        """Number of dofs on the closure of a sub-entity of this type (0 when the cell has none)."""
+        return int(lib().bx_element_subentity_closure_size(self._h, int(entity_type)))
+
+    def subentity_closure_map(self, entity_type, entity_info: int, inverse: bool = False):
+        """Host table of one state: ``src`` with ``out[k] = in[src[k]]`` (inspection / tests; no device needed)."""
+        m = self.subentity_closure_size(entity_type)
+        src = np.zeros(max(m, 1), dtype=np.int32)
+        check(lib().bx_element_subentity_closure_map(self._h, int(entity_type), int(bool(inverse)),
+                                                     int(entity_info) & 0xFFFFFFFF, src.ctypes.data))
+        return src[:m]
+
+    def _closure(self, inverse: int, d, info, entity_type, entity_index):
+        da = _Arg(d, np.int32, "indices", writable=True)
+        if len(da.shape) != 2:
+            raise TypeError("batched indices must have shape (ncells, closure size)")
+        nc, m = da.shape
+        ia = _Arg(info, np.uint32, "info")
+        if ia.shape != (nc,):
+            raise RuntimeError("info must have one entry per cell")
+        mem = _same_mem(da, ia)
+        stream, _ = _stream_and_like(da)
+        check(lib().bx_permute_subentity_closure_i32(self._h, inverse, da.ptr, nc, m, ia.ptr, int(entity_type),
+                                                     -1 if entity_index is None else int(entity_index), mem, stream))
+
+    def permute_subentity_closure(self, indices, cell_or_entity_info: int, entity_type, entity_index=None):
+        """``FiniteElement.permute_subentity_closure`` (python/basix/finite_element.py:322-347;
+        finite-element.h:860-985): returns the permuted copy of ``indices``, as the reference wrapper does."""
+        out = np.ascontiguousarray(indices, dtype=np.int32).copy().reshape(1, -1)
+        self._closure(0, out, np.asarray([int(cell_or_entity_info) & 0xFFFFFFFF], dtype=np.uint32), entity_type,
+                      entity_index)
+        return out[0]
+
+    def permute_subentity_closure_inv(self, indices, cell_or_entity_info: int, entity_type, entity_index=None):
+        """``FiniteElement.permute_subentity_closure_inv`` (python/basix/finite_element.py:349-374)."""
+        out = np.ascontiguousarray(indices, dtype=np.int32).copy().reshape(1, -1)
+        self._closure(1, out, np.asarray([int(cell_or_entity_info) & 0xFFFFFFFF], dtype=np.uint32), entity_type,
+                      entity_index)
+        return out[0]
+
+    def permute_subentity_closure_batch(self, d, info, entity_type, entity_index=None, inverse: bool = False) -> None:
+        """In place on d[ncells][closure size] (numpy int32 or CUDA torch int32), one ``info`` word per cell."""
+        self._closure(int(bool(inverse)), d, info, entity_type, entity_index)
+
 
 def create_element(family, celltype, degree: int, lagrange_variant=LagrangeVariant.unset,
                    dpc_variant=DPCVariant.unset, discontinuous: bool = False, dof_ordering=None,

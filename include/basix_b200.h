@@ -257,6 +257,25 @@ extern "C"
   int bx_permute_i32(const bx_element* e, int inverse, int32_t* d, size_t nc, const uint32_t* cell_info,
                      int mem, bx_stream_t stream);
 
+  /* ---- permute_subentity_closure ------------------------------------------------------------
+   * Replaces FiniteElement::permute_subentity_closure / _inv (finite-element.h:860-1035; tables built at
+   * finite-element.cpp:1449-1705; python/basix/finite_element.py:322-374), batched over cells:
+   * d[nc][m] holds, per cell, the dofs on the closure of ONE sub-entity of type `entity_type` (a bx_cell:
+   * interval, triangle or quadrilateral; m = bx_element_subentity_closure_size); row c is permuted in place.
+   * entity_index < 0: info[c] is the entity's own bits (bit 0 reflected, bits 1-2 rotations) -- the reference's
+   * (d, entity_info, entity_type) overload; entity_index >= 0: info[c] is the cell's cell_info and the bits of
+   * entity `entity_index` are extracted as the reference does -- the (d, cell_info, entity_type, entity_index)
+   * overload.  Permutation elements only (same error text as the reference otherwise).  The reference API is
+   * the nc == 1 case. */
+  int bx_permute_subentity_closure_i32(const bx_element* e, int inverse, int32_t* d, size_t nc, size_t m,
+                                       const uint32_t* info, int entity_type, int entity_index, int mem,
+                                       bx_stream_t stream);
+  /* Number of dofs on the closure of a sub-entity of type `entity_type` (0: none on this cell; -1: bad argument). */
+  int bx_element_subentity_closure_size(const bx_element* e, int entity_type);
+  /* Host table behind the call above: src[m] with out[k] = in[src[k]] for one entity_info (testing / inspection). */
+  int bx_element_subentity_closure_map(const bx_element* e, int entity_type, int inverse, uint32_t entity_info,
+                                       int32_t* src);
+
 #ifdef __cplusplus
 }
 #endif

@@ -241,6 +241,34 @@ public:
     check(bx_permute_i32(_h, inverse ? 1 : 0, d, nc, cell_info, mem, stream));
   }
 
+  /// (finite-element.h:860-985 / 997-1035): `d` = the dofs on the closure of one sub-entity.
+  /// entity_info overloads: the entity's own bits; cell_info overloads: the cell's bits + the entity's index.
+  void permute_subentity_closure(std::int32_t* d, std::size_t m, std::uint32_t entity_info, int entity_type) const
+  {
+    check(bx_permute_subentity_closure_i32(_h, 0, d, 1, m, &entity_info, entity_type, -1, BX_MEM_HOST, nullptr));
+  }
+  void permute_subentity_closure_inv(std::int32_t* d, std::size_t m, std::uint32_t entity_info, int entity_type) const
+  {
+    check(bx_permute_subentity_closure_i32(_h, 1, d, 1, m, &entity_info, entity_type, -1, BX_MEM_HOST, nullptr));
+  }
+  void permute_subentity_closure(std::int32_t* d, std::size_t m, std::uint32_t cell_info, int entity_type,
+                                 int entity_index) const
+  {
+    check(bx_permute_subentity_closure_i32(_h, 0, d, 1, m, &cell_info, entity_type, entity_index, BX_MEM_HOST, nullptr));
+  }
+  void permute_subentity_closure_inv(std::int32_t* d, std::size_t m, std::uint32_t cell_info, int entity_type,
+                                     int entity_index) const
+  {
+    check(bx_permute_subentity_closure_i32(_h, 1, d, 1, m, &cell_info, entity_type, entity_index, BX_MEM_HOST, nullptr));
+  }
+  void permute_subentity_closure_batch(std::int32_t* d, std::size_t nc, std::size_t m, const std::uint32_t* info,
+                                       int entity_type, int entity_index = -1, bool inverse = false,
+                                       int mem = BX_MEM_HOST, bx_stream_t stream = nullptr) const
+  {
+    check(bx_permute_subentity_closure_i32(_h, inverse ? 1 : 0, d, nc, m, info, entity_type, entity_index, mem, stream));
+  }
+  int subentity_closure_size(int entity_type) const { return bx_element_subentity_closure_size(_h, entity_type); }
+
 private:
   FiniteElement() = default;
   void read_info()

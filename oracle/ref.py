@@ -61,6 +61,8 @@ def lib():
                                         C.c_void_p]
         L.bxref_permute_i32.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p,
                                         C.c_int]
+        L.bxref_permute_subentity_closure_i32.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t,
+                                                          C.c_void_p, C.c_int, C.c_int]
         _lib = L
     return _lib
 
@@ -218,4 +220,14 @@ class RefElement:
         ci = np.ascontiguousarray(cell_info, dtype=np.uint32)
         _check(lib().bxref_permute_i32(self._h, int(inverse), _ptr(d), d.shape[0], d.shape[1], _ptr(ci),
                                        int(nthreads)))
+        return d
+
+    def permute_subentity_closure_batch(self, d: np.ndarray, info: np.ndarray, entity_type: int,
+                                        entity_index: int | None = None, inverse: bool = False):
+        """FiniteElement::permute_subentity_closure{,_inv} per row of d (finite-element.h:860-1035); ``info`` holds
+        entity_info when ``entity_index`` is None, else cell_info."""
+        assert d.dtype == np.int32 and d.flags.c_contiguous and d.ndim == 2
+        ci = np.ascontiguousarray(info, dtype=np.uint32)
+        _check(lib().bxref_permute_subentity_closure_i32(self._h, int(inverse), _ptr(d), d.shape[0], d.shape[1], _ptr(ci),
+                                                         int(entity_type), -1 if entity_index is None else int(entity_index)))
         return d

@@ -420,4 +420,35 @@ int bxref_permute_i32(void* h, int inverse, std::int32_t* d, std::size_t nc,
           throw std::runtime_error(err);
       });
 }
+// d[nc][m] int32 (dofs on the closure of one sub-entity), permuted in place, one reference call per cell.
+// entity_index < 0: info[c] is the entity's own bits (finite-element.h:942-985 / 997-1035);
+// entity_index >= 0: info[c] is the cell's cell_info (finite-element.h:860-930).
+int bxref_permute_subentity_closure_i32(void* h, int inverse, std::int32_t* d, std::size_t nc, std::size_t m,
+                                        const std::uint32_t* info, int entity_type, int entity_index)
+{
+  const FE& e = *static_cast<FE*>(h);
+  return guarded(
+      [&]()
+      {
+        const auto et = static_cast<basix::cell::type>(entity_type);
+        for (std::size_t c = 0; c < nc; ++c)
+        {
+          std::span<std::int32_t> s(d + c * m, m);
+          if (entity_index < 0)
+          {
+            if (inverse)
+              e.permute_subentity_closure_inv(s, info[c], et);
+            else
+              e.permute_subentity_closure(s, info[c], et);
+          }
+          else
+          {
+            if (inverse)
+              e.permute_subentity_closure_inv(s, info[c], et, entity_index);
+            else
+              e.permute_subentity_closure(s, info[c], et, entity_index);
+          }
+        }
+      });
+}
 } // extern "C"
