@@ -551,6 +551,28 @@ def run_ours(args, w, rank, local_rank, world):
                "d2h_bytes_per_step": int(w.d2h), "steps": e2e_steps, "ms_per_step": dt * 1e3}
         e2e.update(extra)
 
+    # ---- gather bandwidth (N > 1 only; SURVEY 8e: reported separately, never part of `value`) ----
+    gather = None
+    if dist is not None:
+        from basix_b200.sharding import gather_cells
+
+        rows = (256 << 20) // 448  # 256 MiB per rank of 56-double rows: one derivative slab of a point slice
+        part = torch.full((rows, 56), float(rank), dtype=torch.float64, device="cuda")
+        gather_cells(part, rows * world)  # warm-up (NCCL channel set-up)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(3):
+            full = gather_cells(part, rows * world)
+        g1.record()
+        barrier()
+        ms = max_over_ranks(g0.elapsed_time(g1)) / 3
+        ok = bool((full[:: rows, 0] == torch.arange(world, dtype=torch.float64, device="cuda")).all())
+        gather = {"collective": "all_gather of one 256 MiB result slab per rank (torch.distributed, NCCL over NVLink)",
+                  "bytes_per_rank": int(part.numel() * 8), "ms": ms, "correct": ok,
+                  "algbw_GBps": part.numel() * 8 * world / (ms * 1e-3) / 1e9}
+        del part, full
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference(w, 2, 1)
@@ -565,7 +587,7 @@ def run_ours(args, w, rank, local_rank, world):
             "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32" if getattr(w, "permute", False) else "f64", "data": "synthetic",
             "config": cfg, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "gather": gather,
         })
     if dist is not None:
         dist.destroy_process_group()
