@@ -41,6 +41,9 @@ class ElementDesc(C.Structure):
         ("etrans_triangle_dim", C.c_int),
         ("etrans_quadrilateral", C.c_void_p),
         ("etrans_quadrilateral_dim", C.c_int),
+        ("points", C.c_void_p),
+        ("npts", C.c_int),
+        ("interpolation_matrix", C.c_void_p),
     ]
 
 
@@ -84,6 +87,10 @@ SIGNATURES = {
     "bx_T_apply_f32": (_I, [_P, _I, _P, _SIZE, _SIZE, _I, _P, _I, _P]),
     "bx_T_apply_i32": (_I, [_P, _I, _P, _SIZE, _SIZE, _I, _P, _I, _P]),
     "bx_permute_i32": (_I, [_P, _I, _P, _SIZE, _P, _I, _P]),
+    "bx_element_interpolation_shape": (_I, [_P, _P]),
+    "bx_element_points": (_I, [_P, _P]),
+    "bx_element_interpolation_matrix": (_I, [_P, _P]),
+    "bx_interpolate_f64": (_I, [_P, _I, _P, _SIZE, _P, _I, _P]),
     "bx_permute_subentity_closure_i32": (_I, [_P, _I, _P, _SIZE, _SIZE, _P, _I, _I, _I, _P]),
     "bx_element_subentity_closure_size": (_I, [_P, _I]),
     "bx_element_subentity_closure_map": (_I, [_P, _I, _I, C.c_uint32, _P]),

@@ -813,8 +813,37 @@ bx_element* build_vector_element(int cell, int degree, int map_type, Vec B, DofS
   }
   if (flat.empty())
     flat.push_back(0);
+  // points() and interpolation_matrix() (finite-element.cpp:1121-1188): the dof points of all entities in entity
+  // order, and M[dof][j * npts + p] assembled from the per-entity moment matrices
+  size_t npts_all = 0;
+  for (int d = 0; d <= tdim; ++d)
+    for (const Vec& xe : dofs.x[d])
+      npts_all += xe.size() / tdim;
+  Vec allx, Mall(size_t(ndofs) * vs * npts_all, 0.0);
+  {
+    size_t pt0 = 0;
+    int dof0 = 0;
+    for (int d = 0; d <= tdim; ++d)
+      for (size_t e = 0; e < dofs.x[d].size(); ++e)
+      {
+        const Vec& xe = dofs.x[d][e];
+        const size_t np = xe.size() / tdim;
+        allx.insert(allx.end(), xe.begin(), xe.end());
+        const int nd = dofs.ndofs[d][e];
+        for (int i = 0; i < nd; ++i)
+          for (int j = 0; j < vs; ++j)
+            for (size_t k = 0; k < np; ++k)
+              Mall[(size_t(dof0 + i) * vs + j) * npts_all + pt0 + k] = dofs.M[d][e][(size_t(i) * vs + j) * np + k];
+        dof0 += nd;
+        pt0 += np;
+      }
+  }
+
   static const double none = 0.0;
   bx_element_desc desc{};
+  desc.points = allx.data();
+  desc.npts = int(npts_all);
+  desc.interpolation_matrix = Mall.data();
   desc.cell_type = cell;
   desc.polyset_type = BX_POLYSET_STANDARD;
   desc.degree = degree;
@@ -1008,8 +1037,20 @@ bx_element* create_lagrange(int cell, int degree, int variant, bool discontinuou
   if (flat.empty())
     flat.push_back(0);
 
+  // points() follow the dof order (finite-element.cpp:1228-1236); interpolation_matrix() is the identity
+  Vec xdof(allx.size());
+  for (int q = 0; q < ndofs; ++q)
+    for (int i = 0; i < tdim; ++i)
+      xdof[size_t(n_dof_ordering ? dof_ordering[q] : q) * tdim + i] = allx[size_t(q) * tdim + i];
+  Vec Mid(size_t(ndofs) * ndofs, 0.0);
+  for (int q = 0; q < ndofs; ++q)
+    Mid[size_t(q) * ndofs + q] = 1.0;
+
   static const double none = 0.0;
   bx_element_desc desc{};
+  desc.points = xdof.data();
+  desc.npts = ndofs;
+  desc.interpolation_matrix = Mid.data();
   desc.cell_type = cell;
   desc.polyset_type = BX_POLYSET_STANDARD;
   desc.degree = degree;

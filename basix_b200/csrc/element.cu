@@ -486,6 +486,30 @@ bx_element* element_from_desc(const bx_element_desc& d)
     }
   }
 
+  // ---- interpolation data (optional) ----------------------------------------------------------------
+  if (d.interpolation_matrix and d.points and d.npts > 0)
+  {
+    e->interp_npts = d.npts;
+    e->points.assign(d.points, d.points + size_t(d.npts) * e->tdim);
+    const int K = e->vs * d.npts;
+    e->interp_M.assign(d.interpolation_matrix, d.interpolation_matrix + size_t(e->ndofs) * K);
+    // device operands, one per value layout: B[n][k'] with k' the position of (component j, point p) in the layout
+    const int kp = int(ceil_div(K, 4) * 4);
+    e->interp_kstride = kp % 8 == 4 ? kp : kp + 4;
+    e->interp_npad = int(ceil_div(e->ndofs, 8) * 8);
+    if (e->on_device)
+      for (int layout = 0; layout < 2; ++layout)
+      {
+        std::vector<double> B(size_t(e->interp_npad) * e->interp_kstride, 0.0);
+        for (int n = 0; n < e->ndofs; ++n)
+          for (int j = 0; j < e->vs; ++j)
+            for (int p = 0; p < d.npts; ++p)
+              B[size_t(n) * e->interp_kstride + (layout == 0 ? j * d.npts + p : p * e->vs + j)]
+                  = e->interp_M[size_t(n) * K + j * d.npts + p];
+        e->d_interp[layout] = upload(B);
+      }
+  }
+
   // ---- entity transformations ------------------------------------------------------------------------
   auto take = [&](int cls, const double* p, int n, int ntrans)
   {
@@ -904,4 +928,6 @@ bx_element::~bx_element()
   cudaFree(d_slot_band);
   for (auto& cl : closure)
     cudaFree(cl.d_src);
+  cudaFree(d_interp[0]);
+  cudaFree(d_interp[1]);
 }

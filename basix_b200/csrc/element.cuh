@@ -112,6 +112,13 @@ struct bx_element
   };
   std::array<Closure, 8> closure; // by sub-entity cell type (interval, triangle, quadrilateral)
 
+  // ---- interpolation (optional): points(), interpolation_matrix() and the device operands of interpolate.cu ----
+  int interp_npts = 0;
+  std::vector<double> points;   // [npts][tdim]
+  std::vector<double> interp_M; // [ndofs][vs * npts], reference column order (component major)
+  int interp_kstride = 0, interp_npad = 0; // operand rows: ndofs padded to 8; row stride == 4 (mod 8) doubles
+  double* d_interp[2] = {nullptr, nullptr}; // [layout][npad][kstride]: column order of each value layout
+
   ~bx_element();
   bx_element() = default;
   bx_element(const bx_element&) = delete;

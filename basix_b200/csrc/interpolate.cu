@@ -1,0 +1,183 @@
+// Batched application of the interpolation matrix: coefficients[c][n] = sum_k M[n][k] values[c][k].
+//
+// The reference exposes interpolation_matrix() (cpp/basix/finite-element.h:1222-1226) and leaves the product
+// "coefficients = i_m * values" to the caller, one cell at a time (finite-element.h:1183-1216).  Over many cells
+// it is a tall-skinny FP64 GEMM -- [nc x K] by [K x ndofs], K = value_size * npts -- and the step that follows
+// pull_back when a function is interpolated into the element.  For N1curl degree 3 on the tetrahedron (K = 141,
+// ndofs = 45) that is 12.7 kflop and 1488 B per cell: 8.5 flop/B against a machine balance of 5.7 (37 TFLOP/s
+// DMMA, 6.5 TB/s HBM), so the kernel is bound by the FP64 tensor pipe with HBM close behind.
+//
+// Kernel (the contraction half of tabulate_dop.cu, with the A operand streamed from HBM instead of produced):
+// persistent, one CTA per SM, twelve independent warps.  The operand M (rows padded to 8, row stride == 4 mod 8
+// doubles, column order matching the value layout) stays in shared memory.  A warp owns 16 cells = two m8 row
+// tiles; lane (g, t) loads its A-fragment entries values[c0 + g (+8)][4 ks + t] straight from global memory --
+// the four t-lanes of a row read one full 32-byte sector, so every sector is fetched exactly once -- two k-steps
+// ahead in registers, B fragments one step ahead from shared memory, and every B fragment feeds two DMMAs.
+// Accumulator fragments are stored straight as coefficients[c][n].
+#include "element.cuh"
+
+#include <algorithm>
+
+namespace bx
+{
+namespace
+{
+constexpr int kWarps = 12;
+constexpr int kThreads = 32 * kWarps;
+constexpr int kCells = 16; // cells per warp chunk
+constexpr int kMaxNT = 7;  // 8-column tiles per column group
+
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
+{
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(d0), "+d"(d1)
+      : "d"(a), "d"(b));
+}
+
+struct Params
+{
+  const double* values; // [nc][K]
+  const double* B;      // [npad][kstride]
+  double* out;          // [nc][N]
+  size_t nc;
+  int K, N, npad, kstride, ksteps;
+};
+
+// Column group [n0, n0 + 8 NT) for the 16 cells of one chunk.
+template <int NT>
+__device__ __forceinline__ void run_group(const Params& p, const double* __restrict__ Bs, size_t c0, int n0, int g, int t)
+{
+  double acc[2][NT][2];
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+      acc[m][j][0] = acc[m][j][1] = 0.0;
+  // rows of this lane (clamped: a row past the end is computed and never stored)
+  const size_t r0 = min(c0 + g, p.nc - 1), r1 = min(c0 + g + 8, p.nc - 1);
+  const double* __restrict__ v0 = p.values + r0 * p.K + t;
+  const double* __restrict__ v1 = p.values + r1 * p.K + t;
+  const double* __restrict__ bp = Bs + (n0 + g) * p.kstride + t;
+  const int ts = 8 * p.kstride;
+  const int kt = p.K - t; // entries 4 ks + t < K  <=>  4 ks < kt
+  auto lda = [&](const double* v, int ks) { return 4 * ks < kt ? __ldcs(v + 4 * ks) : 0.0; };
+
+  double a0 = lda(v0, 0), a1 = lda(v1, 0);    // step s
+  double a0n = lda(v0, 1), a1n = lda(v1, 1);  // step s + 1
+  double b[NT];
+#pragma unroll
+  for (int j = 0; j < NT; ++j)
+    b[j] = bp[j * ts];
+#pragma unroll 1
+  for (int ks = 0; ks < p.ksteps; ++ks)
+  {
+    const double a0nn = lda(v0, ks + 2), a1nn = lda(v1, ks + 2); // global: two steps ahead
+    double bn[NT];
+    const int kn = min(ks + 1, p.ksteps - 1);
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+      bn[j] = bp[j * ts + 4 * kn]; // shared: one step ahead
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+    {
+      dmma(acc[0][j][0], acc[0][j][1], a0, b[j]);
+      dmma(acc[1][j][0], acc[1][j][1], a1, b[j]);
+    }
+    a0 = a0n, a1 = a1n;
+    a0n = a0nn, a1n = a1nn;
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+      b[j] = bn[j];
+  }
+  // accumulator fragment: row g = cell, columns 2t, 2t+1 of each 8-column tile
+  const bool even = (p.N & 1) == 0;
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+  {
+    const size_t c = c0 + g + 8 * m;
+    if (c < p.nc)
+    {
+      double* row = p.out + c * p.N;
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+      {
+        const int n = n0 + j * 8 + 2 * t;
+        if (even)
+        {
+          if (n < p.N)
+            __stcs(reinterpret_cast<double2*>(row + n), make_double2(acc[m][j][0], acc[m][j][1]));
+        }
+        else
+        {
+          if (n < p.N)
+            __stcs(row + n, acc[m][j][0]);
+          if (n + 1 < p.N)
+            __stcs(row + n + 1, acc[m][j][1]);
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) interpolate_kernel(const Params p)
+{
+  extern __shared__ __align__(16) double interp_smem[];
+  double* Bs = interp_smem;
+  for (int i = threadIdx.x; i < p.npad * p.kstride; i += kThreads)
+    Bs[i] = p.B[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const size_t nchunks = ceil_div(p.nc, size_t(kCells));
+  const size_t stride = size_t(gridDim.x) * kWarps;
+  for (size_t chunk = size_t(blockIdx.x) * kWarps + warp; chunk < nchunks; chunk += stride)
+  {
+    const size_t c0 = chunk * kCells;
+    for (int n0 = 0; n0 < p.N; n0 += 8 * kMaxNT)
+    {
+      const int nt = min(kMaxNT, (p.N - n0 + 7) >> 3);
+      switch (nt)
+      {
+      case 1: run_group<1>(p, Bs, c0, n0, g, t); break;
+      case 2: run_group<2>(p, Bs, c0, n0, g, t); break;
+      case 3: run_group<3>(p, Bs, c0, n0, g, t); break;
+      case 4: run_group<4>(p, Bs, c0, n0, g, t); break;
+      case 5: run_group<5>(p, Bs, c0, n0, g, t); break;
+      case 6: run_group<6>(p, Bs, c0, n0, g, t); break;
+      default: run_group<7>(p, Bs, c0, n0, g, t); break;
+      }
+    }
+  }
+}
+} // namespace
+
+// values[nc][vs * npts] (layout 0: component major, 1: point major) -> coefficients[nc][ndofs]
+void interpolate_device(const bx_element& e, int layout, const double* values, size_t nc, double* coefficients,
+                        cudaStream_t s)
+{
+  if (e.interp_npts == 0)
+    fail(BX_ERR_RUNTIME, "interpolate: the element was built without points() / interpolation_matrix()");
+  if (layout != 0 and layout != 1)
+    fail(BX_ERR_INVALID_ARG, "interpolate: layout must be BX_INTERP_COMPONENT_MAJOR or BX_INTERP_POINT_MAJOR");
+  if (nc == 0)
+    return;
+  require_device(e);
+  Params p;
+  p.values = values;
+  p.B = e.d_interp[layout];
+  p.out = coefficients;
+  p.nc = nc;
+  p.K = e.vs * e.interp_npts;
+  p.N = e.ndofs;
+  p.npad = e.interp_npad;
+  p.kstride = e.interp_kstride;
+  p.ksteps = int(ceil_div(size_t(p.K), size_t(4)));
+  const size_t smem = size_t(p.npad) * p.kstride * sizeof(double);
+  if (smem > 227 * 1024)
+    fail(BX_ERR_UNSUPPORTED, "interpolate: the interpolation matrix does not fit in shared memory");
+  BX_CUDA(cudaFuncSetAttribute(interpolate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  const size_t nblocks = ceil_div(nc, size_t(kCells) * kWarps);
+  interpolate_kernel<<<unsigned(std::min<size_t>(nblocks, size_t(sm_count()))), kThreads, smem, s>>>(p);
+  BX_LAUNCHED();
+}
+} // namespace bx

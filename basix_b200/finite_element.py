@@ -224,7 +224,7 @@ class FiniteElement:
 
     def __init__(self, *, cell_type, polyset_type, degree, embedded_superdegree, map_type, value_shape,
                  coefficient_matrix, entity_dofs, entity_transformations, dof_ordering=None, family=0,
-                 lagrange_variant=0, dpc_variant=0, discontinuous=False):
+                 lagrange_variant=0, dpc_variant=0, discontinuous=False, points=None, interpolation_matrix=None):
         self._h = None
         self._cell_type = CellType(int(cell_type))
         self._polyset_type = PolysetType(int(polyset_type))
@@ -278,6 +278,17 @@ class FiniteElement:
                 setattr(d, f"etrans_{name}_dim", m.shape[1])
         if coeffs.shape[1] != vs * polyset_dim(cell_type, polyset_type, embedded_superdegree):
             raise ValueError("coefficient_matrix has the wrong number of columns for this polyset")
+        # optional: points() and interpolation_matrix() (needed by interpolate_batch only)
+        self._points = self._interpolation_matrix = None
+        if points is not None and interpolation_matrix is not None:
+            self._points = np.ascontiguousarray(points, dtype=np.float64)
+            self._interpolation_matrix = np.ascontiguousarray(interpolation_matrix, dtype=np.float64)
+            npts = self._points.shape[0]
+            if self._points.ndim != 2 or self._points.shape[1] != tdim or \
+                    self._interpolation_matrix.shape != (coeffs.shape[0], vs * npts):
+                raise ValueError("points must be (npts, tdim) and interpolation_matrix (ndofs, value_size * npts)")
+            d.points, d.npts = self._points.ctypes.data, npts
+            d.interpolation_matrix = self._interpolation_matrix.ctypes.data
         h = C.c_void_p()
         check(lib().bx_element_create_from_arrays(C.byref(d), C.byref(h)))
         self._h = h
@@ -324,6 +335,14 @@ class FiniteElement:
         self._dof_ordering = np.zeros(n, dtype=np.int32)
         if n:
             L.bx_element_dof_ordering(h, self._dof_ordering.ctypes.data)
+        ishape = (C.c_int32 * 4)()
+        check(L.bx_element_interpolation_shape(h, ishape))
+        self._points = self._interpolation_matrix = None
+        if ishape[0] > 0:
+            self._points = np.empty((ishape[0], ishape[1]), dtype=np.float64)
+            self._interpolation_matrix = np.empty((ishape[2], ishape[3]), dtype=np.float64)
+            check(L.bx_element_points(h, self._points.ctypes.data))
+            check(L.bx_element_interpolation_matrix(h, self._interpolation_matrix.ctypes.data))
         return self
 
     def __del__(self):
@@ -370,7 +389,10 @@ class FiniteElement:
                 k += 1
             edofs.append(row)
         etrans = {int(key.split("_")[1]): arrs[key] for key in arrs.keys() if key.startswith("etrans_")}
-        return cls(cell_type=cell, polyset_type=meta[1], degree=meta[2], embedded_superdegree=meta[3],
+        keys = set(arrs.keys())
+        extra = ({"points": arrs["points"], "interpolation_matrix": arrs["interpolation_matrix"]}
+                 if {"points", "interpolation_matrix"} <= keys else {})
+        return cls(**extra, cell_type=cell, polyset_type=meta[1], degree=meta[2], embedded_superdegree=meta[3],
                    map_type=meta[4], family=meta[5], lagrange_variant=meta[6], dpc_variant=meta[7],
                    discontinuous=bool(meta[8]), value_shape=tuple(int(v) for v in arrs["value_shape"]),
                    coefficient_matrix=arrs["coefficient_matrix"], entity_dofs=edofs,
@@ -622,6 +644,36 @@ class FiniteElement:
 
     def permute_batch(self, d, cell_info, inverse: bool = False) -> None:
         self._permute(int(bool(inverse)), d, cell_info, True)
+
+    # ---- interpolation ---------------------------------------------------------------------------------
+    @property
+    def points(self):
+        """``FiniteElement.points`` (finite-element.h:1167-1170): shape (npts, tdim); None when the element was
+        described without interpolation data."""
+        return self._points
+
+    @property
+    def interpolation_matrix(self):
+        """``FiniteElement.interpolation_matrix`` (finite-element.h:1222-1226): shape (ndofs, value_size * npts)."""
+        return self._interpolation_matrix
+
+    def interpolate_batch(self, values, layout: str = "component-major"):
+        """coefficients[c] = interpolation_matrix @ values[c] for every cell (the product the reference leaves to
+        the caller, finite-element.h:1183-1216).  ``values``: (ncells, value_size * npts); layout
+        "component-major" = the reference's column order ``values[c][j * npts + p]``, "point-major" =
+        ``values[c][p * value_size + j]`` (what ``pull_back`` writes with rows = points, reshaped).  numpy in ->
+        numpy out, CUDA torch tensor in -> CUDA torch tensor out."""
+        if self._points is None:
+            raise RuntimeError("interpolate: the element was built without points() / interpolation_matrix()")
+        va = _Arg(values, np.float64, "values")
+        k = self._vs * self._points.shape[0]
+        if len(va.shape) != 2 or va.shape[1] != k:
+            raise RuntimeError(f"values must have shape (ncells, {k})")
+        stream, alloc = _stream_and_like(va)
+        out = alloc((va.shape[0], self._ndofs), np.float64)
+        lay = {"component-major": 0, "point-major": 1}[layout]
+        check(lib().bx_interpolate_f64(self._h, lay, va.ptr, va.shape[0], _ptr_of(out), va.mem, stream))
+        return out
 
     # ---- sub-entity closure permutations ---------------------------------------------------------------
     def subentity_closure_size(self, entity_type) -> int:

@@ -404,6 +404,71 @@ class TApply:
             r.T_apply_batch("T_apply", d, self.bs, ci, nthreads=cores)
 
 
+class Interpolate:
+    """coefficients = interpolation_matrix @ values over many cells (the step after pull_back)."""
+    metric, unit = METRIC_CELLS, "cells/s"
+    bound = "tensor"
+    cpu_kind = "port"  # numpy dgemm with the reference's matrix: the reference has no batched call to time
+
+    def __init__(self, element, ref_args, nc, desc):
+        self.element_name, self.ref_args, self.nc, self.desc = element, ref_args, nc, desc
+
+    def setup(self, rank):
+        import torch
+
+        # the reference's own element (committed arrays of the unmodified reference, tests/golden/elements): its
+        # interpolation points are the reference's Xiao-Gimbutas points; the native factory's Gauss-Jacobi points
+        # give the same functionals with a larger matrix (DESIGN.md 1b)
+        import basix_b200 as bx
+
+        self.e = bx.FiniteElement.from_arrays(np.load(os.path.join(GOLDEN, self.element_name + ".npz")))
+        e, nc = self.e, self.nc
+        self.K, self.N = e.value_size * e.points.shape[0], e.dim
+        g = torch.Generator(device="cuda").manual_seed(21 + rank)
+        self.values = torch.randn(nc, self.K, generator=g, device="cuda", dtype=torch.float64)
+        self.units_per_step = nc
+        self.launches_per_step = 1
+        self.units_per_launch = nc
+        self.alg_bytes = nc * (self.K + self.N) * 8
+        self.flops = 2.0 * self.K * self.N * nc
+        self.config = {"workload": self.desc, "cells_per_gpu": nc, "values_per_cell": self.K, "ndofs": self.N,
+                       "fp64_flops_per_cell": 2 * self.K * self.N,
+                       "l2": "arrays are %.2f GB per step (>> 126 MB L2)" % (self.alg_bytes / 1e9)}
+
+    def step(self):
+        self.result = self.e.interpolate_batch(self.values)
+
+    def e2e_setup(self, avail_bytes):
+        import torch
+
+        self.values_host = self.values.cpu().pin_memory()
+        self.out_host = torch.empty((self.nc, self.N), dtype=torch.float64).pin_memory()
+        self.e2e_units = self.nc
+        self.h2d, self.d2h = self.values_host.numel() * 8, self.out_host.numel() * 8
+        return {"cells_per_gpu": self.nc}
+
+    def e2e_step(self):
+        from basix_b200 import _capi
+
+        _capi.check(_capi.lib().bx_interpolate_f64(self.e._h, 0, self.values_host.data_ptr(), self.nc,
+                                                   self.out_host.data_ptr(), _capi.BX_MEM_HOST, None))
+
+    def cpu_setup(self, cores):
+        # the reference has no batched interpolate: its documented usage is `i_m * values` per cell
+        # (finite-element.h:1183-1216), i.e. one dgemm over a batch of cells with the reference's own matrix
+        from oracle import ref
+
+        r = ref.RefElement(*self.ref_args)
+        n = int(min(self.nc, 2_000_000))
+        self._cpu = (np.ascontiguousarray(r.interpolation_matrix.T), np.random.default_rng(21).standard_normal((n, self.K)))
+        return n, (f"{n} cells per step, values @ interpolation_matrix.T with numpy (OpenBLAS dgemm, all threads), the "
+                   f"reference's documented usage of interpolation_matrix()")
+
+    def cpu_step(self):
+        Mt, v = self._cpu
+        self._cpu_out = v @ Mt
+
+
 WORKLOADS = {
     "tabulate_p5_tet": lambda: Tabulate(
         "P5_tetrahedron_gll", (1, 3, 5, 2), 3, 2, 10_000_000, 1,
@@ -424,6 +489,9 @@ WORKLOADS = {
     "push_forward_n1curl3_rows45": lambda: PushForward(
         "N1curl3_tetrahedron_legendre", (3, 3, 3, 11), 4_000_000, 45, False,
         "N1curl degree 3 tetrahedron, covariant Piola push_forward, 4M cells x 45 rows"),
+    "interpolate_n1curl3": lambda: Interpolate(
+        "N1curl3_tetrahedron_legendre", (3, 3, 3, 11), 20_000_000,
+        "N1curl degree 3 tetrahedron, interpolation_matrix (45 x 141) applied to 20M cells of point values"),
     "t_apply_rt4": lambda: TApply(
         "RT4_tetrahedron_legendre", (2, 3, 4, 11), 50_000_000, 1, False,
         "RT degree 4 tetrahedron, T_apply(block 1) over 50M cells, random cell_info"),
@@ -449,7 +517,8 @@ def cpu_reference(w, steps, warmup):
     for _ in range(steps):
         w.cpu_step()
     dt = (time.perf_counter() - t0) / steps
-    return dict(value=units / dt, unit=w.unit, cores=cores, kind="reference", sample=sample, ms_per_step=dt * 1e3)
+    return dict(value=units / dt, unit=w.unit, cores=cores, kind=getattr(w, "cpu_kind", "reference"), sample=sample,
+                ms_per_step=dt * 1e3)
 
 
 def run_reference(args, w, rank):

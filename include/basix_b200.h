@@ -152,6 +152,12 @@ extern "C"
     int etrans_triangle_dim;
     const double* etrans_quadrilateral;
     int etrans_quadrilateral_dim;
+    /* Optional (NULL / 0 when the element is only tabulated / mapped / transformed): points()
+       (finite-element.h:1167-1170), [npts][tdim], and interpolation_matrix() (finite-element.h:1222-1226),
+       [ndofs][value_size * npts] with column j * npts + p = value component j at point p. */
+    const double* points;
+    int npts;
+    const double* interpolation_matrix;
   } bx_element_desc;
 
   /* Build an element (host tables + device mirror on the current device) from arrays. */
@@ -275,6 +281,28 @@ extern "C"
   /* Host table behind the call above: src[m] with out[k] = in[src[k]] for one entity_info (testing / inspection). */
   int bx_element_subentity_closure_map(const bx_element* e, int entity_type, int inverse, uint32_t entity_info,
                                        int32_t* src);
+
+
+  /* ---- interpolation ------------------------------------------------------------------------
+   * points() / interpolation_matrix() of the reference (finite-element.h:1167-1170, 1222-1226) and the batched
+   * application of the matrix -- the step that follows pull_back when a function is interpolated into the
+   * element: the reference leaves `coefficients = interpolation_matrix * values` to the caller, one cell at a
+   * time (finite-element.h:1183-1216).  values[nc][value_size * npts] -> coefficients[nc][ndofs].
+   * layout BX_INTERP_COMPONENT_MAJOR: values[c][j * npts + p], the reference's column order;
+   * layout BX_INTERP_POINT_MAJOR:     values[c][p * value_size + j], the order pull_back writes
+   *                                   (rows = points), so its output feeds this call without a transpose. */
+  enum
+  {
+    BX_INTERP_COMPONENT_MAJOR = 0,
+    BX_INTERP_POINT_MAJOR = 1
+  };
+  /* shape[0] = npts (0 when the element was built without interpolation data), shape[1] = tdim,
+     shape[2] = ndofs, shape[3] = value_size * npts */
+  int bx_element_interpolation_shape(const bx_element* e, int32_t* shape);
+  int bx_element_points(const bx_element* e, double* out);               /* [npts][tdim] */
+  int bx_element_interpolation_matrix(const bx_element* e, double* out); /* [ndofs][value_size * npts] */
+  int bx_interpolate_f64(const bx_element* e, int layout, const double* values, size_t nc, double* coefficients,
+                         int mem, bx_stream_t stream);
 
 #ifdef __cplusplus
 }

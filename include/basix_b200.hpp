@@ -269,6 +269,33 @@ public:
   }
   int subentity_closure_size(int entity_type) const { return bx_element_subentity_closure_size(_h, entity_type); }
 
+  /// points() / interpolation_matrix() (finite-element.h:1167-1170, 1222-1226) as {data, shape}
+  std::pair<std::vector<double>, std::array<std::size_t, 2>> points() const
+  {
+    std::int32_t s[4];
+    check(bx_element_interpolation_shape(_h, s));
+    std::vector<double> x(std::size_t(s[0]) * s[1]);
+    if (!x.empty())
+      check(bx_element_points(_h, x.data()));
+    return {std::move(x), {std::size_t(s[0]), std::size_t(s[1])}};
+  }
+  std::pair<std::vector<double>, std::array<std::size_t, 2>> interpolation_matrix() const
+  {
+    std::int32_t s[4];
+    check(bx_element_interpolation_shape(_h, s));
+    std::vector<double> m(std::size_t(s[0] ? s[2] : 0) * s[3]);
+    if (!m.empty())
+      check(bx_element_interpolation_matrix(_h, m.data()));
+    return {std::move(m), {std::size_t(s[0] ? s[2] : 0), std::size_t(s[3])}};
+  }
+  /// coefficients[c] = interpolation_matrix() * values[c] over nc cells (values[nc][value_size * npts])
+  void interpolate_batch(const double* values, std::size_t nc, double* coefficients,
+                         int layout = BX_INTERP_COMPONENT_MAJOR, int mem = BX_MEM_HOST,
+                         bx_stream_t stream = nullptr) const
+  {
+    check(bx_interpolate_f64(_h, layout, values, nc, coefficients, mem, stream));
+  }
+
 private:
   FiniteElement() = default;
   void read_info()

@@ -61,6 +61,8 @@ def lib():
                                         C.c_void_p]
         L.bxref_permute_i32.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p,
                                         C.c_int]
+        L.bxref_points.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.bxref_interpolation_matrix.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.bxref_permute_subentity_closure_i32.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t,
                                                           C.c_void_p, C.c_int, C.c_int]
         _lib = L
@@ -140,6 +142,13 @@ class RefElement:
         self.subentity_types = [
             [L.bxref_sub_entity_type(self.cell_type, d, i) for i in range(len(self.entity_dofs[d]))]
             for d in range(self.tdim + 1)]
+        shp = np.zeros(2, dtype=np.int32)
+        L.bxref_points(self._h, _ptr(shp), None)
+        self.points = np.empty((int(shp[0]), int(shp[1])), dtype=np.float64)
+        L.bxref_points(self._h, _ptr(shp), _ptr(self.points))
+        L.bxref_interpolation_matrix(self._h, _ptr(shp), None)
+        self.interpolation_matrix = np.empty((int(shp[0]), int(shp[1])), dtype=np.float64)
+        L.bxref_interpolation_matrix(self._h, _ptr(shp), _ptr(self.interpolation_matrix))
         self.entity_transformations = {}
         for ct in range(8):
             shape = np.zeros(3, dtype=np.int32)

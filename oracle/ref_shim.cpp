@@ -180,6 +180,26 @@ int bxref_entity_transformations(void* h, int ct, int* shape, double* out)
   return 1;
 }
 
+// FiniteElement::points() (finite-element.h:1167-1170): shape (npts, tdim)
+void bxref_points(void* h, int* shape, double* out)
+{
+  const auto& p = static_cast<FE*>(h)->points();
+  shape[0] = static_cast<int>(p.second[0]);
+  shape[1] = static_cast<int>(p.second[1]);
+  if (out)
+    std::copy(p.first.begin(), p.first.end(), out);
+}
+
+// FiniteElement::interpolation_matrix() (finite-element.h:1222-1226): shape (ndofs, value_size * npts)
+void bxref_interpolation_matrix(void* h, int* shape, double* out)
+{
+  const auto& m = static_cast<FE*>(h)->interpolation_matrix();
+  shape[0] = static_cast<int>(m.second[0]);
+  shape[1] = static_cast<int>(m.second[1]);
+  if (out)
+    std::copy(m.first.begin(), m.first.end(), out);
+}
+
 int bxref_polyset_dim(int cell, int ptype, int d)
 {
   return polyset::dim(static_cast<cell::type>(cell),

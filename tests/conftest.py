@@ -57,7 +57,8 @@ def make_pair(ref, family, cell, degree, lvariant=0, dvariant=0, discontinuous=F
             embedded_superdegree=r.embedded_superdegree, map_type=r.map_type, value_shape=r.value_shape,
             coefficient_matrix=r.coefficient_matrix, entity_dofs=r.entity_dofs,
             entity_transformations=r.entity_transformations, dof_ordering=r.dof_ordering, family=family,
-            lagrange_variant=lvariant, dpc_variant=dvariant, discontinuous=discontinuous)
+            lagrange_variant=lvariant, dpc_variant=dvariant, discontinuous=discontinuous, points=r.points,
+            interpolation_matrix=r.interpolation_matrix)
         _ELEMENT_CACHE[key] = (r, e)
     return _ELEMENT_CACHE[key]
 

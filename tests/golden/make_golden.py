@@ -59,6 +59,8 @@ def element_arrays(r, family, lvariant):
         "dof_ordering": r.dof_ordering,
         "entity_dof_offsets": np.asarray(offs, dtype=np.int32),
         "entity_dofs_flat": np.asarray(flat, dtype=np.int32),
+        "points": r.points,
+        "interpolation_matrix": r.interpolation_matrix,
     }
     for ct, m in r.entity_transformations.items():
         out[f"etrans_{ct}"] = m

@@ -1,0 +1,129 @@
+"""points() / interpolation_matrix() (reference finite-element.h:1167-1170, 1222-1226) and the batched product
+``coefficients = interpolation_matrix @ values`` the reference leaves to the caller (finite-element.h:1183-1216).
+
+CPU part: the native factory's points / matrix against the compiled reference.  The native RT / N1curl elements
+use Gauss-Jacobi rules where the reference uses Xiao-Gimbutas tables, so their points differ while
+the functionals agree: both matrices are checked to give the same coefficients for polynomial fields, and to be the
+dual of the element's own basis.  GPU part: the kernel against numpy with the reference's matrix, 1e-12 relative.
+"""
+
+import numpy as np
+import pytest
+
+from conftest import make_pair
+
+P, RT, N1E = 1, 2, 3
+INTERVAL, TRI, TET, QUAD, HEX = 1, 2, 3, 4, 5
+EQ, GLL, LEG = 1, 2, 11
+
+
+@pytest.mark.parametrize("cell,degree,variant", [(INTERVAL, 4, GLL), (TRI, 1, 0), (TRI, 4, GLL), (TET, 5, GLL), (QUAD, 3, EQ),
+                                                 (HEX, 2, 0), (HEX, 4, GLL)])
+def test_native_lagrange_points_and_matrix(ref, cell, degree, variant):
+    import basix_b200 as bx
+
+    r = ref.RefElement(P, cell, degree, variant)
+    e = bx.create_element(P, cell, degree, variant)
+    assert e.points.shape == r.points.shape and np.max(np.abs(e.points - r.points)) <= 1e-13
+    assert np.array_equal(e.interpolation_matrix, r.interpolation_matrix)  # the identity
+
+
+def test_native_lagrange_points_follow_dof_ordering(ref):
+    import basix_b200 as bx
+
+    order = [int(v) for v in np.random.default_rng(1).permutation(10)]
+    r = ref.RefElement(P, TRI, 3, GLL, 0, False, order)
+    e = bx.create_element(P, TRI, 3, GLL, dof_ordering=order)
+    assert np.max(np.abs(e.points - r.points)) <= 1e-13
+
+
+def _poly_field(x, vs, degree, seed):
+    """Random polynomial vector field of total degree <= degree at the points x: (npts, vs)."""
+    rng = np.random.default_rng(seed)
+    tdim = x.shape[1]
+    out = np.zeros((x.shape[0], vs))
+    for j in range(vs):
+        for _ in range(6):
+            pw = rng.integers(0, degree + 1, tdim)
+            while pw.sum() > degree:
+                pw = rng.integers(0, degree + 1, tdim)
+            out[:, j] += rng.standard_normal() * np.prod(x ** pw, axis=1)
+    return out
+
+
+@pytest.mark.parametrize("family,cell,degree,variant", [(RT, TRI, 2, LEG), (RT, TET, 1, LEG), (RT, TET, 4, LEG), (N1E, TRI, 3, LEG),
+                                                        (N1E, TET, 2, GLL), (N1E, TET, 3, LEG)])
+def test_native_vector_interpolation_functionals(ref, family, cell, degree, variant):
+    import basix_b200 as bx
+
+    r = ref.RefElement(family, cell, degree, variant)
+    e = bx.create_element(family, cell, degree, variant)
+    vs, n = r.value_size, r.dim
+    assert e.interpolation_matrix.shape == (n, vs * e.points.shape[0])
+    for seed in range(3):
+        fe = _poly_field(e.points, vs, degree, seed).T.reshape(-1)  # component major: values[j * npts + p]
+        fr = _poly_field(r.points, vs, degree, seed).T.reshape(-1)
+        want = r.interpolation_matrix @ fr
+        got = e.interpolation_matrix @ fe
+        assert np.max(np.abs(got - want)) <= 1e-11 * max(1.0, np.max(np.abs(want)))
+    # dual basis: interpolating the element's own basis functions gives the identity
+    phi = r.tabulate(0, e.points)[0]  # (npts, ndofs, vs) from the reference at the native points
+    vals = phi.transpose(2, 0, 1).reshape(vs * e.points.shape[0], n)
+    assert np.max(np.abs(e.interpolation_matrix @ vals - np.eye(n))) <= 1e-10
+
+
+# ---- GPU ------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("family,cell,degree,variant", [(N1E, TET, 3, LEG), (RT, TET, 4, LEG), (P, TET, 5, GLL), (RT, TRI, 2, LEG),
+                                                        (P, HEX, 4, GLL), (N1E, TET, 1, LEG)])
+def test_interpolate_batch_matches_numpy(ref, family, cell, degree, variant):
+    import torch
+
+    r, e = make_pair(ref, family, cell, degree, variant)
+    M, npts, vs = r.interpolation_matrix, r.points.shape[0], r.value_size
+    rng = np.random.default_rng(degree)
+    for nc in (1, 15, 16, 17, 5003):
+        v = rng.standard_normal((nc, vs * npts))
+        want = v @ M.T
+        scale = np.max(np.abs(want))
+        got = e.interpolate_batch(v)  # host pointers, reference column order
+        assert got.shape == (nc, r.dim) and np.max(np.abs(got - want)) <= 1e-12 * scale
+        got = e.interpolate_batch(torch.from_numpy(v).cuda()).cpu().numpy()  # device pointers
+        assert np.max(np.abs(got - want)) <= 1e-12 * scale
+        # the order pull_back writes: values[c][p][j]
+        vp = np.ascontiguousarray(v.reshape(nc, vs, npts).transpose(0, 2, 1)).reshape(nc, -1)
+        got = e.interpolate_batch(vp, layout="point-major")
+        assert np.max(np.abs(got - want)) <= 1e-12 * scale
+
+
+@pytest.mark.gpu
+def test_interpolate_after_pull_back_reproduces_coefficients(ref):
+    """Interpolating a function of the element's own space returns its coefficients: tabulate at points(),
+    combine with random coefficients, push forward to a physical cell, pull back, interpolate."""
+    r, e = make_pair(ref, N1E, TET, 3, LEG)
+    rng = np.random.default_rng(3)
+    nc, npts, n = 257, r.points.shape[0], r.dim
+    phi = e.tabulate(0, r.points)[0]  # (npts, ndofs, 3)
+    coef = rng.standard_normal((nc, n))
+    U = np.einsum("cn,pnj->cpj", coef, phi)  # reference values at the interpolation points
+    J = np.eye(3)[None] + 0.2 * rng.standard_normal((nc, 3, 3))
+    detJ, K = np.linalg.det(J), np.linalg.inv(J)
+    u = e.push_forward(U, J, detJ, K)
+    back = e.pull_back(u, J, detJ, K)  # (nc, npts, 3): point major
+    got = e.interpolate_batch(back.reshape(nc, -1), layout="point-major")
+    assert np.max(np.abs(got - coef)) <= 1e-10 * np.max(np.abs(coef))
+
+
+@pytest.mark.gpu
+def test_interpolate_errors(ref):
+    import basix_b200 as bx
+
+    r, e = make_pair(ref, N1E, TET, 1, LEG)
+    with pytest.raises(RuntimeError):
+        e.interpolate_batch(np.zeros((3, 5)))
+    bare = bx.FiniteElement(cell_type=r.cell_type, polyset_type=r.polyset_type, degree=r.degree,
+                            embedded_superdegree=r.embedded_superdegree, map_type=r.map_type, value_shape=r.value_shape,
+                            coefficient_matrix=r.coefficient_matrix, entity_dofs=r.entity_dofs,
+                            entity_transformations=r.entity_transformations)
+    with pytest.raises(RuntimeError, match="without points"):
+        bare.interpolate_batch(np.zeros((3, 18)))
