@@ -8,14 +8,14 @@
 // DMMA, 6.5 TB/s HBM), so the kernel is bound by the FP64 tensor pipe with HBM close behind.
 //
 // Kernel (the contraction half of tabulate_dop.cu, with the A operand streamed from HBM instead of produced):
-// persistent, one CTA per SM, twelve independent warps.  The operand M (rows padded to 8, row stride == 4 mod 8
+// persistent, one CTA per SM, sixteen independent warps (four per SM sub-partition).  The operand M (rows padded to 8, row stride == 4 mod 8
 // doubles, column order matching the value layout) stays in shared memory.  A warp owns 16 cells = two m8 row
 // tiles; lane (g, t) loads its A-fragment entries values[c0 + g (+8)][4 ks + t] straight from global memory --
-// the four t-lanes of a row read 32 consecutive bytes -- six k-steps ahead in registers, B fragments one step ahead
+// the four t-lanes of a row read 32 consecutive bytes -- four k-steps ahead in registers, B fragments one step ahead
 // from shared memory, and every B fragment feeds two DMMAs.  The k loop is unrolled with compile-time register
 // roles: a rolled loop rotates its prefetch registers with two dozen moves per step and is issue-bound (measured
-// 14.5 ms per 20 M cells against 8.5 ms unrolled).  Accumulator fragments are stored straight as
-// coefficients[c][n].  Measured on N1curl degree 3, 20 M cells: 8.5 ms = 88 % of the DMMA peak on the executed
+// 14.5 ms per 20 M cells against 8.3 ms unrolled).  Accumulator fragments are stored straight as
+// coefficients[c][n].  Measured on N1curl degree 3, 20 M cells: 8.3 ms = 90 % of the DMMA peak on the executed
 // (padded 48 x 144) flops.
 #include "element.cuh"
 
@@ -27,7 +27,7 @@ namespace bx
 {
 namespace
 {
-constexpr int kWarps = 12;
+constexpr int kWarps = 16;
 constexpr int kThreads = 32 * kWarps;
 constexpr int kCells = 16; // cells per warp chunk
 constexpr int kMaxNT = 7;  // 8-column tiles per column group
@@ -192,8 +192,8 @@ void interpolate_device(const bx_element& e, int layout, const double* values, s
     fail(BX_ERR_UNSUPPORTED, "interpolate: the interpolation matrix does not fit in shared memory");
   const size_t nblocks = ceil_div(nc, size_t(kCells) * kWarps);
   const unsigned grid = unsigned(std::min<size_t>(nblocks, size_t(sm_count())));
-  // tuning aid (development only): BX_INTERP_TUNE = "<depth><s|c>", e.g. "6c" (default), "2s", "4c"
-  static const std::string tune = std::getenv("BX_INTERP_TUNE") ? std::getenv("BX_INTERP_TUNE") : "6c";
+  // tuning aid (development only): BX_INTERP_TUNE = "<depth><s|c>", e.g. "4c" (default), "2s", "6c"
+  static const std::string tune = std::getenv("BX_INTERP_TUNE") ? std::getenv("BX_INTERP_TUNE") : "4c";
   auto go = [&](auto kern, int depth)
   {
     p.ksteps = int(ceil_div(size_t(p.ksteps), size_t(depth)) * depth);
@@ -208,12 +208,12 @@ void interpolate_device(const bx_element& e, int layout, const double* values, s
     go(interpolate_kernel<2, false>, 2);
   else if (tune == "4s")
     go(interpolate_kernel<4, true>, 4);
-  else if (tune == "4c")
-    go(interpolate_kernel<4, false>, 4);
+  else if (tune == "6c")
+    go(interpolate_kernel<6, false>, 6);
   else if (tune == "6s")
     go(interpolate_kernel<6, true>, 6);
   else
-    go(interpolate_kernel<6, false>, 6);
+    go(interpolate_kernel<4, false>, 4);
   BX_LAUNCHED();
 }
 } // namespace bx
