@@ -40,9 +40,11 @@ def kernel_launch_count() -> int:
 class tabulate_paths:
     """Context manager narrowing which tabulate kernels may be used (tests / profiling): names from
     ``FiniteElement.tabulate_path`` -- "fused", "tensor-product", "register", "derivative-operator"; the generic
-    path is always available."""
+    path is always available.  "tensor-product-staged" additionally allows the staged variant of the
+    tensor-product kernel (same path name; on by default)."""
 
-    _BITS = {"generic": 0, "fused": 1, "tensor-product": 2, "register": 3, "derivative-operator": 4}
+    _BITS = {"generic": 0, "fused": 1, "tensor-product": 2, "register": 3, "derivative-operator": 4,
+             "tensor-product-staged": 5}
 
     def __init__(self, *allowed: str):
         self.mask = 1

@@ -10,6 +10,7 @@
 #include "jets.cuh"
 
 #include <algorithm>
+#include <cstring>
 #include <cmath>
 #include <limits>
 #include <memory>
@@ -165,11 +166,47 @@ void factor_tensor_product(bx_element& e)
       for (int q = 0; q < n1; ++q)
         tp.A[(size_t(a) * tp.fstride + j) * n1 + q] = funs[a][j][q] * std::sqrt(double(2 * q + 1));
   tp.valid = true;
+  // lexicographic (i, j, k) -> column table for the staged kernel, when the columns are a full tensor grid
+  {
+    const int nf = tp.nfun[0];
+    bool grid = nf >= 2;
+    for (int a = 1; a < tdim; ++a)
+      grid = grid and tp.nfun[a] == nf;
+    int total = 1;
+    for (int a = 0; a < tdim; ++a)
+      total *= nf;
+    grid = grid and total == N;
+    if (grid)
+    {
+      std::vector<double2> order(size_t(N), make_double2(0.0, -1.0)); // .y: -1 = unset, then the column's raw bits
+      for (int n = 0; n < N and grid; ++n)
+      {
+        const int i = tp.ijk[n] & 255, j = (tp.ijk[n] >> 8) & 255, k = (tp.ijk[n] >> 16) & 255;
+        const int idx = tdim == 2 ? i * nf + j : (i * nf + j) * nf + k;
+        if (idx >= N or order[idx].y >= 0.0)
+          grid = false;
+        else
+          order[idx] = make_double2(tp.scale[n], double(n));
+      }
+      for (double2& o : order) // the kernel reads the column as an integer without a conversion instruction
+      {
+        const long long col = (long long)(o.y);
+        std::memcpy(&o.y, &col, sizeof(col));
+      }
+      if (grid)
+      {
+        tp.nf = nf;
+        tp.order = order;
+      }
+    }
+  }
   if (e.on_device)
   {
     tp.d_A = upload(tp.A);
     tp.d_ijk = upload(tp.ijk);
     tp.d_scale = upload(tp.scale);
+    if (!tp.order.empty())
+      tp.d_order = upload(tp.order);
   }
 }
 } // namespace
@@ -917,6 +954,7 @@ bx_element::~bx_element()
   cudaFree(tp.d_A);
   cudaFree(tp.d_ijk);
   cudaFree(tp.d_scale);
+  cudaFree(tp.d_order);
   cudaFree(d_dof_slot);
   cudaFree(d_dof_loc);
   cudaFree(d_slot_info);

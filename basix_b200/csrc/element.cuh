@@ -61,6 +61,11 @@ struct bx_element
     double* d_A = nullptr;
     int32_t* d_ijk = nullptr;
     double* d_scale = nullptr;
+    // staged kernel (tabulate_tp_staged.cu): when every axis has nf functions and the columns are exactly the
+    // nf^tdim index triples, entry (i * nf + j) * nf + k = {scale, column} of that triple; else empty
+    int nf = 0;
+    std::vector<double2> order; // .x = scale, .y = raw int64 bits of the column
+    double2* d_order = nullptr;
   } tp;
 
   // ---- DOF transformations ----------------------------------------------------------------------

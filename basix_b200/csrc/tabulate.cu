@@ -192,9 +192,10 @@ __global__ void narrow_slabs_kernel(const double* __restrict__ in, size_t run, i
 // All enabled by default; tests and profiling runs narrow the mask to reach a specific kernel.
 std::atomic<unsigned> g_path_mask{~0u};
 unsigned tabulate_path_mask(unsigned mask) { return g_path_mask.exchange(mask); }
+bool tabulate_path_allowed(int path) { return (g_path_mask.load(std::memory_order_relaxed) >> path) & 1u; }
 namespace
 {
-bool allowed(int path) { return (g_path_mask.load(std::memory_order_relaxed) >> path) & 1u; }
+bool allowed(int path) { return tabulate_path_allowed(path); }
 } // namespace
 
 // Which device path tabulate() takes: 0 generic, 1 fused simplex, 2 tensor product, 3 register path,

@@ -205,7 +205,8 @@ extern "C"
      2 tensor-product kernel, 3 register path (low-degree simplex elements),
      4 derivative-operator kernel (simplex elements: all slabs from the values of the orthonormal set). */
   int bx_element_tabulate_path(const bx_element* e, int nd);
-  /* Testing / profiling hook: bit i of `mask` allows path i above (the generic path 0 is always available).
+  /* Testing / profiling hook: bit i of `mask` allows path i above (the generic path 0 is always available);
+     bit 5 allows the staged variant of the tensor-product kernel (tabulate_tp_staged.cu, same path number 2).
      Returns the previous mask; the default allows everything. */
   unsigned bx_tabulate_path_mask(unsigned mask);
 

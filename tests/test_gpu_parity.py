@@ -408,6 +408,23 @@ def test_tabulate_tensor_product_path(ref, family, cell, degree, variant, nd):
         slab_close(e.tabulate(nd, x), r.tabulate(nd, x), 1e-12)
 
 
+@pytest.mark.parametrize("cell,degree", [(QUAD, 1), (QUAD, 4), (QUAD, 6), (HEX, 1), (HEX, 2), (HEX, 3), (HEX, 4)])
+@pytest.mark.parametrize("nd", [0, 1])
+def test_tabulate_tensor_product_staged_and_unstaged_kernels(ref, cell, degree, nd):
+    """Both tensor-product kernels (tabulate_tp_staged.cu: one slab of a 32-point tile at a time through shared
+    memory; tabulate_tp.cu: direct stores) against the reference: ragged tails, odd and even point counts (16- and
+    8-byte copy-out), odd and even column counts (dense and padded tile pitch)."""
+    import basix_b200 as bx
+
+    r, e = make_pair(ref, P, cell, degree, GLL if degree > 2 else 0)
+    for allowed in (("tensor-product",), ("tensor-product", "tensor-product-staged")):
+        with bx.tabulate_paths(*allowed):
+            assert e.tabulate_path(nd) == "tensor-product"
+            for npts in (1, 31, 32, 33, 64, 4098, 20011):
+                x = random_points(cell, npts, seed=npts + degree)
+                slab_close(e.tabulate(nd, x), r.tabulate(nd, x), 1e-12)
+
+
 def test_tabulate_non_tensor_product_elements_take_generic_path(ref):
     """Serendipity on a quadrilateral is not a tensor product: the rank-1 test must reject it."""
     r, e = make_pair(ref, 10, QUAD, 3, LEG, 7)
