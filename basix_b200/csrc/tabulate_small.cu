@@ -37,7 +37,7 @@ struct RegSink
 template <int TDIM, int DEG, int ND, typename T>
 __global__ void __launch_bounds__(kThreads)
     tabulate_small_kernel(const T* __restrict__ x, size_t npts, const double* __restrict__ Cq,
-                          T* __restrict__ basis, int N, int NP, unsigned inv_n)
+                          T* __restrict__ basis, int N, int NP, unsigned inv_n, int bulk)
 {
   constexpr int NDER = jets::nder(TDIM, ND);
   constexpr int K = jets::psize(TDIM, DEG);
@@ -82,9 +82,32 @@ __global__ void __launch_bounds__(kThreads)
       for (int d = 0; d < NDER; ++d)
         mine[d * (kThreads * NP) + n] = acc[d];
     }
-    __syncthreads();
     // each derivative slab of the tile is one contiguous run of np * N doubles in global memory
     const unsigned run = np * unsigned(N);
+    if constexpr (sizeof(T) == 8)
+    {
+      if (bulk and (run & 1) == 0)
+      {
+        // dense tile rows (odd N), 16-byte aligned slabs: one TMA bulk copy shared -> global per slab; the CTA only
+        // waits until the engine has read the tile, the HBM write completes in the background
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+#pragma unroll
+          for (int d = 0; d < NDER; ++d)
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
+                             basis + (size_t(d) * npts + pt0) * N),
+                         "r"(uint32_t(__cvta_generic_to_shared(tile + d * (kThreads * NP)))), "r"(run * 8u)
+                         : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        __syncthreads();
+        continue;
+      }
+    }
+    __syncthreads();
 #pragma unroll
     for (int d = 0; d < NDER; ++d)
     {
@@ -124,7 +147,12 @@ bool launch(const bx_element& e, const T* x, size_t npts, T* basis, cudaStream_t
   const unsigned inv_n = N > 1 ? unsigned((1ull << 32) / unsigned(N) + 1) : 0u;
   if (N == 1)
     fail(BX_ERR_RUNTIME, "tabulate (register path): single-column element"); // never on the menu (see below)
-  kern<<<unsigned(std::min(ntiles, cap)), kThreads, smem, s>>>(x, npts, e.d_Cq, basis, N, NP, inv_n);
+  // TMA bulk copy-out: dense tile rows and every slab region 16-byte aligned
+  const int bulk = (NP == N and reinterpret_cast<uintptr_t>(basis) % 16 == 0 and (npts * size_t(N)) % 2 == 0
+                    and (size_t(NDER) * kThreads * NP) % 2 == 0 and ((N * K + 1) & ~1) % 2 == 0)
+                       ? 1
+                       : 0;
+  kern<<<unsigned(std::min(ntiles, cap)), kThreads, smem, s>>>(x, npts, e.d_Cq, basis, N, NP, inv_n, bulk);
   BX_LAUNCHED();
   return true;
 }

@@ -11,7 +11,9 @@
 // values and derivatives of its point in REGISTERS (no shared-memory round trip for the factors), walks the
 // (i, j, k) index grid with compile-time indices, and writes each product into a warp-private shared-memory tile
 // [point][column] (odd pitch: conflict free); the finished 32 x N tile is exactly the contiguous run
-// basis[d][32 tile .. 32 tile + 32)[0 .. N) and leaves with 16-byte streaming stores.
+// basis[d][32 tile .. 32 tile + 32)[0 .. N) and leaves as ONE TMA bulk copy (cp.async.bulk shared -> global): the
+// warp waits only until the engine has read the tile, the HBM write completes in the background.  Measured on Q4
+// hexahedron, nd = 1, 50 M points: 32.0 ms = 96 % of the HBM copy peak (tabulate_tp.cu: 39.2 ms, 78 %).
 #include "element.cuh"
 
 #include <algorithm>
