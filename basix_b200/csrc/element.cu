@@ -531,7 +531,7 @@ bx_element* element_from_desc(const bx_element_desc& d)
     const int K = e->vs * d.npts;
     e->interp_M.assign(d.interpolation_matrix, d.interpolation_matrix + size_t(e->ndofs) * K);
     // device operands, one per value layout: B[n][k'] with k' the position of (component j, point p) in the layout
-    const int kp = int(ceil_div(K, 24) * 24); // k-steps of 4, unrolled by up to 6 in interpolate.cu: zero columns
+    const int kp = int(ceil_div(K, 48) * 48); // k-steps of 4, unrolled by 2, 4 or 6 in interpolate.cu: zero columns
     e->interp_kstride = kp % 8 == 4 ? kp : kp + 4;
     e->interp_npad = int(ceil_div(e->ndofs, 8) * 8);
     if (e->on_device)
