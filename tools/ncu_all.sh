@@ -8,7 +8,7 @@ cap() { # name workload kernel-regex units
   tail -1 gpurun_out/ncu_$1.log
 }
 cap dop_p5tet tabulate_p5_tet tabulate_dop 2000000
-cap tp_q4hex tabulate_q4_hex tabulate_tp 10000000
+cap tp_q4hex tabulate_q4_hex tabulate_tp_staged 10000000
 cap small_p1tri tabulate_p1_tri tabulate_small
 cap map_rows1 push_forward_n1curl3 map_kernel
 cap map_rows45 push_forward_n1curl3_rows45 map_kernel 1000000
