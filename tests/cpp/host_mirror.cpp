@@ -173,6 +173,16 @@ int main(int argc, char** argv)
   e.T_apply(u, 56, 1, 0x00001);
   for (int i = 0; i < 6; ++i)
     REQUIRE(u[28 + i] == double(want[i]));
+  // sub-entity closure permutations (finite-element.h:860-1035): a triangular face of P5 carries 3 + 3 x 4 + 6 dofs
+  REQUIRE(e.subentity_closure_size(BX_CELL_TRIANGLE) == 21 and e.subentity_closure_size(BX_CELL_INTERVAL) == 6);
+  std::int32_t cl[21];
+  for (int i = 0; i < 21; ++i)
+    cl[i] = i;
+  e.permute_subentity_closure(cl, 21, /*entity_info=*/3, BX_CELL_TRIANGLE);
+  REQUIRE(cl[0] == 1 and cl[1] == 0 and cl[2] == 2); // rotate, then reflect: the vertex blocks
+  e.permute_subentity_closure_inv(cl, 21, 3, BX_CELL_TRIANGLE);
+  for (int i = 0; i < 21; ++i)
+    REQUIRE(cl[i] == i);
   std::puts("host mirror ok (gpu)");
   return 0;
 }
