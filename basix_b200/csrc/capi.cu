@@ -144,8 +144,8 @@ void polyset_tabulate_device(int cell, int ptype, int degree, int nd, const T* x
 template <typename T>
 void tabulate_device(const bx_element& e, int nd, const T* x, size_t npts, T* basis, size_t out_pts, cudaStream_t s);
 int tabulate_path(const bx_element& e, int nd);
-void interpolate_device(const bx_element& e, int layout, const double* values, size_t nc, double* coefficients,
-                        cudaStream_t s);
+template <typename T>
+void interpolate_device(const bx_element& e, int layout, const T* values, size_t nc, T* coefficients, cudaStream_t s);
 void closure_permute_device(const bx_element& e, int inverse, int32_t* d, size_t nc, size_t m, const uint32_t* info,
                             int entity_type, int entity_index, cudaStream_t s);
 unsigned tabulate_path_mask(unsigned mask);
@@ -497,29 +497,29 @@ void transform_any(const bx_element* e, int op, T* data, size_t nc, size_t cell_
   st.sync();
   st.trim();
 }
-void interpolate_any(const bx_element* e, int layout, const double* values, size_t nc, double* out, int mem,
-                     bx_stream_t stream)
+template <typename T>
+void interpolate_any(const bx_element* e, int layout, const T* values, size_t nc, T* out, int mem, bx_stream_t stream)
 {
   check_mem(mem);
   require(e != nullptr, "interpolate: null element");
   require(nc == 0 or (values and out), "interpolate: null pointer");
   if (mem == BX_MEM_DEVICE)
   {
-    interpolate_device(*e, layout, values, nc, out, static_cast<cudaStream_t>(stream));
+    interpolate_device<T>(*e, layout, values, nc, out, static_cast<cudaStream_t>(stream));
     return;
   }
-  interpolate_device(*e, layout, nullptr, 0, nullptr, nullptr); // validate before staging
+  interpolate_device<T>(*e, layout, nullptr, 0, nullptr, nullptr); // validate before staging
   if (nc == 0)
     return;
   const size_t K = size_t(e->vs) * e->interp_npts, N = size_t(e->ndofs);
-  const size_t chunk = chunk_units(nc, (K + N) * sizeof(double), 1);
+  const size_t chunk = chunk_units(nc, (K + N) * sizeof(T), 1);
   StagePool& st = stage_pool();
   DrainOnExit drain{st};
-  double *dv[2], *dout[2];
+  T *dv[2], *dout[2];
   for (int b = 0; b < 2; ++b)
   {
-    dv[b] = st.get<double>(0, b, chunk * K * sizeof(double));
-    dout[b] = st.get<double>(1, b, chunk * N * sizeof(double));
+    dv[b] = st.get<T>(0, b, chunk * K * sizeof(T));
+    dout[b] = st.get<T>(1, b, chunk * N * sizeof(T));
   }
   size_t i = 0;
   for (size_t c0 = 0; c0 < nc; c0 += chunk, ++i)
@@ -527,9 +527,9 @@ void interpolate_any(const bx_element* e, int layout, const double* values, size
     const int b = int(i & 1);
     const size_t k = std::min(chunk, nc - c0);
     cudaStream_t s = st.s[b];
-    BX_CUDA(cudaMemcpyAsync(dv[b], values + c0 * K, k * K * sizeof(double), cudaMemcpyHostToDevice, s));
-    interpolate_device(*e, layout, dv[b], k, dout[b], s);
-    BX_CUDA(cudaMemcpyAsync(out + c0 * N, dout[b], k * N * sizeof(double), cudaMemcpyDeviceToHost, s));
+    BX_CUDA(cudaMemcpyAsync(dv[b], values + c0 * K, k * K * sizeof(T), cudaMemcpyHostToDevice, s));
+    interpolate_device<T>(*e, layout, dv[b], k, dout[b], s);
+    BX_CUDA(cudaMemcpyAsync(out + c0 * N, dout[b], k * N * sizeof(T), cudaMemcpyDeviceToHost, s));
   }
   st.sync();
   st.trim();
@@ -886,7 +886,12 @@ extern "C"
   int bx_interpolate_f64(const bx_element* e, int layout, const double* values, size_t nc, double* coefficients, int mem,
                          bx_stream_t stream)
   {
-    return bx::guarded([&]() { bx::interpolate_any(e, layout, values, nc, coefficients, mem, stream); });
+    return bx::guarded([&]() { bx::interpolate_any<double>(e, layout, values, nc, coefficients, mem, stream); });
+  }
+  int bx_interpolate_f32(const bx_element* e, int layout, const float* values, size_t nc, float* coefficients, int mem,
+                         bx_stream_t stream)
+  {
+    return bx::guarded([&]() { bx::interpolate_any<float>(e, layout, values, nc, coefficients, mem, stream); });
   }
 
   int bx_element_subentity_closure_size(const bx_element* e, int entity_type)

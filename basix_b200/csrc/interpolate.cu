@@ -39,19 +39,22 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
       : "d"(a), "d"(b));
 }
 
+// T = type of the values and coefficients (double, or float for the float32 API: loads widen, stores narrow, the
+// operand and the arithmetic are double either way)
+template <typename T>
 struct Params
 {
-  const double* values; // [nc][K]
+  const T* values;      // [nc][K]
   const double* B;      // [npad][kstride]
-  double* out;          // [nc][N]
+  T* out;               // [nc][N]
   size_t nc;
   int K, N, npad, kstride, ksteps;
 };
 
 // Column group [n0, n0 + 8 NT) for the 16 cells of one chunk.
 // kDepth = k-steps of A fragments in flight per lane; kStreaming = evict-first loads of the values
-template <int NT, int kDepth, bool kStreaming>
-__device__ __forceinline__ void run_group(const Params& p, const double* __restrict__ Bs, size_t c0, int n0, int g, int t)
+template <int NT, int kDepth, bool kStreaming, typename T>
+__device__ __forceinline__ void run_group(const Params<T>& p, const double* __restrict__ Bs, size_t c0, int n0, int g, int t)
 {
   double acc[2][NT][2];
 #pragma unroll
@@ -61,12 +64,13 @@ __device__ __forceinline__ void run_group(const Params& p, const double* __restr
       acc[m][j][0] = acc[m][j][1] = 0.0;
   // rows of this lane (clamped: a row past the end is computed and never stored)
   const size_t r0 = min(c0 + g, p.nc - 1), r1 = min(c0 + g + 8, p.nc - 1);
-  const double* __restrict__ v0 = p.values + r0 * p.K + t;
-  const double* __restrict__ v1 = p.values + r1 * p.K + t;
+  const T* __restrict__ v0 = p.values + r0 * p.K + t;
+  const T* __restrict__ v1 = p.values + r1 * p.K + t;
   const double* __restrict__ bp = Bs + (n0 + g) * p.kstride + t;
   const int ts = 8 * p.kstride;
   const int kt = p.K - t; // entries 4 ks + t < K  <=>  4 ks < kt
-  auto lda = [&](const double* v, int ks) { return 4 * ks < kt ? (kStreaming ? __ldcs(v + 4 * ks) : __ldg(v + 4 * ks)) : 0.0; };
+  auto lda = [&](const T* v, int ks) -> double
+  { return 4 * ks < kt ? double(kStreaming ? __ldcs(v + 4 * ks) : __ldg(v + 4 * ks)) : 0.0; };
 
   // The k loop is unrolled by kDepth with compile-time register roles, so nothing is copied between steps (a
   // rolled loop spends two dozen register moves per step rotating its prefetch queue and is issue-bound, not
@@ -111,30 +115,31 @@ __device__ __forceinline__ void run_group(const Params& p, const double* __restr
     const size_t c = c0 + g + 8 * m;
     if (c < p.nc)
     {
-      double* row = p.out + c * p.N;
+      T* row = p.out + c * p.N;
 #pragma unroll
       for (int j = 0; j < NT; ++j)
       {
         const int n = n0 + j * 8 + 2 * t;
-        if (even)
+        if constexpr (sizeof(T) == 8)
         {
-          if (n < p.N)
-            __stcs(reinterpret_cast<double2*>(row + n), make_double2(acc[m][j][0], acc[m][j][1]));
+          if (even)
+          {
+            if (n < p.N)
+              __stcs(reinterpret_cast<double2*>(row + n), make_double2(acc[m][j][0], acc[m][j][1]));
+            continue;
+          }
         }
-        else
-        {
-          if (n < p.N)
-            __stcs(row + n, acc[m][j][0]);
-          if (n + 1 < p.N)
-            __stcs(row + n + 1, acc[m][j][1]);
-        }
+        if (n < p.N)
+          __stcs(row + n, static_cast<T>(acc[m][j][0]));
+        if (n + 1 < p.N)
+          __stcs(row + n + 1, static_cast<T>(acc[m][j][1]));
       }
     }
   }
 }
 
-template <int kDepth, bool kStreaming>
-__global__ void __launch_bounds__(kThreads, 1) interpolate_kernel(const Params p)
+template <int kDepth, bool kStreaming, typename T>
+__global__ void __launch_bounds__(kThreads, 1) interpolate_kernel(const Params<T> p)
 {
   extern __shared__ __align__(16) double interp_smem[];
   double* Bs = interp_smem;
@@ -153,13 +158,13 @@ __global__ void __launch_bounds__(kThreads, 1) interpolate_kernel(const Params p
       const int nt = min(kMaxNT, (p.N - n0 + 7) >> 3);
       switch (nt)
       {
-      case 1: run_group<1, kDepth, kStreaming>(p, Bs, c0, n0, g, t); break;
-      case 2: run_group<2, kDepth, kStreaming>(p, Bs, c0, n0, g, t); break;
-      case 3: run_group<3, kDepth, kStreaming>(p, Bs, c0, n0, g, t); break;
-      case 4: run_group<4, kDepth, kStreaming>(p, Bs, c0, n0, g, t); break;
-      case 5: run_group<5, kDepth, kStreaming>(p, Bs, c0, n0, g, t); break;
-      case 6: run_group<6, kDepth, kStreaming>(p, Bs, c0, n0, g, t); break;
-      default: run_group<7, kDepth, kStreaming>(p, Bs, c0, n0, g, t); break;
+      case 1: run_group<1, kDepth, kStreaming, T>(p, Bs, c0, n0, g, t); break;
+      case 2: run_group<2, kDepth, kStreaming, T>(p, Bs, c0, n0, g, t); break;
+      case 3: run_group<3, kDepth, kStreaming, T>(p, Bs, c0, n0, g, t); break;
+      case 4: run_group<4, kDepth, kStreaming, T>(p, Bs, c0, n0, g, t); break;
+      case 5: run_group<5, kDepth, kStreaming, T>(p, Bs, c0, n0, g, t); break;
+      case 6: run_group<6, kDepth, kStreaming, T>(p, Bs, c0, n0, g, t); break;
+      default: run_group<7, kDepth, kStreaming, T>(p, Bs, c0, n0, g, t); break;
       }
     }
   }
@@ -167,8 +172,8 @@ __global__ void __launch_bounds__(kThreads, 1) interpolate_kernel(const Params p
 } // namespace
 
 // values[nc][vs * npts] (layout 0: component major, 1: point major) -> coefficients[nc][ndofs]
-void interpolate_device(const bx_element& e, int layout, const double* values, size_t nc, double* coefficients,
-                        cudaStream_t s)
+template <typename T>
+void interpolate_device(const bx_element& e, int layout, const T* values, size_t nc, T* coefficients, cudaStream_t s)
 {
   if (e.interp_npts == 0)
     fail(BX_ERR_RUNTIME, "interpolate: the element was built without points() / interpolation_matrix()");
@@ -177,7 +182,7 @@ void interpolate_device(const bx_element& e, int layout, const double* values, s
   if (nc == 0)
     return;
   require_device(e);
-  Params p;
+  Params<T> p;
   p.values = values;
   p.B = e.d_interp[layout];
   p.out = coefficients;
@@ -203,17 +208,19 @@ void interpolate_device(const bx_element& e, int layout, const double* values, s
     kern<<<grid, kThreads, smem, s>>>(p);
   };
   if (tune == "2s")
-    go(interpolate_kernel<2, true>, 2);
+    go(interpolate_kernel<2, true, T>, 2);
   else if (tune == "2c")
-    go(interpolate_kernel<2, false>, 2);
+    go(interpolate_kernel<2, false, T>, 2);
   else if (tune == "4s")
-    go(interpolate_kernel<4, true>, 4);
+    go(interpolate_kernel<4, true, T>, 4);
   else if (tune == "6c")
-    go(interpolate_kernel<6, false>, 6);
+    go(interpolate_kernel<6, false, T>, 6);
   else if (tune == "6s")
-    go(interpolate_kernel<6, true>, 6);
+    go(interpolate_kernel<6, true, T>, 6);
   else
-    go(interpolate_kernel<4, false>, 4);
+    go(interpolate_kernel<4, false, T>, 4);
   BX_LAUNCHED();
 }
+template void interpolate_device<double>(const bx_element&, int, const double*, size_t, double*, cudaStream_t);
+template void interpolate_device<float>(const bx_element&, int, const float*, size_t, float*, cudaStream_t);
 } // namespace bx

@@ -665,14 +665,16 @@ class FiniteElement:
         numpy out, CUDA torch tensor in -> CUDA torch tensor out."""
         if self._points is None:
             raise RuntimeError("interpolate: the element was built without points() / interpolation_matrix()")
-        va = _Arg(values, np.float64, "values")
+        dt = _float_dtype(values)
+        va = _Arg(values, dt, "values")
         k = self._vs * self._points.shape[0]
         if len(va.shape) != 2 or va.shape[1] != k:
             raise RuntimeError(f"values must have shape (ncells, {k})")
         stream, alloc = _stream_and_like(va)
-        out = alloc((va.shape[0], self._ndofs), np.float64)
+        out = alloc((va.shape[0], self._ndofs), dt)
         lay = {"component-major": 0, "point-major": 1}[layout]
-        check(lib().bx_interpolate_f64(self._h, lay, va.ptr, va.shape[0], _ptr_of(out), va.mem, stream))
+        fn = lib().bx_interpolate_f32 if dt is np.float32 else lib().bx_interpolate_f64
+        check(fn(self._h, lay, va.ptr, va.shape[0], _ptr_of(out), va.mem, stream))
         return out
 
     # ---- sub-entity closure permutations ---------------------------------------------------------------

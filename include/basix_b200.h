@@ -304,6 +304,9 @@ extern "C"
   int bx_element_interpolation_matrix(const bx_element* e, double* out); /* [ndofs][value_size * npts] */
   int bx_interpolate_f64(const bx_element* e, int layout, const double* values, size_t nc, double* coefficients,
                          int mem, bx_stream_t stream);
+  /* float32 values / coefficients (the reference's FiniteElement<float>); the matrix and the arithmetic are float64 */
+  int bx_interpolate_f32(const bx_element* e, int layout, const float* values, size_t nc, float* coefficients,
+                         int mem, bx_stream_t stream);
 
 #ifdef __cplusplus
 }

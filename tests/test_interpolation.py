@@ -97,6 +97,22 @@ def test_interpolate_batch_matches_numpy(ref, family, cell, degree, variant):
 
 
 @pytest.mark.gpu
+def test_interpolate_batch_float32(ref):
+    """float32 values in, float32 coefficients out (matrix and arithmetic stay float64)."""
+    import torch
+
+    r, e = make_pair(ref, 3, 3, 3, 11)
+    M = r.interpolation_matrix
+    v = np.random.default_rng(5).standard_normal((3001, M.shape[1])).astype(np.float32)
+    want = v.astype(np.float64) @ M.T
+    tol = 4e-7 * np.max(np.abs(want))
+    got = e.interpolate_batch(v)
+    assert got.dtype == np.float32 and np.max(np.abs(got - want)) <= tol
+    got = e.interpolate_batch(torch.from_numpy(v).cuda(), layout="component-major")
+    assert got.dtype == torch.float32 and np.max(np.abs(got.cpu().numpy() - want)) <= tol
+
+
+@pytest.mark.gpu
 def test_interpolate_after_pull_back_reproduces_coefficients(ref):
     """Interpolating a function of the element's own space returns its coefficients: tabulate at points(),
     combine with random coefficients, push forward to a physical cell, pull back, interpolate."""
