@@ -78,6 +78,8 @@ SIGNATURES = {
     "bx_tabulate_f32": (_I, [_P, _I, _P, _SIZE, _I, _P, _I, _P]),
     "bx_map_f32": (_I, [_I, _I, _P, _P, _P, _P, _SIZE, _SIZE, _I, _I, _I, _P, _I, _P]),
     "bx_push_forward_f32": (_I, [_P, _P, _P, _P, _P, _SIZE, _SIZE, _I, _I, _I, _P, _I, _P]),
+    "bx_push_forward_broadcast_f64": (_I, [_P, _P, _P, _P, _P, _SIZE, _SIZE, _I, _I, _I, _P, _I, _P]),
+    "bx_push_forward_broadcast_f32": (_I, [_P, _P, _P, _P, _P, _SIZE, _SIZE, _I, _I, _I, _P, _I, _P]),
     "bx_pull_back_f32": (_I, [_P, _P, _P, _P, _P, _SIZE, _SIZE, _I, _I, _I, _P, _I, _P]),
     "bx_map_value_size": (_I, [_I, _I, _I, _I, _I]),
     "bx_map_f64": (_I, [_I, _I, _P, _P, _P, _P, _SIZE, _SIZE, _I, _I, _I, _P, _I, _P]),

@@ -152,7 +152,7 @@ unsigned tabulate_path_mask(unsigned mask);
 int map_value_size(int map_type, int pull, int in_vs, int gdim, int tdim);
 template <typename T>
 void map_device(int map_type, int pull, const T* U, const T* J, const T* detJ, const T* K, size_t nc, size_t rows,
-                int in_vs, int gdim, int tdim, T* out, cudaStream_t s);
+                int in_vs, int gdim, int tdim, T* out, cudaStream_t s, int bcast = 0);
 template <typename T>
 void dof_transform_device(const bx_element& e, int op, T* data, size_t nc, size_t cell_size, int n,
                           const uint32_t* cell_info, cudaStream_t s);
@@ -379,7 +379,7 @@ void tabulate_any(const bx_element& e, int nd, const T* x, size_t npts, int tdim
 
 template <typename T>
 void map_any(int map_type, int pull, const T* U, const T* J, const T* detJ, const T* K, size_t nc, size_t rows, int in_vs,
-             int gdim, int tdim, T* out, int mem, bx_stream_t stream)
+             int gdim, int tdim, T* out, int mem, bx_stream_t stream, int bcast = 0)
 {
   check_mem(mem);
   require(in_vs > 0 and gdim >= 1 and gdim <= 3 and tdim >= 1 and tdim <= 3, "map: bad value size or Jacobian shape");
@@ -389,7 +389,8 @@ void map_any(int map_type, int pull, const T* U, const T* J, const T* detJ, cons
   require(U and J and detJ and K and out, "map: null pointer");
   if (mem == BX_MEM_DEVICE)
   {
-    map_device<T>(map_type, pull, U, J, detJ, K, nc, rows, in_vs, gdim, tdim, out, static_cast<cudaStream_t>(stream));
+    map_device<T>(map_type, pull, U, J, detJ, K, nc, rows, in_vs, gdim, tdim, out, static_cast<cudaStream_t>(stream),
+                  bcast);
     return;
   }
   const size_t jsz = size_t(gdim) * tdim;
@@ -401,14 +402,15 @@ void map_any(int map_type, int pull, const T* U, const T* J, const T* detJ, cons
   const bool need_det = uses_Jarg;
   const bool need_J = pull ? uses_Karg : uses_Jarg;
   const bool need_K = pull ? uses_Jarg : uses_Karg;
-  const size_t per_cell = (rows * (in_vs + out_vs) + (need_J ? jsz : 0) + (need_K ? jsz : 0) + (need_det ? 1 : 0)) * sizeof(T);
+  const size_t per_cell = (rows * ((bcast ? 0 : in_vs) + out_vs) + (need_J ? jsz : 0) + (need_K ? jsz : 0) + (need_det ? 1 : 0))
+                          * sizeof(T);
   const size_t chunk = chunk_units(nc, per_cell, 1);
   StagePool& st = stage_pool();
   DrainOnExit drain{st};
   T *dU[2], *dJ[2], *dd[2], *dK[2], *dout[2];
   for (int b = 0; b < 2; ++b)
   {
-    dU[b] = st.get<T>(0, b, chunk * rows * in_vs * sizeof(T));
+    dU[b] = st.get<T>(0, b, (bcast ? 1 : chunk) * rows * in_vs * sizeof(T));
     dJ[b] = st.get<T>(1, b, chunk * jsz * sizeof(T));
     dd[b] = st.get<T>(2, b, chunk * sizeof(T));
     dK[b] = st.get<T>(3, b, chunk * jsz * sizeof(T));
@@ -420,14 +422,17 @@ void map_any(int map_type, int pull, const T* U, const T* J, const T* detJ, cons
     const int b = int(i & 1);
     const size_t n = std::min(chunk, nc - c0);
     cudaStream_t s = st.s[b];
-    BX_CUDA(cudaMemcpyAsync(dU[b], U + c0 * rows * in_vs, n * rows * in_vs * sizeof(T), cudaMemcpyHostToDevice, s));
+    if (!bcast)
+      BX_CUDA(cudaMemcpyAsync(dU[b], U + c0 * rows * in_vs, n * rows * in_vs * sizeof(T), cudaMemcpyHostToDevice, s));
+    else if (i < 2) // the shared slab of reference values goes up once per pipeline half
+      BX_CUDA(cudaMemcpyAsync(dU[b], U, rows * in_vs * sizeof(T), cudaMemcpyHostToDevice, s));
     if (need_J)
       BX_CUDA(cudaMemcpyAsync(dJ[b], J + c0 * jsz, n * jsz * sizeof(T), cudaMemcpyHostToDevice, s));
     if (need_det)
       BX_CUDA(cudaMemcpyAsync(dd[b], detJ + c0, n * sizeof(T), cudaMemcpyHostToDevice, s));
     if (need_K)
       BX_CUDA(cudaMemcpyAsync(dK[b], K + c0 * jsz, n * jsz * sizeof(T), cudaMemcpyHostToDevice, s));
-    map_device<T>(map_type, pull, dU[b], dJ[b], dd[b], dK[b], n, rows, in_vs, gdim, tdim, dout[b], s);
+    map_device<T>(map_type, pull, dU[b], dJ[b], dd[b], dK[b], n, rows, in_vs, gdim, tdim, dout[b], s, bcast);
     BX_CUDA(cudaMemcpyAsync(out + c0 * rows * out_vs, dout[b], n * rows * out_vs * sizeof(T), cudaMemcpyDeviceToHost, s));
   }
   st.sync();
@@ -797,6 +802,18 @@ extern "C"
         });
   }
 
+  int bx_push_forward_broadcast_f64(const bx_element* e, const double* U, const double* J, const double* detJ,
+                                    const double* K, size_t nc, size_t rows, int in_vs, int gdim, int tdim, double* out,
+                                    int mem, bx_stream_t stream)
+  {
+    return bx::guarded(
+        [&]()
+        {
+          bx::require(e != nullptr, "push_forward: null element");
+          bx::map_any<double>(e->map_type, 0, U, J, detJ, K, nc, rows, in_vs, gdim, tdim, out, mem, stream, 1);
+        });
+  }
+
   int bx_pull_back_f64(const bx_element* e, const double* u, const double* J, const double* detJ, const double* K,
                        size_t nc, size_t rows, int in_vs, int gdim, int tdim, double* out, int mem, bx_stream_t stream)
   {
@@ -823,6 +840,18 @@ extern "C"
         {
           bx::require(e != nullptr, "push_forward: null element");
           bx::map_any<float>(e->map_type, 0, U, J, detJ, K, nc, rows, in_vs, gdim, tdim, out, mem, stream);
+        });
+  }
+
+  int bx_push_forward_broadcast_f32(const bx_element* e, const float* U, const float* J, const float* detJ, const float* K,
+                                    size_t nc, size_t rows, int in_vs, int gdim, int tdim, float* out, int mem,
+                                    bx_stream_t stream)
+  {
+    return bx::guarded(
+        [&]()
+        {
+          bx::require(e != nullptr, "push_forward: null element");
+          bx::map_any<float>(e->map_type, 0, U, J, detJ, K, nc, rows, in_vs, gdim, tdim, out, mem, stream, 1);
         });
   }
 

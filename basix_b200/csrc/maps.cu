@@ -30,7 +30,7 @@ constexpr int kThreads = 256;
 template <typename T, int MAP, int RA, int CA, bool STAGE>
 __global__ void __launch_bounds__(kThreads)
     map_kernel(const T* __restrict__ in, const T* __restrict__ A, const T* __restrict__ detJ,
-               int invert_det, size_t nc, size_t rows, T* __restrict__ out)
+               int invert_det, size_t nc, size_t rows, int bcast, T* __restrict__ out)
 {
   constexpr int IN_VS = MAP == BX_MAP_COVARIANT_PIOLA            ? RA
                         : MAP == BX_MAP_CONTRAVARIANT_PIOLA      ? CA
@@ -68,10 +68,13 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
       for (int j = 0; j < CA; ++j)
         a[i][j] = STAGE ? sA[(c - c_first) * (RA * CA) + i * CA + j] : A[c * (RA * CA) + i * CA + j];
+    // bcast: one slab of reference values in[rows][IN_VS] serves every cell (the tabulated reference basis is the
+    // same on all cells); it stays in L1 / L2 and only the cell matrices and the result cross HBM
+    const size_t tin = bcast ? t - c * rows : t;
     T u[IN_VS];
 #pragma unroll
     for (int i = 0; i < IN_VS; ++i)
-      u[i] = in[t * IN_VS + i];
+      u[i] = in[tin * IN_VS + i];
     T r[OUT_VS];
     if constexpr (MAP == BX_MAP_COVARIANT_PIOLA)
     {
@@ -138,13 +141,93 @@ __global__ void __launch_bounds__(kThreads)
   }
 }
 
+// Broadcast push (one slab of reference values in[rows][IN_VS] for every cell), covariant / contravariant Piola:
+// a WARP owns a cell and its lanes own consecutive OUTPUT ENTRIES e = row * OUT_VS + i of that cell, so every store
+// instruction writes 256 contiguous bytes; the reference values a lane needs never change (registers for the whole
+// kernel) and the cell matrix is read with warp-uniform loads.  The thread-per-row kernel above spends 63 LSU
+// wavefronts per 45-row cell (8-byte accesses at a 24-byte stride, matrix reads from shared memory) and is bound by
+// the load/store pipe (2.98e9 cells/s on the 45-row N1curl workload); this form needs 19 and reaches 3.32e9 cells/s,
+// now limited by instruction issue (the component of an entry is lane dependent: selects).  Same accumulation order
+// as maps.h, bit-identical results.
+template <typename T, int MAP, int RA, int CA, int SLOTS>
+__global__ void __launch_bounds__(kThreads)
+    map_bcast_kernel(const T* __restrict__ in, const T* __restrict__ A, const T* __restrict__ detJ, size_t nc, int rows,
+                     T* __restrict__ out)
+{
+  constexpr int IN_VS = MAP == BX_MAP_COVARIANT_PIOLA ? RA : CA;
+  constexpr int OUT_VS = MAP == BX_MAP_COVARIANT_PIOLA ? CA : RA;
+  const int lane = threadIdx.x & 31;
+  const int E = rows * OUT_VS;
+  T u[SLOTS][IN_VS];
+  int comp[SLOTS];
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s)
+  {
+    const int e = lane + 32 * s, r = min(e, E - 1) / OUT_VS;
+    comp[s] = e < E ? e - r * OUT_VS : -1;
+#pragma unroll
+    for (int k = 0; k < IN_VS; ++k)
+      u[s][k] = in[r * IN_VS + k];
+  }
+  const size_t warps = size_t(gridDim.x) * (kThreads / 32);
+  for (size_t c = size_t(blockIdx.x) * (kThreads / 32) + (threadIdx.x >> 5); c < nc; c += warps)
+  {
+    T a[RA][CA];
+#pragma unroll
+    for (int i = 0; i < RA; ++i)
+#pragma unroll
+      for (int j = 0; j < CA; ++j)
+        a[i][j] = A[c * (RA * CA) + i * CA + j];
+    [[maybe_unused]] T det = T(1);
+    if constexpr (MAP == BX_MAP_CONTRAVARIANT_PIOLA)
+      det = detJ[c];
+    T* o = out + c * size_t(E) + lane;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s)
+    {
+      const int i = comp[s];
+      if (i < 0)
+        continue;
+      T acc = 0;
+      if constexpr (MAP == BX_MAP_COVARIANT_PIOLA)
+      {
+        // out[i] = sum_k A[k][i] in[k]   (maps.h:73-94)
+#pragma unroll
+        for (int k = 0; k < RA; ++k)
+        {
+          T aki = a[k][0];
+#pragma unroll
+          for (int j = 1; j < CA; ++j)
+            aki = i == j ? a[k][j] : aki;
+          acc += aki * u[s][k];
+        }
+      }
+      else
+      {
+        // out[i] = (sum_k A[i][k] in[k]) / det   (maps.h:100-124)
+#pragma unroll
+        for (int k = 0; k < CA; ++k)
+        {
+          T aik = a[0][k];
+#pragma unroll
+          for (int j = 1; j < RA; ++j)
+            aik = i == j ? a[j][k] : aik;
+          acc += aik * u[s][k];
+        }
+        acc = acc / det;
+      }
+      o[32 * s] = acc;
+    }
+  }
+}
+
 // identity map: u(i, j) = U(i, j)  (finite-element.h:632-640)
 template <typename T>
-__global__ void __launch_bounds__(kThreads) copy_kernel(const T* __restrict__ in, size_t n, T* __restrict__ out)
+__global__ void __launch_bounds__(kThreads) copy_kernel(const T* __restrict__ in, size_t n, size_t period, T* __restrict__ out)
 {
   const size_t stride = size_t(gridDim.x) * blockDim.x;
   for (size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += stride)
-    out[t] = in[t];
+    out[t] = in[period ? t % period : t];
 }
 
 // Persistent grid-stride launch: exactly the CTAs that are resident at once (no ragged last wave).
@@ -159,44 +242,74 @@ int grid_for(K kern, size_t n, size_t smem)
 }
 
 template <typename T, int MAP, int RA, int CA>
-void launch_one(const T* in, const T* A, const T* detJ, int inv, size_t nc, size_t rows, T* out, cudaStream_t s)
+void launch_one(const T* in, const T* A, const T* detJ, int inv, size_t nc, size_t rows, int bcast, T* out, cudaStream_t s)
 {
+  if constexpr (MAP == BX_MAP_COVARIANT_PIOLA or MAP == BX_MAP_CONTRAVARIANT_PIOLA)
+  {
+    constexpr int OUT_VS = MAP == BX_MAP_COVARIANT_PIOLA ? CA : RA;
+    const size_t E = rows * OUT_VS;
+    if (bcast and !inv and E <= 256)
+    {
+      const int slots = int((E + 31) / 32);
+      auto go = [&](auto kern)
+      {
+        int per_sm = 1;
+        BX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0));
+        const size_t want = ceil_div(nc, size_t(kThreads / 32));
+        const size_t cap = size_t(sm_count()) * std::max(per_sm, 1);
+        kern<<<unsigned(std::max<size_t>(1, std::min(want, cap))), kThreads, 0, s>>>(in, A, detJ, nc, int(rows), out);
+      };
+      switch (slots)
+      {
+      case 1: go(map_bcast_kernel<T, MAP, RA, CA, 1>); break;
+      case 2: go(map_bcast_kernel<T, MAP, RA, CA, 2>); break;
+      case 3: go(map_bcast_kernel<T, MAP, RA, CA, 3>); break;
+      case 4: go(map_bcast_kernel<T, MAP, RA, CA, 4>); break;
+      case 5: go(map_bcast_kernel<T, MAP, RA, CA, 5>); break;
+      case 6: go(map_bcast_kernel<T, MAP, RA, CA, 6>); break;
+      case 7: go(map_bcast_kernel<T, MAP, RA, CA, 7>); break;
+      default: go(map_bcast_kernel<T, MAP, RA, CA, 8>); break;
+      }
+      return;
+    }
+  }
   if (rows >= 2)
   {
     auto kern = map_kernel<T, MAP, RA, CA, true>;
     // a tile of kThreads rows touches at most kThreads / rows + 2 cells
     const size_t smem = (kThreads / rows + 2) * (RA * CA) * sizeof(T);
-    kern<<<grid_for(kern, nc * rows, smem), kThreads, smem, s>>>(in, A, detJ, inv, nc, rows, out);
+    kern<<<grid_for(kern, nc * rows, smem), kThreads, smem, s>>>(in, A, detJ, inv, nc, rows, bcast, out);
   }
   else
   {
     auto kern = map_kernel<T, MAP, RA, CA, false>;
-    kern<<<grid_for(kern, nc * rows, 0), kThreads, 0, s>>>(in, A, detJ, inv, nc, rows, out);
+    kern<<<grid_for(kern, nc * rows, 0), kThreads, 0, s>>>(in, A, detJ, inv, nc, rows, bcast, out);
   }
 }
 
 template <typename T, int MAP, int RA>
-void launch_ca(int ca, const T* in, const T* A, const T* detJ, int inv, size_t nc, size_t rows, T* out, cudaStream_t s)
+void launch_ca(int ca, const T* in, const T* A, const T* detJ, int inv, size_t nc, size_t rows, int bcast, T* out,
+               cudaStream_t s)
 {
   switch (ca)
   {
-  case 1: launch_one<T, MAP, RA, 1>(in, A, detJ, inv, nc, rows, out, s); break;
-  case 2: launch_one<T, MAP, RA, 2>(in, A, detJ, inv, nc, rows, out, s); break;
-  case 3: launch_one<T, MAP, RA, 3>(in, A, detJ, inv, nc, rows, out, s); break;
+  case 1: launch_one<T, MAP, RA, 1>(in, A, detJ, inv, nc, rows, bcast, out, s); break;
+  case 2: launch_one<T, MAP, RA, 2>(in, A, detJ, inv, nc, rows, bcast, out, s); break;
+  case 3: launch_one<T, MAP, RA, 3>(in, A, detJ, inv, nc, rows, bcast, out, s); break;
   default: fail(BX_ERR_INVALID_ARG, "map: Jacobian dimensions must be between 1 and 3");
   }
   BX_LAUNCHED();
 }
 
 template <typename T, int MAP>
-void launch_ra(int ra, int ca, const T* in, const T* A, const T* detJ, int inv, size_t nc, size_t rows, T* out,
-               cudaStream_t s)
+void launch_ra(int ra, int ca, const T* in, const T* A, const T* detJ, int inv, size_t nc, size_t rows, int bcast,
+               T* out, cudaStream_t s)
 {
   switch (ra)
   {
-  case 1: launch_ca<T, MAP, 1>(ca, in, A, detJ, inv, nc, rows, out, s); break;
-  case 2: launch_ca<T, MAP, 2>(ca, in, A, detJ, inv, nc, rows, out, s); break;
-  case 3: launch_ca<T, MAP, 3>(ca, in, A, detJ, inv, nc, rows, out, s); break;
+  case 1: launch_ca<T, MAP, 1>(ca, in, A, detJ, inv, nc, rows, bcast, out, s); break;
+  case 2: launch_ca<T, MAP, 2>(ca, in, A, detJ, inv, nc, rows, bcast, out, s); break;
+  case 3: launch_ca<T, MAP, 3>(ca, in, A, detJ, inv, nc, rows, bcast, out, s); break;
   default: fail(BX_ERR_INVALID_ARG, "map: Jacobian dimensions must be between 1 and 3");
   }
 }
@@ -219,10 +332,11 @@ int map_value_size(int map_type, int pull, int in_vs, int gdim, int tdim)
   }
 }
 
-// Device pointers.  U[nc][rows][in_vs], J[nc][gdim][tdim], detJ[nc], K[nc][tdim][gdim].
+// Device pointers.  U[nc][rows][in_vs] (bcast: U[rows][in_vs], shared by all cells), J[nc][gdim][tdim], detJ[nc],
+// K[nc][tdim][gdim].
 template <typename T>
 void map_device(int map_type, int pull, const T* U, const T* J, const T* detJ, const T* K, size_t nc, size_t rows,
-                int in_vs, int gdim, int tdim, T* out, cudaStream_t s)
+                int in_vs, int gdim, int tdim, T* out, cudaStream_t s, int bcast)
 {
   const int out_vs = map_value_size(map_type, pull, in_vs, gdim, tdim);
   if (nc == 0 or rows == 0)
@@ -244,31 +358,32 @@ void map_device(int map_type, int pull, const T* U, const T* J, const T* detJ, c
   case BX_MAP_IDENTITY:
     if (in_vs != out_vs)
       fail(BX_ERR_INVALID_ARG, "map: identity map needs matching value sizes");
-    copy_kernel<T><<<grid_for(copy_kernel<T>, nc * rows * in_vs, 0), kThreads, 0, s>>>(U, nc * rows * in_vs, out);
+    copy_kernel<T><<<grid_for(copy_kernel<T>, nc * rows * in_vs, 0), kThreads, 0, s>>>(U, nc * rows * in_vs,
+                                                                                      bcast ? rows * in_vs : 0, out);
     BX_LAUNCHED();
     return;
   case BX_MAP_COVARIANT_PIOLA:
     need(dim_in);
-    launch_ra<T, BX_MAP_COVARIANT_PIOLA>(Kr, Kc, U, Karg, detJ, pull, nc, rows, out, s);
+    launch_ra<T, BX_MAP_COVARIANT_PIOLA>(Kr, Kc, U, Karg, detJ, pull, nc, rows, bcast, out, s);
     return;
   case BX_MAP_CONTRAVARIANT_PIOLA:
     need(dim_in);
-    launch_ra<T, BX_MAP_CONTRAVARIANT_PIOLA>(Jr, Jc, U, Jarg, detJ, pull, nc, rows, out, s);
+    launch_ra<T, BX_MAP_CONTRAVARIANT_PIOLA>(Jr, Jc, U, Jarg, detJ, pull, nc, rows, bcast, out, s);
     return;
   case BX_MAP_DOUBLE_COVARIANT_PIOLA:
     need(dim_in * dim_in);
-    launch_ra<T, BX_MAP_DOUBLE_COVARIANT_PIOLA>(Kr, Kc, U, Karg, detJ, pull, nc, rows, out, s);
+    launch_ra<T, BX_MAP_DOUBLE_COVARIANT_PIOLA>(Kr, Kc, U, Karg, detJ, pull, nc, rows, bcast, out, s);
     return;
   case BX_MAP_DOUBLE_CONTRAVARIANT_PIOLA:
     need(dim_in * dim_in);
-    launch_ra<T, BX_MAP_DOUBLE_CONTRAVARIANT_PIOLA>(Jr, Jc, U, Jarg, detJ, pull, nc, rows, out, s);
+    launch_ra<T, BX_MAP_DOUBLE_CONTRAVARIANT_PIOLA>(Jr, Jc, U, Jarg, detJ, pull, nc, rows, bcast, out, s);
     return;
   default: fail(BX_ERR_UNSUPPORTED, "Map not implemented");
   }
 }
 
 template void map_device<double>(int, int, const double*, const double*, const double*, const double*, size_t, size_t, int,
-                                 int, int, double*, cudaStream_t);
+                                 int, int, double*, cudaStream_t, int);
 template void map_device<float>(int, int, const float*, const float*, const float*, const float*, size_t, size_t, int, int,
-                                int, float*, cudaStream_t);
+                                int, float*, cudaStream_t, int);
 } // namespace bx

@@ -518,6 +518,29 @@ class FiniteElement:
         check(fn(self._h, int(n), xa.ptr, npts, xdim, _ptr_of(out), xa.mem, stream))
         return out
 
+    def push_forward_broadcast(self, U, J, detJ, K):
+        """``push_forward`` of one slab of reference values ``U`` (rows, value_size) onto every cell: same result as
+        ``push_forward(np.broadcast_to(U, (ncells, rows, value_size)), J, detJ, K)`` without replicating ``U`` (the
+        tabulated reference basis is the same on all cells).  Returns (ncells, rows, physical value size)."""
+        dt = _float_dtype(J)
+        Ua, Ja = _Arg(U, dt, "U"), _Arg(J, dt, "J")
+        da, Ka = _Arg(detJ, dt, "detJ"), _Arg(K, dt, "K")
+        mem = _same_mem(Ua, Ja, da, Ka)
+        if len(Ua.shape) != 2 or len(Ja.shape) != 3 or len(Ka.shape) != 3 or len(da.shape) != 1:
+            raise TypeError("expected U (rows, vs), J (nc, gdim, tdim), detJ (nc,), K (nc, tdim, gdim)")
+        rows, in_vs = Ua.shape
+        nc, gdim, tdim = Ja.shape
+        if da.shape[0] != nc or Ka.shape != (nc, tdim, gdim):
+            raise RuntimeError("push_forward: inconsistent array shapes")
+        out_vs = lib().bx_map_value_size(int(self._map_type), 0, in_vs, gdim, tdim)
+        if out_vs < 0:
+            check(1)
+        stream, alloc = _stream_and_like(Ja)
+        out = alloc((nc, rows, out_vs), dt)
+        fn = lib().bx_push_forward_broadcast_f32 if dt is np.float32 else lib().bx_push_forward_broadcast_f64
+        check(fn(self._h, Ua.ptr, Ja.ptr, da.ptr, Ka.ptr, nc, rows, in_vs, gdim, tdim, _ptr_of(out), mem, stream))
+        return out
+
     def _map(self, pull: int, U, J, detJ, K):
         dt = _float_dtype(U)
         Ua, Ja = _Arg(U, dt, "U"), _Arg(J, dt, "J")

@@ -274,8 +274,9 @@ class PushForward:
     metric, unit = METRIC_CELLS, "cells/s"
     bound = "hbm"
 
-    def __init__(self, element, ref_args, nc, rows, pull, desc):
+    def __init__(self, element, ref_args, nc, rows, pull, desc, bcast=False):
         self.element_name, self.ref_args, self.nc, self.rows, self.pull, self.desc = element, ref_args, nc, rows, pull, desc
+        self.bcast = bcast  # one slab of reference values for all cells (push_forward_broadcast)
 
     def setup(self, rank):
         import torch
@@ -283,7 +284,7 @@ class PushForward:
         self.e = load_element(self.element_name, self.ref_args)
         nc, rows = self.nc, self.rows
         J, detJ, K = random_jacobians(nc, 7 + rank)
-        U = np.random.default_rng(8 + rank).standard_normal((nc, rows, 3))
+        U = np.random.default_rng(8 + rank).standard_normal((rows, 3) if self.bcast else (nc, rows, 3))
         self.host = [torch.from_numpy(a).pin_memory() for a in (U, J, detJ, K)]
         self.dev = [t.cuda() for t in self.host]
         self.units_per_step = nc
@@ -291,13 +292,13 @@ class PushForward:
         self.units_per_launch = nc
         # covariant push reads U and K, pull reads u and J; contravariant also reads detJ
         contra = int(self.e.map_type) == 3
-        self.alg_bytes = nc * (2 * rows * 3 * 8 + 72 + (8 if contra else 0))
+        self.alg_bytes = nc * ((1 if self.bcast else 2) * rows * 3 * 8 + 72 + (8 if contra else 0))
         self.flops = 18.0 * rows * nc
         self.config = {"workload": self.desc, "cells_per_gpu": nc, "rows": rows,
                        "l2": "arrays are %.2f GB per step (>> 126 MB L2)" % (self.alg_bytes / 1e9)}
 
     def step(self):
-        f = self.e.pull_back if self.pull else self.e.push_forward
+        f = self.e.push_forward_broadcast if self.bcast else self.e.pull_back if self.pull else self.e.push_forward
         self.result = f(*self.dev)
 
     def e2e_setup(self, avail_bytes):
@@ -305,7 +306,12 @@ class PushForward:
 
         self.out_host = torch.empty((self.nc, self.rows, 3), dtype=torch.float64).pin_memory()
         self.e2e_units = self.nc
-        self.h2d = sum(t.numel() * 8 for t in self.host)
+        # the library ships only the arrays the map reads (csrc/capi.cu map_any): covariant maps the "K" argument,
+        # contravariant maps the "J" argument and detJ; pull_back swaps J and K
+        U, J, d, K = self.host
+        contra = int(self.e.map_type) == 3
+        mats = ([K if self.pull else J, d] if contra else [J if self.pull else K])
+        self.h2d = sum(t.numel() * 8 for t in [U] + mats)
         self.d2h = self.out_host.numel() * 8
         return {"cells_per_gpu": self.nc}
 
@@ -313,7 +319,8 @@ class PushForward:
         from basix_b200 import _capi
 
         U, J, d, K = self.host
-        fn = _capi.lib().bx_pull_back_f64 if self.pull else _capi.lib().bx_push_forward_f64
+        L = _capi.lib()
+        fn = L.bx_push_forward_broadcast_f64 if self.bcast else L.bx_pull_back_f64 if self.pull else L.bx_push_forward_f64
         _capi.check(fn(self.e._h, U.data_ptr(), J.data_ptr(), d.data_ptr(), K.data_ptr(), self.nc, self.rows, 3, 3, 3,
                        self.out_host.data_ptr(), _capi.BX_MEM_HOST, None))
 
@@ -323,7 +330,7 @@ class PushForward:
         r = ref.RefElement(*self.ref_args)
         n = int(min(self.nc, max(100_000, 4e7 * cores / self.rows)))
         J, detJ, K = random_jacobians(n, 7)
-        U = np.random.default_rng(8).standard_normal((n, self.rows, 3))
+        U = np.random.default_rng(8).standard_normal((n, self.rows, 3))  # the reference needs the replicated array
         self._cpu = (r, U, J, detJ, K, cores)
         return n, f"{n} cells per step over {cores} std::threads, oracle/_ref (unmodified reference, g++ -O2)"
 
@@ -500,6 +507,10 @@ WORKLOADS = {
     "interpolate_n1curl3": lambda: Interpolate(
         "N1curl3_tetrahedron_legendre", (3, 3, 3, 11), 20_000_000,
         "N1curl degree 3 tetrahedron, interpolation_matrix (45 x 141) applied to 20M cells of point values"),
+    "push_forward_bcast_n1curl3_rows45": lambda: PushForward(
+        "N1curl3_tetrahedron_legendre", (3, 3, 3, 11), 8_000_000, 45, False,
+        "N1curl degree 3 tetrahedron, covariant Piola push_forward of ONE 45-row slab of reference values onto 8M cells "
+        "(push_forward_broadcast)", bcast=True),
     "t_apply_rt4": lambda: TApply(
         "RT4_tetrahedron_legendre", (2, 3, 4, 11), 50_000_000, 1, False,
         "RT degree 4 tetrahedron, T_apply(block 1) over 50M cells, random cell_info"),

@@ -235,6 +235,15 @@ extern "C"
   int bx_push_forward_f64(const bx_element* e, const double* U, const double* J, const double* detJ,
                           const double* K, size_t nc, size_t rows, int in_vs, int gdim, int tdim,
                           double* out, int mem, bx_stream_t stream);
+  /* push_forward of ONE slab of reference values U[rows][in_vs] onto every cell (the tabulated reference basis is
+     the same on all cells: the reference API makes the caller replicate it nc times, finite-element.cpp:1971-2005).
+     Same result as bx_push_forward_* on the replicated array; only J / detJ / K and the result cross HBM. */
+  int bx_push_forward_broadcast_f64(const bx_element* e, const double* U, const double* J, const double* detJ,
+                                    const double* K, size_t nc, size_t rows, int in_vs, int gdim, int tdim, double* out,
+                                    int mem, bx_stream_t stream);
+  int bx_push_forward_broadcast_f32(const bx_element* e, const float* U, const float* J, const float* detJ, const float* K,
+                                    size_t nc, size_t rows, int in_vs, int gdim, int tdim, float* out, int mem,
+                                    bx_stream_t stream);
   int bx_pull_back_f64(const bx_element* e, const double* u, const double* J, const double* detJ,
                        const double* K, size_t nc, size_t rows, int in_vs, int gdim, int tdim, double* out,
                        int mem, bx_stream_t stream);

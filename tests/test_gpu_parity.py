@@ -187,6 +187,28 @@ def test_push_pull_manifold(ref, family, variant, vs):
     assert np.array_equal(e.pull_back(got, J, detJ, K), r.pull_back(want, J, detJ, K))
 
 
+@pytest.mark.parametrize("family,cell,degree,variant,vs", [(N1E, TET, 3, LEG, 3), (RT, TET, 4, LEG, 3), (RT, TRI, 2, LEG, 2),
+                                                          (P, TET, 2, EQ, 1), (7, TET, 1, 0, 9)])
+def test_push_forward_broadcast(ref, family, cell, degree, variant, vs):
+    """One slab of reference values for all cells == the reference's push_forward on the replicated array
+    (bit for bit: same kernel arithmetic); host and device pointers, float64 and float32."""
+    import torch
+
+    r, e = make_pair(ref, family, cell, degree, variant)
+    tdim = 3 if cell == TET else 2
+    rng = np.random.default_rng(degree)
+    for nc, rows in ((1, 1), (37, 5), (1201, 45)):
+        J, detJ, K = jacobians(nc, tdim, tdim, seed=nc)
+        U0 = rng.standard_normal((rows, vs))
+        want = r.push_forward(np.ascontiguousarray(np.broadcast_to(U0, (nc, rows, vs))), J, detJ, K)
+        got = e.push_forward_broadcast(U0, J, detJ, K)
+        assert np.array_equal(got, want)
+        dev = [torch.from_numpy(a).cuda() for a in (U0, J, detJ, K)]
+        assert np.array_equal(e.push_forward_broadcast(*dev).cpu().numpy(), want)
+        got32 = e.push_forward_broadcast(*[a.astype(np.float32) for a in (U0, J, detJ, K)])
+        assert got32.dtype == np.float32 and np.allclose(got32, want, rtol=2e-4, atol=2e-4 * np.max(np.abs(want)))
+
+
 def test_map_device_pointers_and_golden(ref):
     import torch
 

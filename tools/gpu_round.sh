@@ -7,7 +7,7 @@ timeout 300 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -1 gpurun_out/smoke.log
 timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
-for w in tabulate_p1_tri tabulate_q4_hex push_forward_n1curl3 pull_back_n1curl3 push_forward_n1curl3_rows45 t_apply_rt4 permute_p5_tet interpolate_n1curl3; do
+for w in tabulate_p1_tri tabulate_q4_hex push_forward_n1curl3 pull_back_n1curl3 push_forward_n1curl3_rows45 push_forward_bcast_n1curl3_rows45 t_apply_rt4 permute_p5_tet interpolate_n1curl3; do
   timeout 900 python bench.py --workload $w --steps 10 --warmup 3 ${EXTRA:-} > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err
 done
 python - <<'PY'
