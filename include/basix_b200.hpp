@@ -192,6 +192,15 @@ public:
     check(bx_push_forward_f64(_h, U, J, detJ, K, nc, rows, in_vs, gdim, tdim, u, mem, stream));
     return bx_map_value_size(_map, 0, in_vs, gdim, tdim);
   }
+  /// push_forward of ONE slab U[rows][in_vs] of reference values onto every cell (same result as push_forward on the
+  /// array replicated nc times, which is what the reference API requires).
+  int push_forward_broadcast(const double* U, const double* J, const double* detJ, const double* K, std::size_t nc,
+                             std::size_t rows, int in_vs, int gdim, int tdim, double* u, int mem = BX_MEM_HOST,
+                             bx_stream_t stream = nullptr) const
+  {
+    check(bx_push_forward_broadcast_f64(_h, U, J, detJ, K, nc, rows, in_vs, gdim, tdim, u, mem, stream));
+    return bx_map_value_size(_map, 0, in_vs, gdim, tdim);
+  }
   /// (finite-element.h:592-594)
   int pull_back(const double* u, const double* J, const double* detJ, const double* K, std::size_t nc,
                 std::size_t rows, int in_vs, int gdim, int tdim, double* U, int mem = BX_MEM_HOST,
