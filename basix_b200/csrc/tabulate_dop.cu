@@ -36,7 +36,6 @@
 
 #include <algorithm>
 #include <type_traits>
-#include <cstdio>
 #include <cstdlib>
 #include <map>
 #include <mutex>
@@ -73,8 +72,6 @@ struct Params
   double* basis;
   int N, K, kpad;    // output columns, basis functions, rows of a point slab (multiple of 4)
   int b_doubles, nsteps;
-  int debug;         // profiling only: bit 0 = no stores, bit 2 = record phase clocks into `timing`
-  unsigned long long* timing; // [warp][3]: produce, contract, chunks
 };
 
 // Point slab: element (k, c), c = point 0..15, lives at 16 k + (c ^ 4 (k & 3)); both the producer's row writes
@@ -395,13 +392,8 @@ __global__ void __launch_bounds__(32 * WARPS, 1) tabulate_dop_kernel(const Param
   double xr[TDIM];
   if (chunk < nchunks)
     load_x(chunk, xr);
-  const bool timed = p.debug & 4;
-  long long t_prod = 0, t_con = 0, n_chunks = 0;
   for (; chunk < nchunks; chunk += stride)
   {
-    long long c0 = 0, c1 = 0;
-    if (timed)
-      c0 = clock64();
     // ---- values of the orthonormal set: lane = point (lanes 16..31 idle) ----
     if (lane < kChunkPts)
     {
@@ -413,30 +405,17 @@ __global__ void __launch_bounds__(32 * WARPS, 1) tabulate_dop_kernel(const Param
         values_tetrahedron<DEG>(xr[0], xr[1], xr[2], sink);
     }
     __syncwarp();
-    if (timed)
-      c1 = clock64();
     if (chunk + stride < nchunks)
       load_x(chunk + stride, xr); // in flight during the contraction
 
     // ---- FP64 tensor cores: every slab on this warp's two row tiles ----
     const size_t pt = chunk * kChunkPts + g;
-    const bool lean = n_even and (chunk + 1) * kChunkPts <= p.npts and !(p.debug & 1);
+    const bool lean = n_even and (chunk + 1) * kChunkPts <= p.npts;
     if (lean)
       run_groups<true>(steps, p.nsteps, A0, A1, Bgt, g, t, p.basis, p.npts, p.npts, p.N, pt);
     else
-      run_groups<false>(steps, p.nsteps, A0, A1, Bgt, g, t, p.basis, p.npts, (p.debug & 1) ? 0 : p.npts, p.N, pt);
+      run_groups<false>(steps, p.nsteps, A0, A1, Bgt, g, t, p.basis, p.npts, p.npts, p.N, pt);
     __syncwarp(); // the slab is overwritten by the next chunk
-    if (timed)
-    {
-      t_prod += c1 - c0;
-      t_con += clock64() - c1;
-      ++n_chunks;
-    }
-  }
-  if (timed and lane == 0)
-  {
-    unsigned long long* o = p.timing + (size_t(blockIdx.x) * WARPS + warp) * 3;
-    o[0] = t_prod, o[1] = t_con, o[2] = n_chunks;
   }
 }
 
@@ -619,26 +598,9 @@ void launch_warps(const Operand& op, const bx_element& e, const double* x, size_
   p.kpad = op.kpad;
   p.b_doubles = op.b_doubles;
   p.nsteps = op.nsteps;
-  static const int debug = std::getenv("BX_DOP_DEBUG") ? std::atoi(std::getenv("BX_DOP_DEBUG")) : 0;
-  p.debug = debug;
   const size_t nblocks = ceil_div(npts, size_t(kChunkPts) * WARPS);
-  const unsigned grid = unsigned(std::min<size_t>(nblocks, size_t(sm_count())));
-  p.timing = nullptr;
-  if (debug & 4)
-    BX_CUDA(cudaMalloc(&p.timing, size_t(grid) * WARPS * 3 * sizeof(unsigned long long)));
-  kern<<<grid, 32 * WARPS, op.smem, s>>>(p);
+  kern<<<unsigned(std::min<size_t>(nblocks, size_t(sm_count()))), 32 * WARPS, op.smem, s>>>(p);
   BX_LAUNCHED();
-  if (debug & 4)
-  {
-    std::vector<unsigned long long> h(size_t(grid) * WARPS * 3);
-    BX_CUDA(cudaMemcpy(h.data(), p.timing, h.size() * 8, cudaMemcpyDeviceToHost));
-    BX_CUDA(cudaFree(p.timing));
-    double a[3] = {0, 0, 0};
-    for (size_t i = 0; i < h.size(); ++i)
-      a[i % 3] += double(h[i]);
-    fprintf(stderr, "dop timing: per chunk cycles produce %.0f contract+store %.0f (chunks/warp %.1f)\n", a[0] / a[2],
-            a[1] / a[2], a[2] / (double(grid) * WARPS));
-  }
 }
 
 template <int TDIM, int DEG>
