@@ -20,8 +20,6 @@
 #include "element.cuh"
 
 #include <algorithm>
-#include <cstdlib>
-#include <string>
 
 namespace bx
 {
@@ -197,28 +195,14 @@ void interpolate_device(const bx_element& e, int layout, const T* values, size_t
     fail(BX_ERR_UNSUPPORTED, "interpolate: the interpolation matrix does not fit in shared memory");
   const size_t nblocks = ceil_div(nc, size_t(kCells) * kWarps);
   const unsigned grid = unsigned(std::min<size_t>(nblocks, size_t(sm_count())));
-  // tuning aid (development only): BX_INTERP_TUNE = "<depth><s|c>", e.g. "4c" (default), "2s", "6c"
-  static const std::string tune = std::getenv("BX_INTERP_TUNE") ? std::getenv("BX_INTERP_TUNE") : "4c";
-  auto go = [&](auto kern, int depth)
-  {
-    p.ksteps = int(ceil_div(size_t(p.ksteps), size_t(depth)) * depth);
-    if (4 * p.ksteps > p.kstride)
-      fail(BX_ERR_RUNTIME, "interpolate: operand padding too small for the unroll factor");
-    BX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    kern<<<grid, kThreads, smem, s>>>(p);
-  };
-  if (tune == "2s")
-    go(interpolate_kernel<2, true, T>, 2);
-  else if (tune == "2c")
-    go(interpolate_kernel<2, false, T>, 2);
-  else if (tune == "4s")
-    go(interpolate_kernel<4, true, T>, 4);
-  else if (tune == "6c")
-    go(interpolate_kernel<6, false, T>, 6);
-  else if (tune == "6s")
-    go(interpolate_kernel<6, true, T>, 6);
-  else
-    go(interpolate_kernel<4, false, T>, 4);
+  // A fragments four k-steps ahead, default caching (measured best of depth 2 / 4 / 6 and streaming / default loads)
+  constexpr int kDepth = 4;
+  p.ksteps = int(ceil_div(size_t(p.ksteps), size_t(kDepth)) * kDepth);
+  if (4 * p.ksteps > p.kstride)
+    fail(BX_ERR_RUNTIME, "interpolate: operand padding too small for the unroll factor");
+  auto kern = interpolate_kernel<kDepth, false, T>;
+  BX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  kern<<<grid, kThreads, smem, s>>>(p);
   BX_LAUNCHED();
 }
 template void interpolate_device<double>(const bx_element&, int, const double*, size_t, double*, cudaStream_t);

@@ -149,7 +149,8 @@ bool launch_any(const bx_element& e, int nd, const T* x, size_t npts, T* basis, 
 }
 namespace dop
 {
-bool launch_any(const bx_element& e, int nd, const double* x, size_t npts, double* basis, cudaStream_t s, bool dry_run);
+template <typename T>
+bool launch_any(const bx_element& e, int nd, const T* x, size_t npts, T* basis, cudaStream_t s, bool dry_run);
 }
 namespace
 {
@@ -204,7 +205,7 @@ int tabulate_path(const bx_element& e, int nd)
 {
   if (allowed(3) and small::launch_any<double>(e, nd, nullptr, 0, nullptr, nullptr, true))
     return 3;
-  if (allowed(4) and dop::launch_any(e, nd, nullptr, 0, nullptr, nullptr, true))
+  if (allowed(4) and dop::launch_any<double>(e, nd, nullptr, 0, nullptr, nullptr, true))
     return 4;
   if (allowed(1) and try_fused(e, nd, nullptr, 0, nullptr, nullptr, true))
     return 1;
@@ -221,7 +222,7 @@ void tabulate_device<double>(const bx_element& e, int nd, const double* x, size_
   // the single-kernel paths write a dense [nder][npts][N] table; a chunk of a larger table takes the generic path
   if (out_pts == npts and allowed(3) and small::launch_any<double>(e, nd, x, npts, basis, s, false))
     return;
-  if (out_pts == npts and allowed(4) and dop::launch_any(e, nd, x, npts, basis, s, false))
+  if (out_pts == npts and allowed(4) and dop::launch_any<double>(e, nd, x, npts, basis, s, false))
     return;
   if (out_pts == npts and allowed(1) and try_fused(e, nd, x, npts, basis, s, false))
     return;
@@ -236,6 +237,8 @@ void tabulate_device<float>(const bx_element& e, int nd, const float* x, size_t 
 {
   require_device(e);
   if (out_pts == npts and allowed(3) and small::launch_any<float>(e, nd, x, npts, basis, s, false))
+    return;
+  if (out_pts == npts and allowed(4) and dop::launch_any<float>(e, nd, x, npts, basis, s, false))
     return;
   if (out_pts == npts and allowed(2) and tabulate_tp_device<float>(e, nd, x, npts, basis, s, false))
     return;

@@ -63,13 +63,16 @@ struct __align__(16) Step
   int last;    // 0, or 1 + derivative slab index when this is the last k-step of that slab
 };
 
+// T = type of the points and of the table (double, or float for the float32 API: loads widen, stores narrow, the
+// operands and the arithmetic are double either way)
+template <typename T>
 struct Params
 {
-  const double* x;
+  const T* x;
   size_t npts;
   const double* B;   // all slab operands
   const Step* steps; // nsteps + 1 entries (the last one repeats its predecessor: prefetch target)
-  double* basis;
+  T* basis;
   int N, K, kpad;    // output columns, basis functions, rows of a point slab (multiple of 4)
   int b_doubles, nsteps;
 };
@@ -230,10 +233,10 @@ __device__ __forceinline__ void values_tetrahedron(double x0, double x1, double 
 }
 
 // All slabs for the column group [n0, n0 + 8 NT) of this warp's 16 points.
-template <int NT, bool LEAN>
+template <int NT, bool LEAN, typename T>
 __device__ __forceinline__ void run_group(const Step* __restrict__ steps, int nsteps, const double* __restrict__ A0,
                                           const double* __restrict__ A1, const double* __restrict__ Bgt, int n0,
-                                          int g, int t, double* __restrict__ basis, size_t npts, size_t npts_st, int N,
+                                          int g, int t, T* __restrict__ basis, size_t npts, size_t npts_st, int N,
                                           size_t pt)
 {
   double acc[2][NT][2];
@@ -277,16 +280,24 @@ __device__ __forceinline__ void run_group(const Step* __restrict__ steps, int ns
       {
         // whole chunk inside the table, N even: 16-byte stores at compile-time offsets from one row pointer;
         // only the last column tile of the operand can run past N
-        double* row = basis + (slab * npts + pt) * N + n0 + 2 * t;
+        T* row = basis + (slab * npts + pt) * N + n0 + 2 * t;
+        using T2 = typename std::conditional<sizeof(T) == 8, double2, float2>::type;
+        auto pair = [](double a, double b)
+        {
+          T2 v;
+          v.x = static_cast<T>(a);
+          v.y = static_cast<T>(b);
+          return v;
+        };
         const bool last_ok = n0 + (NT - 1) * 8 + 2 * t < N;
 #pragma unroll
         for (int m = 0; m < 2; ++m)
         {
 #pragma unroll
           for (int j = 0; j < NT - 1; ++j)
-            __stcs(reinterpret_cast<double2*>(row + j * 8), make_double2(acc[m][j][0], acc[m][j][1]));
+            __stcs(reinterpret_cast<T2*>(row + j * 8), pair(acc[m][j][0], acc[m][j][1]));
           if (last_ok)
-            __stcs(reinterpret_cast<double2*>(row + (NT - 1) * 8), make_double2(acc[m][NT - 1][0], acc[m][NT - 1][1]));
+            __stcs(reinterpret_cast<T2*>(row + (NT - 1) * 8), pair(acc[m][NT - 1][0], acc[m][NT - 1][1]));
           row += size_t(8) * N;
         }
       }
@@ -298,15 +309,15 @@ __device__ __forceinline__ void run_group(const Step* __restrict__ steps, int ns
           const size_t q = pt + 8 * m;
           if (q < npts_st)
           {
-            double* row = basis + (slab * npts + q) * N;
+            T* row = basis + (slab * npts + q) * N;
 #pragma unroll
             for (int j = 0; j < NT; ++j)
             {
               const int n = n0 + j * 8 + 2 * t;
               if (n < N)
-                __stcs(row + n, acc[m][j][0]);
+                __stcs(row + n, static_cast<T>(acc[m][j][0]));
               if (n + 1 < N)
-                __stcs(row + n + 1, acc[m][j][1]);
+                __stcs(row + n + 1, static_cast<T>(acc[m][j][1]));
             }
           }
         }
@@ -326,9 +337,9 @@ __device__ __forceinline__ void run_group(const Step* __restrict__ steps, int ns
   }
 }
 
-template <bool LEAN>
+template <bool LEAN, typename T>
 __device__ __forceinline__ void run_groups(const Step* steps, int nsteps, const double* A0, const double* A1,
-                                           const double* Bgt, int g, int t, double* basis, size_t npts, size_t npts_st,
+                                           const double* Bgt, int g, int t, T* basis, size_t npts, size_t npts_st,
                                            int N, size_t pt)
 {
   for (int n0 = 0; n0 < N; n0 += 8 * kMaxNT)
@@ -336,19 +347,19 @@ __device__ __forceinline__ void run_groups(const Step* steps, int nsteps, const 
     const int nt = min(kMaxNT, (N - n0 + 7) >> 3);
     switch (nt)
     {
-    case 1: run_group<1, LEAN>(steps, nsteps, A0, A1, Bgt, n0, g, t, basis, npts, npts_st, N, pt); break;
-    case 2: run_group<2, LEAN>(steps, nsteps, A0, A1, Bgt, n0, g, t, basis, npts, npts_st, N, pt); break;
-    case 3: run_group<3, LEAN>(steps, nsteps, A0, A1, Bgt, n0, g, t, basis, npts, npts_st, N, pt); break;
-    case 4: run_group<4, LEAN>(steps, nsteps, A0, A1, Bgt, n0, g, t, basis, npts, npts_st, N, pt); break;
-    case 5: run_group<5, LEAN>(steps, nsteps, A0, A1, Bgt, n0, g, t, basis, npts, npts_st, N, pt); break;
-    case 6: run_group<6, LEAN>(steps, nsteps, A0, A1, Bgt, n0, g, t, basis, npts, npts_st, N, pt); break;
-    default: run_group<7, LEAN>(steps, nsteps, A0, A1, Bgt, n0, g, t, basis, npts, npts_st, N, pt); break;
+    case 1: run_group<1, LEAN, T>(steps, nsteps, A0, A1, Bgt, n0, g, t, basis, npts, npts_st, N, pt); break;
+    case 2: run_group<2, LEAN, T>(steps, nsteps, A0, A1, Bgt, n0, g, t, basis, npts, npts_st, N, pt); break;
+    case 3: run_group<3, LEAN, T>(steps, nsteps, A0, A1, Bgt, n0, g, t, basis, npts, npts_st, N, pt); break;
+    case 4: run_group<4, LEAN, T>(steps, nsteps, A0, A1, Bgt, n0, g, t, basis, npts, npts_st, N, pt); break;
+    case 5: run_group<5, LEAN, T>(steps, nsteps, A0, A1, Bgt, n0, g, t, basis, npts, npts_st, N, pt); break;
+    case 6: run_group<6, LEAN, T>(steps, nsteps, A0, A1, Bgt, n0, g, t, basis, npts, npts_st, N, pt); break;
+    default: run_group<7, LEAN, T>(steps, nsteps, A0, A1, Bgt, n0, g, t, basis, npts, npts_st, N, pt); break;
     }
   }
 }
 
-template <int TDIM, int DEG, int WARPS>
-__global__ void __launch_bounds__(32 * WARPS, 1) tabulate_dop_kernel(const Params p)
+template <int TDIM, int DEG, int WARPS, typename T>
+__global__ void __launch_bounds__(32 * WARPS, 1) tabulate_dop_kernel(const Params<T> p)
 {
   constexpr int K = jets::psize(TDIM, DEG);
   constexpr int kThreads = 32 * WARPS;
@@ -385,7 +396,7 @@ __global__ void __launch_bounds__(32 * WARPS, 1) tabulate_dop_kernel(const Param
     pt = pt < p.npts ? pt : p.npts - 1; // ragged tail: recompute the last point, stores are predicated
 #pragma unroll
     for (int a = 0; a < TDIM; ++a)
-      xr[a] = __ldg(p.x + TDIM * pt + a);
+      xr[a] = double(__ldg(p.x + TDIM * pt + a));
   };
 
   size_t chunk = size_t(blockIdx.x) * WARPS + warp;
@@ -412,9 +423,9 @@ __global__ void __launch_bounds__(32 * WARPS, 1) tabulate_dop_kernel(const Param
     const size_t pt = chunk * kChunkPts + g;
     const bool lean = n_even and (chunk + 1) * kChunkPts <= p.npts;
     if (lean)
-      run_groups<true>(steps, p.nsteps, A0, A1, Bgt, g, t, p.basis, p.npts, p.npts, p.N, pt);
+      run_groups<true, T>(steps, p.nsteps, A0, A1, Bgt, g, t, p.basis, p.npts, p.npts, p.N, pt);
     else
-      run_groups<false>(steps, p.nsteps, A0, A1, Bgt, g, t, p.basis, p.npts, p.npts, p.N, pt);
+      run_groups<false, T>(steps, p.nsteps, A0, A1, Bgt, g, t, p.basis, p.npts, p.npts, p.N, pt);
     __syncwarp(); // the slab is overwritten by the next chunk
   }
 }
@@ -582,12 +593,12 @@ Operand build_operand(const bx_element& e, int nd, bool upload_to_device)
   return op;
 }
 
-template <int TDIM, int DEG, int WARPS>
-void launch_warps(const Operand& op, const bx_element& e, const double* x, size_t npts, double* basis, cudaStream_t s)
+template <int TDIM, int DEG, int WARPS, typename T>
+void launch_warps(const Operand& op, const bx_element& e, const T* x, size_t npts, T* basis, cudaStream_t s)
 {
-  auto kern = tabulate_dop_kernel<TDIM, DEG, WARPS>;
+  auto kern = tabulate_dop_kernel<TDIM, DEG, WARPS, T>;
   BX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(op.smem)));
-  Params p;
+  Params<T> p;
   p.x = x;
   p.npts = npts;
   p.B = op.d_B;
@@ -603,26 +614,27 @@ void launch_warps(const Operand& op, const bx_element& e, const double* x, size_
   BX_LAUNCHED();
 }
 
-template <int TDIM, int DEG>
-void launch(const Operand& op, const bx_element& e, const double* x, size_t npts, double* basis, cudaStream_t s)
+template <int TDIM, int DEG, typename T>
+void launch(const Operand& op, const bx_element& e, const T* x, size_t npts, T* basis, cudaStream_t s)
 {
   if (op.warps == 12)
-    launch_warps<TDIM, DEG, 12>(op, e, x, npts, basis, s);
+    launch_warps<TDIM, DEG, 12, T>(op, e, x, npts, basis, s);
   else
-    launch_warps<TDIM, DEG, 8>(op, e, x, npts, basis, s);
+    launch_warps<TDIM, DEG, 8, T>(op, e, x, npts, basis, s);
 }
 
 #define BX_DOP(T, DEG)                                                                                     \
   if (e.tdim == T and e.superdegree == DEG)                                                                \
   {                                                                                                        \
     if (!dry_run)                                                                                          \
-      launch<T, DEG>(*op, e, x, npts, basis, s);                                                           \
+      launch<T, DEG, U>(*op, e, x, npts, basis, s);                                                           \
     return true;                                                                                           \
   }
 } // namespace
 
 // Returns false when the element / derivative order is outside this path (caller falls through).
-bool launch_any(const bx_element& e, int nd, const double* x, size_t npts, double* basis, cudaStream_t s, bool dry_run)
+template <typename U>
+bool launch_any(const bx_element& e, int nd, const U* x, size_t npts, U* basis, cudaStream_t s, bool dry_run)
 {
   if (e.polyset_type != BX_POLYSET_STANDARD or nd < 0 or nd > 4 or !e.dop_cache)
     return false;
@@ -647,5 +659,7 @@ bool launch_any(const bx_element& e, int nd, const double* x, size_t npts, doubl
   BX_DOP(3, 1) BX_DOP(3, 2) BX_DOP(3, 3) BX_DOP(3, 4) BX_DOP(3, 5) BX_DOP(3, 6)
   return false;
 }
+template bool launch_any<double>(const bx_element&, int, const double*, size_t, double*, cudaStream_t, bool);
+template bool launch_any<float>(const bx_element&, int, const float*, size_t, float*, cudaStream_t, bool);
 } // namespace dop
 } // namespace bx
