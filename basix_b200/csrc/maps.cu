@@ -142,36 +142,36 @@ __global__ void __launch_bounds__(kThreads)
 }
 
 // Broadcast push (one slab of reference values in[rows][IN_VS] for every cell), covariant / contravariant Piola:
-// a WARP owns a cell and its lanes own consecutive OUTPUT ENTRIES e = row * OUT_VS + i of that cell, so every store
-// instruction writes 256 contiguous bytes; the reference values a lane needs never change (registers for the whole
-// kernel) and the cell matrix is read with warp-uniform loads.  The thread-per-row kernel above spends 63 LSU
-// wavefronts per 45-row cell (8-byte accesses at a 24-byte stride, matrix reads from shared memory) and is bound by
-// the load/store pipe (2.98e9 cells/s on the 45-row N1curl workload); this form needs 19 and reaches 3.32e9 cells/s,
-// now limited by instruction issue (the component of an entry is lane dependent: selects).  Same accumulation order
-// as maps.h, bit-identical results.
-template <typename T, int MAP, int RA, int CA, int SLOTS>
+// a WARP owns a cell.  Lanes own ROWS for the arithmetic (the row's reference values stay in registers for the whole
+// kernel, the cell matrix is read with warp-uniform loads, every component index is compile-time) and write the
+// mapped rows into a warp-private shared-memory slice; the slice -- the cell's rows * OUT_VS contiguous output
+// entries -- then leaves with lane-consecutive stores, 256 contiguous bytes per instruction.  The thread-per-row
+// kernel above spends 63 LSU wavefronts per 45-row cell (8-byte accesses at a 24-byte stride, matrix reads from
+// shared memory) and is bound by the load/store pipe.  Same accumulation order as maps.h, bit-identical results.
+template <typename T, int MAP, int RA, int CA, int PASSES>
 __global__ void __launch_bounds__(kThreads)
     map_bcast_kernel(const T* __restrict__ in, const T* __restrict__ A, const T* __restrict__ detJ, size_t nc, int rows,
                      T* __restrict__ out)
 {
   constexpr int IN_VS = MAP == BX_MAP_COVARIANT_PIOLA ? RA : CA;
   constexpr int OUT_VS = MAP == BX_MAP_COVARIANT_PIOLA ? CA : RA;
+  extern __shared__ __align__(16) unsigned char bcast_smem[];
   const int lane = threadIdx.x & 31;
   const int E = rows * OUT_VS;
-  T u[SLOTS][IN_VS];
-  int comp[SLOTS];
+  T* slice = reinterpret_cast<T*>(bcast_smem) + (threadIdx.x >> 5) * E;
+  T u[PASSES][IN_VS];
 #pragma unroll
-  for (int s = 0; s < SLOTS; ++s)
+  for (int p = 0; p < PASSES; ++p)
   {
-    const int e = lane + 32 * s, r = min(e, E - 1) / OUT_VS;
-    comp[s] = e < E ? e - r * OUT_VS : -1;
+    const int r = min(lane + 32 * p, rows - 1);
 #pragma unroll
     for (int k = 0; k < IN_VS; ++k)
-      u[s][k] = in[r * IN_VS + k];
+      u[p][k] = in[r * IN_VS + k];
   }
   const size_t warps = size_t(gridDim.x) * (kThreads / 32);
   for (size_t c = size_t(blockIdx.x) * (kThreads / 32) + (threadIdx.x >> 5); c < nc; c += warps)
   {
+    // (prefetching the next cell's matrix into a second register set was measured slower: 2.42 against 2.16 ms)
     T a[RA][CA];
 #pragma unroll
     for (int i = 0; i < RA; ++i)
@@ -181,43 +181,40 @@ __global__ void __launch_bounds__(kThreads)
     [[maybe_unused]] T det = T(1);
     if constexpr (MAP == BX_MAP_CONTRAVARIANT_PIOLA)
       det = detJ[c];
-    T* o = out + c * size_t(E) + lane;
 #pragma unroll
-    for (int s = 0; s < SLOTS; ++s)
+    for (int p = 0; p < PASSES; ++p)
     {
-      const int i = comp[s];
-      if (i < 0)
-        continue;
-      T acc = 0;
-      if constexpr (MAP == BX_MAP_COVARIANT_PIOLA)
+      const int r = lane + 32 * p;
+      if (r < rows)
       {
-        // out[i] = sum_k A[k][i] in[k]   (maps.h:73-94)
 #pragma unroll
-        for (int k = 0; k < RA; ++k)
+        for (int i = 0; i < OUT_VS; ++i)
         {
-          T aki = a[k][0];
+          T acc = 0;
+          if constexpr (MAP == BX_MAP_COVARIANT_PIOLA)
+          {
+            // out[i] = sum_k A[k][i] in[k]   (maps.h:73-94)
 #pragma unroll
-          for (int j = 1; j < CA; ++j)
-            aki = i == j ? a[k][j] : aki;
-          acc += aki * u[s][k];
+            for (int k = 0; k < RA; ++k)
+              acc += a[k][i] * u[p][k];
+          }
+          else
+          {
+            // out[i] = (sum_k A[i][k] in[k]) / det   (maps.h:100-124)
+#pragma unroll
+            for (int k = 0; k < CA; ++k)
+              acc += a[i][k] * u[p][k];
+            acc = acc / det;
+          }
+          slice[r * OUT_VS + i] = acc;
         }
       }
-      else
-      {
-        // out[i] = (sum_k A[i][k] in[k]) / det   (maps.h:100-124)
-#pragma unroll
-        for (int k = 0; k < CA; ++k)
-        {
-          T aik = a[0][k];
-#pragma unroll
-          for (int j = 1; j < RA; ++j)
-            aik = i == j ? a[j][k] : aik;
-          acc += aik * u[s][k];
-        }
-        acc = acc / det;
-      }
-      o[32 * s] = acc;
     }
+    __syncwarp();
+    T* o = out + c * size_t(E);
+    for (int e = lane; e < E; e += 32)
+      o[e] = slice[e];
+    __syncwarp(); // the slice is overwritten by the next cell
   }
 }
 
@@ -248,16 +245,17 @@ void launch_one(const T* in, const T* A, const T* detJ, int inv, size_t nc, size
   {
     constexpr int OUT_VS = MAP == BX_MAP_COVARIANT_PIOLA ? CA : RA;
     const size_t E = rows * OUT_VS;
-    if (bcast and !inv and E <= 256)
+    if (bcast and !inv and rows <= 256)
     {
-      const int slots = int((E + 31) / 32);
+      const int slots = int((rows + 31) / 32);
+      const size_t smem = size_t(kThreads / 32) * E * sizeof(T);
       auto go = [&](auto kern)
       {
         int per_sm = 1;
-        BX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0));
+        BX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
         const size_t want = ceil_div(nc, size_t(kThreads / 32));
         const size_t cap = size_t(sm_count()) * std::max(per_sm, 1);
-        kern<<<unsigned(std::max<size_t>(1, std::min(want, cap))), kThreads, 0, s>>>(in, A, detJ, nc, int(rows), out);
+        kern<<<unsigned(std::max<size_t>(1, std::min(want, cap))), kThreads, smem, s>>>(in, A, detJ, nc, int(rows), out);
       };
       switch (slots)
       {
