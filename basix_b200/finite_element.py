@@ -110,6 +110,23 @@ _TDIM = {0: 0, 1: 1, 2: 2, 3: 3, 4: 2, 5: 3, 6: 3, 7: 3}
 _NUM_ENTITIES = {0: (1,), 1: (2, 1), 2: (3, 3, 1), 3: (4, 6, 4, 1), 4: (4, 4, 1), 5: (8, 12, 6, 1),
                  6: (6, 9, 5, 1), 7: (5, 8, 5, 1)}
 
+# cell::topology (cpp/basix/cell.cpp:52-141): vertices of every sub-entity, per dimension
+_TOPOLOGY = {
+    0: [[[0]]],
+    1: [[[0], [1]], [[0, 1]]],
+    2: [[[0], [1], [2]], [[1, 2], [0, 2], [0, 1]], [[0, 1, 2]]],
+    3: [[[0], [1], [2], [3]], [[2, 3], [1, 3], [1, 2], [0, 3], [0, 2], [0, 1]],
+        [[1, 2, 3], [0, 2, 3], [0, 1, 3], [0, 1, 2]], [[0, 1, 2, 3]]],
+    4: [[[0], [1], [2], [3]], [[0, 1], [0, 2], [1, 3], [2, 3]], [[0, 1, 2, 3]]],
+    5: [[[i] for i in range(8)],
+        [[0, 1], [0, 2], [0, 4], [1, 3], [1, 5], [2, 3], [2, 6], [3, 7], [4, 5], [4, 6], [5, 7], [6, 7]],
+        [[0, 1, 2, 3], [0, 1, 4, 5], [0, 2, 4, 6], [1, 3, 5, 7], [2, 3, 6, 7], [4, 5, 6, 7]], [list(range(8))]],
+    6: [[[i] for i in range(6)], [[0, 1], [0, 2], [0, 3], [1, 2], [1, 4], [2, 5], [3, 4], [3, 5], [4, 5]],
+        [[0, 1, 2], [0, 1, 3, 4], [0, 2, 3, 5], [1, 2, 4, 5], [3, 4, 5]], [list(range(6))]],
+    7: [[[i] for i in range(5)], [[0, 1], [0, 2], [0, 4], [1, 3], [1, 4], [2, 3], [2, 4], [3, 4]],
+        [[0, 1, 2, 3], [0, 1, 4], [0, 2, 4], [1, 3, 4], [2, 3, 4]], [list(range(5))]],
+}
+
 T_OPS = {"T_apply": 0, "Tt_apply": 1, "Tt_inv_apply": 2, "Tinv_apply": 3, "Tt_apply_right": 4,
          "Tinv_apply_right": 5, "T_apply_right": 6, "Tt_inv_apply_right": 7}
 
@@ -466,6 +483,93 @@ class FiniteElement:
     @property
     def dof_ordering(self):
         return [int(v) for v in self._dof_ordering]
+
+    # ---- element metadata derived from the defining arrays (set-up side of the reference, host only) -------
+    @property
+    def dtype(self):
+        """``FiniteElement.dtype``: the element object serves float64 and float32 arrays alike; float64 is the type
+        of its own tables."""
+        return np.float64
+
+    @property
+    def num_entity_dofs(self):
+        """``FiniteElement.num_entity_dofs`` (finite-element.h:658-663)."""
+        return [[len(e) for e in row] for row in self._entity_dofs]
+
+    @property
+    def entity_closure_dofs(self):
+        """``FiniteElement.entity_closure_dofs`` (finite-element.h:686-690; built at finite-element.cpp:1238-1256): the
+        dofs of every sub-entity contained in the entity, sorted."""
+        topo = _TOPOLOGY[int(self._cell_type)]
+        out = []
+        for d, ents in enumerate(topo):
+            row = []
+            for verts in ents:
+                vs = set(verts)
+                dofs = [q for dim in range(d + 1) for i, sub in enumerate(topo[dim]) if set(sub) <= vs
+                        for q in self._entity_dofs[dim][i]]
+                row.append(sorted(dofs))
+            out.append(row)
+        return out
+
+    @property
+    def num_entity_closure_dofs(self):
+        """``FiniteElement.num_entity_closure_dofs`` (finite-element.h:673-678)."""
+        return [[len(e) for e in row] for row in self.entity_closure_dofs]
+
+    @property
+    def interpolation_is_identity(self) -> bool:
+        """``FiniteElement.interpolation_is_identity`` (finite-element.cpp:1707-1722); None without interpolation data."""
+        M = self._interpolation_matrix
+        if M is None:
+            return None
+        return bool(M.shape[0] == M.shape[1] and np.all(np.abs(M - np.eye(M.shape[0])) <= 100 * np.finfo(np.float64).eps))
+
+    def base_transformations(self) -> np.ndarray:
+        """``FiniteElement.base_transformations`` (finite-element.cpp:1902-1969): one (ndofs, ndofs) matrix per edge
+        (reversal) and two per face (rotation, reflection), the entity's block placed on the running dof offset."""
+        tdim, n = self._tdim, self._ndofs
+        mats = []
+        start = sum(len(v) for v in self._entity_dofs[0]) if tdim > 0 else 0
+        if tdim > 1:
+            t = self._entity_transformations[1]
+            for e in self._entity_dofs[1]:
+                k = len(e)
+                m = np.eye(n)
+                m[start:start + k, start:start + k] = t[0, :k, :k]
+                mats.append(m)
+                start += k
+        if tdim > 2:
+            face_type = {3: lambda f: 2, 5: lambda f: 4, 6: lambda f: 2 if f in (0, 4) else 4, 7: lambda f: 4 if f == 0 else 2}
+            for f, e in enumerate(self._entity_dofs[2]):
+                k = len(e)
+                if k == 0:
+                    continue
+                t = self._entity_transformations[face_type[int(self._cell_type)](f)]
+                for i in range(2):
+                    m = np.eye(n)
+                    m[start:start + k, start:start + k] = t[i, :k, :k]
+                    mats.append(m)
+                start += k
+        # num_transformations(cell) matrices are returned; faces without dofs leave identities at the END of the
+        # array (the reference does not advance its counter for them, finite-element.cpp:1948-1963)
+        nt = (len(self._entity_dofs[1]) if tdim > 1 else 0) + (2 * len(self._entity_dofs[2]) if tdim > 2 else 0)
+        mats += [np.eye(n)] * (nt - len(mats))
+        return np.array(mats).reshape(nt, n, n)
+
+    def __eq__(self, other) -> bool:
+        """``FiniteElement.__eq__`` (finite-element.cpp:1727-1764): same defining data."""
+        if not isinstance(other, FiniteElement):
+            return NotImplemented
+        return (self._cell_type == other._cell_type and self._polyset_type == other._polyset_type
+                and self._map_type == other._map_type and self._value_shape == other._value_shape
+                and self._embedded_superdegree == other._embedded_superdegree
+                and self._entity_dofs == other._entity_dofs and self.dof_ordering == other.dof_ordering
+                and self._coeffs.shape == other._coeffs.shape and bool(np.allclose(self._coeffs, other._coeffs, rtol=0, atol=1e-12)))
+
+    def __hash__(self) -> int:
+        return hash((int(self._cell_type), int(self._map_type), self._value_shape, self._embedded_superdegree, self._ndofs,
+                     tuple(self.dof_ordering)))
 
     def entity_transformations(self) -> dict:
         names = {1: "interval", 2: "triangle", 4: "quadrilateral"}

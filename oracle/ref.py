@@ -61,6 +61,8 @@ def lib():
                                         C.c_void_p]
         L.bxref_permute_i32.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p,
                                         C.c_int]
+        L.bxref_base_transformations.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.bxref_entity_closure_dofs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.bxref_points.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.bxref_interpolation_matrix.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.bxref_permute_subentity_closure_i32.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t,
@@ -230,6 +232,26 @@ class RefElement:
         _check(lib().bxref_permute_i32(self._h, int(inverse), _ptr(d), d.shape[0], d.shape[1], _ptr(ci),
                                        int(nthreads)))
         return d
+
+    def base_transformations(self) -> np.ndarray:
+        shp = np.zeros(3, dtype=np.int32)
+        lib().bxref_base_transformations(self._h, _ptr(shp), None)
+        out = np.empty(tuple(int(v) for v in shp), dtype=np.float64)
+        lib().bxref_base_transformations(self._h, _ptr(shp), _ptr(out))
+        return out
+
+    @property
+    def entity_closure_dofs(self):
+        L, out = lib(), []
+        for d in range(self.tdim + 1):
+            row = []
+            for i in range(len(self.entity_dofs[d])):
+                n = L.bxref_entity_closure_dofs(self._h, d, i, None)
+                buf = np.zeros(max(n, 1), dtype=np.int32)
+                L.bxref_entity_closure_dofs(self._h, d, i, _ptr(buf))
+                row.append([int(v) for v in buf[:n]])
+            out.append(row)
+        return out
 
     def permute_subentity_closure_batch(self, d: np.ndarray, info: np.ndarray, entity_type: int,
                                         entity_index: int | None = None, inverse: bool = False):

@@ -180,6 +180,25 @@ int bxref_entity_transformations(void* h, int ct, int* shape, double* out)
   return 1;
 }
 
+// FiniteElement::base_transformations() (finite-element.cpp:1902-1969): shape (nt, ndofs, ndofs)
+void bxref_base_transformations(void* h, int* shape, double* out)
+{
+  auto [data, shp] = static_cast<FE*>(h)->base_transformations();
+  for (int i = 0; i < 3; ++i)
+    shape[i] = static_cast<int>(shp[i]);
+  if (out)
+    std::copy(data.begin(), data.end(), out);
+}
+
+// FiniteElement::entity_closure_dofs()[d][i] (finite-element.h:686-690); returns the count
+int bxref_entity_closure_dofs(void* h, int d, int i, int* out)
+{
+  const auto& v = static_cast<FE*>(h)->entity_closure_dofs()[d][i];
+  if (out)
+    std::copy(v.begin(), v.end(), out);
+  return static_cast<int>(v.size());
+}
+
 // FiniteElement::points() (finite-element.h:1167-1170): shape (npts, tdim)
 void bxref_points(void* h, int* shape, double* out)
 {

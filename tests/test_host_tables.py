@@ -72,3 +72,20 @@ def test_right_variants_share_operators(ref):
             A = e.net_operator(int(c), right)
             assert np.allclose(want, data @ A.T, rtol=0, atol=1e-13)
             assert np.array_equal(A, e.net_operator(int(c), left))
+
+
+@pytest.mark.parametrize("family,cell,degree,variant", [(P, TRI, 3, GLL), (P, TET, 4, GLL), (P, QUAD, 2, GLL), (P, HEX, 3, GLL),
+                                                        (RT, TET, 2, LEG), (N1E, TET, 3, LEG), (N1E, TRI, 2, LEG), (P, 6, 2, 0),
+                                                        (P, 7, 2, 0), (P, INTERVAL, 4, GLL)])
+def test_metadata_matches_reference(ref, family, cell, degree, variant):
+    """num_entity_dofs, entity_closure_dofs, base_transformations, interpolation_is_identity, == (host only)."""
+    r, e = make_pair(ref, family, cell, degree, variant)
+    assert e.num_entity_dofs == [[len(v) for v in row] for row in r.entity_dofs]
+    assert e.entity_closure_dofs == r.entity_closure_dofs
+    assert e.num_entity_closure_dofs == [[len(v) for v in row] for row in r.entity_closure_dofs]
+    bt, want = e.base_transformations(), r.base_transformations()
+    assert bt.shape == want.shape and np.array_equal(bt, want)
+    assert e.interpolation_is_identity == (family == P)
+    assert e.dtype is np.float64 and e == e and hash(e) == hash(e)
+    r2, e2 = make_pair(ref, P, TRI, 1)
+    assert not (e == e2)
