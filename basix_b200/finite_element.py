@@ -525,6 +525,34 @@ class FiniteElement:
             return None
         return bool(M.shape[0] == M.shape[1] and np.all(np.abs(M - np.eye(M.shape[0])) <= 100 * np.finfo(np.float64).eps))
 
+    @property
+    def interpolation_nderivs(self) -> int:
+        """``FiniteElement.interpolation_nderivs``: 0 for every family built here (point evaluations and integral
+        moments of values)."""
+        return 0
+
+    @property
+    def embedded_subdegree(self) -> int:
+        """``FiniteElement.embedded_subdegree`` for the natively built families (e-lagrange.cpp:660-664: degree;
+        e-raviart-thomas.cpp:160-164, e-nedelec.cpp:342-346: degree - 1)."""
+        fam = int(self._family)
+        if fam == 1:
+            return self._degree
+        if fam in (2, 3):
+            return self._degree - 1
+        raise RuntimeError("embedded_subdegree: only known for the families built natively (P, RT, N1E)")
+
+    @property
+    def sobolev_space(self) -> int:
+        """``FiniteElement.sobolev_space`` as the reference's enum value (sobolev-spaces.h:12-22): L2 = 0 for
+        discontinuous elements, else H1 = 1 (P), HDiv = 10 (RT), HCurl = 11 (N1E)."""
+        if self._discontinuous:
+            return 0
+        fam = int(self._family)
+        if fam in (1, 2, 3):
+            return {1: 1, 2: 10, 3: 11}[fam]
+        raise RuntimeError("sobolev_space: only known for the families built natively (P, RT, N1E)")
+
     def base_transformations(self) -> np.ndarray:
         """``FiniteElement.base_transformations`` (finite-element.cpp:1902-1969): one (ndofs, ndofs) matrix per edge
         (reversal) and two per face (rotation, reflection), the entity's block placed on the running dof offset."""
