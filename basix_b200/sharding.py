@@ -91,6 +91,23 @@ def map_sharded(element, pull: bool, U, J, detJ, K, gather: bool = False, dst: i
     return gather_cells(local, U.shape[0], dst, group) if gather else local
 
 
+def push_forward_broadcast_sharded(element, U, J, detJ, K, gather: bool = False, dst: int | None = None, group=None):
+    """``push_forward_broadcast`` (one slab of reference values ``U`` for all cells) on this rank's slice of the cells."""
+    _, world, rank = _dist(group)
+    lo, hi = shard_bounds(J.shape[0], world, rank)
+    local = element.push_forward_broadcast(U, J[lo:hi], detJ[lo:hi], K[lo:hi])
+    return gather_cells(local, J.shape[0], dst, group) if gather else local
+
+
+def interpolate_sharded(element, values, layout: str = "component-major", gather: bool = False, dst: int | None = None,
+                        group=None):
+    """``interpolate_batch`` on this rank's slice of the cells of ``values[ncells][value_size * npts]``."""
+    _, world, rank = _dist(group)
+    lo, hi = shard_bounds(values.shape[0], world, rank)
+    local = element.interpolate_batch(values[lo:hi], layout=layout)
+    return gather_cells(local, values.shape[0], dst, group) if gather else local
+
+
 def T_apply_sharded(element, data, block_size: int, cell_info, op: str = "T_apply"):
     """In-place DOF transformation of this rank's slice of the cells of ``data[ncells][ndofs*block_size]``;
     returns the slice bounds.  (In place: there is nothing to gather unless the caller wants the slices

@@ -32,7 +32,9 @@ class _OracleElement:
     def __init__(self, name):
         from oracle import restate as R
 
-        self.e = R.RestatedElement(np.load(os.path.join(ROOT, "tests", "golden", "elements", name + ".npz")))
+        arrs = np.load(os.path.join(ROOT, "tests", "golden", "elements", name + ".npz"))
+        self.e = R.RestatedElement(arrs)
+        self.M = arrs["interpolation_matrix"]
 
     def tabulate(self, nd, x):
         import torch
@@ -51,6 +53,18 @@ class _OracleElement:
 
     def T_apply_batch(self, data, bs, ci, op="T_apply"):
         self.e.T_apply_batch(op, data.numpy(), bs, ci.numpy())
+
+    def push_forward_broadcast(self, U, J, detJ, K):
+        import torch
+
+        rep = np.ascontiguousarray(np.broadcast_to(U.numpy(), (J.shape[0],) + tuple(U.shape)))
+        return torch.from_numpy(self.e.push_forward(rep, J.numpy(), detJ.numpy(), K.numpy()))
+
+    def interpolate_batch(self, values, layout="component-major"):
+        import torch
+
+        assert layout == "component-major"
+        return torch.from_numpy(values.numpy() @ self.M.T)
 
 
 def _worker(rank, world, port, out_dir):
@@ -83,6 +97,12 @@ def _worker(rank, world, port, out_dir):
                 (rng.standard_normal((33, 4, 3)), J, np.linalg.det(J), np.linalg.inv(J))]
         assert torch.equal(sharding.map_sharded(e, False, *args, gather=True), e.push_forward(*args))
         assert torch.equal(sharding.map_sharded(e, True, *args, gather=True), e.pull_back(*args))
+        # one slab of reference values for all cells; batched interpolation of 33 cells
+        U0 = torch.from_numpy(rng.standard_normal((4, 3)))
+        want = e.push_forward_broadcast(U0, *args[1:])
+        assert torch.equal(sharding.push_forward_broadcast_sharded(e, U0, *args[1:], gather=True), want)
+        vals = torch.from_numpy(rng.standard_normal((33, e.M.shape[1])))
+        assert torch.equal(sharding.interpolate_sharded(e, vals, gather=True), e.interpolate_batch(vals))
         # in-place sharded T_apply, then exchange of the slices
         e = _OracleElement("RT2_tetrahedron_legendre")
         data = torch.from_numpy(rng.standard_normal((21, 15)))
