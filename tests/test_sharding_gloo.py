@@ -102,7 +102,8 @@ def _worker(rank, world, port, out_dir):
         want = e.push_forward_broadcast(U0, *args[1:])
         assert torch.equal(sharding.push_forward_broadcast_sharded(e, U0, *args[1:], gather=True), want)
         vals = torch.from_numpy(rng.standard_normal((33, e.M.shape[1])))
-        assert torch.equal(sharding.interpolate_sharded(e, vals, gather=True), e.interpolate_batch(vals))
+        # (the stand-in's dgemm blocks a slice differently from the whole array: compare to rounding)
+        assert torch.allclose(sharding.interpolate_sharded(e, vals, gather=True), e.interpolate_batch(vals), rtol=0, atol=1e-12)
         # in-place sharded T_apply, then exchange of the slices
         e = _OracleElement("RT2_tetrahedron_legendre")
         data = torch.from_numpy(rng.standard_normal((21, 15)))
