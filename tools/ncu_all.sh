@@ -15,3 +15,4 @@ cap map_rows45 push_forward_n1curl3_rows45 map_kernel 1000000
 cap dof_matrix_rt4 t_apply_rt4 dof_ 4000000
 cap dof_perm_p5tet permute_p5_tet dof_ 4000000
 cap interp_n1curl3 interpolate_n1curl3 interpolate_kernel 4000000
+cap map_bcast_rows45 push_forward_bcast_n1curl3_rows45 map_bcast 2000000
