@@ -54,6 +54,17 @@ def test_no_cpu_fallback_without_a_device():
     e5 = bx.FiniteElement.from_arrays(np.load(os.path.join(ROOT, "tests", "golden", "elements", "P5_tetrahedron_gll.npz")))
     with pytest.raises(RuntimeError):
         e5.permute_batch(np.zeros((2, 56), dtype=np.int32), np.ones(2, dtype=np.uint32))
+    # the entry points added for the callers either side of the path fail the same way
+    with pytest.raises(RuntimeError):
+        e5.permute_subentity_closure(np.arange(21, dtype=np.int32), 3, 2)
+    en = bx.FiniteElement.from_arrays(np.load(os.path.join(ROOT, "tests", "golden", "elements", "N1curl3_tetrahedron_legendre.npz")))
+    with pytest.raises(RuntimeError):
+        en.interpolate_batch(np.zeros((2, en.interpolation_matrix.shape[1])))
+    J = np.tile(np.eye(3), (2, 1, 1))
+    with pytest.raises(RuntimeError):
+        en.push_forward_broadcast(np.zeros((4, 3)), J, np.ones(2), J)
+    # ... while the host tables stay inspectable
+    assert e5.subentity_closure_size(2) == 21 and len(e5.subentity_closure_map(2, 3)) == 21
     # wrong point dimension is an argument error with the reference's message, device or not
     with pytest.raises(RuntimeError, match=r"Point dim \(3\) does not match element dim \(2\)\."):
         e.tabulate(1, np.zeros((5, 3)))
