@@ -82,6 +82,24 @@ def test_restatement_and_host_tables_vs_compiled_reference(ref, cell, degree):
                 assert np.array_equal(d[0][e.subentity_closure_map(sub, info, inverse)], want), (sub, info, inverse)
 
 
+def test_host_tables_with_dof_ordering_and_native_factory(ref):
+    """A custom dof_ordering renumbers entity dofs but not the closure-local numbering; the native factory builds
+    the same tables as an element described by the reference's arrays."""
+    import basix_b200 as bx
+
+    order = [int(v) for v in np.random.default_rng(7).permutation(20)]
+    r, e = make_pair(ref, P, TET, 3, GLL, dof_ordering=order)
+    native = bx.create_element(P, TET, 3, GLL, dof_ordering=order)
+    for sub in (INTERVAL, TRI):
+        m = closure_size(r, sub)
+        for info in range(2 if sub == INTERVAL else 8):
+            for inverse in (False, True):
+                d = np.arange(m, dtype=np.int32)[None].copy()
+                want = r.permute_subentity_closure_batch(d.copy(), np.array([info], dtype=np.uint32), sub, None, inverse)[0]
+                assert np.array_equal(d[0][e.subentity_closure_map(sub, info, inverse)], want)
+                assert np.array_equal(d[0][native.subentity_closure_map(sub, info, inverse)], want)
+
+
 # ---- GPU: the batched kernel through the C ABI ------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("cell,degree", [(TRI, 3), (QUAD, 4), (TET, 1), (TET, 2), (TET, 5), (HEX, 2), (HEX, 4), (PRISM, 3),
