@@ -241,6 +241,8 @@ bool launch_any(const bx_element& e, int nd, const double* x, size_t npts, doubl
   BX_STAGED(2, 1, 2) BX_STAGED(2, 1, 3) BX_STAGED(2, 1, 4) BX_STAGED(2, 1, 5) BX_STAGED(2, 1, 6) BX_STAGED(2, 1, 7)
   BX_STAGED(3, 0, 2) BX_STAGED(3, 0, 3) BX_STAGED(3, 0, 4) BX_STAGED(3, 0, 5)
   BX_STAGED(3, 1, 2) BX_STAGED(3, 1, 3) BX_STAGED(3, 1, 4) BX_STAGED(3, 1, 5)
+  BX_STAGED(2, 2, 2) BX_STAGED(2, 2, 3) BX_STAGED(2, 2, 4) BX_STAGED(2, 2, 5) BX_STAGED(2, 2, 6) BX_STAGED(2, 2, 7)
+  BX_STAGED(3, 2, 2) BX_STAGED(3, 2, 3) BX_STAGED(3, 2, 4) BX_STAGED(3, 2, 5)
   return false;
 }
 } // namespace staged

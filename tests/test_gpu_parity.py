@@ -431,7 +431,7 @@ def test_tabulate_tensor_product_path(ref, family, cell, degree, variant, nd):
 
 
 @pytest.mark.parametrize("cell,degree", [(QUAD, 1), (QUAD, 4), (QUAD, 6), (HEX, 1), (HEX, 2), (HEX, 3), (HEX, 4)])
-@pytest.mark.parametrize("nd", [0, 1])
+@pytest.mark.parametrize("nd", [0, 1, 2])
 def test_tabulate_tensor_product_staged_and_unstaged_kernels(ref, cell, degree, nd):
     """Both tensor-product kernels (tabulate_tp_staged.cu: one slab of a 32-point tile at a time through shared
     memory; tabulate_tp.cu: direct stores) against the reference: ragged tails, odd and even point counts (16- and
