@@ -271,7 +271,8 @@ void launch_md(int md, const TPParams<T>& p, size_t smem, int grid, cudaStream_t
 bool tabulate_path_allowed(int path);
 namespace staged
 {
-bool launch_any(const bx_element& e, int nd, const double* x, size_t npts, double* basis, cudaStream_t s, bool dry_run);
+template <typename T>
+bool launch_any(const bx_element& e, int nd, const T* x, size_t npts, T* basis, cudaStream_t s, bool dry_run);
 }
 
 // Returns false when the element has no tensor-product factorisation or the shape is outside the menu.
@@ -280,14 +281,11 @@ bool tabulate_tp_device(const bx_element& e, int nd, const T* x, size_t npts, T*
 {
   if (!e.tp.valid or nd < 0 or nd > 2)
     return false;
-  if constexpr (std::is_same_v<T, double>)
-  {
-    // full tensor grids (Lagrange-type Q elements): one slab of a point tile at a time, staged through shared
-    // memory and written as contiguous 16-byte runs (tabulate_tp_staged.cu); bit 5 of the path mask
-    // (bx_tabulate_path_mask) disables it for tests / profiling of the kernel below
-    if (tabulate_path_allowed(5) and staged::launch_any(e, nd, x, npts, basis, s, dry_run))
-      return true;
-  }
+  // full tensor grids (Lagrange-type Q elements): one slab of a point tile at a time, staged through shared
+  // memory and written as contiguous runs by the TMA engine (tabulate_tp_staged.cu); bit 5 of the path mask
+  // (bx_tabulate_path_mask) disables it for tests / profiling of the kernel below
+  if (tabulate_path_allowed(5) and staged::launch_any<T>(e, nd, x, npts, basis, s, dry_run))
+    return true;
   const int tdim = e.tdim;
   const int n1 = e.superdegree + 1;
   if (n1 > kMaxN1 or e.N > 24 * 32)

@@ -1,4 +1,5 @@
-// Staged tensor-product tabulate for Lagrange-type Q elements on quadrilateral / hexahedron (float64).
+// Staged tensor-product tabulate for Lagrange-type Q elements on quadrilateral / hexahedron (float64 and float32
+// tables; the arithmetic is float64 either way).
 //
 // Same factorisation as tabulate_tp.cu (reference cpp/basix/polyset.cpp:2241-2702 + finite-element.cpp:1867-1872
 // collapse to  basis[d][pt][n] = s_n phi_x[kx][i_n](x) phi_y[ky][j_n](y) phi_z[kz][k_n](z)), different data flow.
@@ -22,11 +23,12 @@ namespace bx
 {
 namespace staged
 {
+template <typename T>
 struct Params
 {
-  const double* x;
+  const T* x;
   size_t npts;
-  double* basis;
+  T* basis;
   const double* A;      // [TDIM][NF][NF] 1-D expansion coefficients w.r.t. un-normalised Legendre (norms folded in)
   const double2* order; // [NF^TDIM] {scale, column as raw int64 bits} of index triple (i, j, k), lexicographic
   int N, pitch, warps;
@@ -60,25 +62,25 @@ __device__ __forceinline__ void legendre(double (&L)[NK][NF], double x)
 }
 
 // warps per CTA: as many 32 x pitch tiles as fit in 200 KB beside the tables, at most 16
-template <int TDIM, int NF>
+template <int TDIM, int NF, typename T>
 constexpr int warps_for()
 {
   constexpr int N = TDIM == 2 ? NF * NF : NF * NF * NF;
   constexpr int pitch = (N & 1) ? N : N + 1;
   constexpr long fixed = (2L * N + ((TDIM * NF * NF + 1) & ~1)) * 8;
-  constexpr long w = (200L * 1024 - fixed) / (32L * pitch * 8);
+  constexpr long w = (200L * 1024 - fixed) / (32L * pitch * long(sizeof(T)));
   return int(w > 16 ? 16 : w);
 }
 
-template <int TDIM, int ND, int NF>
-__global__ void __launch_bounds__(32 * warps_for<TDIM, NF>()) tabulate_tp_staged_kernel(const Params p)
+template <int TDIM, int ND, int NF, typename T>
+__global__ void __launch_bounds__(32 * warps_for<TDIM, NF, T>()) tabulate_tp_staged_kernel(const Params<T> p)
 {
   constexpr int NK = ND + 1;
   constexpr int NGRID = TDIM == 2 ? NF * NF : NF * NF * NF;
   extern __shared__ __align__(16) double smem_staged[];
   double2* s_order = reinterpret_cast<double2*>(smem_staged);  // [NGRID]
   double* s_A = smem_staged + 2 * NGRID;                        // [TDIM][NF][NF]
-  double* tiles = s_A + ((TDIM * NF * NF + 1) & ~1);            // [warps][32 * pitch]
+  T* tiles = reinterpret_cast<T*>(s_A + ((TDIM * NF * NF + 1) & ~1)); // [warps][32 * pitch]
   for (int i = threadIdx.x; i < NGRID; i += blockDim.x)
     s_order[i] = p.order[i];
   for (int i = threadIdx.x; i < TDIM * NF * NF; i += blockDim.x)
@@ -87,8 +89,8 @@ __global__ void __launch_bounds__(32 * warps_for<TDIM, NF>()) tabulate_tp_staged
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = p.N, pitch = p.pitch;
-  double* tile = tiles + size_t(warp) * 32 * pitch;
-  double* mine = tile + lane * pitch;
+  T* tile = tiles + size_t(warp) * 32 * pitch;
+  T* mine = tile + lane * pitch;
   const size_t ntiles = ceil_div(p.npts, size_t(32));
   for (size_t tl = size_t(blockIdx.x) * p.warps + warp; tl < ntiles; tl += size_t(gridDim.x) * p.warps)
   {
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(32 * warps_for<TDIM, NF>()) tabulate_tp_staged
     for (int a = 0; a < TDIM; ++a)
     {
       double L[NK][NF];
-      legendre<NK, NF>(L, p.x[pt * TDIM + a]);
+      legendre<NK, NF>(L, double(p.x[pt * TDIM + a]));
 #pragma unroll
       for (int fn = 0; fn < NF; ++fn)
 #pragma unroll
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(32 * warps_for<TDIM, NF>()) tabulate_tp_staged
               if constexpr (TDIM == 2)
               {
                 const double2 o = s_order[i * NF + j];
-                mine[int(__double_as_longlong(o.y))] = pxy * o.x;
+                mine[int(__double_as_longlong(o.y))] = static_cast<T>(pxy * o.x);
               }
               else
               {
@@ -141,12 +143,12 @@ __global__ void __launch_bounds__(32 * warps_for<TDIM, NF>()) tabulate_tp_staged
                 for (int k = 0; k < NF; ++k)
                 {
                   const double2 o = s_order[(i * NF + j) * NF + k];
-                  mine[int(__double_as_longlong(o.y))] = (pxy * f[2][kz][k]) * o.x;
+                  mine[int(__double_as_longlong(o.y))] = static_cast<T>((pxy * f[2][kz][k]) * o.x);
                 }
               }
             }
-          double* g = p.basis + (size_t(d) * p.npts + tl * 32) * N;
-          if (pitch == N and p.aligned16 and (run & 1) == 0)
+          T* g = p.basis + (size_t(d) * p.npts + tl * 32) * N;
+          if (pitch == N and p.aligned16 and (run * sizeof(T)) % 16 == 0)
           {
             // the tile IS the contiguous run g[0 .. run): one bulk copy shared -> global by the TMA engine.  The
             // warp only waits until the engine has READ the tile (then the next slab may overwrite it); the
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(32 * warps_for<TDIM, NF>()) tabulate_tp_staged
             if (lane == 0)
             {
               asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g),
-                           "r"(uint32_t(__cvta_generic_to_shared(tile))), "r"(run * 8u)
+                           "r"(uint32_t(__cvta_generic_to_shared(tile))), "r"(run * unsigned(sizeof(T)))
                            : "memory");
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
               asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -165,19 +167,7 @@ __global__ void __launch_bounds__(32 * warps_for<TDIM, NF>()) tabulate_tp_staged
             continue;
           }
           __syncwarp();
-          if (pitch == N and p.aligned16)
-          {
-            // odd tail run: 16-byte streaming stores + one element
-            const double2* t2 = reinterpret_cast<const double2*>(tile);
-            double2* g2 = reinterpret_cast<double2*>(g);
-            const unsigned pairs = run >> 1;
-#pragma unroll 4
-            for (unsigned q = lane; q < pairs; q += 32)
-              __stcs(g2 + q, t2[q]);
-            if ((run & 1) and lane == 0)
-              __stcs(g + run - 1, tile[run - 1]);
-          }
-          else if (pitch == N)
+          if (pitch == N)
           {
 #pragma unroll 4
             for (unsigned q = lane; q < run; q += 32)
@@ -185,7 +175,7 @@ __global__ void __launch_bounds__(32 * warps_for<TDIM, NF>()) tabulate_tp_staged
           }
           else
           {
-            // padded rows (even N): row by row, 8-byte stores
+            // padded rows (even N): row by row
             for (unsigned r = 0; r < nrows; ++r)
               for (int n = lane; n < N; n += 32)
                 __stcs(g + size_t(r) * N + n, tile[r * pitch + n]);
@@ -195,10 +185,10 @@ __global__ void __launch_bounds__(32 * warps_for<TDIM, NF>()) tabulate_tp_staged
   }
 }
 
-template <int TDIM, int ND, int NF>
-void launch(const bx_element& e, const double* x, size_t npts, double* basis, cudaStream_t s)
+template <int TDIM, int ND, int NF, typename T>
+void launch(const bx_element& e, const T* x, size_t npts, T* basis, cudaStream_t s)
 {
-  Params p;
+  Params<T> p;
   p.x = x;
   p.npts = npts;
   p.basis = basis;
@@ -206,12 +196,12 @@ void launch(const bx_element& e, const double* x, size_t npts, double* basis, cu
   p.order = e.tp.d_order;
   p.N = e.N;
   p.pitch = (e.N & 1) ? e.N : e.N + 1;
-  p.aligned16 = (reinterpret_cast<uintptr_t>(basis) % 16 == 0 and (npts * size_t(e.N)) % 2 == 0) ? 1 : 0;
+  p.aligned16 = (reinterpret_cast<uintptr_t>(basis) % 16 == 0 and (npts * size_t(e.N) * sizeof(T)) % 16 == 0) ? 1 : 0;
   const size_t fixed = (size_t(2) * e.N + ((TDIM * NF * NF + 1) & ~1)) * sizeof(double);
-  const size_t per_warp = size_t(32) * p.pitch * sizeof(double);
-  p.warps = warps_for<TDIM, NF>();
+  const size_t per_warp = size_t(32) * p.pitch * sizeof(T);
+  p.warps = warps_for<TDIM, NF, T>();
   const size_t smem = fixed + size_t(p.warps) * per_warp;
-  auto kern = tabulate_tp_staged_kernel<TDIM, ND, NF>;
+  auto kern = tabulate_tp_staged_kernel<TDIM, ND, NF, T>;
   BX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   const size_t ntiles = ceil_div(npts, size_t(32));
   const size_t want = ceil_div(ntiles, size_t(p.warps));
@@ -223,19 +213,20 @@ void launch(const bx_element& e, const double* x, size_t npts, double* basis, cu
   if (e.tdim == TD and nd == ND_ and e.tp.nf == NF_)                                                      \
   {                                                                                                      \
     if (!dry_run)                                                                                        \
-      launch<TD, ND_, NF_>(e, x, npts, basis, s);                                                        \
+      launch<TD, ND_, NF_, T>(e, x, npts, basis, s);                                                        \
     return true;                                                                                         \
   }
 
 // Returns false when the element / derivative order is outside this kernel's menu (caller uses tabulate_tp.cu).
-bool launch_any(const bx_element& e, int nd, const double* x, size_t npts, double* basis, cudaStream_t s, bool dry_run)
+template <typename T>
+bool launch_any(const bx_element& e, int nd, const T* x, size_t npts, T* basis, cudaStream_t s, bool dry_run)
 {
   if (!e.tp.valid or e.tp.order.empty() or e.tp.nf != e.superdegree + 1 or e.tp.fstride != e.tp.nf)
     return false;
   if (!dry_run and !e.tp.d_order)
     return false;
   // at least four warps must fit beside each other (tile = 32 x N doubles per warp)
-  if (size_t(32) * (e.N | 1) * sizeof(double) * 4 > size_t(196) * 1024)
+  if (size_t(32) * (e.N | 1) * sizeof(T) * 4 > size_t(196) * 1024)
     return false;
   BX_STAGED(2, 0, 2) BX_STAGED(2, 0, 3) BX_STAGED(2, 0, 4) BX_STAGED(2, 0, 5) BX_STAGED(2, 0, 6) BX_STAGED(2, 0, 7)
   BX_STAGED(2, 1, 2) BX_STAGED(2, 1, 3) BX_STAGED(2, 1, 4) BX_STAGED(2, 1, 5) BX_STAGED(2, 1, 6) BX_STAGED(2, 1, 7)
@@ -245,5 +236,7 @@ bool launch_any(const bx_element& e, int nd, const double* x, size_t npts, doubl
   BX_STAGED(3, 2, 2) BX_STAGED(3, 2, 3) BX_STAGED(3, 2, 4) BX_STAGED(3, 2, 5)
   return false;
 }
+template bool launch_any<double>(const bx_element&, int, const double*, size_t, double*, cudaStream_t, bool);
+template bool launch_any<float>(const bx_element&, int, const float*, size_t, float*, cudaStream_t, bool);
 } // namespace staged
 } // namespace bx
