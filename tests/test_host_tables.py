@@ -89,3 +89,21 @@ def test_metadata_matches_reference(ref, family, cell, degree, variant):
     assert e.dtype is np.float64 and e == e and hash(e) == hash(e)
     r2, e2 = make_pair(ref, P, TRI, 1)
     assert not (e == e2)
+
+
+def test_tabulate_dispatch_of_the_baseline_configs():
+    """Which kernel tabulate() takes is decided on the host (no device needed): BASELINE configs and fall-backs."""
+    import basix_b200 as bx
+
+    assert bx.create_element(P, TRI, 1, GLL).tabulate_path(1) == "register"                 # cfg 1
+    p5 = bx.create_element(P, TET, 5, GLL)
+    assert p5.tabulate_path(2) == "derivative-operator"                                     # cfg 2
+    assert bx.create_element(P, HEX, 4, GLL).tabulate_path(1) == "tensor-product"           # cfg 3
+    assert bx.create_element(N1E, TET, 3, LEG).tabulate_path(1) == "derivative-operator"    # vector valued
+    p6 = bx.create_element(P, TET, 6, GLL)
+    assert p6.tabulate_path(0) == "derivative-operator" and p6.tabulate_path(1) == "fused"  # operators too large
+    with bx.tabulate_paths("fused"):
+        assert p5.tabulate_path(2) == "fused"
+    with bx.tabulate_paths():
+        assert p5.tabulate_path(2) == "generic"
+    assert p5.tabulate_path(2) == "derivative-operator"
