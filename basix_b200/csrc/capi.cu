@@ -326,9 +326,14 @@ void polyset_any(int cell, int ptype, int degree, int nd, const T* x, size_t npt
     if (tdim > 0)
       BX_CUDA(cudaMemcpyAsync(dx[b], x + p0 * tdim, np * tdim * sizeof(T), cudaMemcpyHostToDevice, st.s[b]));
     polyset_tabulate_device<T>(cell, ptype, degree, nd, dx[b], np, dP[b], st.s[b]);
-    // table rows are npts apart on the host, np apart on the device
-    BX_CUDA(cudaMemcpy2DAsync(P + p0, npts * sizeof(T), dP[b], np * sizeof(T), np * sizeof(T), rows,
-                              cudaMemcpyDeviceToHost, st.s[b]));
+    // table rows are npts apart on the host, np apart on the device.  A 2-D copy is limited to pitches below
+    // cudaDeviceProp::memPitch (2 GiB), which huge host tables exceed: those go row by row (the rows are few).
+    if (npts * sizeof(T) < (size_t(1) << 31))
+      BX_CUDA(cudaMemcpy2DAsync(P + p0, npts * sizeof(T), dP[b], np * sizeof(T), np * sizeof(T), rows,
+                                cudaMemcpyDeviceToHost, st.s[b]));
+    else
+      for (size_t r = 0; r < rows; ++r)
+        BX_CUDA(cudaMemcpyAsync(P + r * npts + p0, dP[b] + r * np, np * sizeof(T), cudaMemcpyDeviceToHost, st.s[b]));
   }
   st.sync();
   st.trim();

@@ -889,6 +889,14 @@ void require_device(const bx_element& e)
 {
   if (!e.on_device)
     fail(BX_ERR_CUDA, "basix_b200: no usable CUDA device (the element holds host tables only; there is no CPU fallback)");
+  // the device mirror lives on the GPU that was current at creation: a kernel launched on another device would
+  // dereference pointers of the wrong address space (sticky illegal-address fault), so refuse here instead
+  int dev = -1;
+  BX_CUDA(cudaGetDevice(&dev));
+  if (dev != e.device)
+    fail(BX_ERR_INVALID_ARG, "basix_b200: the element was created on CUDA device " + std::to_string(e.device)
+                                 + " but device " + std::to_string(dev)
+                                 + " is current (create one element per GPU, or call bx_set_device first)");
 }
 
 void element_net_operator(const bx_element& e, int kind, uint32_t cell_info, int32_t* src, double* A)

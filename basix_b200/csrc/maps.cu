@@ -271,6 +271,9 @@ void launch_one(const T* in, const T* A, const T* detJ, int inv, size_t nc, size
       const size_t smem = size_t(kThreads / 32) * (E + kBcastBatch * (RA * CA + 1)) * sizeof(T);
       auto go = [&](auto kern)
       {
+        // 243..256 rows of three doubles need more than the 48 KB a kernel gets without opting in
+        if (smem > 48 * 1024)
+          BX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         int per_sm = 1;
         BX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
         const size_t want = ceil_div(nc, size_t(kThreads / 32) * kBcastBatch);

@@ -35,9 +35,55 @@ def _dist(group=None):
     return dist, dist.get_world_size(group), dist.get_rank(group)
 
 
-def gather_cells(local, n_total: int, dst: int | None = None, group=None):
+def _gather_into(out, local, sizes, rank, dst, group):
+    """Collect the per-rank blocks ``local`` into ``out`` (contiguous, first axis = all units in rank order) with no
+    intermediate copy when the slices are equal: ``all_gather_into_tensor`` writes every rank's block straight into
+    its place in ``out`` (NCCL all-gather over NVLink on CUDA tensors); with ``dst`` the root receives each block
+    straight into its view of ``out``.  Ragged slices (lengths differing by one unit) go through padded blocks."""
+    import torch
+
+    dist, world, _ = _dist(group)
+    equal = min(sizes) == max(sizes)
+    if dst is None:
+        if equal:
+            dist.all_gather_into_tensor(out, local, group=group)
+            return
+        smax = max(sizes)
+        padded = torch.zeros((smax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        padded[: local.shape[0]] = local
+        flat = torch.empty((world * smax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(flat, padded, group=group)
+        lo = 0
+        for r, s in enumerate(sizes):
+            out[lo:lo + s] = flat[r * smax:r * smax + s]
+            lo += s
+        return
+    dst_global = dist.get_global_rank(group, dst) if group is not None else dst
+    if equal:
+        views = None
+        if rank == dst:
+            views, lo = [], 0
+            for s in sizes:
+                views.append(out[lo:lo + s])
+                lo += s
+        dist.gather(local, views, dst=dst_global, group=group)
+        return
+    smax = max(sizes)
+    padded = torch.zeros((smax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    padded[: local.shape[0]] = local
+    parts = [torch.empty_like(padded) for _ in sizes] if rank == dst else None
+    dist.gather(padded, parts, dst=dst_global, group=group)
+    if rank == dst:
+        lo = 0
+        for p, s in zip(parts, sizes):
+            out[lo:lo + s] = p[:s]
+            lo += s
+
+
+def gather_cells(local, n_total: int, dst: int | None = None, group=None, out=None):
     """Gather a unit-major array (first axis = this rank's slice of the ``n_total`` units) onto every rank
-    (``dst=None``) or onto rank ``dst`` only (other ranks get ``None``).  Slices may differ in length by one."""
+    (``dst=None``) or onto rank ``dst`` of the group only (other ranks get ``None``).  Slices may differ in length by
+    one.  ``out`` (optional, contiguous ``[n_total, ...]``) receives the result in place."""
     import torch
 
     dist, world, rank = _dist(group)
@@ -46,31 +92,33 @@ def gather_cells(local, n_total: int, dst: int | None = None, group=None):
         raise ValueError(f"rank {rank}: expected {sizes[rank]} units, got {local.shape[0]}")
     local = local.contiguous()
     if world == 1:
+        if out is not None:
+            out.copy_(local)
+            return out
         return local
-    # collectives need equal shapes: pad the (at most one unit) shorter slices, trim after the exchange
-    smax = max(sizes)
-    if local.shape[0] < smax:
-        pad = torch.zeros((smax - local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-        local = torch.cat([local, pad], dim=0)
-    parts = [torch.empty_like(local) for _ in sizes]
-    if dst is None:
-        dist.all_gather(parts, local, group=group)
-    else:
-        dist.gather(local, parts if rank == dst else None, dst=dst, group=group)
-        if rank != dst:
-            return None
-    return torch.cat([p[:s] for p, s in zip(parts, sizes)], dim=0)
+    need = dst is None or rank == dst
+    if need and out is None:
+        out = torch.empty((n_total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    if need and (not out.is_contiguous() or tuple(out.shape) != (n_total,) + tuple(local.shape[1:])):
+        raise ValueError("gather_cells: out must be contiguous with shape (n_total, ...)")
+    _gather_into(out, local, sizes, rank, dst, group)
+    return out if need else None
 
 
 def gather_tabulate(local_basis, npts_total: int, dst: int | None = None, group=None):
     """Gather a point-sharded tabulate result ``[nderivs][npts_local][ndofs][vs]`` into
-    ``[nderivs][npts_total][ndofs][vs]``: one gather per derivative slab (each slab is contiguous per rank)."""
+    ``[nderivs][npts_total][ndofs][vs]``: the result is allocated once and every derivative slab -- one contiguous
+    run per rank on both sides -- is gathered straight into its place (no concatenation or stacking copies)."""
     import torch
 
-    slabs = [gather_cells(local_basis[d], npts_total, dst, group) for d in range(local_basis.shape[0])]
-    if any(s is None for s in slabs):
-        return None
-    return torch.stack(slabs, dim=0)
+    dist, world, rank = _dist(group)
+    nder = local_basis.shape[0]
+    need = dst is None or rank == dst
+    out = (torch.empty((nder, npts_total) + tuple(local_basis.shape[2:]), dtype=local_basis.dtype,
+                       device=local_basis.device) if need else None)
+    for d in range(nder):
+        gather_cells(local_basis[d], npts_total, dst, group, out=out[d] if need else None)
+    return out
 
 
 def tabulate_sharded(element, nd: int, x, gather: bool = False, dst: int | None = None, group=None):
@@ -108,11 +156,11 @@ def interpolate_sharded(element, values, layout: str = "component-major", gather
     return gather_cells(local, values.shape[0], dst, group) if gather else local
 
 
-def T_apply_sharded(element, data, block_size: int, cell_info, op: str = "T_apply"):
+def T_apply_sharded(element, data, block_size: int, cell_info, op: str = "T_apply", group=None):
     """In-place DOF transformation of this rank's slice of the cells of ``data[ncells][ndofs*block_size]``;
     returns the slice bounds.  (In place: there is nothing to gather unless the caller wants the slices
     exchanged, for which :func:`gather_cells` applies to ``data[lo:hi]``.)"""
-    _, world, rank = _dist(group=None)
+    _, world, rank = _dist(group)
     lo, hi = shard_bounds(data.shape[0], world, rank)
     element.T_apply_batch(data[lo:hi], block_size, cell_info[lo:hi], op=op)
     return lo, hi

@@ -67,6 +67,13 @@ def lib():
         L.bxref_interpolation_matrix.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.bxref_permute_subentity_closure_i32.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t,
                                                           C.c_void_p, C.c_int, C.c_int]
+        L.bxref32_create_element.restype = C.c_void_p
+        L.bxref32_create_element.argtypes = [C.c_int] * 6 + [C.c_void_p, C.c_int]
+        L.bxref32_destroy_element.argtypes = [C.c_void_p]
+        L.bxref32_polyset_tabulate.argtypes = [C.c_int] * 4 + [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+        L.bxref32_tabulate.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+        L.bxref32_map.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_size_t] * 5 + [C.c_void_p, C.c_void_p]
+        L.bxref32_T_apply.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p]
         _lib = L
     return _lib
 
@@ -262,3 +269,68 @@ class RefElement:
         _check(lib().bxref_permute_subentity_closure_i32(self._h, int(inverse), _ptr(d), d.shape[0], d.shape[1], _ptr(ci),
                                                          int(entity_type), -1 if entity_index is None else int(entity_index)))
         return d
+
+
+# ---- the reference's float32 instantiation (FiniteElement<float>, finite-element.cpp:2051) ------------------------
+def tabulate_polynomial_set_f32(cell: int, ptype: int, d: int, n: int, x: np.ndarray) -> np.ndarray:
+    """reference polyset::tabulate<float> (polyset.cpp:2995-2997)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    if x.ndim == 1:
+        x = x.reshape(-1, 1)
+    npts, tdim = x.shape
+    P = np.empty((polyset_nderivs(cell, n), polyset_dim(cell, ptype, d), npts), dtype=np.float32)
+    _check(lib().bxref32_polyset_tabulate(int(cell), int(ptype), int(d), int(n), _ptr(x), npts, tdim, _ptr(P)))
+    return P
+
+
+class RefElement32:
+    """Reference ``basix::FiniteElement<float>`` handle: the hot-path calls on float32 arrays."""
+
+    def __init__(self, family, cell, degree, lagrange_variant=0, dpc_variant=0, discontinuous=False, dof_ordering=None):
+        L = lib()
+        ord_ = np.asarray(dof_ordering if dof_ordering is not None else [], dtype=np.int32)
+        self._h = L.bxref32_create_element(int(family), int(cell), int(degree), int(lagrange_variant), int(dpc_variant),
+                                           int(bool(discontinuous)), _ptr(ord_), len(ord_))
+        if not self._h:
+            raise RuntimeError(L.bxref_last_error().decode())
+        d = RefElement(family, cell, degree, lagrange_variant, dpc_variant, discontinuous, dof_ordering)
+        self.cell_type, self.dim, self.value_size = d.cell_type, d.dim, d.value_size
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().bxref32_destroy_element(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def tabulate(self, nd: int, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        out = np.empty((polyset_nderivs(self.cell_type, nd), x.shape[0], self.dim, self.value_size), dtype=np.float32)
+        _check(lib().bxref32_tabulate(self._h, int(nd), _ptr(x), x.shape[0], x.shape[1], _ptr(out)))
+        return out
+
+    def _map(self, pull, U, J, detJ, K):
+        U, J, detJ, K = (np.ascontiguousarray(a, dtype=np.float32) for a in (U, J, detJ, K))
+        nc, rows, in_vs = U.shape
+        gdim, tdim = J.shape[1], J.shape[2]
+        ovs = C.c_int(0)
+        L = lib()
+        _check(L.bxref32_map(self._h, pull, _ptr(U), _ptr(J), _ptr(detJ), _ptr(K), 1, rows, in_vs, gdim, tdim, None,
+                             C.byref(ovs)))
+        out = np.empty((nc, rows, ovs.value), dtype=np.float32)
+        _check(L.bxref32_map(self._h, pull, _ptr(U), _ptr(J), _ptr(detJ), _ptr(K), nc, rows, in_vs, gdim, tdim,
+                             _ptr(out), C.byref(ovs)))
+        return out
+
+    def push_forward(self, U, J, detJ, K):
+        return self._map(0, U, J, detJ, K)
+
+    def pull_back(self, u, J, detJ, K):
+        return self._map(1, u, J, detJ, K)
+
+    def T_apply_batch(self, op: str, data: np.ndarray, n: int, cell_info: np.ndarray):
+        assert data.dtype == np.float32 and data.flags.c_contiguous and data.ndim == 2
+        ci = np.ascontiguousarray(cell_info, dtype=np.uint32)
+        _check(lib().bxref32_T_apply(self._h, T_OPS[op], _ptr(data), data.shape[0], data.shape[1], int(n), _ptr(ci)))
+        return data

@@ -490,4 +490,92 @@ int bxref_permute_subentity_closure_i32(void* h, int inverse, std::int32_t* d, s
         }
       });
 }
+// ---- the reference's float instantiation: FiniteElement<float> (finite-element.cpp:2051), polyset::tabulate<float>
+// (polyset.cpp:2995-2997).  Same forwarding as above, single-threaded (parity checks only). ----
+using FE32 = FiniteElement<float>;
+
+void* bxref32_create_element(int family, int cell, int degree, int lvariant, int dvariant, int discontinuous,
+                             const int* dof_ordering, int n_dof_ordering)
+{
+  FE32* e = nullptr;
+  guarded(
+      [&]()
+      {
+        std::vector<int> ord(dof_ordering, dof_ordering + n_dof_ordering);
+        e = new FE32(basix::create_element<float>(static_cast<element::family>(family), static_cast<cell::type>(cell),
+                                                  degree, static_cast<element::lagrange_variant>(lvariant),
+                                                  static_cast<element::dpc_variant>(dvariant), discontinuous != 0, ord));
+      });
+  return e;
+}
+
+void bxref32_destroy_element(void* h) { delete static_cast<FE32*>(h); }
+
+int bxref32_polyset_tabulate(int cell, int ptype, int d, int n, const float* x, std::size_t npts, int tdim, float* P)
+{
+  return guarded(
+      [&]()
+      {
+        const auto ct = static_cast<cell::type>(cell);
+        const auto pt = static_cast<polyset::type>(ptype);
+        mds<float, 3> Pm(P, polyset::nderivs(ct, n), polyset::dim(ct, pt, d), npts);
+        mds<const float, 2> xm(x, npts, tdim);
+        polyset::tabulate(Pm, ct, pt, d, n, xm);
+      });
+}
+
+int bxref32_tabulate(void* h, int nd, const float* x, std::size_t npts, int xdim, float* basis)
+{
+  const FE32& e = *static_cast<FE32*>(h);
+  return guarded(
+      [&]()
+      {
+        const auto full = e.tabulate_shape(nd, npts);
+        e.tabulate(nd, std::span<const float>(x, npts * xdim), {npts, static_cast<std::size_t>(xdim)},
+                   std::span<float>(basis, full[0] * full[1] * full[2] * full[3]));
+      });
+}
+
+int bxref32_map(void* h, int pull, const float* U, const float* J, const float* detJ, const float* K, std::size_t nc,
+                std::size_t rows, std::size_t in_vs, std::size_t gdim, std::size_t tdim, float* out, int* out_vs)
+{
+  const FE32& e = *static_cast<FE32*>(h);
+  return guarded(
+      [&]()
+      {
+        mds<const float, 3> Um(U, nc, rows, in_vs);
+        mds<const float, 3> Jm(J, nc, gdim, tdim);
+        mds<const float, 3> Km(K, nc, tdim, gdim);
+        std::span<const float> dj(detJ, nc);
+        auto [data, shape] = pull ? e.pull_back(Um, Jm, dj, Km) : e.push_forward(Um, Jm, dj, Km);
+        *out_vs = static_cast<int>(shape[2]);
+        if (out)
+          std::copy(data.begin(), data.end(), out);
+      });
+}
+
+int bxref32_T_apply(void* h, int op, float* data, std::size_t nc, std::size_t cell_size, int n, const std::uint32_t* ci)
+{
+  const FE32& e = *static_cast<FE32*>(h);
+  return guarded(
+      [&]()
+      {
+        for (std::size_t c = 0; c < nc; ++c)
+        {
+          std::span<float> u(data + c * cell_size, cell_size);
+          switch (op)
+          {
+          case 0: e.T_apply(u, n, ci[c]); break;
+          case 1: e.Tt_apply(u, n, ci[c]); break;
+          case 2: e.Tt_inv_apply(u, n, ci[c]); break;
+          case 3: e.Tinv_apply(u, n, ci[c]); break;
+          case 4: e.Tt_apply_right(u, n, ci[c]); break;
+          case 5: e.Tinv_apply_right(u, n, ci[c]); break;
+          case 6: e.T_apply_right(u, n, ci[c]); break;
+          case 7: e.Tt_inv_apply_right(u, n, ci[c]); break;
+          default: throw std::runtime_error("bad op");
+          }
+        }
+      });
+}
 } // extern "C"

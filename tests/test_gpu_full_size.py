@@ -172,3 +172,95 @@ def test_permute_round_trip_50m_cells(ref):
     assert bool((d == torch.arange(56, dtype=torch.int32, device="cuda")[None]).all())
     del d
     _free()
+
+
+def test_tabulate_p1_tri_1m_points(ref):
+    """BASELINE config 1: P1 triangle, nd = 1, 1 M points -- the WHOLE table against the compiled reference."""
+    from conftest import random_points
+
+    r, e = make_pair(ref, P, 2, 1, GLL)
+    x = random_points(2, 1_000_000, seed=42)
+    want = r.tabulate(1, x, chunk=65536, nthreads=8)
+    got = e.tabulate(1, x)
+    assert got.shape == want.shape == (3, 1_000_000, 3, 1)
+    for d in range(3):
+        assert np.max(np.abs(got[d] - want[d])) <= 1e-12 * np.max(np.abs(want[d]))
+    assert np.max(np.abs(got[0].sum(axis=1) - 1)) < 1e-13 and np.max(np.abs(got[1:].sum(axis=2))) < 1e-13
+
+
+def _jacobians_device(nc, seed):
+    import torch
+
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    J = torch.eye(3, dtype=torch.float64, device="cuda")[None] + 0.3 * torch.randn(nc, 3, 3, generator=g, device="cuda",
+                                                                                 dtype=torch.float64)
+
+    def det_and_inverse(J):
+        a, b, c, d, e_, f, g_, h, i = (J[:, r_, c_] for r_ in range(3) for c_ in range(3))
+        co = torch.stack([e_ * i - f * h, c * h - b * i, b * f - c * e_, f * g_ - d * i, a * i - c * g_, c * d - a * f,
+                          d * h - e_ * g_, b * g_ - a * h, a * e_ - b * d], dim=1)
+        det = a * co[:, 0] + b * co[:, 3] + c * co[:, 6]
+        return det.contiguous(), (co / det[:, None]).reshape(-1, 3, 3).contiguous()
+
+    detJ, K = det_and_inverse(J)
+    J[detJ.abs() < 0.1] = torch.eye(3, dtype=torch.float64, device="cuda")
+    detJ, K = det_and_inverse(J)
+    return J, detJ, K, g
+
+
+@pytest.mark.parametrize("family,degree", [(N1E, 3), (RT, 4)])
+def test_push_pull_rows45_4m_cells(ref, family, degree):
+    """BASELINE config 4 with rows = ndofs of N1curl3 (45, the shape the reference's tests use, test_mappings.py:39-53),
+    4 M cells (4.3 GB per array): push_forward AND pull_back sampled against the compiled reference bit for bit, round
+    trip over all cells; covariant (N1curl) and contravariant (RT) Piola."""
+    import torch
+
+    r, e = make_pair(ref, family, TET, degree, LEG)
+    nc, rows = 4_000_000, 45
+    J, detJ, K, g = _jacobians_device(nc, 17)
+    U = torch.randn(nc, rows, 3, generator=g, device="cuda", dtype=torch.float64)
+    u = e.push_forward(U, J, detJ, K)
+    back = e.pull_back(u, J, detJ, K)
+    assert float(((back - U).abs().amax(dim=(1, 2)) / (1 + U.abs().amax(dim=(1, 2)))).max()) < 1e-9
+    idx = torch.from_numpy(_sample(nc, 3000, 6)).cuda()
+    a = [v[idx].cpu().numpy() for v in (U, J, detJ, K)]
+    ui = u[idx].cpu().numpy()
+    assert np.array_equal(ui, r.push_forward(*a))
+    assert np.array_equal(back[idx].cpu().numpy(), r.pull_back(ui, *a[1:]))
+    # pull_back of independent data (not a round trip)
+    v = torch.randn(nc, rows, 3, generator=g, device="cuda", dtype=torch.float64)
+    pv = e.pull_back(v, J, detJ, K)
+    assert np.array_equal(pv[idx].cpu().numpy(), r.pull_back(v[idx].cpu().numpy(), *a[1:]))
+    del J, K, U, u, back, v, pv
+    _free()
+
+
+def test_T_apply_block3_50m_cells(ref):
+    """BASELINE config 5 (i) with block size 3 (SURVEY 8d "also n=3"): RT degree 4 tetrahedron, 50 M cells x 210 doubles
+    (84 GB in place); sample against the compiled reference, interior dofs untouched, Tinv_apply restores the input."""
+    import torch
+
+    r, e = make_pair(ref, RT, TET, 4, LEG)
+    nc, bs, chunk = 50_000_000, 3, 5_000_000
+    ci, ci64 = _cell_info(nc, 21)
+    data = torch.empty(nc, 70 * bs, device="cuda", dtype=torch.float64)
+
+    def regenerate(c):
+        g = torch.Generator(device="cuda").manual_seed(1000 + c)
+        return torch.randn(chunk, 70 * bs, generator=g, device="cuda", dtype=torch.float64)
+
+    for c in range(nc // chunk):
+        data[c * chunk:(c + 1) * chunk] = regenerate(c)
+    idx = torch.from_numpy(_sample(nc, 4000, 8)).cuda()
+    before = data[idx].cpu().numpy()
+    e.T_apply_batch(data, bs, ci)
+    want = r.T_apply_batch("T_apply", before.copy(), bs, ci64[idx].cpu().numpy().astype(np.uint32))
+    got = data[idx].cpu().numpy()
+    assert np.max(np.abs(got - want)) <= 1e-12 * np.max(np.abs(want))
+    for c in range(nc // chunk):  # the 30 interior dofs (x 3 block entries) never move
+        assert torch.equal(data[c * chunk:(c + 1) * chunk, 40 * bs:], regenerate(c)[:, 40 * bs:])
+    e.T_apply_batch(data, bs, ci, op="Tinv_apply")
+    for c in range(nc // chunk):
+        assert float((data[c * chunk:(c + 1) * chunk] - regenerate(c)).abs().max()) < 1e-11
+    del data
+    _free()

@@ -594,3 +594,89 @@ def test_push_pull_float32(ref, family, cell, degree, variant, vs):
     # float arithmetic through K^T (.) K / J (.) J^T: the double Piola maps square the conditioning of J
     tol = 1e-3 if vs >= 4 else 1e-4
     assert back.dtype == np.float32 and np.max(np.abs(back - want_back)) <= tol * np.max(np.abs(want_back))
+
+
+# ---- float32 against the reference's OWN float instantiation (FiniteElement<float>, oracle/ref_shim.cpp bxref32_*) ----
+@pytest.mark.parametrize("family,cell,degree,variant,nd", F32_TAB)
+def test_tabulate_float32_vs_reference_float(ref, family, cell, degree, variant, nd):
+    """The library narrows a float64 evaluation, the reference's FiniteElement<float> computes in float: the two agree
+    to within the rounding error of the reference's float path (measured here against the reference's double path at
+    the same points), and the library's table is the more accurate of the two."""
+    r64, e = make_pair(ref, family, cell, degree, variant)
+    r32 = ref.RefElement32(family, cell, degree, variant)
+    x32 = random_points(cell, 4099, seed=7).astype(np.float32)
+    exact = r64.tabulate(nd, x32.astype(np.float64))
+    want = r32.tabulate(nd, x32)
+    got = e.tabulate(nd, x32)
+    assert got.dtype == want.dtype == np.float32 and got.shape == want.shape
+    eps = float(np.finfo(np.float32).eps)
+    for d in range(want.shape[0]):
+        scale = np.max(np.abs(exact[d]))
+        ref_err = np.max(np.abs(want[d].astype(np.float64) - exact[d]))
+        our_err = np.max(np.abs(got[d].astype(np.float64) - exact[d]))
+        assert our_err <= eps * scale, (d, our_err, scale)
+        assert np.max(np.abs(got[d].astype(np.float64) - want[d])) <= ref_err + eps * scale, (d, ref_err, scale)
+
+
+@pytest.mark.parametrize("family,cell,degree,variant,vs", MAP_ELEMENTS)
+def test_push_pull_float32_vs_reference_float_bit_exact(ref, family, cell, degree, variant, vs):
+    """The float32 maps run the reference's operation order in float arithmetic: identical bits to FiniteElement<float>."""
+    _, e = make_pair(ref, family, cell, degree, variant)
+    r32 = ref.RefElement32(family, cell, degree, variant)
+    tdim = {TRI: 2, TET: 3}[cell]
+    nc, rows = 2049, 3
+    J, detJ, K = jacobians(nc, tdim, tdim)
+    U = np.random.default_rng(3).standard_normal((nc, rows, vs))
+    a32 = [a.astype(np.float32) for a in (U, J, detJ, K)]
+    u = e.push_forward(*a32)
+    want = r32.push_forward(*a32)
+    assert u.dtype == np.float32 and np.array_equal(u, want)
+    assert np.array_equal(e.pull_back(u, *a32[1:]), r32.pull_back(want, *a32[1:]))
+
+
+@pytest.mark.parametrize("family,cell,degree,variant", [(RT, TET, 4, LEG), (N1E, TET, 3, LEG), (P, TET, 5, GLL)])
+@pytest.mark.parametrize("op", ["T_apply", "Tinv_apply", "Tt_apply_right"])
+def test_T_apply_float32_vs_reference_float(ref, family, cell, degree, variant, op):
+    """float32 data: against FiniteElement<float> (float LU sweeps) to float rounding; permutation elements bit for bit."""
+    r64, e = make_pair(ref, family, cell, degree, variant)
+    r32 = ref.RefElement32(family, cell, degree, variant)
+    nc, bs = 3001, 2
+    ci = cell_infos(nc)
+    data = np.random.default_rng(5).standard_normal((nc, r64.dim * bs)).astype(np.float32)
+    want = r32.T_apply_batch(op, data.copy(), bs, ci)
+    got = data.copy()
+    e.T_apply_batch(got, bs, ci, op=op)
+    if r64.dof_transformations_are_permutations:
+        assert np.array_equal(got, want)
+    else:
+        assert np.max(np.abs(got - want)) <= 2e-5 * np.max(np.abs(want))
+
+
+def test_polyset_float32_vs_reference_float(ref):
+    import basix_b200 as bx
+    from basix_b200 import _capi
+
+    eps = float(np.finfo(np.float32).eps)
+    for cell, degree, nd in ((TRI, 4, 2), (TET, 5, 1), (HEX, 3, 1), (INTERVAL, 6, 2)):
+        x32 = random_points(cell, 1025, seed=3).astype(np.float32)
+        want = ref.tabulate_polynomial_set_f32(cell, 0, degree, nd, x32)
+        exact = ref.tabulate_polynomial_set(cell, 0, degree, nd, x32.astype(np.float64))
+        got = np.empty_like(want)
+        _capi.check(_capi.lib().bx_polyset_tabulate_f32(cell, 0, degree, nd, x32.ctypes.data, len(x32), got.ctypes.data,
+                                                        _capi.BX_MEM_HOST, None))
+        for d in range(want.shape[0]):
+            scale = np.max(np.abs(exact[d]))
+            ref_err = np.max(np.abs(want[d].astype(np.float64) - exact[d]))
+            assert np.max(np.abs(got[d].astype(np.float64) - want[d])) <= ref_err + 4 * eps * scale
+
+
+def test_push_forward_broadcast_256_rows(ref):
+    """243..256 rows of three doubles need more than 48 KB of dynamic shared memory (opt-in attribute)."""
+    r, e = make_pair(ref, N1E, TET, 3, LEG)
+    rng = np.random.default_rng(9)
+    for rows in (242, 243, 256, 257):
+        nc = 301
+        J, detJ, K = jacobians(nc, 3, 3, seed=rows)
+        U0 = rng.standard_normal((rows, 3))
+        want = r.push_forward(np.ascontiguousarray(np.broadcast_to(U0, (nc, rows, 3))), J, detJ, K)
+        assert np.array_equal(e.push_forward_broadcast(U0, J, detJ, K), want)

@@ -113,6 +113,25 @@ def _worker(rank, world, port, out_dir):
         lo, hi = sharding.T_apply_sharded(e, data, 1, ci)
         assert torch.equal(data[lo:hi], want[lo:hi])
         assert torch.equal(sharding.gather_cells(data[lo:hi], 21), want)
+        # equal slices take the copy-free path (all_gather_into_tensor / gather straight into the result)
+        e = _OracleElement("P3_triangle_gll")
+        x = rng.random((100, 2)) / 2
+        full = e.tabulate(1, torch.from_numpy(x))
+        assert torch.equal(sharding.tabulate_sharded(e, 1, torch.from_numpy(x), gather=True), full)
+        only0 = sharding.tabulate_sharded(e, 1, torch.from_numpy(x), gather=True, dst=0)
+        assert (only0 is None) == (rank != 0) and (rank != 0 or torch.equal(only0, full))
+        pre = torch.empty(20, 15, dtype=torch.float64)
+        blk = torch.full((10, 15), float(rank), dtype=torch.float64)
+        assert sharding.gather_cells(blk, 20, out=pre) is pre and torch.equal(pre[::10, 0], torch.tensor([0.0, 1.0]))
+        # a sub-group: slice bounds come from the rank and size IN THE GROUP (here one rank per group: the whole array)
+        groups = [dist.new_group([r]) for r in range(world)]
+        e = _OracleElement("RT2_tetrahedron_legendre")
+        data = torch.from_numpy(rng.standard_normal((21, 15)))
+        ci = torch.from_numpy(rng.integers(0, 2 ** 30, 21).astype(np.int64))
+        want = data.clone()
+        e.T_apply_batch(want, 1, ci)
+        assert sharding.T_apply_sharded(e, data, 1, ci, group=groups[rank]) == (0, 21)
+        assert torch.equal(data, want)
         with open(os.path.join(out_dir, f"ok{rank}"), "w") as f:
             f.write("ok")
     finally:
