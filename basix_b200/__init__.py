@@ -17,6 +17,7 @@ from .finite_element import (
     MapType,
     PolysetType,
     create_element,
+    geometry,
     polyset_dim,
     polyset_nderivs,
     tabulate_polynomial_set,
@@ -71,6 +72,6 @@ def index(p: int, q: int | None = None, r: int | None = None) -> int:
 
 __all__ = [
     "CellType", "DPCVariant", "create_element", "ElementFamily", "FiniteElement", "LagrangeVariant", "MapType", "PolysetType",
-    "device_count", "index", "kernel_launch_count", "polyset_dim", "polyset_nderivs", "set_device", "tabulate_paths",
+    "device_count", "geometry", "index", "kernel_launch_count", "polyset_dim", "polyset_nderivs", "set_device", "tabulate_paths",
     "tabulate_polynomial_set",
 ]

@@ -85,6 +85,11 @@ SIGNATURES = {
     "bx_map_f64": (_I, [_I, _I, _P, _P, _P, _P, _SIZE, _SIZE, _I, _I, _I, _P, _I, _P]),
     "bx_push_forward_f64": (_I, [_P, _P, _P, _P, _P, _SIZE, _SIZE, _I, _I, _I, _P, _I, _P]),
     "bx_pull_back_f64": (_I, [_P, _P, _P, _P, _P, _SIZE, _SIZE, _I, _I, _I, _P, _I, _P]),
+    "bx_geometry_f64": (_I, [_P, _P, _SIZE, _I, _I, _I, _I, _P, _P, _P, _I, _P]),
+    "bx_geometry_f32": (_I, [_P, _P, _SIZE, _I, _I, _I, _I, _P, _P, _P, _I, _P]),
+    "bx_push_forward_fused_f64": (_I, [_P, _I, _P, _SIZE, _P, _P, _P, _P, _P, _SIZE, _I, _P, _I, _P]),
+    "bx_push_forward_fused_f32": (_I, [_P, _I, _P, _SIZE, _P, _P, _P, _P, _P, _SIZE, _I, _P, _I, _P]),
+    "bx_physical_basis_f64": (_I, [_P, _I, _P, _SIZE, _I, _P, _P, _P, _P, _P, _SIZE, _I, _P, _I, _P]),
     "bx_T_apply_f64": (_I, [_P, _I, _P, _SIZE, _SIZE, _I, _P, _I, _P]),
     "bx_T_apply_f32": (_I, [_P, _I, _P, _SIZE, _SIZE, _I, _P, _I, _P]),
     "bx_T_apply_i32": (_I, [_P, _I, _P, _SIZE, _SIZE, _I, _P, _I, _P]),

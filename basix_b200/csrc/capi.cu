@@ -156,6 +156,13 @@ void map_device(int map_type, int pull, const T* U, const T* J, const T* detJ, c
 template <typename T>
 void dof_transform_device(const bx_element& e, int op, T* data, size_t nc, size_t cell_size, int n,
                           const uint32_t* cell_info, cudaStream_t s);
+template <typename T>
+void geometry_device(const T* coords, const T* dphi, size_t nc, int nv, int gdim, int tdim, int npts, T* J, T* detJ, T* K,
+                     cudaStream_t s);
+template <typename T>
+void physical_basis_device(const bx_element& e, int op, const T* U, size_t npts, const T* coords, const T* J,
+                           const T* detJ, const T* K, const uint32_t* cell_info, size_t nc, int gdim, T* out,
+                           cudaStream_t s);
 bx_element* create_lagrange(int cell, int degree, int variant, bool discontinuous, const int32_t* dof_ordering,
                             int n_dof_ordering);
 bx_element* create_rt(int cell, int degree, int lvariant, bool discontinuous);
@@ -540,6 +547,163 @@ void interpolate_any(const bx_element* e, int layout, const T* values, size_t nc
     BX_CUDA(cudaMemcpyAsync(dv[b], values + c0 * K, k * K * sizeof(T), cudaMemcpyHostToDevice, s));
     interpolate_device<T>(*e, layout, dv[b], k, dout[b], s);
     BX_CUDA(cudaMemcpyAsync(out + c0 * N, dout[b], k * N * sizeof(T), cudaMemcpyDeviceToHost, s));
+  }
+  st.sync();
+  st.trim();
+}
+
+// J / detJ / K of nc cells at npts points each; any output may be null.
+template <typename T>
+void geometry_any(const T* coords, const T* dphi, size_t nc, int nv, int gdim, int tdim, int npts, T* J, T* detJ, T* K,
+                  int mem, bx_stream_t stream)
+{
+  check_mem(mem);
+  if (mem == BX_MEM_DEVICE)
+  {
+    geometry_device<T>(coords, dphi, nc, nv, gdim, tdim, npts, J, detJ, K, static_cast<cudaStream_t>(stream));
+    return;
+  }
+  geometry_device<T>(coords, dphi, 0, nv, gdim, tdim, npts, J, detJ, K, nullptr); // validate the shapes
+  if (nc == 0)
+    return;
+  require(coords != nullptr, "geometry: null pointer");
+  const size_t xsz = size_t(nv) * gdim, jsz = size_t(gdim) * tdim * npts;
+  const size_t per_cell = (xsz + (J ? jsz : 0) + (K ? jsz : 0) + (detJ ? size_t(npts) : 0)) * sizeof(T);
+  const size_t chunk = chunk_units(nc, per_cell, 1);
+  StagePool& st = stage_pool();
+  DrainOnExit drain{st};
+  T *dx[2], *dJ[2], *dd[2], *dK[2], *dphi_d = nullptr;
+  for (int b = 0; b < 2; ++b)
+  {
+    dx[b] = st.get<T>(0, b, chunk * xsz * sizeof(T));
+    dJ[b] = J ? st.get<T>(1, b, chunk * jsz * sizeof(T)) : nullptr;
+    dd[b] = detJ ? st.get<T>(2, b, chunk * npts * sizeof(T)) : nullptr;
+    dK[b] = K ? st.get<T>(3, b, chunk * jsz * sizeof(T)) : nullptr;
+  }
+  if (dphi)
+  {
+    // the derivatives of the coordinate element: one small table for all chunks, uploaded on stream 0 and read by
+    // both streams (stream 1 waits for the upload through an event)
+    dphi_d = st.get<T>(4, 0, size_t(tdim) * npts * nv * sizeof(T));
+    BX_CUDA(cudaMemcpyAsync(dphi_d, dphi, size_t(tdim) * npts * nv * sizeof(T), cudaMemcpyHostToDevice, st.s[0]));
+    cudaEvent_t ev;
+    BX_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    BX_CUDA(cudaEventRecord(ev, st.s[0]));
+    BX_CUDA(cudaStreamWaitEvent(st.s[1], ev, 0));
+    BX_CUDA(cudaEventDestroy(ev));
+  }
+  size_t i = 0;
+  for (size_t c0 = 0; c0 < nc; c0 += chunk, ++i)
+  {
+    const int b = int(i & 1);
+    const size_t n = std::min(chunk, nc - c0);
+    cudaStream_t s = st.s[b];
+    BX_CUDA(cudaMemcpyAsync(dx[b], coords + c0 * xsz, n * xsz * sizeof(T), cudaMemcpyHostToDevice, s));
+    geometry_device<T>(dx[b], dphi_d, n, nv, gdim, tdim, npts, dJ[b], dd[b], dK[b], s);
+    if (J)
+      BX_CUDA(cudaMemcpyAsync(J + c0 * jsz, dJ[b], n * jsz * sizeof(T), cudaMemcpyDeviceToHost, s));
+    if (detJ)
+      BX_CUDA(cudaMemcpyAsync(detJ + c0 * npts, dd[b], n * npts * sizeof(T), cudaMemcpyDeviceToHost, s));
+    if (K)
+      BX_CUDA(cudaMemcpyAsync(K + c0 * jsz, dK[b], n * jsz * sizeof(T), cudaMemcpyDeviceToHost, s));
+  }
+  st.sync();
+  st.trim();
+}
+
+// Fused tabulate-once -> T_apply -> push_forward.  X == nullptr: U[npts][ndofs][vs] holds the reference values;
+// otherwise they are tabulated here from the points X[npts][tdim] (on the device; U is ignored).
+template <typename T>
+void physical_basis_any(const bx_element* e, int op, const T* X, const T* U, size_t npts, const T* coords, const T* J,
+                        const T* detJ, const T* K, const uint32_t* cell_info, size_t nc, int gdim, T* out, int mem,
+                        bx_stream_t stream)
+{
+  check_mem(mem);
+  require(e != nullptr, "physical_basis: null element");
+  require(X or U or npts == 0, "physical_basis: neither points nor reference values given");
+  const size_t urow = size_t(e->ndofs) * e->vs;
+  if (mem == BX_MEM_DEVICE)
+  {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (!X or npts == 0 or nc == 0)
+    {
+      physical_basis_device<T>(*e, op, U, npts, coords, J, detJ, K, cell_info, nc, gdim, out, s);
+      return;
+    }
+    T* dU = nullptr;
+    BX_CUDA(cudaMallocAsync(&dU, npts * urow * sizeof(T), s));
+    try
+    {
+      tabulate_device<T>(*e, 0, X, npts, dU, npts, s);
+      physical_basis_device<T>(*e, op, dU, npts, coords, J, detJ, K, cell_info, nc, gdim, out, s);
+    }
+    catch (...)
+    {
+      cudaFreeAsync(dU, s);
+      throw;
+    }
+    BX_CUDA(cudaFreeAsync(dU, s));
+    return;
+  }
+  physical_basis_device<T>(*e, op, U, 0, coords, J, detJ, K, cell_info, 0, gdim, out, nullptr); // validate
+  if (nc == 0 or npts == 0)
+    return;
+  require(out != nullptr, "physical_basis: null pointer");
+  const int tdim = e->tdim, map = e->map_type;
+  const int out_vs = map == BX_MAP_IDENTITY ? e->vs : gdim;
+  const size_t xsz = coords ? size_t(tdim + 1) * gdim : 0, jsz = size_t(gdim) * tdim;
+  const bool need_K = !coords and map == BX_MAP_COVARIANT_PIOLA, need_J = !coords and map == BX_MAP_CONTRAVARIANT_PIOLA;
+  const size_t orow = npts * size_t(e->ndofs) * out_vs;
+  const size_t per_cell = (xsz + ((need_K or need_J) ? jsz : 0) + (need_J ? 1 : 0) + orow) * sizeof(T) + sizeof(uint32_t);
+  const size_t chunk = chunk_units(nc, per_cell, 1);
+  StagePool& st = stage_pool();
+  DrainOnExit drain{st};
+  T *dg[2], *dd[2], *dout[2];
+  uint32_t* dci[2];
+  for (int b = 0; b < 2; ++b)
+  {
+    dg[b] = st.get<T>(0, b, chunk * std::max(xsz, jsz) * sizeof(T));
+    dd[b] = need_J ? st.get<T>(1, b, chunk * sizeof(T)) : nullptr;
+    dci[b] = cell_info ? st.get<uint32_t>(2, b, chunk * sizeof(uint32_t)) : nullptr;
+    dout[b] = st.get<T>(3, b, chunk * orow * sizeof(T));
+  }
+  // reference values: one slab for all chunks, produced on stream 0 (uploaded or tabulated there)
+  T* dU = st.get<T>(4, 0, npts * urow * sizeof(T));
+  if (X)
+  {
+    T* dX = st.get<T>(4, 1, npts * tdim * sizeof(T));
+    BX_CUDA(cudaMemcpyAsync(dX, X, npts * tdim * sizeof(T), cudaMemcpyHostToDevice, st.s[0]));
+    tabulate_device<T>(*e, 0, dX, npts, dU, npts, st.s[0]);
+  }
+  else
+    BX_CUDA(cudaMemcpyAsync(dU, U, npts * urow * sizeof(T), cudaMemcpyHostToDevice, st.s[0]));
+  {
+    cudaEvent_t ev;
+    BX_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    BX_CUDA(cudaEventRecord(ev, st.s[0]));
+    BX_CUDA(cudaStreamWaitEvent(st.s[1], ev, 0));
+    BX_CUDA(cudaEventDestroy(ev));
+  }
+  size_t i = 0;
+  for (size_t c0 = 0; c0 < nc; c0 += chunk, ++i)
+  {
+    const int b = int(i & 1);
+    const size_t n = std::min(chunk, nc - c0);
+    cudaStream_t s = st.s[b];
+    if (coords)
+      BX_CUDA(cudaMemcpyAsync(dg[b], coords + c0 * xsz, n * xsz * sizeof(T), cudaMemcpyHostToDevice, s));
+    else if (need_K)
+      BX_CUDA(cudaMemcpyAsync(dg[b], K + c0 * jsz, n * jsz * sizeof(T), cudaMemcpyHostToDevice, s));
+    else if (need_J)
+    {
+      BX_CUDA(cudaMemcpyAsync(dg[b], J + c0 * jsz, n * jsz * sizeof(T), cudaMemcpyHostToDevice, s));
+      BX_CUDA(cudaMemcpyAsync(dd[b], detJ + c0, n * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    if (cell_info)
+      BX_CUDA(cudaMemcpyAsync(dci[b], cell_info + c0, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    physical_basis_device<T>(*e, op, dU, npts, coords ? dg[b] : nullptr, need_J ? dg[b] : nullptr, dd[b],
+                             need_K ? dg[b] : nullptr, dci[b], n, gdim, dout[b], s);
+    BX_CUDA(cudaMemcpyAsync(out + c0 * orow, dout[b], n * orow * sizeof(T), cudaMemcpyDeviceToHost, s));
   }
   st.sync();
   st.trim();
@@ -956,6 +1120,46 @@ extern "C"
   {
     return bx::guarded(
         [&]() { bx::closure_permute_any(e, inverse, d, nc, m, info, entity_type, entity_index, mem, stream); });
+  }
+
+  int bx_geometry_f64(const double* coords, const double* dphi, size_t nc, int nv, int gdim, int tdim, int npts, double* J,
+                      double* detJ, double* K, int mem, bx_stream_t stream)
+  {
+    return bx::guarded([&]() { bx::geometry_any<double>(coords, dphi, nc, nv, gdim, tdim, npts, J, detJ, K, mem, stream); });
+  }
+  int bx_geometry_f32(const float* coords, const float* dphi, size_t nc, int nv, int gdim, int tdim, int npts, float* J,
+                      float* detJ, float* K, int mem, bx_stream_t stream)
+  {
+    return bx::guarded([&]() { bx::geometry_any<float>(coords, dphi, nc, nv, gdim, tdim, npts, J, detJ, K, mem, stream); });
+  }
+  int bx_push_forward_fused_f64(const bx_element* e, int op, const double* U, size_t npts, const double* coords,
+                                const double* J, const double* detJ, const double* K, const uint32_t* cell_info, size_t nc,
+                                int gdim, double* out, int mem, bx_stream_t stream)
+  {
+    return bx::guarded([&]()
+                       { bx::physical_basis_any<double>(e, op, nullptr, U, npts, coords, J, detJ, K, cell_info, nc, gdim, out, mem, stream); });
+  }
+  int bx_push_forward_fused_f32(const bx_element* e, int op, const float* U, size_t npts, const float* coords,
+                                const float* J, const float* detJ, const float* K, const uint32_t* cell_info, size_t nc,
+                                int gdim, float* out, int mem, bx_stream_t stream)
+  {
+    return bx::guarded([&]()
+                       { bx::physical_basis_any<float>(e, op, nullptr, U, npts, coords, J, detJ, K, cell_info, nc, gdim, out, mem, stream); });
+  }
+  int bx_physical_basis_f64(const bx_element* e, int op, const double* X, size_t npts, int tdim_x, const double* coords,
+                            const double* J, const double* detJ, const double* K, const uint32_t* cell_info, size_t nc,
+                            int gdim, double* out, int mem, bx_stream_t stream)
+  {
+    return bx::guarded(
+        [&]()
+        {
+          bx::require(e != nullptr, "physical_basis: null element");
+          if (tdim_x != e->tdim)
+            bx::fail(BX_ERR_INVALID_ARG, "Point dim (" + std::to_string(tdim_x) + ") does not match element dim ("
+                                             + std::to_string(e->tdim) + ").");
+          bx::require(X != nullptr or npts == 0, "physical_basis: null points");
+          bx::physical_basis_any<double>(e, op, X, nullptr, npts, coords, J, detJ, K, cell_info, nc, gdim, out, mem, stream);
+        });
   }
 
   int bx_permute_i32(const bx_element* e, int inverse, int32_t* d, size_t nc, const uint32_t* cell_info, int mem,

@@ -269,11 +269,12 @@ EncodeTiled encode_tiled()
 }
 
 // data[nc][cell_size] as a 2-D tensor, box = [cpt cells][box_w entries]
-// Tuning aid (development only): BX_DOF_TUNE="cpt=64,nbuf=3,promo=0,skip=0" overrides the tile shape, the
-// number of tile buffers, the L2 promotion of the tensor map, and can skip the arithmetic (data movement only).
+// Tuning aid (development only): BX_DOF_TUNE="cpt=64,nbuf=3,promo=0,skip=0,pad=1" overrides the tile shape, the
+// number of tile buffers, the L2 promotion of the tensor map, can skip the arithmetic (data movement only) and sets the
+// number of 16-byte units the box is padded by (pad=0: never).
 struct Tune
 {
-  int cpt = 0, nbuf = 0, promo = -1, skip = 0;
+  int cpt = 0, nbuf = 0, promo = -1, skip = 0, pad = -1;
 };
 const Tune& tune()
 {
@@ -293,6 +294,7 @@ const Tune& tune()
       get("nbuf=", v.nbuf);
       get("promo=", v.promo);
       get("skip=", v.skip);
+      get("pad=", v.pad);
     }
     return v;
   }();
@@ -395,10 +397,32 @@ bool try_tma(const bx_element& e, int kind, bool right, T* data, size_t nc, size
   p.ndofs = e.ndofs;
   p.r0 = r0 / per16 * per16;
   p.len = r0 + len - p.r0;
-  // box width: whole 16-byte units, nothing more -- the kernels are bound by the HBM stream, so the box is
-  // not padded to an odd number of units (that would remove the 2-way bank conflict of 8 lanes on 8 consecutive
-  // cells when the width is even, at the price of 16 more bytes read and written per cell)
-  const size_t units = (size_t(p.len) * sz + 15) / 16;
+  // box width = shared-memory distance between consecutive cells.  Lanes are consecutive cells, so the number of
+  // distinct bank offsets they hit is 128 / gcd(pitch bytes, 128).  The matrix kernel with 8-byte accesses (block size
+  // > 1, right layout, float data) runs 16 lanes per wavefront: at an 8-way conflict the shared-memory pipe, not HBM,
+  // sets the pace (RT4 tetrahedron, block size 3, 960-byte rows: 29.4 -> 20.2 ms per 50 M cells with one more 16-byte
+  // unit).  With 16-byte accesses (block size 1, left layout, double) the conflict is at most 4-way and the kernel
+  // is bound by the HBM stream: padding only adds bytes (RT4, 320-byte rows: 7.3 -> 7.6 ms), so it is not padded.
+  size_t units = (size_t(p.len) * sz + 15) / 16;
+  {
+    auto gcd = [](size_t a, size_t b)
+    {
+      while (b)
+      {
+        const size_t t = a % b;
+        a = b;
+        b = t;
+      }
+      return a;
+    };
+    const bool wide = std::is_same<T, double>::value and !right and n == 1; // 16-byte accesses (PAIRS form)
+    const size_t distinct = 128 / gcd(units * 16, 128), lanes = wide ? 8 : 128 / sz > 32 ? 32 : 128 / sz;
+    const size_t ways = lanes / std::min(lanes, distinct);
+    if (!e.perms and tune().pad < 0 and ways >= 8)
+      units += 1;
+  }
+  if (tune().pad > 0)
+    units += size_t(tune().pad);
   const size_t pitch_bytes = units * 16;
   p.pitch = int(pitch_bytes / sz);
   if (p.pitch > 256)

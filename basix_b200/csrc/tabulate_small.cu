@@ -7,12 +7,13 @@
 // tile needs to pay off: the kernel is pure HBM streaming (16-24 B in, NDER*N*8 B out per point).  One thread
 // owns one point: jets by the register recurrences of jets.cuh (polyset.cpp:66-120, 1601-1743, 1745-2020),
 // contraction against the norm-scaled coefficient operand broadcast from shared memory, results staged through
-// an odd-pitch shared tile so that every global store instruction writes one contiguous, fully coalesced run
-// of the [d][pt][n] table.
+// a warp-private shared tile that holds, per derivative slab, exactly one contiguous run of the [d][pt][n] table and
+// leaves by TMA bulk copies.
 #include "element.cuh"
 #include "jets.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace bx
 {
@@ -34,36 +35,55 @@ struct RegSink
 
 // T = type of the points and of the table (double, or float for the float32 API: loads widen, stores narrow,
 // the arithmetic is double either way).
-template <int TDIM, int DEG, int ND, typename T>
+//
+// Warps are independent (no block barrier after the operand is in shared memory): a warp owns R * 32 consecutive
+// points -- lane l the points l, l + 32, ... -- and a private shared tile [NDER][R * 32][N] typed like the table, i.e.
+// for every derivative slab exactly the bytes of one contiguous run of the [d][pt][n] table.  All point loads of the
+// warp are issued before the first recurrence; each finished slab leaves as ONE cp.async.bulk shared -> global copy
+// issued by its own lane, and the warp retires as soon as the copy engine has read the tile.  The grid is one warp
+// per tile (not persistent): with 1 M points the kernel lives for ~20 us and a persistent grid loses a quarter of
+// that to the imbalance of 2.2 tiles per resident warp, which the block scheduler does not have.
+template <int TDIM, int DEG, int ND, int R, typename T>
 __global__ void __launch_bounds__(kThreads)
-    tabulate_small_kernel(const T* __restrict__ x, size_t npts, const double* __restrict__ Cq,
-                          T* __restrict__ basis, int N, int NP, unsigned inv_n, int bulk)
+    tabulate_small_kernel(const T* __restrict__ x, size_t npts, const double* __restrict__ Cq, T* __restrict__ basis, int N,
+                          int bulk)
 {
   constexpr int NDER = jets::nder(TDIM, ND);
   constexpr int K = jets::psize(TDIM, DEG);
-  extern __shared__ __align__(16) double smem_small[];
-  double* s_C = smem_small;                     // [N][K]
-  double* tile = smem_small + ((N * K + 1) & ~1); // [NDER][kThreads][NP]
+  constexpr int PW = 32 * R; // points per warp
+  extern __shared__ __align__(128) unsigned char smem_small[];
+  double* s_C = reinterpret_cast<double*>(smem_small); // [N][K]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T* tile = reinterpret_cast<T*>(smem_small + ((size_t(N) * K * 8 + 127) & ~size_t(127))) + size_t(warp) * NDER * PW * N;
   for (int i = threadIdx.x; i < N * K; i += kThreads)
     s_C[i] = Cq[i];
   __syncthreads();
 
-  const size_t ntiles = ceil_div(npts, size_t(kThreads));
-  for (size_t tl = blockIdx.x; tl < ntiles; tl += gridDim.x)
+  const size_t pt0 = (size_t(blockIdx.x) * (kThreads / 32) + warp) * PW;
+  if (pt0 >= npts)
+    return;
+  const unsigned np = unsigned(min(size_t(PW), npts - pt0));
+  double xr[R][TDIM];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
   {
-    const size_t pt0 = tl * kThreads;
-    const unsigned np = unsigned(min(size_t(kThreads), npts - pt0));
-    const size_t pt = min(pt0 + threadIdx.x, npts - 1); // ragged tail: recompute the last point, never stored
+    const size_t pt = min(pt0 + r * 32 + lane, npts - 1); // ragged tail: recompute the last point, never stored
+#pragma unroll
+    for (int a = 0; a < TDIM; ++a)
+      xr[r][a] = double(x[TDIM * pt + a]);
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+  {
     double J[K][NDER];
     RegSink<K, NDER> sink{J};
     if constexpr (TDIM == 1)
-      jets::interval<DEG, ND>(double(x[pt]), sink);
+      jets::interval<DEG, ND>(xr[r][0], sink);
     else if constexpr (TDIM == 2)
-      jets::triangle<DEG, ND>(double(x[2 * pt]), double(x[2 * pt + 1]), sink);
+      jets::triangle<DEG, ND>(xr[r][0], xr[r][1], sink);
     else
-      jets::tetrahedron<DEG, ND>(double(x[3 * pt]), double(x[3 * pt + 1]), double(x[3 * pt + 2]), sink);
-
-    double* mine = tile + threadIdx.x * NP;
+      jets::tetrahedron<DEG, ND>(xr[r][0], xr[r][1], xr[r][2], sink);
+    T* mine = tile + (r * 32 + lane) * N;
     for (int n = 0; n < N; ++n)
     {
       double acc[NDER];
@@ -80,47 +100,53 @@ __global__ void __launch_bounds__(kThreads)
       }
 #pragma unroll
       for (int d = 0; d < NDER; ++d)
-        mine[d * (kThreads * NP) + n] = acc[d];
+        mine[d * (PW * N) + n] = static_cast<T>(acc[d]);
     }
-    // each derivative slab of the tile is one contiguous run of np * N doubles in global memory
-    const unsigned run = np * unsigned(N);
-    if constexpr (sizeof(T) == 8)
-    {
-      if (bulk and (run & 1) == 0)
-      {
-        // dense tile rows (odd N), 16-byte aligned slabs: one TMA bulk copy shared -> global per slab; the CTA only
-        // waits until the engine has read the tile, the HBM write completes in the background
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        if (threadIdx.x == 0)
-        {
-#pragma unroll
-          for (int d = 0; d < NDER; ++d)
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
-                             basis + (size_t(d) * npts + pt0) * N),
-                         "r"(uint32_t(__cvta_generic_to_shared(tile + d * (kThreads * NP)))), "r"(run * 8u)
-                         : "memory");
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        }
-        __syncthreads();
-        continue;
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int d = 0; d < NDER; ++d)
-    {
-      T* g = basis + (size_t(d) * npts + pt0) * N;
-      const double* t = tile + d * (kThreads * NP);
-      for (unsigned i = threadIdx.x; i < run; i += kThreads)
-      {
-        const unsigned p = __umulhi(i, inv_n), n = i - p * unsigned(N); // p = i / N (exact: i < 2^16)
-        g[i] = static_cast<T>(t[p * NP + n]);
-      }
-    }
-    __syncthreads();
   }
+  // each derivative slab of the warp's tile is one contiguous run of np * N entries in global memory
+  const unsigned run = np * unsigned(N);
+  if (bulk and np == PW)
+  {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane < NDER)
+    {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
+                       basis + (size_t(lane) * npts + pt0) * N),
+                   "r"(uint32_t(__cvta_generic_to_shared(tile + lane * (PW * N)))), "r"(run * uint32_t(sizeof(T)))
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    return;
+  }
+  __syncwarp();
+#pragma unroll 1
+  for (int d = 0; d < NDER; ++d)
+  {
+    T* g = basis + (size_t(d) * npts + pt0) * N;
+    const T* t = tile + d * (PW * N);
+    for (unsigned i = lane; i < run; i += 32)
+      g[i] = t[i];
+  }
+}
+
+template <int TDIM, int DEG, int ND, int R, typename T>
+void launch_r(const bx_element& e, const T* x, size_t npts, T* basis, size_t smem, int bulk, cudaStream_t s)
+{
+  auto kern = tabulate_small_kernel<TDIM, DEG, ND, R, T>;
+  if (smem > 48 * 1024)
+    BX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  const size_t nblocks = ceil_div(npts, size_t(kThreads) * R);
+  kern<<<unsigned(nblocks), kThreads, smem, s>>>(x, npts, e.d_Cq, basis, e.N, bulk);
+  BX_LAUNCHED();
+}
+
+// shared memory of one CTA with R * 32 points per warp
+template <typename T>
+size_t smem_bytes(int N, int K, int NDER, int R)
+{
+  return ((size_t(N) * K * 8 + 127) & ~size_t(127)) + size_t(kThreads / 32) * NDER * 32 * R * N * sizeof(T);
 }
 
 template <int TDIM, int DEG, int ND, typename T>
@@ -129,31 +155,45 @@ bool launch(const bx_element& e, const T* x, size_t npts, T* basis, cudaStream_t
   constexpr int NDER = jets::nder(TDIM, ND);
   constexpr int K = jets::psize(TDIM, DEG);
   static_assert(K * NDER <= 40, "jet does not fit in registers");
-  const int N = e.N, NP = N | 1;
-  const size_t smem = (size_t((N * K + 1) & ~1) + size_t(NDER) * kThreads * NP) * sizeof(double);
-  if (e.Cq.empty() or smem > 96 * 1024 or size_t(kThreads) * N >= 65536)
+  const int N = e.N;
+  if (e.Cq.empty() or smem_bytes<T>(N, K, NDER, 1) > 96 * 1024)
     return false;
   if (dry_run)
     return true;
   if (!e.d_Cq)
     return false;
-  auto kern = tabulate_small_kernel<TDIM, DEG, ND, T>;
-  if (smem > 48 * 1024)
-    BX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  int per_sm = 0;
-  BX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
-  const size_t ntiles = ceil_div(npts, size_t(kThreads));
-  const size_t cap = size_t(sm_count()) * std::max(per_sm, 1);
-  const unsigned inv_n = N > 1 ? unsigned((1ull << 32) / unsigned(N) + 1) : 0u;
-  if (N == 1)
-    fail(BX_ERR_RUNTIME, "tabulate (register path): single-column element"); // never on the menu (see below)
-  // TMA bulk copy-out: dense tile rows and every slab region 16-byte aligned
-  const int bulk = (NP == N and reinterpret_cast<uintptr_t>(basis) % 16 == 0 and (npts * size_t(N)) % 2 == 0
-                    and (size_t(NDER) * kThreads * NP) % 2 == 0 and ((N * K + 1) & ~1) % 2 == 0)
+  if (ceil_div(npts, size_t(kThreads)) > 0x7fffffffu)
+    fail(BX_ERR_INVALID_ARG, "tabulate (register path): too many points for one launch");
+  // points per warp: the largest of 128 / 64 / 32 whose tiles leave room for several CTAs per SM
+  static const int forced = []
+  {
+    const char* v = std::getenv("BX_SMALL_R");
+    return v ? std::atoi(v) : 0;
+  }();
+  int R = 1;
+  for (int r : {4, 2})
+    if (smem_bytes<T>(N, K, NDER, r) <= 36 * 1024)
+    {
+      R = r;
+      break;
+    }
+  if (forced == 1 or forced == 2 or forced == 4)
+    if (smem_bytes<T>(N, K, NDER, forced) <= 96 * 1024)
+      R = forced;
+  // TMA bulk copy-out needs every slab run of the table to start on a 16-byte boundary (the runs are 32 * R * N
+  // entries long, a multiple of 16 bytes): base aligned and slab pitch npts * N a multiple of 16 bytes
+  const size_t per16 = 16 / sizeof(T);
+  const int bulk = (reinterpret_cast<uintptr_t>(basis) % 16 == 0 and (npts * size_t(N)) % per16 == 0
+                    and (size_t(32) * N) % per16 == 0)
                        ? 1
                        : 0;
-  kern<<<unsigned(std::min(ntiles, cap)), kThreads, smem, s>>>(x, npts, e.d_Cq, basis, N, NP, inv_n, bulk);
-  BX_LAUNCHED();
+  const size_t smem = smem_bytes<T>(N, K, NDER, R);
+  if (R == 4)
+    launch_r<TDIM, DEG, ND, 4, T>(e, x, npts, basis, smem, bulk, s);
+  else if (R == 2)
+    launch_r<TDIM, DEG, ND, 2, T>(e, x, npts, basis, smem, bulk, s);
+  else
+    launch_r<TDIM, DEG, ND, 1, T>(e, x, npts, basis, smem, bulk, s);
   return true;
 }
 

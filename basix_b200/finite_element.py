@@ -235,6 +235,41 @@ def tabulate_polynomial_set(celltype: int, ptype: int, degree: int, nderiv: int,
     return P
 
 
+# ---- cell geometry -----------------------------------------------------------------------------------
+def geometry(coords, dphi=None, tdim: int | None = None, want=("J", "detJ", "K")):
+    """J, detJ and K of every cell (``bx_geometry_f64`` / ``_f32``): what callers compute before ``push_forward`` /
+    ``pull_back``; the reference's own analogue is the affine case ``cell::entity_jacobians`` (cell.cpp:662-689).
+
+    ``coords``: (ncells, nnodes, gdim).  ``dphi``: (tdim, npts, nnodes), the derivative slabs ``tabulate(1, X)[1:, :, :, 0]``
+    of the scalar coordinate element; ``None`` for affine simplex cells (nnodes = tdim + 1, one point:
+    ``J[:, t] = x[1 + t] - x[0]``).  Returns ``(J, detJ, K)`` with shapes (ncells, npts, gdim, tdim), (ncells, npts),
+    (ncells, npts, tdim, gdim) -- for ``dphi=None`` without the point axis, ready for ``push_forward`` -- or ``None`` for
+    the arrays not named in ``want``.  numpy in -> numpy out, CUDA torch tensors in -> CUDA torch tensors out."""
+    dt = _float_dtype(coords)
+    ca = _Arg(coords, dt, "coords")
+    if len(ca.shape) != 3:
+        raise TypeError("coords must have shape (ncells, nnodes, gdim)")
+    nc, nv, gdim = ca.shape
+    if dphi is None:
+        td, npts, dptr = (nv - 1 if tdim is None else int(tdim)), 1, None
+        mem = ca.mem
+    else:
+        da = _Arg(dphi, dt, "dphi")
+        if len(da.shape) != 3 or da.shape[2] != nv:
+            raise TypeError("dphi must have shape (tdim, npts, nnodes)")
+        td, npts, dptr = da.shape[0], da.shape[1], da.ptr
+        mem = _same_mem(ca, da)
+    stream, alloc = _stream_and_like(ca)
+    lead = (nc,) if dphi is None else (nc, npts)
+    J = alloc(lead + (gdim, td), dt) if "J" in want else None
+    detJ = alloc(lead, dt) if "detJ" in want else None
+    K = alloc(lead + (td, gdim), dt) if "K" in want else None
+    fn = lib().bx_geometry_f32 if dt is np.float32 else lib().bx_geometry_f64
+    check(fn(ca.ptr, dptr, nc, nv, gdim, td, npts, None if J is None else _ptr_of(J), None if detJ is None else _ptr_of(detJ),
+             None if K is None else _ptr_of(K), mem, stream))
+    return J, detJ, K
+
+
 # ---- element ----------------------------------------------------------------------------------------
 class FiniteElement:
     """B200-backed finite element: the hot-path subset of ``basix.finite_element.FiniteElement``."""
@@ -671,6 +706,69 @@ class FiniteElement:
         out = alloc((nc, rows, out_vs), dt)
         fn = lib().bx_push_forward_broadcast_f32 if dt is np.float32 else lib().bx_push_forward_broadcast_f64
         check(fn(self._h, Ua.ptr, Ja.ptr, da.ptr, Ka.ptr, nc, rows, in_vs, gdim, tdim, _ptr_of(out), mem, stream))
+        return out
+
+    def physical_basis(self, X, coords=None, J=None, detJ=None, K=None, cell_info=None, op: str = "T_apply", U=None):
+        """Basis functions of every physical cell in one fused pass (``bx_physical_basis_f64`` /
+        ``bx_push_forward_fused_*``): ``out[c, p] = push_forward(T_op(cell_info[c]) tabulate(0, X)[0][p], J_c, detJ_c, K_c)``
+        -- the reference's three calls (``tabulate`` once; per cell ``T_apply`` on the reference values with block size =
+        value size, then ``push_forward``).  Geometry: ``coords`` (ncells, tdim + 1, gdim) of affine triangle / tetrahedron
+        cells (J, detJ, K are computed on chip), or ``J`` (ncells, gdim, tdim), ``detJ`` (ncells,), ``K`` (ncells, tdim,
+        gdim) per cell.  ``cell_info``: (ncells,) uint32 or None.  Pass ``U`` = ``tabulate(0, X)[0]`` (npts, ndofs,
+        value_size) instead of ``X`` to reuse a table.  Returns (ncells, npts, ndofs, physical value size)."""
+        given = U if X is None else X
+        dt = _float_dtype(given)
+        geo = [a for a in (coords, J, detJ, K) if a is not None]
+        if not geo and int(self._map_type) != 0:
+            raise TypeError("physical_basis: pass coords, or J / detJ / K")
+        args = {}
+        for name, a in (("coords", coords), ("J", J), ("detJ", detJ), ("K", K)):
+            args[name] = None if a is None else _Arg(a, dt, name)
+        ci = None if cell_info is None else _Arg(cell_info, np.uint32, "cell_info")
+        live = [a for a in args.values() if a is not None] + ([ci] if ci is not None else [])
+        ga = _Arg(given, dt, "X" if U is None else "U")
+        mem = _same_mem(ga, *live) if live else ga.mem
+        if args["coords"] is not None:
+            if len(args["coords"].shape) != 3 or args["coords"].shape[1] != self._tdim + 1:
+                raise TypeError("coords must have shape (ncells, tdim + 1, gdim)")
+            nc, gdim = args["coords"].shape[0], args["coords"].shape[2]
+        elif args["K"] is not None or args["J"] is not None:
+            m = args["K"] if args["K"] is not None else args["J"]
+            if len(m.shape) != 3:
+                raise TypeError("J must have shape (ncells, gdim, tdim) and K (ncells, tdim, gdim)")
+            nc = m.shape[0]
+            gdim = m.shape[2] if args["K"] is not None else m.shape[1]
+        else:
+            if ci is None:
+                raise TypeError("physical_basis: the number of cells is unknown (no geometry, no cell_info)")
+            nc, gdim = ci.shape[0], self._tdim
+        if ci is not None and ci.shape != (nc,):
+            raise RuntimeError("cell_info must have one entry per cell")
+        out_vs = self._vs if int(self._map_type) == 0 else gdim
+        stream, alloc = _stream_and_like(ga)
+        ptr = {k: (None if a is None else a.ptr) for k, a in args.items()}
+        if U is None:
+            if len(ga.shape) != 2:
+                raise TypeError("X must have shape (npts, tdim)")
+            npts = ga.shape[0]
+            out = alloc((nc, npts, self._ndofs, out_vs), dt)
+            if dt is np.float32:
+                Ut = self.tabulate(0, X)[0]
+                check(lib().bx_push_forward_fused_f32(self._h, T_OPS[op], _ptr_of(Ut), npts, ptr["coords"], ptr["J"],
+                                                      ptr["detJ"], ptr["K"], None if ci is None else ci.ptr, nc, gdim,
+                                                      _ptr_of(out), mem, stream))
+            else:
+                check(lib().bx_physical_basis_f64(self._h, T_OPS[op], ga.ptr, npts, ga.shape[1], ptr["coords"], ptr["J"],
+                                                  ptr["detJ"], ptr["K"], None if ci is None else ci.ptr, nc, gdim,
+                                                  _ptr_of(out), mem, stream))
+            return out
+        if len(ga.shape) != 3 or ga.shape[1:] != (self._ndofs, self._vs):
+            raise TypeError("U must have shape (npts, ndofs, value_size)")
+        npts = ga.shape[0]
+        out = alloc((nc, npts, self._ndofs, out_vs), dt)
+        fn = lib().bx_push_forward_fused_f32 if dt is np.float32 else lib().bx_push_forward_fused_f64
+        check(fn(self._h, T_OPS[op], ga.ptr, npts, ptr["coords"], ptr["J"], ptr["detJ"], ptr["K"],
+                 None if ci is None else ci.ptr, nc, gdim, _ptr_of(out), mem, stream))
         return out
 
     def _map(self, pull: int, U, J, detJ, K):

@@ -443,6 +443,23 @@ class TApply:
         movable = sum(len(d) for dim in range(1, e._tdim) for d in ed[dim])
         self.alg_bytes = nc * (2 * movable * esize * self.bs + 4)
         self.flops = 0.0
+        # What DRAM can deliver at best for this strided in-place pattern: the movable range of a cell is one run of
+        # `run` bytes every `pitch` bytes; reads arrive in whole 128-byte lines, writes leave in 32-byte sectors
+        # (ncu: dram__bytes of the kernel, profiles/*traffic.json).  Exact count over one period of the alignment.
+        lo = min(min(d) for dim in range(1, e._tdim) for d in ed[dim] if d) * esize * self.bs
+        run, pitch = movable * esize * self.bs, e.dim * esize * self.bs
+        period = 128 // np.gcd(pitch, 128)
+
+        def touched(g):  # distinct g-byte blocks the runs of one period of cells touch, in bytes per cell
+            blocks = set()
+            for c in range(period):
+                blocks.update(range((c * pitch + lo) // g, (c * pitch + lo + run - 1) // g + 1))
+            return len(blocks) * g / period
+
+        rd, wr = touched(128), touched(32)
+        self.line_bytes = nc * (rd + wr + 4)
+        self.line_what = ("movable run of %d B every %d B: %.0f B read per cell in whole 128-byte lines + %.0f B written in "
+                          "32-byte sectors + 4 B cell_info" % (run, pitch, rd, wr))
         self.config = {"workload": self.desc, "cells_per_gpu": nc, "block_size": self.bs, "movable_dofs": movable,
                        "whole_array_bytes_per_cell": 2 * e.dim * esize * self.bs + 4,
                        "l2": "data is %.2f GB per step (>> 126 MB L2)" % (nc * e.dim * esize * self.bs / 1e9)}
@@ -729,11 +746,38 @@ def run_ours(args, w, rank, local_rank, world):
         else:
             roofline = dict(bound="hbm", traffic=None, **hbm)
         roofline["traffic"], roofline["traffic_source"] = measured_traffic(name, w.units_per_launch)
+        if getattr(w, "flush_l2", False):
+            # a launch this short never sees the steady-state copy rate the peak was measured at: time a plain device
+            # copy moving the same bytes (half read, half written) under the same rule -- untimed 512 MB L2 flush, one
+            # event pair per launch -- as the size-matched ceiling
+            src = torch.empty(int(w.alg_bytes) // 2, dtype=torch.uint8, device="cuda")
+            dst = torch.empty_like(src)
+
+            class _Copy:
+                flush_l2 = True
+
+                @staticmethod
+                def step():
+                    dst.copy_(src)
+
+            for _ in range(3):
+                _Copy.step()
+            cms, _ = time_steps(_Copy, 20)
+            roofline["copy_same_bytes_ms"] = cms / 20
+            roofline["frac_of_copy_same_bytes"] = (cms / 20) / ms_launch
+            roofline["copy_same_bytes"] = ("torch copy_ of %d bytes to a second buffer (same bytes read + written as one "
+                                           "launch), same L2 flush and event-pair timing" % (int(w.alg_bytes) // 2))
+            del src, dst
+        if hasattr(w, "line_bytes"):
+            roofline["line_granular"] = {"bytes": w.line_bytes, "frac": w.line_bytes / (ms_launch * 1e-3) / 1e9 / hbm_peak,
+                                         "what": w.line_what}
         roofline["ms_per_launch"] = ms_launch
         roofline["launches_per_step"] = w.launches_per_step
         return roofline
 
-    w.setup(rank)
+    if args.device_only:
+        args.no_e2e = True
+    w.setup(rank, device_only=args.device_only)
     warmup = max(args.warmup, 3)
     for _ in range(warmup):
         w.step()
@@ -868,7 +912,9 @@ def run_ours(args, w, rank, local_rank, world):
                 configs[name] = {"workload": sw.desc, "ms_per_step": sms, "value": sw.units_per_step / (sms * 1e-3),
                                  "unit": sw.unit, "steps": ksteps, "gpu_launches": int(nl),
                                  "roofline": {k: rf[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic",
-                                                                 "ms_per_launch", "launches_per_step")},
+                                                                 "ms_per_launch", "launches_per_step",
+                                                                 "frac_of_copy_same_bytes", "copy_same_bytes_ms",
+                                                                 "line_granular") if k in rf},
                                  "l2": sw.config.get("l2")}
                 if rf["bound"] == "tensor":
                     configs[name]["roofline"]["hbm_frac"] = rf["hbm"]["frac"]
@@ -918,6 +964,8 @@ def main():
     ap.add_argument("--workload", default=DEFAULT, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--device-only", action="store_true",
+                    help="generate the inputs on the GPU (no host copies of them; implies --no-e2e): profiling runs")
     ap.add_argument("--no-configs", action="store_true",
                     help="skip the device-resident passes over the other BASELINE.json configs (default line, N = 1)")
     ap.add_argument("--units", type=int, default=0,

@@ -257,6 +257,41 @@ extern "C"
                        size_t nc, size_t rows, int in_vs, int gdim, int tdim, float* out, int mem,
                        bx_stream_t stream);
 
+  /* ---- cell geometry and the fused physical basis -----------------------------------------
+   * bx_geometry: J, detJ and K of nc cells at npts points each, from the cells' node coordinates and the derivatives of
+   * the coordinate element -- what every caller computes before push_forward / pull_back (the reference's own analogue
+   * is the affine case, cell::entity_jacobians, cell.cpp:662-689):
+   *     J[c][p][g][t] = sum_v coords[c][v][g] * dphi[t][p][v]
+   *     detJ = det J (gdim == tdim) or sqrt(det(J^T J));  K = J^-1 (adjugate / det) or (J^T J)^-1 J^T.
+   * coords[nc][nv][gdim]; dphi[tdim][npts][nv] = slabs 1..tdim of tabulate(1, X) of the scalar coordinate element, or
+   * NULL for affine simplex cells (nv = tdim + 1, npts = 1: J(:, t) = x[1 + t] - x[0], bit-identical to
+   * cell::entity_jacobians).  Outputs J[nc][npts][gdim][tdim], detJ[nc][npts], K[nc][npts][tdim][gdim]; any may be NULL. */
+  int bx_geometry_f64(const double* coords, const double* dphi, size_t nc, int nv, int gdim, int tdim, int npts, double* J,
+                      double* detJ, double* K, int mem, bx_stream_t stream);
+  int bx_geometry_f32(const float* coords, const float* dphi, size_t nc, int nv, int gdim, int tdim, int npts, float* J,
+                      float* detJ, float* K, int mem, bx_stream_t stream);
+  /* Fused tabulate-once -> T_apply -> push_forward: the three reference calls a caller makes to get the basis functions
+   * of every physical cell (FiniteElement::tabulate finite-element.cpp:1834-1888 once; per cell T_apply
+   * finite-element.h:1839-1854 on the reference values with block size = value size, then push_forward
+   * finite-element.cpp:1971-2005), in one pass that writes only the result:
+   *     out[c][p][dof][:] = push_forward( T_op(cell_info[c]) U[p] , J_c, detJ_c, K_c )
+   * U[npts][ndofs][value_size] = tabulate(0, X)[0] (bx_push_forward_fused) or the points X[npts][tdim] themselves
+   * (bx_physical_basis: tabulated on the device first).  Geometry: coords[nc][tdim + 1][gdim] (affine triangle /
+   * tetrahedron cells; J, detJ, K are computed on chip as bx_geometry computes them and never touch memory) or, with
+   * coords == NULL, the per-cell arrays J[nc][gdim][tdim], detJ[nc], K[nc][tdim][gdim] (only the ones the map reads
+   * are dereferenced).  cell_info[nc] may be NULL (no transformation).  op: BX_T_APPLY, BX_TT_APPLY, BX_TT_INV_APPLY or
+   * BX_TINV_APPLY.  Identity, covariant and contravariant Piola maps; elements of up to 256 dofs.
+   * out[nc][npts][ndofs][physical value size].  Equal, bit for bit, to the library's own three-call sequence. */
+  int bx_push_forward_fused_f64(const bx_element* e, int op, const double* U, size_t npts, const double* coords,
+                                const double* J, const double* detJ, const double* K, const uint32_t* cell_info, size_t nc,
+                                int gdim, double* out, int mem, bx_stream_t stream);
+  int bx_push_forward_fused_f32(const bx_element* e, int op, const float* U, size_t npts, const float* coords,
+                                const float* J, const float* detJ, const float* K, const uint32_t* cell_info, size_t nc,
+                                int gdim, float* out, int mem, bx_stream_t stream);
+  int bx_physical_basis_f64(const bx_element* e, int op, const double* X, size_t npts, int tdim_x, const double* coords,
+                            const double* J, const double* detJ, const double* K, const uint32_t* cell_info, size_t nc,
+                            int gdim, double* out, int mem, bx_stream_t stream);
+
   /* ---- DOF transformations ----------------------------------------------------------------
    * Replaces T_apply and its 7 siblings (finite-element.h:1839-1998), i.e. permute_data
    * (finite-element.h:1703-1760) / transform_data (finite-element.h:1762-1837) with

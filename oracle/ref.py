@@ -67,6 +67,8 @@ def lib():
         L.bxref_interpolation_matrix.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.bxref_permute_subentity_closure_i32.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t,
                                                           C.c_void_p, C.c_int, C.c_int]
+        L.bxref_entity_jacobians.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.bxref_sub_entity_geometry.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.bxref32_create_element.restype = C.c_void_p
         L.bxref32_create_element.argtypes = [C.c_int] * 6 + [C.c_void_p, C.c_int]
         L.bxref32_destroy_element.argtypes = [C.c_void_p]
@@ -108,6 +110,24 @@ def tabulate_polynomial_set(cell: int, ptype: int, d: int, n: int, x: np.ndarray
     P = np.empty((polyset_nderivs(cell, n), polyset_dim(cell, ptype, d), npts), dtype=np.float64)
     _check(lib().bxref_polyset_tabulate(int(cell), int(ptype), int(d), int(n), _ptr(x), npts, tdim, _ptr(P)))
     return P
+
+
+def entity_jacobians(cell: int, e_dim: int) -> np.ndarray:
+    """reference cell::entity_jacobians (cell.cpp:662-689): shape (n_entities, tdim, e_dim)."""
+    shp = np.zeros(3, dtype=np.int32)
+    _check(lib().bxref_entity_jacobians(int(cell), int(e_dim), _ptr(shp), None))
+    out = np.empty(tuple(int(v) for v in shp), dtype=np.float64)
+    _check(lib().bxref_entity_jacobians(int(cell), int(e_dim), _ptr(shp), _ptr(out)))
+    return out
+
+
+def sub_entity_geometry(cell: int, dim: int, index: int) -> np.ndarray:
+    """reference cell::sub_entity_geometry: vertex coordinates of one sub-entity, shape (nvertices, tdim)."""
+    shp = np.zeros(2, dtype=np.int32)
+    _check(lib().bxref_sub_entity_geometry(int(cell), int(dim), int(index), _ptr(shp), None))
+    out = np.empty(tuple(int(v) for v in shp), dtype=np.float64)
+    _check(lib().bxref_sub_entity_geometry(int(cell), int(dim), int(index), _ptr(shp), _ptr(out)))
+    return out
 
 
 class RefElement:

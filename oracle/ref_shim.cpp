@@ -490,6 +490,34 @@ int bxref_permute_subentity_closure_i32(void* h, int inverse, std::int32_t* d, s
         }
       });
 }
+// cell::entity_jacobians (cell.cpp:662-689): shape (n_entities, tdim, e_dim)
+int bxref_entity_jacobians(int cell, int e_dim, int* shape, double* out)
+{
+  return guarded(
+      [&]()
+      {
+        auto [data, shp] = cell::entity_jacobians<double>(static_cast<cell::type>(cell), e_dim);
+        for (int i = 0; i < 3; ++i)
+          shape[i] = static_cast<int>(shp[i]);
+        if (out)
+          std::copy(data.begin(), data.end(), out);
+      });
+}
+
+// cell::sub_entity_geometry (cell.cpp): vertex coordinates of sub-entity (dim, index), shape (nvertices, tdim)
+int bxref_sub_entity_geometry(int cell, int dim, int index, int* shape, double* out)
+{
+  return guarded(
+      [&]()
+      {
+        auto [data, shp] = cell::sub_entity_geometry<double>(static_cast<cell::type>(cell), dim, index);
+        shape[0] = static_cast<int>(shp[0]);
+        shape[1] = static_cast<int>(shp[1]);
+        if (out)
+          std::copy(data.begin(), data.end(), out);
+      });
+}
+
 // ---- the reference's float instantiation: FiniteElement<float> (finite-element.cpp:2051), polyset::tabulate<float>
 // (polyset.cpp:2995-2997).  Same forwarding as above, single-threaded (parity checks only). ----
 using FE32 = FiniteElement<float>;
