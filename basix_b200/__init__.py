@@ -16,6 +16,7 @@ from .finite_element import (
     LagrangeVariant,
     MapType,
     PolysetType,
+    compute_interpolation_operator,
     create_element,
     geometry,
     polyset_dim,
@@ -71,7 +72,7 @@ def index(p: int, q: int | None = None, r: int | None = None) -> int:
 
 
 __all__ = [
-    "CellType", "DPCVariant", "create_element", "ElementFamily", "FiniteElement", "LagrangeVariant", "MapType", "PolysetType",
+    "CellType", "DPCVariant", "compute_interpolation_operator", "create_element", "ElementFamily", "FiniteElement", "LagrangeVariant", "MapType", "PolysetType",
     "device_count", "geometry", "index", "kernel_launch_count", "polyset_dim", "polyset_nderivs", "set_device", "tabulate_paths",
     "tabulate_polynomial_set",
 ]

@@ -99,6 +99,7 @@ SIGNATURES = {
     "bx_element_interpolation_matrix": (_I, [_P, _P]),
     "bx_interpolate_f64": (_I, [_P, _I, _P, _SIZE, _P, _I, _P]),
     "bx_interpolate_f32": (_I, [_P, _I, _P, _SIZE, _P, _I, _P]),
+    "bx_compute_interpolation_operator_f64": (_I, [_P, _P, _P, _P, _I, _P]),
     "bx_permute_subentity_closure_i32": (_I, [_P, _I, _P, _SIZE, _SIZE, _P, _I, _I, _I, _P]),
     "bx_element_subentity_closure_size": (_I, [_P, _I]),
     "bx_element_subentity_closure_map": (_I, [_P, _I, _I, C.c_uint32, _P]),

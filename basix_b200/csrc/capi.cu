@@ -163,6 +163,8 @@ template <typename T>
 void physical_basis_device(const bx_element& e, int op, const T* U, size_t npts, const T* coords, const T* J,
                            const T* detJ, const T* K, const uint32_t* cell_info, size_t nc, int gdim, T* out,
                            cudaStream_t s);
+void interpolation_operator_shape(const bx_element& from, const bx_element& to, int32_t shape[2]);
+void interpolation_operator_device(const bx_element& from, const bx_element& to, double* out, cudaStream_t s);
 bx_element* create_lagrange(int cell, int degree, int variant, bool discontinuous, const int32_t* dof_ordering,
                             int n_dof_ordering);
 bx_element* create_rt(int cell, int degree, int lvariant, bool discontinuous);
@@ -1159,6 +1161,32 @@ extern "C"
                                              + std::to_string(e->tdim) + ").");
           bx::require(X != nullptr or npts == 0, "physical_basis: null points");
           bx::physical_basis_any<double>(e, op, X, nullptr, npts, coords, J, detJ, K, cell_info, nc, gdim, out, mem, stream);
+        });
+  }
+
+  int bx_compute_interpolation_operator_f64(const bx_element* from, const bx_element* to, int32_t shape[2], double* out,
+                                            int mem, bx_stream_t stream)
+  {
+    return bx::guarded(
+        [&]()
+        {
+          bx::require(from and to and shape, "compute_interpolation_operator: null argument");
+          bx::check_mem(mem);
+          bx::interpolation_operator_shape(*from, *to, shape);
+          if (!out)
+            return;
+          if (mem == BX_MEM_DEVICE)
+          {
+            bx::interpolation_operator_device(*from, *to, out, static_cast<cudaStream_t>(stream));
+            return;
+          }
+          bx::StagePool& st = bx::stage_pool();
+          bx::DrainOnExit drain{st};
+          const size_t bytes = size_t(shape[0]) * shape[1] * sizeof(double);
+          double* d = st.get<double>(0, 0, bytes);
+          bx::interpolation_operator_device(*from, *to, d, st.s[0]);
+          BX_CUDA(cudaMemcpyAsync(out, d, bytes, cudaMemcpyDeviceToHost, st.s[0]));
+          st.sync();
         });
   }
 

@@ -21,6 +21,9 @@
 #include "element.cuh"
 
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <string>
 #include <vector>
 
 namespace bx
@@ -34,7 +37,6 @@ void tabulate_device(const bx_element& e, int nd, const T* x, size_t npts, T* ba
 namespace geo
 {
 constexpr int kThreads = 256;
-constexpr int kBatch = 4; // cells per warp iteration of the fused kernel
 
 // Unscaled inverse and its divisor: K = adj / div, detJ = div (square) or sqrt(div) (non-square, div = det(J^T J)).
 //   1 x 1, 2 x 2, 3 x 3: adjugate and determinant (first-row cofactor expansion)
@@ -179,6 +181,100 @@ __global__ void __launch_bounds__(kThreads)
   }
 }
 
+// ---- affine simplex cells: J(:, a) = x[1 + a] - x[0] -------------------------------------------------------------
+// The general kernel above is a thread per (cell, point) with strided 8-byte accesses (12 loads and 19 stores per
+// thread, each touching 32 different sectors per warp instruction): 2.4 ms per 20 M tetrahedra, a third of the HBM
+// roofline.  Here a warp owns 32 consecutive cells: their coordinates arrive with coalesced loads into an odd-pitch
+// shared tile, lane = cell computes from registers, and J, K and detJ of the 32 cells -- one contiguous run of each
+// array -- leave as one TMA bulk copy each.
+template <typename T, int G, int TD>
+__global__ void __launch_bounds__(kThreads)
+    geometry_affine_kernel(const T* __restrict__ coords, size_t nc, T* __restrict__ Jout, T* __restrict__ detout,
+                           T* __restrict__ Kout, int bulk)
+{
+  constexpr int NX = (TD + 1) * G, MA = G * TD;
+  constexpr int XP = NX | 1;                               // odd pitch: lane-per-cell reads are conflict free
+  constexpr int MP = (MA & 1) ? MA : MA + 1;               // same for the staged results ...
+  constexpr int kWarpT = ((32 * (XP > MA ? XP : MA) + 3) & ~3) + ((32 * MA + 3) & ~3) + 32; // x / J (dense), K, det
+  extern __shared__ __align__(128) unsigned char aff_smem[];
+  (void)MP;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T* sx = reinterpret_cast<T*>(aff_smem) + size_t(warp) * kWarpT; // coordinates [32][XP], then J [32][MA] dense
+  T* sK = sx + ((32 * (XP > MA ? XP : MA) + 3) & ~3);              // K [32][MA] dense
+  T* sd = sK + ((32 * MA + 3) & ~3);                               // detJ [32]
+  const size_t warps = size_t(gridDim.x) * (kThreads / 32);
+  bool pending = false;
+  for (size_t c0 = (size_t(blockIdx.x) * (kThreads / 32) + warp) * 32; c0 < nc; c0 += warps * 32)
+  {
+    const int nb = int(min(size_t(32), nc - c0));
+    if (pending)
+    {
+      if (lane < 3)
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+      pending = false;
+    }
+    for (int q = lane; q < nb * NX; q += 32)
+      sx[(q / NX) * XP + q % NX] = coords[c0 * NX + q];
+    __syncwarp();
+    T x[NX];
+#pragma unroll
+    for (int k = 0; k < NX; ++k)
+      x[k] = sx[min(lane, nb - 1) * XP + k];
+    __syncwarp(); // the coordinate tile is overwritten by J below
+    T J[G][TD], adj[TD][G], div;
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+      for (int a = 0; a < TD; ++a)
+        J[g][a] = x[(1 + a) * G + g] - x[g];
+    adjugate<T, G, TD>(J, adj, div);
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+      for (int a = 0; a < TD; ++a)
+        sx[lane * MA + g * TD + a] = J[g][a];
+#pragma unroll
+    for (int a = 0; a < TD; ++a)
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+        sK[lane * MA + a * G + g] = adj[a][g] / div;
+    sd[lane] = det_from_div<T, G, TD>(div);
+    if (bulk and nb == 32)
+    {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      T* dst = lane == 0 ? Jout : lane == 1 ? Kout : detout;
+      const T* src = lane == 0 ? sx : lane == 1 ? sK : sd;
+      const uint32_t per = lane < 2 ? MA : 1;
+      if (lane < 3 and dst)
+      {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + c0 * per),
+                     "r"(uint32_t(__cvta_generic_to_shared(src))), "r"(uint32_t(32 * per * sizeof(T)))
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      pending = true;
+    }
+    else
+    {
+      __syncwarp();
+      for (int q = lane; q < nb * MA; q += 32)
+      {
+        if (Jout)
+          Jout[c0 * MA + q] = sx[q];
+        if (Kout)
+          Kout[c0 * MA + q] = sK[q];
+      }
+      if (detout and lane < nb)
+        detout[c0 + lane] = sd[lane];
+      __syncwarp();
+    }
+  }
+  if (pending and lane < 3)
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 // ---- fused physical basis ------------------------------------------------------------------------------------
 struct FusedParams
 {
@@ -187,18 +283,85 @@ struct FusedParams
   int ndofs;
   int tab_stride;   // entries between the tables of consecutive states
   int nstates;      // 8, or 1 when nothing is transformed (no cell_info, identity transformations)
+  int batch;        // cells per slice (one TMA bulk copy-out each)
+  int nbuf;         // slices per warp (1 or 2)
+  int bulk;         // the rows of `batch` consecutive cells are one 16-byte aligned run of `out`: TMA bulk copy-out
+  int vec_coords;   // coords is 16-byte aligned: 16-byte loads
   size_t out_pitch; // entries between consecutive cells of `out` (>= rows * OUT_VS: a chunk of a larger point set)
   const int16_t* dof_slot;  // [ndofs] owning slot or -1
   const int4* slot_info;    // [nslots] {shift, mask, dim, _}
   const uint32_t* cell_info; // [nc] or null
 };
 
+// a / b given rb = RN(1 / b): two FMA correction steps on a * rb.  The residual a - q b of a quotient that is within
+// an ulp is exact in one FMA, and adding residual * rb rounds to the correctly rounded quotient (Markstein); the first
+// step brings a * rb (up to 2 ulp off) within an ulp, the second lands on RN(a / b) -- the value the reference's
+// `acc / detJ` (maps.h:122-123) has.  tools/div_check.cu compares the two over 2 * 10^10 random and adversarial pairs
+// per type (profiles/r02_div_check.json: 0 mismatches).  When the quotient leaves a wide exponent window (zeros,
+// infinities, NaNs -- the caller passes rb = NaN for a divisor outside its own window) the IEEE division decides.
+// (out of line on purpose: inlined, the compiler turns the rare branch into an unconditional division and a select)
+__device__ __noinline__ double ieee_div(double a, double b) { return a / b; }
+__device__ __noinline__ float ieee_div(float a, float b) { return a / b; }
+
+__device__ __forceinline__ double div_by(double a, double b, double rb)
+{
+  double q = a * rb;
+  double r = fma(-q, b, a);
+  q = fma(r, rb, q);
+  r = fma(-q, b, a);
+  q = fma(r, rb, q);
+  const unsigned ex = (unsigned(__double2hiint(q)) >> 20) & 0x7ffu; // biased exponent: 1023 +- 500 passes
+  if (ex - 523u > 1000u)
+    q = ieee_div(a, b);
+  return q;
+}
+__device__ __forceinline__ float div_by(float a, float b, float rb)
+{
+  float q = a * rb;
+  float r = fmaf(-q, b, a);
+  q = fmaf(r, rb, q);
+  r = fmaf(-q, b, a);
+  q = fmaf(r, rb, q);
+  const unsigned ex = (__float_as_uint(q) >> 23) & 0xffu; // 127 +- 60 passes
+  if (ex - 67u > 120u)
+    q = ieee_div(a, b);
+  return q;
+}
+// reciprocal for div_by: NaN unless the divisor is finite and within 2^+-300 (float: 2^+-40), so that every product and
+// residual in div_by stays in range whenever its quotient test passes
+__device__ __forceinline__ double safe_reciprocal(double b)
+{
+  const unsigned ex = (unsigned(__double2hiint(b)) >> 20) & 0x7ffu;
+  return ex - 723u > 600u ? __longlong_as_double(0x7ff8000000000000ll) : 1.0 / b;
+}
+__device__ __forceinline__ float safe_reciprocal(float b)
+{
+  const unsigned ex = (__float_as_uint(b) >> 23) & 0xffu;
+  return ex - 87u > 80u ? __uint_as_float(0x7fc00000u) : 1.0f / b;
+}
+
+__host__ __device__ constexpr int pad4(int n) { return (n + 3) & ~3; }
+// per-cell record of the fused kernel in shared memory: the matrix each row is multiplied by, detJ and 1 / detJ;
+// an odd number of entries, so lane = cell writes are free of bank conflicts
+template <int G, int TD>
+__host__ __device__ constexpr int cell_record() { return (G * TD + 2) | 1; }
+
 // MAP: BX_MAP_IDENTITY (value size VS, no matrix), BX_MAP_COVARIANT_PIOLA, BX_MAP_CONTRAVARIANT_PIOLA.
 // GEOM: J / detJ / K of the affine simplex cell from coords[nc][TD + 1][G]; otherwise A / detJ are read per cell:
 // A = K[nc][TD][G] (covariant) or J[nc][G][TD] (contravariant).
-// tab[8][rows][IN_VS]: the reference values of every row, transformed for state 0..7 of the row's sub-entity.
-template <typename T, int MAP, int G, int TD, bool GEOM, int PASSES, int VS>
-__global__ void __launch_bounds__(kThreads)
+// tab[nstates][rows][IN_VS]: the reference values of every row, transformed for state 0..7 of the row's sub-entity.
+//
+// A warp takes 32 consecutive cells per iteration.
+//   phase A, lane = cell: the cell's vertex coordinates (loaded into registers one iteration ahead), J, its adjugate and
+//     determinant, K = adj / det or 1 / detJ -- all 32 lanes busy, the IEEE divisions of 32 cells for the price of
+//     one -- written as the cell's record to shared memory; cell_info stays in the lane's register.
+//   phase B, `batch` cells at a time: per cell the record is read back with warp-uniform loads into registers, the
+//     lanes walk the cell's rows (descriptor of a row = first cell_info bit and mask of its sub-entity, one word of a
+//     shared table), pick the reference values of the row's state, map them and write the slice; the rows of the batch
+//     are one contiguous run of `out` and leave as ONE TMA bulk copy, the warp going on with the next batch in the
+//     other slice while the copy engine reads.
+template <typename T, int MAP, int G, int TD, bool GEOM, int VS>
+__global__ void __launch_bounds__(kThreads, 3)
     physical_basis_kernel(const T* __restrict__ tab, const T* __restrict__ coords, const T* __restrict__ A,
                           const T* __restrict__ detJ, const FusedParams p, T* __restrict__ out)
 {
@@ -206,125 +369,175 @@ __global__ void __launch_bounds__(kThreads)
   constexpr int OUT_VS = MAP == BX_MAP_IDENTITY ? VS : G;
   constexpr int MA = G * TD;
   constexpr int NX = (TD + 1) * G; // coordinates of an affine simplex cell
-  extern __shared__ __align__(16) unsigned char fused_smem[];
+  constexpr int REC = cell_record<G, TD>();
+  extern __shared__ __align__(128) unsigned char fused_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int rows = p.rows, E = rows * OUT_VS;
-  T* s_tab = reinterpret_cast<T*>(fused_smem); // [nstates][tab_stride]
-  constexpr int kExtra = kBatch * (MA + 1) + (GEOM ? kBatch * NX : 0);
-  T* slice = s_tab + p.nstates * p.tab_stride + warp * (E + kExtra);
-  T* sm = slice + E;                 // [kBatch][MA] matrices, then [kBatch] determinants
-  T* sx = sm + kBatch * (MA + 1);    // GEOM: [kBatch][NX] vertex coordinates
+  const int rows = p.rows, E = rows * OUT_VS, B = p.batch;
+  const int slice_stride = pad4(B * E);
+  T* s_tab = reinterpret_cast<T*>(fused_smem);                                            // [nstates][tab_stride]
+  uint32_t* s_desc = reinterpret_cast<uint32_t*>(s_tab + pad4(p.nstates * p.tab_stride)); // [rows]
+  T* wbase = reinterpret_cast<T*>(s_desc + pad4(rows)) + size_t(warp) * (p.nbuf * slice_stride + pad4(32 * REC));
+  T* slices = wbase;                       // [nbuf][batch][E]
+  T* rec = wbase + p.nbuf * slice_stride;  // [32][REC]
   for (int i = threadIdx.x; i < p.nstates * p.tab_stride; i += kThreads)
     s_tab[i] = tab[i];
-  // per-lane descriptors of the rows this lane owns: first cell_info bit and mask of the row's sub-entity
-  int shift[PASSES], mask[PASSES];
-#pragma unroll
-  for (int q = 0; q < PASSES; ++q)
+  for (int r = threadIdx.x; r < rows; r += kThreads)
   {
-    const int r = lane + 32 * q;
-    shift[q] = mask[q] = 0;
-    if (r < rows and p.cell_info)
+    uint32_t shift = 0, mask = 0;
+    if (p.cell_info)
     {
       const int slot = p.dof_slot[r % p.ndofs];
       if (slot >= 0)
       {
         const int4 si = p.slot_info[slot];
-        shift[q] = si.x;
-        mask[q] = si.y;
+        shift = uint32_t(si.x);
+        mask = uint32_t(si.y);
       }
     }
+    s_desc[r] = shift | mask << 5;
   }
   __syncthreads();
 
   const size_t warps = size_t(gridDim.x) * (kThreads / 32);
-  for (size_t c0 = (size_t(blockIdx.x) * (kThreads / 32) + warp) * kBatch; c0 < p.nc; c0 += warps * kBatch)
+  const size_t first = (size_t(blockIdx.x) * (kThreads / 32) + warp) * 32;
+  // ---- prefetch of the first cell of this lane ----
+  [[maybe_unused]] T pre[GEOM ? NX : (MAP == BX_MAP_IDENTITY ? 1 : MA + 1)];
+  auto fetch = [&](size_t c0)
   {
-    const int nb = int(min(size_t(kBatch), p.nc - c0));
-    uint32_t my_ci = 0;
-    if (p.cell_info and lane < nb)
-      my_ci = p.cell_info[c0 + lane];
+    const size_t c = min(c0 + lane, p.nc - 1);
     if constexpr (GEOM)
     {
-      for (int q = lane; q < nb * NX; q += 32)
-        sx[q] = coords[c0 * NX + q];
-      __syncwarp();
-      if (lane < nb)
+      if (sizeof(T) == 8 and p.vec_coords and NX % 2 == 0)
       {
-        // J(:, a) = x[1 + a] - x[0]: the P1 coordinate element's derivatives are -1 at vertex 0 and +1 at vertex
-        // 1 + a, so the general sum  0 + x0 * (-1) + ... + x[1 + a] * 1  reduces to this difference exactly
-        const T* x = sx + lane * NX;
+        const double2* x2 = reinterpret_cast<const double2*>(coords + c * NX);
+#pragma unroll
+        for (int k = 0; k < NX / 2; ++k)
+        {
+          const double2 v = x2[k];
+          pre[2 * k] = T(v.x);
+          pre[2 * k + 1] = T(v.y);
+        }
+      }
+      else
+      {
+#pragma unroll
+        for (int k = 0; k < NX; ++k)
+          pre[k] = coords[c * NX + k];
+      }
+    }
+    else if constexpr (MAP != BX_MAP_IDENTITY)
+    {
+#pragma unroll
+      for (int k = 0; k < MA; ++k)
+        pre[k] = A[c * MA + k];
+      if constexpr (MAP == BX_MAP_CONTRAVARIANT_PIOLA)
+        pre[MA] = detJ[c];
+    }
+  };
+  if (first < p.nc)
+    fetch(first);
+  int in_flight = 0, cur = 0; // committed bulk groups not yet waited for; slice in use
+  for (size_t c0 = first; c0 < p.nc; c0 += warps * 32)
+  {
+    const int nb = int(min(size_t(32), p.nc - c0));
+    const uint32_t my_ci = (p.cell_info and lane < nb) ? p.cell_info[c0 + lane] : 0u;
+    // ---- phase A: lane = cell ----
+    if constexpr (MAP != BX_MAP_IDENTITY)
+    {
+      T* mine = rec + lane * REC;
+      if constexpr (GEOM)
+      {
         T J[G][TD];
 #pragma unroll
         for (int g = 0; g < G; ++g)
 #pragma unroll
           for (int a = 0; a < TD; ++a)
-            J[g][a] = x[(1 + a) * G + g] - x[g];
+            J[g][a] = pre[(1 + a) * G + g] - pre[g];
         T adj[TD][G], div;
         adjugate<T, G, TD>(J, adj, div);
-        T* m = sm + lane * MA;
         if constexpr (MAP == BX_MAP_COVARIANT_PIOLA)
         {
 #pragma unroll
           for (int a = 0; a < TD; ++a)
 #pragma unroll
             for (int g = 0; g < G; ++g)
-              m[a * G + g] = adj[a][g] / div;
+              mine[a * G + g] = adj[a][g] / div;
         }
-        else if constexpr (MAP == BX_MAP_CONTRAVARIANT_PIOLA)
+        else
         {
 #pragma unroll
           for (int g = 0; g < G; ++g)
 #pragma unroll
             for (int a = 0; a < TD; ++a)
-              m[g * TD + a] = J[g][a];
-          sm[kBatch * MA + lane] = det_from_div<T, G, TD>(div);
+              mine[g * TD + a] = J[g][a];
+          const T det = det_from_div<T, G, TD>(div);
+          mine[MA] = det;
+          mine[MA + 1] = safe_reciprocal(det);
         }
       }
-    }
-    else if constexpr (MAP != BX_MAP_IDENTITY)
-    {
-      for (int q = lane; q < nb * MA; q += 32)
-        sm[q] = A[c0 * MA + q];
-      if constexpr (MAP == BX_MAP_CONTRAVARIANT_PIOLA)
-        if (lane < nb)
-          sm[kBatch * MA + lane] = detJ[c0 + lane];
+      else
+      {
+#pragma unroll
+        for (int k = 0; k < MA; ++k)
+          mine[k] = pre[k];
+        if constexpr (MAP == BX_MAP_CONTRAVARIANT_PIOLA)
+        {
+          mine[MA] = pre[MA];
+          mine[MA + 1] = safe_reciprocal(pre[MA]);
+        }
+      }
+      if (c0 + warps * 32 < p.nc)
+        fetch(c0 + warps * 32); // the next iteration's cell: in flight during phase B
     }
     __syncwarp();
-    for (int bi = 0; bi < nb; ++bi)
+    // ---- phase B ----
+    for (int b0 = 0; b0 < nb; b0 += B)
     {
-      const uint32_t ci = __shfl_sync(0xffffffffu, my_ci, bi);
-      [[maybe_unused]] T a[MAP == BX_MAP_COVARIANT_PIOLA ? TD : G][MAP == BX_MAP_COVARIANT_PIOLA ? G : TD];
-      [[maybe_unused]] T det = T(1);
-      if constexpr (MAP == BX_MAP_COVARIANT_PIOLA)
+      const int cells = min(B, nb - b0);
+      T* slice = slices + cur * slice_stride;
+      if (in_flight >= p.nbuf)
       {
-#pragma unroll
-        for (int i = 0; i < TD; ++i)
-#pragma unroll
-          for (int j = 0; j < G; ++j)
-            a[i][j] = sm[bi * MA + i * G + j];
-      }
-      else if constexpr (MAP == BX_MAP_CONTRAVARIANT_PIOLA)
-      {
-#pragma unroll
-        for (int i = 0; i < G; ++i)
-#pragma unroll
-          for (int j = 0; j < TD; ++j)
-            a[i][j] = sm[bi * MA + i * TD + j];
-        det = sm[kBatch * MA + bi];
-      }
-#pragma unroll
-      for (int q = 0; q < PASSES; ++q)
-      {
-        const int r = lane + 32 * q;
-        if (r < rows)
+        // the copy that last used this slice has been read out of shared memory
+        if (lane == 0)
         {
-          const int st = int(ci >> shift[q]) & mask[q];
+          if (p.nbuf == 2)
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        in_flight = p.nbuf - 1;
+        __syncwarp();
+      }
+      for (int bi = 0; bi < cells; ++bi)
+      {
+        const int cell = b0 + bi;
+        const uint32_t ci = __shfl_sync(0xffffffffu, my_ci, cell);
+        [[maybe_unused]] T m[MA];
+        [[maybe_unused]] T det = T(1), inv = T(1);
+        if constexpr (MAP != BX_MAP_IDENTITY)
+        {
+          const T* rc = rec + cell * REC;
+#pragma unroll
+          for (int k = 0; k < MA; ++k)
+            m[k] = rc[k];
+          if constexpr (MAP == BX_MAP_CONTRAVARIANT_PIOLA)
+          {
+            det = rc[MA];
+            inv = rc[MA + 1];
+          }
+        }
+        T* o = slice + bi * E;
+#pragma unroll 1
+        for (int r = lane; r < rows; r += 32)
+        {
+          const uint32_t d = s_desc[r];
+          const int st = int(ci >> (d & 31u)) & int(d >> 5);
           const T* u = s_tab + st * p.tab_stride + r * IN_VS;
           if constexpr (MAP == BX_MAP_IDENTITY)
           {
 #pragma unroll
             for (int i = 0; i < VS; ++i)
-              slice[r * VS + i] = u[i];
+              o[r * VS + i] = u[i];
           }
           else
           {
@@ -341,28 +554,51 @@ __global__ void __launch_bounds__(kThreads)
                 // out[i] = sum_k K[k][i] in[k]   (maps.h:73-94)
 #pragma unroll
                 for (int k = 0; k < TD; ++k)
-                  acc += a[k][i] * uu[k];
+                  acc += m[k * G + i] * uu[k];
               }
               else
               {
                 // out[i] = (sum_k J[i][k] in[k]) / det   (maps.h:100-124)
 #pragma unroll
                 for (int k = 0; k < TD; ++k)
-                  acc += a[i][k] * uu[k];
-                acc = acc / det;
+                  acc += m[i * TD + k] * uu[k];
+                acc = div_by(acc, det, inv);
               }
-              slice[r * OUT_VS + i] = acc;
+              o[r * OUT_VS + i] = acc;
             }
           }
         }
       }
-      __syncwarp();
-      T* o = out + (c0 + bi) * p.out_pitch;
-      for (int e = lane; e < E; e += 32)
-        o[e] = slice[e];
-      __syncwarp(); // the slice is overwritten by the next cell
+      if (p.bulk and cells == B)
+      {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0)
+        {
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + (c0 + b0) * size_t(E)),
+                       "r"(uint32_t(__cvta_generic_to_shared(slice))), "r"(uint32_t(B * E * sizeof(T)))
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        ++in_flight;
+        cur = cur + 1 == p.nbuf ? 0 : cur + 1;
+      }
+      else
+      {
+        __syncwarp();
+        for (int bi = 0; bi < cells; ++bi)
+        {
+          T* g = out + (c0 + b0 + bi) * p.out_pitch;
+          for (int e = lane; e < E; e += 32)
+            g[e] = slice[bi * E + e];
+        }
+        __syncwarp(); // the slice is overwritten by the next batch
+      }
     }
+    __syncwarp(); // the records are overwritten by the next iteration's phase A
   }
+  if (in_flight > 0 and lane == 0)
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // ---- launchers -------------------------------------------------------------------------------------------------
@@ -382,6 +618,20 @@ int persistent_grid(K kern, size_t want, size_t smem)
 template <typename T, int G, int TD>
 void launch_geometry(const T* coords, const T* dphi, size_t nc, int nv, int npts, T* J, T* detJ, T* K, cudaStream_t s)
 {
+  if (!dphi)
+  {
+    // affine simplex cells: warp-per-32-cells kernel with coalesced loads and bulk copy-out
+    constexpr int NX = (TD + 1) * G, MA = G * TD, XP = NX | 1;
+    constexpr int kWarpT = ((32 * (XP > MA ? XP : MA) + 3) & ~3) + ((32 * MA + 3) & ~3) + 32;
+    auto kern = geometry_affine_kernel<T, G, TD>;
+    const size_t smem = size_t(kThreads / 32) * kWarpT * sizeof(T);
+    auto aligned = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
+    const int bulk = aligned(J) and aligned(K) and aligned(detJ) and (32 * MA * sizeof(T)) % 16 == 0;
+    const int grid = persistent_grid(kern, ceil_div(nc, size_t(kThreads)), smem);
+    kern<<<grid, kThreads, smem, s>>>(coords, nc, J, detJ, K, bulk);
+    BX_LAUNCHED();
+    return;
+  }
   auto kern = geometry_kernel<T, G, TD>;
   const size_t tbl = size_t(TD) * npts * nv * sizeof(T);
   const int in_smem = tbl <= 96 * 1024;
@@ -391,30 +641,71 @@ void launch_geometry(const T* coords, const T* dphi, size_t nc, int nv, int npts
   BX_LAUNCHED();
 }
 
+// Tuning aid (development only): BX_FUSED_TUNE="b=2,nbuf=2" overrides the cells per slice and the slices per warp.
+struct FusedTune
+{
+  int b = 0, nbuf = 0;
+};
+inline const FusedTune& fused_tune()
+{
+  static FusedTune t = []()
+  {
+    FusedTune v;
+    if (const char* e = std::getenv("BX_FUSED_TUNE"))
+    {
+      std::string str(e);
+      auto get = [&](const char* key, int& out)
+      {
+        const size_t k = str.find(key);
+        if (k != std::string::npos)
+          out = std::atoi(str.c_str() + k + std::strlen(key));
+      };
+      get("b=", v.b);
+      get("nbuf=", v.nbuf);
+    }
+    return v;
+  }();
+  return t;
+}
+
 template <typename T, int MAP, int G, int TD, bool GEOM, int VS>
-void launch_fused(const T* tab, const T* coords, const T* A, const T* detJ, const FusedParams& p, T* out, cudaStream_t s)
+void launch_fused(const T* tab, const T* coords, const T* A, const T* detJ, FusedParams p, T* out, cudaStream_t s)
 {
   constexpr int OUT_VS = MAP == BX_MAP_IDENTITY ? VS : G;
-  constexpr int kExtra = kBatch * (G * TD + 1) + (GEOM ? kBatch * (TD + 1) * G : 0);
-  const size_t smem = (size_t(p.nstates) * p.tab_stride + size_t(kThreads / 32) * (size_t(p.rows) * OUT_VS + kExtra)) * sizeof(T);
+  constexpr int REC = cell_record<G, TD>();
+  const int E = p.rows * OUT_VS;
+  auto smem_of = [&](int batch, int nbuf)
+  {
+    return size_t(pad4(p.nstates * p.tab_stride)) * sizeof(T) + size_t(pad4(p.rows)) * 4
+           + size_t(kThreads / 32) * (size_t(nbuf) * pad4(batch * E) + pad4(32 * REC)) * sizeof(T);
+  };
+  const bool contiguous = p.out_pitch == size_t(E) and reinterpret_cast<uintptr_t>(out) % 16 == 0;
+  // cells per slice and slices per warp: the largest configuration that leaves three CTAs per SM (24 warps); a batch
+  // whose rows are a whole number of 16-byte units leaves by TMA bulk copy
+  p.batch = 1;
+  p.nbuf = 1;
+  static const int menu[][2] = {{4, 2}, {2, 2}, {4, 1}, {2, 1}, {1, 2}};
+  for (const auto& m : menu)
+    if (smem_of(m[0], m[1]) <= 72 * 1024 and (size_t(m[0]) * E * sizeof(T)) % 16 == 0)
+    {
+      p.batch = m[0];
+      p.nbuf = m[1];
+      break;
+    }
+  if (fused_tune().b > 0 and fused_tune().b <= 32)
+    p.batch = fused_tune().b;
+  if (fused_tune().nbuf == 1 or fused_tune().nbuf == 2)
+    p.nbuf = fused_tune().nbuf;
+  p.bulk = contiguous and (size_t(p.batch) * E * sizeof(T)) % 16 == 0;
+  p.vec_coords = reinterpret_cast<uintptr_t>(coords) % 16 == 0;
+  const size_t smem = smem_of(p.batch, p.nbuf);
   if (smem > 200 * 1024)
     fail(BX_ERR_UNSUPPORTED, "physical_basis: the point chunk does not fit in shared memory");
-  const size_t want = ceil_div(p.nc, size_t(kThreads / 32) * kBatch);
-  auto go = [&](auto kern)
-  {
-    const int grid = persistent_grid(kern, want, smem);
-    kern<<<grid, kThreads, smem, s>>>(tab, coords, A, detJ, p, out);
-    BX_LAUNCHED();
-  };
-  const int passes = (p.rows + 31) / 32;
-  if (passes <= 1)
-    go(physical_basis_kernel<T, MAP, G, TD, GEOM, 1, VS>);
-  else if (passes <= 2)
-    go(physical_basis_kernel<T, MAP, G, TD, GEOM, 2, VS>);
-  else if (passes <= 4)
-    go(physical_basis_kernel<T, MAP, G, TD, GEOM, 4, VS>);
-  else
-    go(physical_basis_kernel<T, MAP, G, TD, GEOM, 8, VS>);
+  const size_t want = ceil_div(p.nc, size_t(kThreads));
+  auto kern = physical_basis_kernel<T, MAP, G, TD, GEOM, VS>;
+  const int grid = persistent_grid(kern, want, smem);
+  kern<<<grid, kThreads, smem, s>>>(tab, coords, A, detJ, p, out);
+  BX_LAUNCHED();
 }
 
 template <typename T, int MAP, bool GEOM>

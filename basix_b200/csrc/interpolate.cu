@@ -207,4 +207,132 @@ void interpolate_device(const bx_element& e, int layout, const T* values, size_t
 }
 template void interpolate_device<double>(const bx_element&, int, const double*, size_t, double*, cudaStream_t);
 template void interpolate_device<float>(const bx_element&, int, const float*, size_t, float*, cudaStream_t);
+// ---- compute_interpolation_operator (reference cpp/basix/interpolation.cpp:16-116) --------------------------------
+// The matrix that maps the coefficients of a function in `from` to the coefficients of its interpolant in `to`:
+// tabulate `from` at the interpolation points of `to`, apply `to`'s interpolation matrix.  Composition of two device
+// paths of this library: FiniteElement::tabulate (any kernel of tabulate.cu) and the batched interpolation above, with
+// the columns of the operator playing the role of cells; two small kernels reorder the table into `to`'s value layout
+// and the coefficients into the reference's output layout.
+namespace
+{
+// values[(j, i)][c]: one "cell" per column of the operator, in the component-major layout of `to`
+//   equal value sizes   (cells = dim_from, i = 0):          values[j][k * npts + l] = tab[l][j][k]
+//   vs_to == 1          (cells = dim_from * vs_from):       values[(j, i)][l]       = tab[l][j][i]
+//   vs_from == 1        (cells = dim_from * vs_to):         values[(j, i)][c]       = c in block i ? tab[l][j][0] : 0
+__global__ void interp_op_gather_kernel(const double* __restrict__ tab, int npts, int dim_from, int vs_from, int vs_to,
+                                        double* __restrict__ values)
+{
+  const int K = vs_to * npts;
+  const int per = vs_from == vs_to ? 1 : (vs_to == 1 ? vs_from : vs_to);
+  const size_t total = size_t(dim_from) * per * K;
+  for (size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += size_t(gridDim.x) * blockDim.x)
+  {
+    const int c = int(t % K);
+    const int cell = int(t / K), j = cell / per, i = cell % per;
+    const int k = c / npts, l = c % npts;
+    double v;
+    if (vs_from == vs_to)
+      v = tab[(size_t(l) * dim_from + j) * vs_from + k];
+    else if (vs_to == 1)
+      v = tab[(size_t(l) * dim_from + j) * vs_from + i];
+    else
+      v = k == i ? tab[size_t(l) * dim_from + j] : 0.0;
+    values[t] = v;
+  }
+}
+
+// coefficients[(j, i)][d] -> out: equal value sizes out[d][j]; vs_to == 1 out[i + d * vs_from][j]; vs_from == 1
+// out[d][i + j * vs_to]
+__global__ void interp_op_scatter_kernel(const double* __restrict__ coef, int dim_to, int dim_from, int vs_from, int vs_to,
+                                         double* __restrict__ out)
+{
+  const int per = vs_from == vs_to ? 1 : (vs_to == 1 ? vs_from : vs_to);
+  const size_t total = size_t(dim_from) * per * dim_to;
+  for (size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += size_t(gridDim.x) * blockDim.x)
+  {
+    const int d = int(t % dim_to);
+    const int cell = int(t / dim_to), j = cell / per, i = cell % per;
+    size_t o;
+    if (vs_from == vs_to)
+      o = size_t(d) * dim_from + j;
+    else if (vs_to == 1)
+      o = (size_t(i) + size_t(d) * vs_from) * dim_from + j;
+    else
+      o = size_t(d) * (size_t(dim_from) * vs_to) + i + size_t(j) * vs_to;
+    out[o] = coef[t];
+  }
+}
+} // namespace
+
+void interpolation_operator_shape(const bx_element& from, const bx_element& to, int32_t shape[2])
+{
+  if (from.cell_type != to.cell_type)
+    fail(BX_ERR_RUNTIME, "Cannot interpolate between elements defined on different cell types.");
+  if (from.vs == to.vs)
+  {
+    shape[0] = to.ndofs;
+    shape[1] = from.ndofs;
+  }
+  else if (to.vs == 1)
+  {
+    shape[0] = to.ndofs * from.vs;
+    shape[1] = from.ndofs;
+  }
+  else if (from.vs == 1)
+  {
+    shape[0] = to.ndofs;
+    shape[1] = from.ndofs * to.vs;
+  }
+  else
+    fail(BX_ERR_RUNTIME, "Cannot interpolate between elements with this combination of value sizes.");
+}
+
+template <typename T>
+void tabulate_device(const bx_element& e, int nd, const T* x, size_t npts, T* basis, size_t out_pts, cudaStream_t s);
+
+// out: device pointer, shape as interpolation_operator_shape, row-major
+void interpolation_operator_device(const bx_element& from, const bx_element& to, double* out, cudaStream_t s)
+{
+  int32_t shape[2];
+  interpolation_operator_shape(from, to, shape);
+  if (to.interp_npts == 0)
+    fail(BX_ERR_RUNTIME, "compute_interpolation_operator: the target element was built without points() / "
+                         "interpolation_matrix()");
+  require_device(from);
+  require_device(to);
+  const int npts = to.interp_npts, K = to.vs * npts;
+  const int per = from.vs == to.vs ? 1 : (to.vs == 1 ? from.vs : to.vs);
+  const size_t ncells = size_t(from.ndofs) * per;
+  double *x = nullptr, *tab = nullptr, *values = nullptr, *coef = nullptr;
+  BX_CUDA(cudaMallocAsync(&x, size_t(npts) * to.tdim * sizeof(double), s));
+  BX_CUDA(cudaMallocAsync(&tab, size_t(npts) * from.ndofs * from.vs * sizeof(double), s));
+  BX_CUDA(cudaMallocAsync(&values, (ncells * K + 64) * sizeof(double), s)); // slack: the kernel prefetches A fragments
+  BX_CUDA(cudaMallocAsync(&coef, ncells * to.ndofs * sizeof(double), s));
+  auto release = [&]()
+  {
+    cudaFreeAsync(x, s);
+    cudaFreeAsync(tab, s);
+    cudaFreeAsync(values, s);
+    cudaFreeAsync(coef, s);
+  };
+  try
+  {
+    BX_CUDA(cudaMemcpyAsync(x, to.points.data(), size_t(npts) * to.tdim * sizeof(double), cudaMemcpyHostToDevice, s));
+    tabulate_device<double>(from, 0, x, size_t(npts), tab, size_t(npts), s);
+    BX_CUDA(cudaMemsetAsync(values + ncells * K, 0, 64 * sizeof(double), s));
+    const int grid = int(std::min<size_t>(ceil_div(ncells * K, size_t(256)), size_t(sm_count()) * 8));
+    interp_op_gather_kernel<<<std::max(grid, 1), 256, 0, s>>>(tab, npts, from.ndofs, from.vs, to.vs, values);
+    BX_LAUNCHED();
+    interpolate_device<double>(to, BX_INTERP_COMPONENT_MAJOR, values, ncells, coef, s);
+    const int grid2 = int(std::min<size_t>(ceil_div(ncells * to.ndofs, size_t(256)), size_t(sm_count()) * 8));
+    interp_op_scatter_kernel<<<std::max(grid2, 1), 256, 0, s>>>(coef, to.ndofs, from.ndofs, from.vs, to.vs, out);
+    BX_LAUNCHED();
+  }
+  catch (...)
+  {
+    release();
+    throw;
+  }
+  release();
+}
 } // namespace bx

@@ -1003,3 +1003,22 @@ def create_element(family, celltype, degree: int, lagrange_variant=LagrangeVaria
         lv = int(LagrangeVariant.gll_warped)  # the reference resolves "unset" the same way (e-lagrange.cpp:491-500)
     return FiniteElement._from_handle(h, family=family, lagrange_variant=lv, dpc_variant=dpc_variant,
                                       discontinuous=discontinuous, degree=degree)
+
+
+def compute_interpolation_operator(e0: FiniteElement, e1: FiniteElement, device=None):
+    """``basix.compute_interpolation_operator`` (python/basix/interpolation.py; interpolation.cpp:16-116): the matrix
+    mapping coefficients in ``e0`` to the coefficients of the interpolant in ``e1``, composed on the device from
+    ``tabulate`` (e0 at e1's points) and the batched interpolation (e1's matrix).  Returns a numpy array, or a CUDA
+    torch tensor when ``device`` (a torch device) is given."""
+    shape = (C.c_int32 * 2)()
+    check(lib().bx_compute_interpolation_operator_f64(e0._h, e1._h, shape, None, BX_MEM_HOST, None))
+    if device is None:
+        out = np.empty((shape[0], shape[1]), dtype=np.float64)
+        check(lib().bx_compute_interpolation_operator_f64(e0._h, e1._h, shape, out.ctypes.data, BX_MEM_HOST, None))
+        return out
+    import torch
+
+    out = torch.empty((shape[0], shape[1]), dtype=torch.float64, device=device)
+    check(lib().bx_compute_interpolation_operator_f64(e0._h, e1._h, shape, out.data_ptr(), BX_MEM_DEVICE,
+                                                      torch.cuda.current_stream(out.device).cuda_stream))
+    return out

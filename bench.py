@@ -508,6 +508,131 @@ class TApply:
             r.T_apply_batch("T_apply", d, self.bs, ci, nthreads=cores)
 
 
+def device_tet_coords(nc, seed):
+    """Vertex coordinates of nc affine tetrahedra: the reference tetrahedron + 0.2 N(0,1) per coordinate."""
+    import torch
+
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    base = torch.zeros(4, 3, dtype=torch.float64, device="cuda")
+    base[1:] = torch.eye(3, dtype=torch.float64, device="cuda")
+    return (base[None] + 0.2 * torch.randn(nc, 4, 3, generator=g, device="cuda", dtype=torch.float64)).contiguous()
+
+
+class PhysicalBasis:
+    """tabulate-once -> T_apply -> push_forward fused (geometry from vertex coordinates on chip), or
+    the cell geometry alone (J, detJ, K from vertex coordinates)."""
+    metric, unit = METRIC_CELLS, "cells/s"
+    bound = "hbm"
+
+    def __init__(self, element, ref_args, nc, npts, desc, geometry_only=False):
+        self.element_name, self.ref_args, self.nc, self.npts, self.desc = element, ref_args, nc, npts, desc
+        self.geometry_only = geometry_only
+
+    def setup(self, rank, device_only=False):
+        import torch
+
+        import basix_b200 as bx
+
+        self.e = load_element(self.element_name, self.ref_args)
+        e, nc = self.e, self.nc
+        self.coords = device_tet_coords(nc, 31 + rank)
+        self.ci = device_cell_info(nc, 11 + rank)
+        self.X = device_points(3, self.npts, 5)
+        self.U = e.tabulate(0, self.X)[0].contiguous()
+        self.units_per_step = self.units_per_launch = nc
+        self.launches_per_step = 1
+        self.geometry = bx.geometry
+        if self.geometry_only:
+            self.alg_bytes = nc * (96 + 72 + 8 + 72)
+            self.config = {"workload": self.desc, "cells_per_gpu": nc,
+                           "l2": "arrays are %.2f GB per step (>> 126 MB L2)" % (self.alg_bytes / 1e9)}
+        else:
+            rows = self.npts * e.dim
+            self.out_bytes = rows * 3 * 8
+            self.alg_bytes = nc * (96 + 4 + self.out_bytes)
+            # the same result through the separate calls: geometry writes J / detJ / K; the replicated reference values
+            # are transformed in place (read + write of the movable dofs) and pushed forward (read values and K, write)
+            ed = e.entity_dofs
+            movable = sum(len(d) for dim in range(1, 3) for d in ed[dim])
+            unfused = 96 + 152 + self.npts * 2 * movable * 24 + 4 + (rows * 24 + 72) + rows * 24
+            self.config = {"workload": self.desc, "cells_per_gpu": nc, "points_per_cell": self.npts, "rows_per_cell": rows,
+                           "bytes_per_cell_fused": 100 + self.out_bytes, "bytes_per_cell_three_calls": unfused,
+                           "l2": "arrays are %.2f GB per step (>> 126 MB L2)" % (self.alg_bytes / 1e9)}
+        self.flops = 0.0
+        if not device_only:
+            self.coords_host = self.coords.cpu().pin_memory()
+            self.ci_host = self.ci.cpu().pin_memory()
+
+    def step(self):
+        if self.geometry_only:
+            self.result = self.geometry(self.coords)
+        else:
+            self.result = self.e.physical_basis(None, U=self.U, coords=self.coords, cell_info=self.ci)
+
+    def e2e_setup(self, avail_bytes):
+        import torch
+
+        self.e2e_units = self.nc
+        self.result = None
+        torch.cuda.empty_cache()
+        if self.geometry_only:
+            self.out_host = [torch.empty(s, dtype=torch.float64).pin_memory() for s in
+                             ((self.nc, 3, 3), (self.nc,), (self.nc, 3, 3))]
+            self.h2d, self.d2h = self.nc * 96, self.nc * 152
+        else:
+            self.out_host = torch.empty((self.nc, self.npts, self.e.dim, 3), dtype=torch.float64).pin_memory()
+            self.X_host = self.X.cpu()
+            self.h2d, self.d2h = self.nc * 100 + self.X_host.numel() * 8, self.out_host.numel() * 8
+        return {"cells_per_gpu": self.nc}
+
+    def e2e_step(self):
+        from basix_b200 import _capi
+
+        L = _capi.lib()
+        if self.geometry_only:
+            J, d, K = self.out_host
+            _capi.check(L.bx_geometry_f64(self.coords_host.data_ptr(), None, self.nc, 4, 3, 3, 1, J.data_ptr(), d.data_ptr(),
+                                          K.data_ptr(), _capi.BX_MEM_HOST, None))
+        else:
+            # points in, physical basis functions out: the reference values never exist on the host
+            _capi.check(L.bx_physical_basis_f64(self.e._h, 0, self.X_host.data_ptr(), self.npts, 3,
+                                                self.coords_host.data_ptr(), None, None, None, self.ci_host.data_ptr(),
+                                                self.nc, 3, self.out_host.data_ptr(), _capi.BX_MEM_HOST, None))
+
+    cpu_kind = "reference"
+
+    def cpu_setup(self, cores):
+        from oracle import ref, restate
+
+        r = ref.RefElement(*self.ref_args)
+        n = int(min(self.nc, max(50_000, 2e6 * cores / (self.npts * r.dim))))
+        rng = np.random.default_rng(31)
+        base = np.zeros((4, 3))
+        base[1:] = np.eye(3)
+        coords = base[None] + 0.2 * rng.standard_normal((n, 4, 3))
+        if self.geometry_only:
+            self.cpu_kind = "port"
+            self._cpu = (restate, coords)
+            return n, f"{n} cells per step, oracle/restate.py geometry (numpy, vectorised over cells; the reference has no batched geometry)"
+        X = random_points(3, self.npts, 5)
+        U = r.tabulate(0, X)[0]
+        self._cpu = (r, restate, coords, random_cell_info(n, 11), U, cores)
+        return n, (f"{n} cells per step over {cores} std::threads: the reference's T_apply (block size 3) on the replicated "
+                   f"reference values and push_forward, oracle/_ref (unmodified reference, g++ -O2); geometry by numpy")
+
+    def cpu_step(self):
+        if self.geometry_only:
+            restate, coords = self._cpu
+            self._cpu_out = restate.geometry(coords)
+            return
+        r, restate, coords, ci, U, cores = self._cpu
+        n, npts = len(coords), self.npts
+        J, detJ, K = restate.geometry(coords)
+        rep = np.ascontiguousarray(np.broadcast_to(U.reshape(1, npts, -1), (n, npts, U.shape[1] * 3))).reshape(n * npts, -1)
+        r.T_apply_batch("T_apply", rep, 3, np.repeat(ci, npts), nthreads=cores)
+        self._cpu_out = r.push_forward(rep.reshape(n, npts * U.shape[1], 3), J, detJ, K, nthreads=cores)
+
+
 class Interpolate:
     """coefficients = interpolation_matrix @ values over many cells (the step after pull_back)."""
     metric, unit = METRIC_CELLS, "cells/s"
@@ -599,6 +724,20 @@ WORKLOADS = {
     "t_apply_rt4_block3": lambda: TApply(
         "RT4_tetrahedron_legendre", (2, 3, 4, 11), 20_000_000, 3, False,
         "RT degree 4 tetrahedron, T_apply(block 3) over 20M cells, random cell_info"),
+    "geometry_tet": lambda: PhysicalBasis(
+        "N1curl3_tetrahedron_legendre", (3, 3, 3, 11), 20_000_000, 1,
+        "J, detJ, K of 20M affine tetrahedra from their vertex coordinates", geometry_only=True),
+    "physical_basis_n1curl3": lambda: PhysicalBasis(
+        "N1curl3_tetrahedron_legendre", (3, 3, 3, 11), 20_000_000, 1,
+        "N1curl degree 3 tetrahedron: tabulate-once -> T_apply -> covariant Piola push_forward fused, geometry from vertex "
+        "coordinates on chip, 20M cells x 1 point (45 rows)"),
+    "physical_basis_rt4": lambda: PhysicalBasis(
+        "RT4_tetrahedron_legendre", (2, 3, 4, 11), 10_000_000, 1,
+        "RT degree 4 tetrahedron: tabulate-once -> T_apply -> contravariant Piola push_forward fused, geometry from vertex "
+        "coordinates on chip, 10M cells x 1 point (70 rows)"),
+    "physical_basis_n1curl3_4pts": lambda: PhysicalBasis(
+        "N1curl3_tetrahedron_legendre", (3, 3, 3, 11), 5_000_000, 4,
+        "N1curl degree 3 tetrahedron: fused physical basis at 4 points per cell (180 rows), 5M cells"),
     "interpolate_n1curl3": lambda: Interpolate(
         "N1curl3_tetrahedron_legendre", (3, 3, 3, 11), 20_000_000,
         "N1curl degree 3 tetrahedron, interpolation_matrix (45 x 141) applied to 20M cells of point values"),
@@ -628,6 +767,9 @@ SIDE_CONFIGS = [
     ("t_apply_rt4_block3", {"nc": 50_000_000}),
     ("permute_p5_tet", {}),
     ("interpolate_n1curl3", {}),
+    ("geometry_tet", {}),
+    ("physical_basis_n1curl3", {}),
+    ("physical_basis_rt4", {}),
 ]
 
 
@@ -977,7 +1119,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     w = WORKLOADS[args.workload]()
     if args.units > 0:
-        if hasattr(w, "npts"):
+        if isinstance(w, Tabulate):
             w.npts = args.units
         else:
             w.nc = args.units

@@ -352,6 +352,15 @@ extern "C"
   int bx_interpolate_f32(const bx_element* e, int layout, const float* values, size_t nc, float* coefficients,
                          int mem, bx_stream_t stream);
 
+  /* Replaces basix::compute_interpolation_operator (interpolation.cpp:16-116; python
+     basix.compute_interpolation_operator): the matrix taking the coefficients of a function in `from` to those of its
+     interpolant in `to` -- `from` tabulated at to's points(), to's interpolation_matrix() applied -- composed on the
+     device from bx_tabulate and bx_interpolate.  shape: {dim_to, dim_from} (equal value sizes), {dim_to * vs_from,
+     dim_from} (scalar target) or {dim_to, dim_from * vs_to} (scalar source); same errors as the reference otherwise.
+     out[shape[0]][shape[1]] row-major; out == NULL returns the shape only. */
+  int bx_compute_interpolation_operator_f64(const bx_element* from, const bx_element* to, int32_t shape[2], double* out,
+                                            int mem, bx_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

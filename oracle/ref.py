@@ -69,6 +69,7 @@ def lib():
                                                           C.c_void_p, C.c_int, C.c_int]
         L.bxref_entity_jacobians.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.bxref_sub_entity_geometry.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.bxref_compute_interpolation_operator.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.bxref32_create_element.restype = C.c_void_p
         L.bxref32_create_element.argtypes = [C.c_int] * 6 + [C.c_void_p, C.c_int]
         L.bxref32_destroy_element.argtypes = [C.c_void_p]
@@ -127,6 +128,15 @@ def sub_entity_geometry(cell: int, dim: int, index: int) -> np.ndarray:
     _check(lib().bxref_sub_entity_geometry(int(cell), int(dim), int(index), _ptr(shp), None))
     out = np.empty(tuple(int(v) for v in shp), dtype=np.float64)
     _check(lib().bxref_sub_entity_geometry(int(cell), int(dim), int(index), _ptr(shp), _ptr(out)))
+    return out
+
+
+def compute_interpolation_operator(e0: "RefElement", e1: "RefElement") -> np.ndarray:
+    """reference basix::compute_interpolation_operator (interpolation.cpp:16-116)."""
+    shp = np.zeros(2, dtype=np.int32)
+    _check(lib().bxref_compute_interpolation_operator(e0._h, e1._h, _ptr(shp), None))
+    out = np.empty((int(shp[0]), int(shp[1])), dtype=np.float64)
+    _check(lib().bxref_compute_interpolation_operator(e0._h, e1._h, _ptr(shp), _ptr(out)))
     return out
 
 

@@ -16,6 +16,7 @@
 // only call the reference once per cell/chunk (the reference itself is serial).
 #include <basix/cell.h>
 #include <basix/finite-element.h>
+#include <basix/interpolation.h>
 #include <basix/polyset.h>
 
 #include <algorithm>
@@ -511,6 +512,20 @@ int bxref_sub_entity_geometry(int cell, int dim, int index, int* shape, double* 
       [&]()
       {
         auto [data, shp] = cell::sub_entity_geometry<double>(static_cast<cell::type>(cell), dim, index);
+        shape[0] = static_cast<int>(shp[0]);
+        shape[1] = static_cast<int>(shp[1]);
+        if (out)
+          std::copy(data.begin(), data.end(), out);
+      });
+}
+
+// basix::compute_interpolation_operator (interpolation.cpp:16-116): shape (rows, cols)
+int bxref_compute_interpolation_operator(void* from, void* to, int* shape, double* out)
+{
+  return guarded(
+      [&]()
+      {
+        auto [data, shp] = basix::compute_interpolation_operator<double>(*static_cast<FE*>(from), *static_cast<FE*>(to));
         shape[0] = static_cast<int>(shp[0]);
         shape[1] = static_cast<int>(shp[1]);
         if (out)

@@ -143,3 +143,55 @@ def test_interpolate_errors(ref):
                             entity_transformations=r.entity_transformations)
     with pytest.raises(RuntimeError, match="without points"):
         bare.interpolate_batch(np.zeros((3, 18)))
+
+
+# ---- compute_interpolation_operator (interpolation.cpp:16-116) on the device --------------------------------------------
+OPERATOR_PAIRS = [
+    ((1, 3, 2, 2), (1, 3, 3, 2)),      # P2 -> P3 tetrahedron (equal value sizes)
+    ((1, 3, 3, 2), (1, 3, 1, 2)),      # P3 -> P1
+    ((3, 3, 2, 11), (2, 3, 2, 11)),    # N1curl2 -> RT2 (vector to vector)
+    ((2, 2, 2, 11), (3, 2, 3, 11)),    # RT2 -> N1curl3 triangle
+    ((3, 3, 1, 11), (1, 3, 2, 2)),     # vector source, scalar target: one block per component
+    ((1, 2, 3, 2), (2, 2, 2, 11)),     # scalar source, vector target
+    ((1, 5, 2, 2), (1, 5, 1, 2)),      # Q2 -> Q1 hexahedron
+    ((1, 4, 3, 2), (1, 4, 3, 1)),      # Q3 gll -> Q3 equispaced quadrilateral
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("a0,a1", OPERATOR_PAIRS)
+def test_compute_interpolation_operator(ref, a0, a1):
+    """Same matrix as basix::compute_interpolation_operator on the same pair of (reference-built) elements."""
+    import torch
+
+    import basix_b200 as bx
+    from conftest import make_pair
+
+    r0, e0 = make_pair(ref, *a0)
+    r1, e1 = make_pair(ref, *a1)
+    want = ref.compute_interpolation_operator(r0, r1)
+    got = bx.compute_interpolation_operator(e0, e1)
+    assert got.shape == want.shape
+    assert np.max(np.abs(got - want)) <= 1e-12 * max(1.0, np.max(np.abs(want)))
+    dev = bx.compute_interpolation_operator(e0, e1, device=torch.device("cuda"))
+    assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), got)
+
+
+@pytest.mark.gpu
+def test_compute_interpolation_operator_errors_and_native_elements(ref):
+    import basix_b200 as bx
+    from conftest import make_pair
+
+    _, tri = make_pair(ref, 1, 2, 2, 2)
+    _, tet = make_pair(ref, 1, 3, 2, 2)
+    with pytest.raises(RuntimeError, match="different cell types"):
+        bx.compute_interpolation_operator(tri, tet)
+    # interpolating an element into itself gives the identity; natively built elements (Gauss-Jacobi points)
+    for args in ((1, 3, 4, 2), (3, 3, 2, 11), (2, 2, 3, 11)):
+        e = bx.create_element(*args)
+        op = bx.compute_interpolation_operator(e, e)
+        assert np.max(np.abs(op - np.eye(e.dim))) < 1e-11
+    # P2 -> P3 of the native factory against the reference pair
+    want = ref.compute_interpolation_operator(ref.RefElement(1, 3, 2, 2), ref.RefElement(1, 3, 3, 2))
+    got = bx.compute_interpolation_operator(bx.create_element(1, 3, 2, 2), bx.create_element(1, 3, 3, 2))
+    assert np.max(np.abs(got - want)) <= 1e-12
