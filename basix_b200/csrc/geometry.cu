@@ -24,6 +24,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 namespace bx
@@ -37,6 +38,11 @@ void tabulate_device(const bx_element& e, int nd, const T* x, size_t npts, T* ba
 namespace geo
 {
 constexpr int kThreads = 256;
+#ifndef BX_FUSED_PAIR
+#define BX_FUSED_PAIR 1
+#endif
+constexpr int kFusedMaxThreads = 512; // the fused kernel runs 4, 8 or 16 warps per CTA (launch_fused)
+constexpr int kPair = BX_FUSED_PAIR; // row passes per trip of the fused kernel's row loop
 
 // Unscaled inverse and its divisor: K = adj / div, detJ = div (square) or sqrt(div) (non-square, div = det(J^T J)).
 //   1 x 1, 2 x 2, 3 x 3: adjugate and determinant (first-row cofactor expansion)
@@ -303,29 +309,49 @@ struct FusedParams
 __device__ __noinline__ double ieee_div(double a, double b) { return a / b; }
 __device__ __noinline__ float ieee_div(float a, float b) { return a / b; }
 
-__device__ __forceinline__ double div_by(double a, double b, double rb)
+__device__ __forceinline__ double div_core(double a, double b, double rb)
 {
   double q = a * rb;
   double r = fma(-q, b, a);
   q = fma(r, rb, q);
   r = fma(-q, b, a);
-  q = fma(r, rb, q);
-  const unsigned ex = (unsigned(__double2hiint(q)) >> 20) & 0x7ffu; // biased exponent: 1023 +- 500 passes
-  if (ex - 523u > 1000u)
-    q = ieee_div(a, b);
-  return q;
+  return fma(r, rb, q);
 }
-__device__ __forceinline__ float div_by(float a, float b, float rb)
+__device__ __forceinline__ float div_core(float a, float b, float rb)
 {
   float q = a * rb;
   float r = fmaf(-q, b, a);
   q = fmaf(r, rb, q);
   r = fmaf(-q, b, a);
-  q = fmaf(r, rb, q);
-  const unsigned ex = (__float_as_uint(q) >> 23) & 0xffu; // 127 +- 60 passes
-  if (ex - 67u > 120u)
-    q = ieee_div(a, b);
-  return q;
+  return fmaf(r, rb, q);
+}
+// quotient outside the window in which div_core is trusted: biased exponent 1023 +- 500 (float: 127 +- 60)
+__device__ __forceinline__ bool outside_window(double q)
+{
+  return ((unsigned(__double2hiint(q)) >> 20) & 0x7ffu) - 523u > 1000u;
+}
+__device__ __forceinline__ bool outside_window(float q) { return ((__float_as_uint(q) >> 23) & 0xffu) - 67u > 120u; }
+// N quotients by the same divisor; one test (and one rarely taken branch) for all of them
+template <typename T, int N>
+__device__ __forceinline__ void div_by(T (&a)[N], T b, T rb)
+{
+  T q[N];
+  bool bad = false;
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+  {
+    q[i] = div_core(a[i], b, rb);
+    bad = bad or outside_window(q[i]);
+  }
+  if (bad)
+  {
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      q[i] = ieee_div(a[i], b);
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    a[i] = q[i];
 }
 // reciprocal for div_by: NaN unless the divisor is finite and within 2^+-300 (float: 2^+-40), so that every product and
 // residual in div_by stays in range whenever its quotient test passes
@@ -345,6 +371,12 @@ __host__ __device__ constexpr int pad4(int n) { return (n + 3) & ~3; }
 // an odd number of entries, so lane = cell writes are free of bank conflicts
 template <int G, int TD>
 __host__ __device__ constexpr int cell_record() { return (G * TD + 2) | 1; }
+// entries a lane prefetches for its cell: vertex coordinates, or the given matrix (and detJ)
+template <int MAP, int G, int TD, bool GEOM>
+__host__ __device__ constexpr int prefetch_entries()
+{
+  return GEOM ? (TD + 1) * G : (MAP == BX_MAP_IDENTITY ? 0 : G * TD + (MAP == BX_MAP_CONTRAVARIANT_PIOLA ? 1 : 0));
+}
 
 // MAP: BX_MAP_IDENTITY (value size VS, no matrix), BX_MAP_COVARIANT_PIOLA, BX_MAP_CONTRAVARIANT_PIOLA.
 // GEOM: J / detJ / K of the affine simplex cell from coords[nc][TD + 1][G]; otherwise A / detJ are read per cell:
@@ -361,7 +393,7 @@ __host__ __device__ constexpr int cell_record() { return (G * TD + 2) | 1; }
 //     are one contiguous run of `out` and leave as ONE TMA bulk copy, the warp going on with the next batch in the
 //     other slice while the copy engine reads.
 template <typename T, int MAP, int G, int TD, bool GEOM, int VS>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kFusedMaxThreads, 1)
     physical_basis_kernel(const T* __restrict__ tab, const T* __restrict__ coords, const T* __restrict__ A,
                           const T* __restrict__ detJ, const FusedParams p, T* __restrict__ out)
 {
@@ -370,18 +402,19 @@ __global__ void __launch_bounds__(kThreads, 3)
   constexpr int MA = G * TD;
   constexpr int NX = (TD + 1) * G; // coordinates of an affine simplex cell
   constexpr int REC = cell_record<G, TD>();
+  constexpr int NPRE_ALL = prefetch_entries<MAP, G, TD, GEOM>();
   extern __shared__ __align__(128) unsigned char fused_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rows = p.rows, E = rows * OUT_VS, B = p.batch;
   const int slice_stride = pad4(B * E);
   T* s_tab = reinterpret_cast<T*>(fused_smem);                                            // [nstates][tab_stride]
   uint32_t* s_desc = reinterpret_cast<uint32_t*>(s_tab + pad4(p.nstates * p.tab_stride)); // [rows]
-  T* wbase = reinterpret_cast<T*>(s_desc + pad4(rows)) + size_t(warp) * (p.nbuf * slice_stride + pad4(32 * REC));
+  T* wbase = reinterpret_cast<T*>(s_desc + pad4(rows)) + size_t(warp) * (p.nbuf * slice_stride + pad4(32 * REC) + pad4(32 * NPRE_ALL));
   T* slices = wbase;                       // [nbuf][batch][E]
   T* rec = wbase + p.nbuf * slice_stride;  // [32][REC]
-  for (int i = threadIdx.x; i < p.nstates * p.tab_stride; i += kThreads)
+  for (int i = threadIdx.x; i < p.nstates * p.tab_stride; i += blockDim.x)
     s_tab[i] = tab[i];
-  for (int r = threadIdx.x; r < rows; r += kThreads)
+  for (int r = threadIdx.x; r < rows; r += blockDim.x)
   {
     uint32_t shift = 0, mask = 0;
     if (p.cell_info)
@@ -398,40 +431,44 @@ __global__ void __launch_bounds__(kThreads, 3)
   }
   __syncthreads();
 
-  const size_t warps = size_t(gridDim.x) * (kThreads / 32);
-  const size_t first = (size_t(blockIdx.x) * (kThreads / 32) + warp) * 32;
-  // ---- prefetch of the first cell of this lane ----
-  [[maybe_unused]] T pre[GEOM ? NX : (MAP == BX_MAP_IDENTITY ? 1 : MA + 1)];
+  const size_t warps = size_t(gridDim.x) * (blockDim.x / 32);
+  const size_t first = (size_t(blockIdx.x) * (blockDim.x / 32) + warp) * 32;
+  // ---- prefetch: the cell of this lane for the NEXT iteration travels global -> shared by cp.async (no registers
+  // held across phase B); every lane reads back only what it copied itself ----
+  constexpr int NPRE = NPRE_ALL;
+  [[maybe_unused]] T* pf = rec + pad4(32 * REC) + lane * NPRE; // [32][NPRE]
   auto fetch = [&](size_t c0)
   {
-    const size_t c = min(c0 + lane, p.nc - 1);
-    if constexpr (GEOM)
+    if constexpr (NPRE > 0)
     {
-      if (sizeof(T) == 8 and p.vec_coords and NX % 2 == 0)
+      const size_t c = min(c0 + lane, p.nc - 1);
+      const uint32_t dst = uint32_t(__cvta_generic_to_shared(pf));
+      if constexpr (GEOM)
       {
-        const double2* x2 = reinterpret_cast<const double2*>(coords + c * NX);
-#pragma unroll
-        for (int k = 0; k < NX / 2; ++k)
+        const T* src = coords + c * NX;
+        if ((NX * sizeof(T)) % 16 == 0 and p.vec_coords)
         {
-          const double2 v = x2[k];
-          pre[2 * k] = T(v.x);
-          pre[2 * k + 1] = T(v.y);
+#pragma unroll
+          for (int k = 0; k < int(NX * sizeof(T) / 16); ++k)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * k), "l"(reinterpret_cast<const char*>(src) + 16 * k) : "memory");
+        }
+        else
+        {
+#pragma unroll
+          for (int k = 0; k < NX; ++k)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst + uint32_t(sizeof(T)) * k), "l"(src + k), "n"(sizeof(T)) : "memory");
         }
       }
       else
       {
+        const T* src = A + c * MA;
 #pragma unroll
-        for (int k = 0; k < NX; ++k)
-          pre[k] = coords[c * NX + k];
+        for (int k = 0; k < MA; ++k)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst + uint32_t(sizeof(T)) * k), "l"(src + k), "n"(sizeof(T)) : "memory");
+        if constexpr (MAP == BX_MAP_CONTRAVARIANT_PIOLA)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst + uint32_t(sizeof(T)) * MA), "l"(detJ + c), "n"(sizeof(T)) : "memory");
       }
-    }
-    else if constexpr (MAP != BX_MAP_IDENTITY)
-    {
-#pragma unroll
-      for (int k = 0; k < MA; ++k)
-        pre[k] = A[c * MA + k];
-      if constexpr (MAP == BX_MAP_CONTRAVARIANT_PIOLA)
-        pre[MA] = detJ[c];
+      asm volatile("cp.async.commit_group;" ::: "memory");
     }
   };
   if (first < p.nc)
@@ -444,6 +481,13 @@ __global__ void __launch_bounds__(kThreads, 3)
     // ---- phase A: lane = cell ----
     if constexpr (MAP != BX_MAP_IDENTITY)
     {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      T pre[NPRE];
+#pragma unroll
+      for (int k = 0; k < NPRE; ++k)
+        pre[k] = pf[k];
+      if (c0 + warps * 32 < p.nc)
+        fetch(c0 + warps * 32); // the next iteration's cell: in flight during the rest of this one
       T* mine = rec + lane * REC;
       if constexpr (GEOM)
       {
@@ -486,8 +530,6 @@ __global__ void __launch_bounds__(kThreads, 3)
           mine[MA + 1] = safe_reciprocal(pre[MA]);
         }
       }
-      if (c0 + warps * 32 < p.nc)
-        fetch(c0 + warps * 32); // the next iteration's cell: in flight during phase B
     }
     __syncwarp();
     // ---- phase B ----
@@ -527,46 +569,85 @@ __global__ void __launch_bounds__(kThreads, 3)
           }
         }
         T* o = slice + bi * E;
-#pragma unroll 1
-        for (int r = lane; r < rows; r += 32)
+        // two row passes per trip when both exist (independent chains for the FP64 pipe), else one
+        auto pass = [&](auto nh, int r0)
         {
-          const uint32_t d = s_desc[r];
-          const int st = int(ci >> (d & 31u)) & int(d >> 5);
-          const T* u = s_tab + st * p.tab_stride + r * IN_VS;
+          constexpr int NH = decltype(nh)::value;
+          int r[NH];
+          const T* u[NH];
+#pragma unroll
+          for (int h = 0; h < NH; ++h)
+          {
+            r[h] = r0 + 32 * h + lane;
+            const int rc = min(r[h], rows - 1); // lanes past the last row repeat it and do not store
+            const uint32_t d = s_desc[rc];
+            const int st = int(ci >> (d & 31u)) & int(d >> 5);
+            u[h] = s_tab + st * p.tab_stride + rc * IN_VS;
+          }
           if constexpr (MAP == BX_MAP_IDENTITY)
           {
 #pragma unroll
-            for (int i = 0; i < VS; ++i)
-              o[r * VS + i] = u[i];
+            for (int h = 0; h < NH; ++h)
+              if (r[h] < rows)
+              {
+#pragma unroll
+                for (int i = 0; i < VS; ++i)
+                  o[r[h] * VS + i] = u[h][i];
+              }
           }
           else
           {
-            T uu[IN_VS];
+            T uu[NH][IN_VS], acc[NH][OUT_VS];
 #pragma unroll
-            for (int k = 0; k < IN_VS; ++k)
-              uu[k] = u[k];
+            for (int h = 0; h < NH; ++h)
+#pragma unroll
+              for (int k = 0; k < IN_VS; ++k)
+                uu[h][k] = u[h][k];
 #pragma unroll
             for (int i = 0; i < OUT_VS; ++i)
+#pragma unroll
+              for (int h = 0; h < NH; ++h)
+              {
+                T a = 0;
+                if constexpr (MAP == BX_MAP_COVARIANT_PIOLA)
+                {
+                  // out[i] = sum_k K[k][i] in[k]   (maps.h:73-94)
+#pragma unroll
+                  for (int k = 0; k < TD; ++k)
+                    a += m[k * G + i] * uu[h][k];
+                }
+                else
+                {
+                  // out[i] = (sum_k J[i][k] in[k]) / det   (maps.h:100-124)
+#pragma unroll
+                  for (int k = 0; k < TD; ++k)
+                    a += m[i * TD + k] * uu[h][k];
+                }
+                acc[h][i] = a;
+              }
+            if constexpr (MAP == BX_MAP_CONTRAVARIANT_PIOLA)
             {
-              T acc = 0;
-              if constexpr (MAP == BX_MAP_COVARIANT_PIOLA)
-              {
-                // out[i] = sum_k K[k][i] in[k]   (maps.h:73-94)
 #pragma unroll
-                for (int k = 0; k < TD; ++k)
-                  acc += m[k * G + i] * uu[k];
-              }
-              else
-              {
-                // out[i] = (sum_k J[i][k] in[k]) / det   (maps.h:100-124)
-#pragma unroll
-                for (int k = 0; k < TD; ++k)
-                  acc += m[i * TD + k] * uu[k];
-                acc = div_by(acc, det, inv);
-              }
-              o[r * OUT_VS + i] = acc;
+              for (int h = 0; h < NH; ++h)
+                div_by<T, OUT_VS>(acc[h], det, inv);
             }
+#pragma unroll
+            for (int h = 0; h < NH; ++h)
+              if (r[h] < rows)
+              {
+#pragma unroll
+                for (int i = 0; i < OUT_VS; ++i)
+                  o[r[h] * OUT_VS + i] = acc[h][i];
+              }
           }
+        };
+#pragma unroll 1
+        for (int r0 = 0; r0 < rows; r0 += 32 * kPair)
+        {
+          if (kPair == 2 and r0 + 32 < rows)
+            pass(std::integral_constant<int, kPair>{}, r0);
+          else
+            pass(std::integral_constant<int, 1>{}, r0);
         }
       }
       if (p.bulk and cells == B)
@@ -641,10 +722,10 @@ void launch_geometry(const T* coords, const T* dphi, size_t nc, int nv, int npts
   BX_LAUNCHED();
 }
 
-// Tuning aid (development only): BX_FUSED_TUNE="b=2,nbuf=2" overrides the cells per slice and the slices per warp.
+// Tuning aid (development only): BX_FUSED_TUNE="b=2,nbuf=2,nw=8" overrides the cells per slice, the slices per warp and the warps per CTA.
 struct FusedTune
 {
-  int b = 0, nbuf = 0;
+  int b = 0, nbuf = 0, nw = 0;
 };
 inline const FusedTune& fused_tune()
 {
@@ -662,6 +743,7 @@ inline const FusedTune& fused_tune()
       };
       get("b=", v.b);
       get("nbuf=", v.nbuf);
+      get("nw=", v.nw);
     }
     return v;
   }();
@@ -674,37 +756,74 @@ void launch_fused(const T* tab, const T* coords, const T* A, const T* detJ, Fuse
   constexpr int OUT_VS = MAP == BX_MAP_IDENTITY ? VS : G;
   constexpr int REC = cell_record<G, TD>();
   const int E = p.rows * OUT_VS;
-  auto smem_of = [&](int batch, int nbuf)
+  auto smem_of = [&](int batch, int nbuf, int nw)
   {
     return size_t(pad4(p.nstates * p.tab_stride)) * sizeof(T) + size_t(pad4(p.rows)) * 4
-           + size_t(kThreads / 32) * (size_t(nbuf) * pad4(batch * E) + pad4(32 * REC)) * sizeof(T);
+           + size_t(nw) * (size_t(nbuf) * pad4(batch * E) + pad4(32 * REC) + pad4(32 * prefetch_entries<MAP, G, TD, GEOM>())) * sizeof(T);
   };
   const bool contiguous = p.out_pitch == size_t(E) and reinterpret_cast<uintptr_t>(out) % 16 == 0;
-  // cells per slice and slices per warp: the largest configuration that leaves three CTAs per SM (24 warps); a batch
-  // whose rows are a whole number of 16-byte units leaves by TMA bulk copy
+  auto kern = physical_basis_kernel<T, MAP, G, TD, GEOM, VS>;
+  static const size_t smem_max = [&]
+  {
+    int dev = 0, v = 0;
+    BX_CUDA(cudaGetDevice(&dev));
+    BX_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    return size_t(v);
+  }();
+  cudaFuncAttributes fa;
+  BX_CUDA(cudaFuncGetAttributes(&fa, kern));
+  // Warps per CTA (4 / 8 / 16), cells per slice and slices per warp: the configuration with the most resident warps per
+  // SM (the state tables are per CTA: 34 KB for 180 rows), then the largest batch, then double buffering.  A batch
+  // whose rows are a whole number of 16-byte units leaves by TMA bulk copy.
+  int best_nw = 0, best_warps = -1, best_rank = -1;
   p.batch = 1;
   p.nbuf = 1;
-  static const int menu[][2] = {{4, 2}, {2, 2}, {4, 1}, {2, 1}, {1, 2}};
-  for (const auto& m : menu)
-    if (smem_of(m[0], m[1]) <= 72 * 1024 and (size_t(m[0]) * E * sizeof(T)) % 16 == 0)
+  static const int menu[][2] = {{1, 1}, {1, 2}, {2, 1}, {4, 1}, {2, 2}, {4, 2}};
+  for (int nw : {4, 8, 16})
+    for (int mi = 0; mi < 6; ++mi)
     {
-      p.batch = m[0];
-      p.nbuf = m[1];
-      break;
+      const int b = menu[mi][0], nbuf = menu[mi][1];
+      if (mi > 0 and (size_t(b) * E * sizeof(T)) % 16 != 0)
+        continue;
+      const size_t sm = smem_of(b, nbuf, nw);
+      if (sm > smem_max)
+        continue;
+      const int by_smem = int((size_t(228) * 1024 - 1024) / (sm + 1024));
+      const int by_regs = int(65536 / (std::max(fa.numRegs, 1) * nw * 32));
+      const int resident = nw * std::min({by_smem, by_regs, 64 / nw});
+      // prefer more resident warps up to 24 per SM (beyond that the kernel does not gain), then the richer slicing
+      const int capped = std::min(resident, 24);
+      if (capped > best_warps or (capped == best_warps and mi > best_rank))
+      {
+        best_warps = capped;
+        best_rank = mi;
+        best_nw = nw;
+        p.batch = b;
+        p.nbuf = nbuf;
+      }
     }
+  if (best_nw == 0)
+    fail(BX_ERR_UNSUPPORTED, "physical_basis: the point chunk does not fit in shared memory");
   if (fused_tune().b > 0 and fused_tune().b <= 32)
     p.batch = fused_tune().b;
   if (fused_tune().nbuf == 1 or fused_tune().nbuf == 2)
     p.nbuf = fused_tune().nbuf;
+  if (fused_tune().nw == 4 or fused_tune().nw == 8 or fused_tune().nw == 16)
+    best_nw = fused_tune().nw;
   p.bulk = contiguous and (size_t(p.batch) * E * sizeof(T)) % 16 == 0;
   p.vec_coords = reinterpret_cast<uintptr_t>(coords) % 16 == 0;
-  const size_t smem = smem_of(p.batch, p.nbuf);
-  if (smem > 200 * 1024)
+  const size_t smem = smem_of(p.batch, p.nbuf, best_nw);
+  if (smem > smem_max)
     fail(BX_ERR_UNSUPPORTED, "physical_basis: the point chunk does not fit in shared memory");
-  const size_t want = ceil_div(p.nc, size_t(kThreads));
-  auto kern = physical_basis_kernel<T, MAP, G, TD, GEOM, VS>;
-  const int grid = persistent_grid(kern, want, smem);
-  kern<<<grid, kThreads, smem, s>>>(tab, coords, A, detJ, p, out);
+  if (smem > 48 * 1024)
+    BX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  int per_sm = 1;
+  BX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, best_nw * 32, smem));
+  if (per_sm < 1)
+    fail(BX_ERR_UNSUPPORTED, "physical_basis: the kernel does not fit on an SM");
+  const size_t want = ceil_div(p.nc, size_t(best_nw) * 32);
+  const int grid = int(std::max<size_t>(1, std::min(want, size_t(sm_count()) * per_sm)));
+  kern<<<grid, best_nw * 32, smem, s>>>(tab, coords, A, detJ, p, out);
   BX_LAUNCHED();
 }
 

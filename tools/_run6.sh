@@ -3,5 +3,4 @@ cap() { # name workload kernel-regex units
     python bench.py --workload $2 ${4:+--units $4} --steps 1 --warmup 3 --device-only --no-cpu-baseline > gpurun_out/ncu_$1.log 2>&1
   tail -1 gpurun_out/ncu_$1.log
 }
-cap fused_n1curl3 physical_basis_n1curl3 physical_basis_kernel 4000000
 cap fused_rt4 physical_basis_rt4 physical_basis_kernel 2000000
