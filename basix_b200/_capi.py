@@ -100,6 +100,8 @@ SIGNATURES = {
     "bx_interpolate_f64": (_I, [_P, _I, _P, _SIZE, _P, _I, _P]),
     "bx_interpolate_f32": (_I, [_P, _I, _P, _SIZE, _P, _I, _P]),
     "bx_compute_interpolation_operator_f64": (_I, [_P, _P, _P, _P, _I, _P]),
+    "bx_make_quadrature": (_I, [_I, _I, _P, _P, C.POINTER(C.c_size_t)]),
+    "bx_create_lattice": (_I, [_I, _I, _I, _I, _I, _P, C.POINTER(C.c_size_t)]),
     "bx_permute_subentity_closure_i32": (_I, [_P, _I, _P, _SIZE, _SIZE, _P, _I, _I, _I, _P]),
     "bx_element_subentity_closure_size": (_I, [_P, _I]),
     "bx_element_subentity_closure_map": (_I, [_P, _I, _I, C.c_uint32, _P]),

@@ -165,6 +165,8 @@ void physical_basis_device(const bx_element& e, int op, const T* U, size_t npts,
                            cudaStream_t s);
 void interpolation_operator_shape(const bx_element& from, const bx_element& to, int32_t shape[2]);
 void interpolation_operator_device(const bx_element& from, const bx_element& to, double* out, cudaStream_t s);
+void make_quadrature_gauss_jacobi(int cell, int q, std::vector<double>& x, std::vector<double>& w);
+std::vector<double> create_lattice_points(int cell, int n, int lattice_type, int exterior, int simplex_method);
 bx_element* create_lagrange(int cell, int degree, int variant, bool discontinuous, const int32_t* dof_ordering,
                             int n_dof_ordering);
 bx_element* create_rt(int cell, int degree, int lvariant, bool discontinuous);
@@ -1187,6 +1189,36 @@ extern "C"
           bx::interpolation_operator_device(*from, *to, d, st.s[0]);
           BX_CUDA(cudaMemcpyAsync(out, d, bytes, cudaMemcpyDeviceToHost, st.s[0]));
           st.sync();
+        });
+  }
+
+  int bx_create_lattice(int cell_type, int n, int lattice_type, int exterior, int simplex_method, double* out, size_t* npts)
+  {
+    return bx::guarded(
+        [&]()
+        {
+          bx::require(npts != nullptr, "create_lattice: null argument");
+          const std::vector<double> x = bx::create_lattice_points(cell_type, n, lattice_type, exterior, simplex_method);
+          const int tdim = bx::cell_tdim(cell_type);
+          *npts = tdim > 0 ? x.size() / size_t(tdim) : 1;
+          if (out)
+            std::copy(x.begin(), x.end(), out);
+        });
+  }
+
+  int bx_make_quadrature(int cell_type, int degree, double* points, double* weights, size_t* npts)
+  {
+    return bx::guarded(
+        [&]()
+        {
+          bx::require(npts != nullptr, "make_quadrature: null argument");
+          std::vector<double> x, w;
+          bx::make_quadrature_gauss_jacobi(cell_type, degree, x, w);
+          *npts = w.size();
+          if (points)
+            std::copy(x.begin(), x.end(), points);
+          if (weights)
+            std::copy(w.begin(), w.end(), weights);
         });
   }
 

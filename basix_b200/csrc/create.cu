@@ -496,6 +496,56 @@ void make_quadrature(int cell, int q, Vec& x, Vec& w)
       }
     return;
   }
+  if (cell == BX_CELL_QUADRILATERAL or cell == BX_CELL_HEXAHEDRON)
+  {
+    // tensor Gauss-Legendre, first coordinate slowest
+    const int tdim = cell == BX_CELL_QUADRILATERAL ? 2 : 3;
+    const int n = tdim == 2 ? m * m : m * m * m;
+    for (int q3 = 0; q3 < n; ++q3)
+    {
+      const int i = tdim == 2 ? q3 / m : q3 / (m * m), j = tdim == 2 ? q3 % m : (q3 / m) % m, k = q3 % m;
+      x.push_back(0.5 * (px[i] + 1.0));
+      x.push_back(0.5 * (px[j] + 1.0));
+      double wt = 0.25 * wx[i] * wx[j];
+      if (tdim == 3)
+      {
+        x.push_back(0.5 * (px[k] + 1.0));
+        wt *= 0.5 * wx[k];
+      }
+      w.push_back(wt);
+    }
+    return;
+  }
+  if (cell == BX_CELL_PRISM)
+  {
+    // collapsed triangle rule in (x, y), Gauss-Legendre in z
+    for (int i = 0; i < m; ++i)
+      for (int j = 0; j < m; ++j)
+        for (int k = 0; k < m; ++k)
+        {
+          x.push_back(0.25 * (1.0 + px[i]) * (1.0 - py[j]));
+          x.push_back(0.5 * (1.0 + py[j]));
+          x.push_back(0.5 * (px[k] + 1.0));
+          w.push_back(wx[i] * wy[j] * 0.125 * 0.5 * wx[k]);
+        }
+    return;
+  }
+  if (cell == BX_CELL_PYRAMID)
+  {
+    // x = (1 + xi)(1 - z) / 2, y = (1 + eta)(1 - z) / 2, z = (1 + zeta) / 2: weight (1 - zeta)^2, two more points in z
+    // (the pyramid's polynomial set is rational in z)
+    gauss_jacobi(2.0, m + 2, pz, wz);
+    for (int i = 0; i < m; ++i)
+      for (int j = 0; j < m; ++j)
+        for (int k = 0; k < m + 2; ++k)
+        {
+          x.push_back(0.25 * (1.0 + px[i]) * (1.0 - pz[k]));
+          x.push_back(0.25 * (1.0 + px[j]) * (1.0 - pz[k]));
+          x.push_back(0.5 * (1.0 + pz[k]));
+          w.push_back(wx[i] * wx[j] * wz[k] * 0.125 * 0.25);
+        }
+    return;
+  }
   if (cell != BX_CELL_TETRAHEDRON)
     fail(BX_ERR_UNSUPPORTED, "create_element: quadrature on this cell is not available in the native factory");
   gauss_jacobi(2.0, m, pz, wz);
@@ -1102,6 +1152,9 @@ void space_quadrature(int cell, int degree, Vec& pts, Vec& wts, Vec& phi)
 // basix::element::create_rt (e-raviart-thomas.cpp:20-173), triangle / tetrahedron
 bx_element* create_rt(int cell, int degree, int lvariant, bool discontinuous)
 {
+  if (cell == BX_CELL_QUADRILATERAL or cell == BX_CELL_HEXAHEDRON)
+    fail(BX_ERR_UNSUPPORTED, "create_element: the native factory builds RT on triangles and tetrahedra (the reference's "
+                             "quadrilateral / hexahedron variants: describe them with bx_element_create_from_arrays)");
   if (cell != BX_CELL_TRIANGLE and cell != BX_CELL_TETRAHEDRON)
     fail(BX_ERR_RUNTIME, "Unsupported cell type");
   if (degree < 1)
@@ -1153,6 +1206,9 @@ bx_element* create_rt(int cell, int degree, int lvariant, bool discontinuous)
 // basix::element::create_nedelec (e-nedelec.cpp:24-380), first kind, triangle / tetrahedron
 bx_element* create_nedelec(int cell, int degree, int lvariant, bool discontinuous)
 {
+  if (cell == BX_CELL_QUADRILATERAL or cell == BX_CELL_HEXAHEDRON)
+    fail(BX_ERR_UNSUPPORTED, "create_element: the native factory builds N1E on triangles and tetrahedra (the reference's "
+                             "quadrilateral / hexahedron variants: describe them with bx_element_create_from_arrays)");
   if (cell != BX_CELL_TRIANGLE and cell != BX_CELL_TETRAHEDRON)
     fail(BX_ERR_RUNTIME, "Invalid celltype in Nedelec");
   if (degree < 1)
@@ -1257,4 +1313,31 @@ std::vector<double> polyset_tabulate(int cell, int degree, int nd, const std::ve
 }
 void quadrature(int cell, int q, std::vector<double>& x, std::vector<double>& w) { make_quadrature(cell, q, x, w); }
 } // namespace host
+// lattice::create (cpp/basix/lattice.cpp:636-700) for the lattice types this factory builds its elements from:
+// equispaced (0) and gll (1; simplices by the warp method).  Returns the points row-major [npts][tdim].
+std::vector<double> create_lattice_points(int cell, int n, int lattice_type, int exterior, int simplex_method)
+{
+  if (cell < BX_CELL_POINT or cell > BX_CELL_PYRAMID)
+    fail(BX_ERR_INVALID_ARG, "Unsupported cell type");
+  if (n < 0)
+    fail(BX_ERR_INVALID_ARG, "create_lattice: negative size");
+  if (lattice_type != 0 and lattice_type != 1)
+    fail(BX_ERR_UNSUPPORTED, "create_lattice: equispaced and gll lattices are built natively");
+  const bool simplex = cell == BX_CELL_TRIANGLE or cell == BX_CELL_TETRAHEDRON;
+  if (lattice_type == 1 and simplex and simplex_method != 1)
+    fail(BX_ERR_UNSUPPORTED, "create_lattice: gll lattices on simplices are built with the warp method only");
+  if (cell == BX_CELL_PRISM or cell == BX_CELL_PYRAMID)
+    fail(BX_ERR_UNSUPPORTED, "create_lattice: prism and pyramid lattices are not built natively");
+  return lattice_create(cell, n, lattice_type == 1, exterior != 0);
+}
+// quadrature::make_quadrature (quadrature.cpp:4960-5020) with the Gauss-Jacobi scheme (quadrature.cpp:215-372): points
+// [npts][tdim] and weights of a rule exact for polynomials of degree q.
+void make_quadrature_gauss_jacobi(int cell, int q, std::vector<double>& x, std::vector<double>& w)
+{
+  if (cell < BX_CELL_INTERVAL or cell > BX_CELL_PYRAMID)
+    fail(BX_ERR_INVALID_ARG, "make_quadrature: unsupported cell type");
+  if (q < 0)
+    fail(BX_ERR_INVALID_ARG, "make_quadrature: negative degree");
+  make_quadrature(cell, q, x, w);
+}
 } // namespace bx

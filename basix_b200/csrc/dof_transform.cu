@@ -564,7 +564,48 @@ void dof_transform_device(const bx_element& e, int op, T* data, size_t nc, size_
   p.by_len = FastDiv(unsigned(p.len), (unsigned long long)(p.len) << lg);
   p.by_n = FastDiv(unsigned(n), (unsigned long long)(p.nslots) * n);
   if (smem_bytes(p, !e.perms, sizeof(T)) > 200 * 1024)
-    fail(BX_ERR_UNSUPPORTED, "T_apply: a single cell does not fit in shared memory");
+  {
+    // One cell is larger than shared memory: a caller transforming whole element tensors passes block sizes as large as
+    // the element (T_apply(data, n = ndofs, ...): 216 x 216 doubles for a degree-5 hexahedron).  The operators act on
+    // the dof axis and leave the block index alone, so the blocks are processed a slab at a time through a contiguous
+    // copy: left layout u[dof][b] -> columns [b0, b0 + w) of every row; right layout u[b][dof] -> w consecutive blocks.
+    const size_t row = size_t(e.ndofs) * sizeof(T);
+    int w = int(std::min<size_t>(size_t(n), std::max<size_t>(1, (32 * 1024) / row)));
+    if (n == 1 or row > 150 * 1024)
+      fail(BX_ERR_UNSUPPORTED, "T_apply: a single block of the cell does not fit in shared memory");
+    T* scratch = nullptr;
+    BX_CUDA(cudaMallocAsync(&scratch, nc * size_t(e.ndofs) * w * sizeof(T), s));
+    try
+    {
+      for (int b0 = 0; b0 < n; b0 += w)
+      {
+        const int wb = std::min(w, n - b0);
+        if (right)
+        {
+          BX_CUDA(cudaMemcpy2DAsync(scratch, size_t(wb) * row, data + size_t(b0) * e.ndofs, cell_size * sizeof(T), size_t(wb) * row,
+                                    nc, cudaMemcpyDeviceToDevice, s));
+          dof_transform_device<T>(e, op, scratch, nc, size_t(e.ndofs) * wb, wb, cell_info, s);
+          BX_CUDA(cudaMemcpy2DAsync(data + size_t(b0) * e.ndofs, cell_size * sizeof(T), scratch, size_t(wb) * row, size_t(wb) * row,
+                                    nc, cudaMemcpyDeviceToDevice, s));
+        }
+        else
+        {
+          BX_CUDA(cudaMemcpy2DAsync(scratch, size_t(wb) * sizeof(T), data + b0, size_t(n) * sizeof(T), size_t(wb) * sizeof(T),
+                                    nc * size_t(e.ndofs), cudaMemcpyDeviceToDevice, s));
+          dof_transform_device<T>(e, op, scratch, nc, size_t(e.ndofs) * wb, wb, cell_info, s);
+          BX_CUDA(cudaMemcpy2DAsync(data + b0, size_t(n) * sizeof(T), scratch, size_t(wb) * sizeof(T), size_t(wb) * sizeof(T),
+                                    nc * size_t(e.ndofs), cudaMemcpyDeviceToDevice, s));
+        }
+      }
+    }
+    catch (...)
+    {
+      cudaFreeAsync(scratch, s);
+      throw;
+    }
+    BX_CUDA(cudaFreeAsync(scratch, s));
+    return;
+  }
 
   if (e.perms)
   {

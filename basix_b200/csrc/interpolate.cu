@@ -47,6 +47,7 @@ struct Params
   T* out;               // [nc][N]
   size_t nc;
   int K, N, npad, kstride, ksteps;
+  int n_base, out_stride; // this launch computes columns [n_base, n_base + N) of out[nc][out_stride]
 };
 
 // Column group [n0, n0 + 8 NT) for the 16 cells of one chunk.
@@ -106,14 +107,14 @@ __device__ __forceinline__ void run_group(const Params<T>& p, const double* __re
     }
   }
   // accumulator fragment: row g = cell, columns 2t, 2t+1 of each 8-column tile
-  const bool even = (p.N & 1) == 0;
+  const bool even = ((p.out_stride | p.n_base) & 1) == 0;
 #pragma unroll
   for (int m = 0; m < 2; ++m)
   {
     const size_t c = c0 + g + 8 * m;
     if (c < p.nc)
     {
-      T* row = p.out + c * p.N;
+      T* row = p.out + c * size_t(p.out_stride) + p.n_base;
 #pragma unroll
       for (int j = 0; j < NT; ++j)
       {
@@ -182,28 +183,38 @@ void interpolate_device(const bx_element& e, int layout, const T* values, size_t
   require_device(e);
   Params<T> p;
   p.values = values;
-  p.B = e.d_interp[layout];
   p.out = coefficients;
   p.nc = nc;
   p.K = e.vs * e.interp_npts;
-  p.N = e.ndofs;
-  p.npad = e.interp_npad;
   p.kstride = e.interp_kstride;
+  p.out_stride = e.ndofs;
   p.ksteps = int(ceil_div(size_t(p.K), size_t(4))); // rounded up to the unroll factor below
-  const size_t smem = size_t(p.npad) * p.kstride * sizeof(double);
-  if (smem > 227 * 1024)
-    fail(BX_ERR_UNSUPPORTED, "interpolate: the interpolation matrix does not fit in shared memory");
-  const size_t nblocks = ceil_div(nc, size_t(kCells) * kWarps);
-  const unsigned grid = unsigned(std::min<size_t>(nblocks, size_t(sm_count())));
   // A fragments four k-steps ahead, default caching (measured best of depth 2 / 4 / 6 and streaming / default loads)
   constexpr int kDepth = 4;
   p.ksteps = int(ceil_div(size_t(p.ksteps), size_t(kDepth)) * kDepth);
   if (4 * p.ksteps > p.kstride)
     fail(BX_ERR_RUNTIME, "interpolate: operand padding too small for the unroll factor");
+  // The operand [npad][kstride] stays resident in shared memory.  A matrix that does not fit (a degree-5 hexahedron
+  // element interpolated into itself is 216 x 216) is applied in blocks of rows: each block of the operand is a
+  // contiguous sub-array and fills its own columns of the result.
+  const size_t row_bytes = size_t(p.kstride) * sizeof(double);
+  const int rows_fit = int(std::min<size_t>(size_t(e.interp_npad), (size_t(200) * 1024 / row_bytes) / 8 * 8));
+  if (rows_fit < 8)
+    fail(BX_ERR_UNSUPPORTED, "interpolate: a block of eight rows of the interpolation matrix does not fit in shared memory");
+  const size_t nblocks = ceil_div(nc, size_t(kCells) * kWarps);
+  const unsigned grid = unsigned(std::min<size_t>(nblocks, size_t(sm_count())));
   auto kern = interpolate_kernel<kDepth, false, T>;
-  BX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  kern<<<grid, kThreads, smem, s>>>(p);
-  BX_LAUNCHED();
+  for (int n0 = 0; n0 < e.ndofs; n0 += rows_fit)
+  {
+    p.n_base = n0;
+    p.N = std::min(rows_fit, e.ndofs - n0);
+    p.npad = std::min(rows_fit, e.interp_npad - n0);
+    p.B = e.d_interp[layout] + size_t(n0) * p.kstride;
+    const size_t smem = size_t(p.npad) * row_bytes;
+    BX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    kern<<<grid, kThreads, smem, s>>>(p);
+    BX_LAUNCHED();
+  }
 }
 template void interpolate_device<double>(const bx_element&, int, const double*, size_t, double*, cudaStream_t);
 template void interpolate_device<float>(const bx_element&, int, const float*, size_t, float*, cudaStream_t);

@@ -361,6 +361,17 @@ extern "C"
   int bx_compute_interpolation_operator_f64(const bx_element* from, const bx_element* to, int32_t shape[2], double* out,
                                             int mem, bx_stream_t stream);
 
+  /* Replaces lattice::create (lattice.cpp:636-700; python basix.create_lattice) for the lattices the native factory
+     builds its elements from: lattice_type 0 equispaced, 1 gll (simplices: warp method, simplex_method = 1).  Host
+     set-up code.  out[npts][tdim] (NULL: only *npts is returned). */
+  int bx_create_lattice(int cell_type, int n, int lattice_type, int exterior, int simplex_method, double* out, size_t* npts);
+
+  /* quadrature::make_quadrature with the Gauss-Jacobi scheme (quadrature.cpp:215-372; python basix.make_quadrature(...,
+     rule=QuadratureType.gauss_jacobi)): a rule exact for polynomials of degree `degree` on any cell.  Host set-up code
+     (the native element factory integrates its moments with it).  points[npts][tdim], weights[npts]; NULL outputs
+     return *npts only. */
+  int bx_make_quadrature(int cell_type, int degree, double* points, double* weights, size_t* npts);
+
 #ifdef __cplusplus
 }
 #endif

@@ -684,3 +684,23 @@ def test_push_forward_broadcast_256_rows(ref):
         U0 = rng.standard_normal((rows, 3))
         want = r.push_forward(np.ascontiguousarray(np.broadcast_to(U0, (nc, rows, 3))), J, detJ, K)
         assert np.array_equal(e.push_forward_broadcast(U0, J, detJ, K), want)
+
+
+@pytest.mark.parametrize("op", ["T_apply", "Tt_apply_right", "Tinv_apply"])
+def test_T_apply_block_size_of_a_whole_element_tensor(ref, op):
+    """Block size = ndofs (a caller transforming an element matrix, reference test_dof_transformations.py:45-66) on an
+    element whose single cell (216 x 216 doubles) is larger than shared memory: processed in slabs of blocks."""
+    r, e = make_pair(ref, P, HEX, 5, GLL)
+    n = r.dim
+    ci = cell_infos(3)
+    data = np.random.default_rng(1).standard_normal((3, n * n))
+    want = r.T_apply_batch(op, data.copy(), n, ci)
+    got = data.copy()
+    e.T_apply_batch(got, n, ci, op=op)
+    assert np.array_equal(got, want)  # permutation element: pure moves
+    r, e = make_pair(ref, N1E, TET, 3, LEG)
+    data = np.random.default_rng(2).standard_normal((5, 45 * 1200))
+    want = r.T_apply_batch(op, data.copy(), 1200, cell_infos(5))
+    got = data.copy()
+    e.T_apply_batch(got, 1200, cell_infos(5), op=op)
+    assert np.max(np.abs(got - want)) <= 1e-12 * np.max(np.abs(want))
