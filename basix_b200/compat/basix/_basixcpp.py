@@ -75,6 +75,7 @@ def index(p, q=None, r=None):
 
 
 def tabulate_polynomial_set_float64(celltype, ptype, d, n, x):
+    """``_basixcpp.tabulate_polynomial_set_float64`` (basix_wrappers.h:467-475)."""
     return _bx.tabulate_polynomial_set(int(celltype), int(ptype), d, n, np.asarray(x, dtype=np.float64))
 
 

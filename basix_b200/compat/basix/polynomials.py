@@ -28,3 +28,14 @@ def tabulate_polynomials(ptype, celltype, degree, pts):
     pts = np.asarray(pts)
     fn = tabulate_polynomial_set_float32 if pts.dtype == np.float32 else tabulate_polynomial_set_float64
     return fn(celltype, PolysetType.standard, degree, 0, pts)[0]
+
+
+def tabulate_polynomial_set(celltype, ptype, degree, nderiv, pts):
+    """``basix.polynomials.tabulate_polynomial_set`` (python/basix/polynomials.py:207-231; polyset::tabulate,
+    polyset.cpp:2914-2978): shape (nderivs, psize, npts), on the device."""
+    pts = np.asarray(pts)
+    if pts.dtype == np.float32:
+        return tabulate_polynomial_set_float32(celltype, ptype, degree, nderiv, pts)
+    if pts.dtype == np.float64:
+        return tabulate_polynomial_set_float64(celltype, ptype, degree, nderiv, pts)
+    raise RuntimeError(f"Unsupported data dtype: {pts.dtype}")

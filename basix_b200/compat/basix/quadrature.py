@@ -22,8 +22,8 @@ def make_quadrature(cell, degree, rule=QuadratureType.default, polyset_type=Poly
     """``basix.make_quadrature(cell, degree, rule, polyset_type)`` -> (points, weights).  The Gauss-Jacobi scheme
     (quadrature.cpp:215-372) is the one rule built natively; ``default`` resolves to it (the reference picks a tabulated
     Xiao-Gimbutas rule for low-degree simplices: a different point set of the same exactness)."""
-    if int(rule) not in (QuadratureType.default, QuadratureType.gauss_jacobi) or int(polyset_type) != PolysetType.standard:
-        raise NotBuiltNatively("make_quadrature: the Gauss-Jacobi scheme on the standard polyset is built natively")
+    if int(rule) not in (QuadratureType.default, QuadratureType.gauss_jacobi):
+        raise NotBuiltNatively("make_quadrature: the Gauss-Jacobi scheme is the rule built natively")
     from basix_b200 import _capi
     from basix_b200.finite_element import _TDIM
 
@@ -33,4 +33,28 @@ def make_quadrature(cell, degree, rule=QuadratureType.default, polyset_type=Poly
     pts = np.empty((n.value, _TDIM[int(cell)]), dtype=np.float64)
     wts = np.empty(n.value, dtype=np.float64)
     _capi.check(L.bx_make_quadrature(int(cell), int(degree), pts.ctypes.data, wts.ctypes.data, C.byref(n)))
-    return pts, wts
+    if int(polyset_type) == PolysetType.standard:
+        return pts, wts
+    # macroedge polysets are piecewise polynomials on the cell split at the edge midpoints: the rule is repeated on
+    # every sub-cell (quadrature.cpp: make_macroedge_quadrature)
+    c = int(cell)
+    if c == 1:
+        subs = [np.array([[0.0], [0.5]]), np.array([[0.5], [1.0]])]
+    elif c == 2:
+        a, b, d, e, f, g = (0, 0), (1, 0), (0, 1), (0.5, 0), (0.5, 0.5), (0, 0.5)
+        subs = [np.array(v, dtype=float) for v in ((a, e, g), (e, b, f), (g, f, d), (e, f, g))]
+    elif c in (4, 5):
+        tdim = 2 if c == 4 else 3
+        subs = []
+        for corner in np.ndindex(*([2] * tdim)):
+            o = 0.5 * np.array(corner, dtype=float)
+            subs.append(np.vstack([o] + [o + 0.5 * np.eye(tdim)[k] for k in range(tdim)]))
+    else:
+        raise NotBuiltNatively("make_quadrature: macroedge rules are built for intervals, triangles, quadrilaterals and "
+                               "hexahedra")
+    out_p, out_w = [], []
+    for v in subs:
+        J = (v[1:] - v[0]).T  # affine map of the reference cell onto the sub-cell
+        out_p.append(v[0] + pts @ J.T)
+        out_w.append(wts * abs(np.linalg.det(J)))
+    return np.vstack(out_p), np.concatenate(out_w)

@@ -100,15 +100,23 @@ int grid_for(size_t n, int threads, int per_sm)
 }
 } // namespace
 
+template <typename T>
+void polyset_macroedge_device(int cell, int degree, int nd, const T* x, size_t npts, T* P, cudaStream_t s);
+
 // Device-pointer entry: x[npts][tdim] and P[nderivs][psize][npts] on the device.
 template <typename T>
 void polyset_tabulate_device(int cell, int ptype, int degree, int nd, const T* x, size_t npts, T* P,
                              cudaStream_t stream)
 {
-  if (ptype != BX_POLYSET_STANDARD)
-    fail(BX_ERR_UNSUPPORTED, "Polynomial set: macroedge polysets are not implemented on the device yet");
   if (degree < 0 or nd < 0)
     fail(BX_ERR_INVALID_ARG, "Polynomial set: negative degree or derivative order");
+  if (ptype == BX_POLYSET_MACROEDGE and cell != BX_CELL_POINT)
+  {
+    polyset_macroedge_device<T>(cell, degree, nd, x, npts, P, stream);
+    return;
+  }
+  if (ptype != BX_POLYSET_STANDARD and ptype != BX_POLYSET_MACROEDGE)
+    fail(BX_ERR_INVALID_ARG, "Polynomial set: unknown polyset type");
   if (npts == 0)
     return;
   const int psize = polyset_dim(cell, ptype, degree);

@@ -692,8 +692,8 @@ def test_T_apply_block_size_of_a_whole_element_tensor(ref, op):
     element whose single cell (216 x 216 doubles) is larger than shared memory: processed in slabs of blocks."""
     r, e = make_pair(ref, P, HEX, 5, GLL)
     n = r.dim
-    ci = cell_infos(3)
-    data = np.random.default_rng(1).standard_normal((3, n * n))
+    ci = cell_infos(5)
+    data = np.random.default_rng(1).standard_normal((5, n * n))
     want = r.T_apply_batch(op, data.copy(), n, ci)
     got = data.copy()
     e.T_apply_batch(got, n, ci, op=op)
@@ -704,3 +704,56 @@ def test_T_apply_block_size_of_a_whole_element_tensor(ref, op):
     got = data.copy()
     e.T_apply_batch(got, 1200, cell_infos(5), op=op)
     assert np.max(np.abs(got - want)) <= 1e-12 * np.max(np.abs(want))
+
+
+# ---- macroedge polynomial sets (polyset.cpp:126-1591) ---------------------------------------------------------------
+MACRO = [(INTERVAL, 0, 0), (INTERVAL, 1, 0), (INTERVAL, 3, 0), (INTERVAL, 4, 2), (INTERVAL, 2, 1), (QUAD, 0, 1), (QUAD, 1, 0),
+         (QUAD, 3, 0), (QUAD, 2, 2), (HEX, 1, 0), (HEX, 2, 0), (HEX, 2, 1), (TRI, 0, 1), (TRI, 1, 0), (TRI, 1, 2), (TRI, 2, 0),
+         (TRI, 2, 1), (TRI, 2, 3), (TET, 0, 1), (TET, 1, 0), (TET, 1, 1), (TET, 1, 2)]
+
+
+@pytest.mark.parametrize("cell,degree,nd", MACRO)
+def test_polyset_macroedge(ref, cell, degree, nd):
+    """Identical to the reference, including its derivative slabs as they are (the 1-D code multiplies by `-i` for an
+    unsigned i, so slabs of order >= 1 hold entries of magnitude 1e19): triangle / tetrahedron bit for bit (same
+    expressions), interval / quadrilateral / hexahedron to rounding of pow()."""
+    import torch
+
+    import basix_b200 as bx
+
+    x = random_points(cell, 2003, seed=degree + 7 * nd)
+    # points on the inner edges and at the vertices of the sub-cells
+    x[:4] = {INTERVAL: [[0.5], [0.0], [1.0], [0.25]], TRI: [[0.5, 0.0], [0.25, 0.25], [0.0, 0.5], [0.5, 0.5]],
+             QUAD: [[0.5, 0.5], [0.5, 0.1], [0.2, 0.5], [0.0, 1.0]], HEX: [[0.5, 0.5, 0.5], [0.5, 0.2, 0.7], [0, 0, 0], [1, 1, 1]],
+             TET: [[0.5, 0, 0], [0.25, 0.25, 0], [0.25, 0.25, 0.25], [0, 0.5, 0.5]]}[cell]
+    want = ref.tabulate_polynomial_set(cell, 1, degree, nd, x)
+    got = bx.tabulate_polynomial_set(cell, 1, degree, nd, x)
+    assert got.shape == want.shape == (bx.polyset_nderivs(cell, nd), bx.polyset_dim(cell, 1, degree), len(x))
+    if cell in (TRI, TET):
+        assert np.array_equal(got, want)
+    else:
+        assert np.array_equal(np.isfinite(got), np.isfinite(want))
+        for d in range(want.shape[0]):
+            for f in range(want.shape[1]):
+                w, g = want[d, f], got[d, f]
+                assert np.max(np.abs(g - w)) <= 1e-13 * max(np.max(np.abs(w)), 1e-300), (d, f)
+    dev = bx.tabulate_polynomial_set(cell, 1, degree, nd, torch.from_numpy(x).cuda())
+    assert np.array_equal(dev.cpu().numpy(), got)
+
+
+def test_polyset_macroedge_orthonormal_and_limits(ref):
+    """Reference test_orthonormal_basis.py:120-146: the sets are orthonormal (piecewise quadrature: the Gauss-Jacobi rule
+    of each sub-interval / sub-cell)."""
+    import basix_b200 as bx
+
+    # interval, degree 3: integrate over [0, 1/2] and [1/2, 1] separately
+    g, w = np.polynomial.legendre.leggauss(8)
+    xs = np.concatenate([(g + 1) / 4, (g + 1) / 4 + 0.5])[:, None]
+    ws = np.concatenate([w / 4, w / 4])
+    for degree in range(0, 5):
+        B = bx.tabulate_polynomial_set(INTERVAL, 1, degree, 0, xs)[0]
+        assert np.allclose((B * ws) @ B.T, np.eye(2 * degree + 1), atol=1e-12)
+    with pytest.raises(RuntimeError, match="Only degree 0 to 2"):
+        bx.tabulate_polynomial_set(TRI, 1, 3, 0, np.zeros((1, 2)))
+    with pytest.raises(RuntimeError, match="Only degree 0 and 1"):
+        bx.tabulate_polynomial_set(TET, 1, 2, 0, np.zeros((1, 3)))
