@@ -72,6 +72,7 @@ SIGNATURES = {
     "bx_element_info": (_I, [_P, _P]),
     "bx_element_tabulate_shape": (_I, [_P, _I, _SIZE, _P]),
     "bx_element_tabulate_path": (_I, [_P, _I]),
+    "bx_element_prepare": (_I, [_P, _I]),
     "bx_tabulate_path_mask": (C.c_uint, [C.c_uint]),
     "bx_element_net_operator": (_I, [_P, _I, C.c_uint32, _P, _P]),
     "bx_tabulate_f64": (_I, [_P, _I, _P, _SIZE, _I, _P, _I, _P]),

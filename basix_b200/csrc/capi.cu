@@ -1222,6 +1222,17 @@ extern "C"
         });
   }
 
+  int bx_element_prepare(const bx_element* e, int nd)
+  {
+    return bx::guarded(
+        [&]()
+        {
+          bx::require(e != nullptr and nd >= 0, "element_prepare: bad argument");
+          for (int k = 0; k <= nd; ++k)
+            (void)bx::tabulate_path(*e, k); // builds and uploads the operands of order k on first use
+        });
+  }
+
   int bx_permute_i32(const bx_element* e, int inverse, int32_t* d, size_t nc, const uint32_t* cell_info, int mem,
                      bx_stream_t stream)
   {

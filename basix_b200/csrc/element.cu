@@ -396,6 +396,20 @@ void build_closure_tables(bx_element& e, const StepMaps& fwd, const StepMaps& in
         cl.d_src = upload(cl.src);
 }
 
+int tabulate_path(const bx_element& e, int nd);
+namespace
+{
+// The tabulate operands of derivative orders 0..2 (derivative-operator kernel: composed per order) are built and
+// uploaded at creation, so device-pointer calls only launch kernels (bx_element_prepare does the same for higher orders).
+void prepare_tabulate(const bx_element& e)
+{
+  if (!e.on_device)
+    return;
+  for (int nd = 0; nd <= 2; ++nd)
+    (void)tabulate_path(e, nd);
+}
+} // namespace
+
 bx_element* element_from_desc(const bx_element_desc& d)
 {
   if (d.cell_type < BX_CELL_POINT or d.cell_type > BX_CELL_PYRAMID)
@@ -606,6 +620,7 @@ bx_element* element_from_desc(const bx_element_desc& d)
   {
     if (e->tdim >= 2)
       build_closure_tables(*e, {}, {}); // vertex and edge blocks still move with the entity
+    prepare_tabulate(*e);
     return e.release();
   }
 
@@ -882,6 +897,7 @@ bx_element* element_from_desc(const bx_element_desc& d)
     }
     e->d_slot_band = upload(slot_band);
   }
+  prepare_tabulate(*e);
   return e.release();
 }
 

@@ -655,6 +655,12 @@ class FiniteElement:
         check(lib().bx_element_tabulate_shape(self._h, int(nd), int(npts), shape))
         return tuple(int(s) for s in shape)
 
+    def prepare(self, nd: int) -> None:
+        """Build and upload the tabulate operands for derivative orders 0..nd now (``bx_element_prepare``): afterwards
+        device-pointer ``tabulate`` calls only launch kernels (safe to capture into a CUDA graph).  Done at creation for
+        nd <= 2."""
+        check(lib().bx_element_prepare(self._h, int(nd)))
+
     def tabulate_path(self, nd: int) -> str:
         return {0: "generic", 1: "fused", 2: "tensor-product", 3: "register", 4: "derivative-operator"}.get(lib().bx_element_tabulate_path(self._h, int(nd)), "?")
 

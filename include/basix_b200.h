@@ -200,6 +200,12 @@ extern "C"
      A[ndofs][ndofs]: out = A in.  Either may be NULL.  Generalises
      FiniteElement::base_transformations (finite-element.cpp:1902-1969) to arbitrary cell_info. */
   int bx_element_net_operator(const bx_element* e, int op, uint32_t cell_info, int32_t* src, double* A);
+  /* Build and upload, now, every operand tabulate() needs for derivative orders 0..nd (the derivative-operator
+     kernel composes its operators per order on first use, with a synchronous allocation and copy).  Elements are
+     prepared for nd <= 2 when they are created; call this for higher orders before capturing bx_tabulate_* into a
+     CUDA graph or timing a first call.  After it, BX_MEM_DEVICE calls only launch kernels and stream-ordered
+     allocations (capturable). */
+  int bx_element_prepare(const bx_element* e, int nd);
   /* Which device path tabulate() will take for derivative order nd:
      0 generic (polyset kernel + DMMA contraction), 1 fused simplex kernel,
      2 tensor-product kernel, 3 register path (low-degree simplex elements),
