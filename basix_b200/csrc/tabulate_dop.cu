@@ -54,14 +54,15 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
       : "d"(a), "d"(b));
 }
 
-// One k-step of the flat contraction loop: rows 4 ks .. 4 ks + 3 of the point slab against slab operand `slab`.
-struct __align__(16) Step
-{
-  int boff;    // offset (doubles) of B_slab[0][4 ks] inside the operand block
-  int kstride; // row stride of B_slab (>= 4 * ksteps, == 4 mod 8: conflict-free fragment loads)
-  int aoff;    // offset (doubles) of slab row 4 ks: 64 ks
-  int last;    // 0, or 1 + derivative slab index when this is the last k-step of that slab
-};
+// One k-step of the flat contraction loop = one packed table entry: rows 4 ks .. 4 ks + 3 of the point slab against
+// the operand of one derivative slab.  The operands are stored FRAGMENT-MAJOR, in the order the loop consumes them:
+//   Bf[column group][step][j < NT][lane] = B_slab[n0 + 8 j + (lane >> 2)][4 ks + (lane & 3)]
+// so every B-fragment load of a step is one conflict-free LDS at an immediate offset from ONE pointer that advances
+// by NT * 32 doubles per step: no per-step address arithmetic, no padding of the operand rows.
+using Step = int;
+constexpr int kStepKsMask = 0xff;   // bits 0..7: ks (slab row 4 ks of the point slab = offset 64 ks doubles)
+constexpr int kStepLastShift = 8;   // bits 8..15: 0, or 1 + derivative slab index when this is the last k-step of it
+constexpr int kStepFirst = 1 << 16; // bit 16: first k-step of its slab (the accumulators start from zero)
 
 // T = type of the points and of the table (double, or float for the float32 API: loads widen, stores narrow, the
 // operands and the arithmetic are double either way)
@@ -70,11 +71,12 @@ struct Params
 {
   const T* x;
   size_t npts;
-  const double* B;   // all slab operands
-  const Step* steps; // nsteps + 1 entries (the last one repeats its predecessor: prefetch target)
+  const double* B;   // all slab operands, fragment-major (+ one step of zero padding: prefetch target)
+  const Step* steps; // nsteps + 2 entries (the last two repeat the last step: prefetch targets)
   T* basis;
-  int N, K, kpad;    // output columns, basis functions, rows of a point slab (multiple of 4)
-  int b_doubles, nsteps;
+  size_t slab_stride; // npts * N: elements between derivative slabs of the table
+  int N, K, kpad;     // output columns, basis functions, rows of a point slab (multiple of 4)
+  int b_doubles, nsteps, steps_pad; // steps_pad: table entries rounded up to a multiple of 4 (16-byte granules)
 };
 
 // Point slab: element (k, c), c = point 0..15, lives at 16 k + (c ^ 4 (k & 3)); both the producer's row writes
@@ -232,12 +234,109 @@ __device__ __forceinline__ void values_tetrahedron(double x0, double x1, double 
       });
 }
 
-// All slabs for the column group [n0, n0 + 8 NT) of this warp's 16 points.
+// First k-step of a slab: D = A B (the C operand is the zero register, nothing to clear after the stores).
+__device__ __forceinline__ void dmma_first(double& d0, double& d1, double a, double b)
+{
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+      : "=d"(d0), "=d"(d1)
+      : "d"(a), "d"(b), "d"(0.0), "d"(0.0));
+}
+
+// Everything run_group needs to place an accumulator fragment in the table.
+template <typename T>
+struct Out
+{
+  T* row0;            // LEAN: basis + pt * N + n0 + 2 t (row g of the first row tile, this lane's column pair)
+  T* basis;           // general form
+  size_t slab_stride; // npts * N
+  size_t npts, pt;
+  int N, n0, t;
+};
+
+// One k-step on this warp's two row tiles: 2 NT DMMAs, then -- on the last step of a slab -- the stores.
+template <int NT, bool LEAN, typename T>
+__device__ __forceinline__ void step_compute(int st, double (&acc)[2][NT][2], double a0, double a1,
+                                             const double (&b)[NT], const Out<T>& o)
+{
+  if (st & kStepFirst)
+  {
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+    {
+      dmma_first(acc[0][j][0], acc[0][j][1], a0, b[j]);
+      dmma_first(acc[1][j][0], acc[1][j][1], a1, b[j]);
+    }
+  }
+  else
+  {
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+    {
+      dmma(acc[0][j][0], acc[0][j][1], a0, b[j]);
+      dmma(acc[1][j][0], acc[1][j][1], a1, b[j]);
+    }
+  }
+  const int last = (st >> kStepLastShift) & 0xff;
+  if (last)
+  {
+    // accumulator fragment: row g = point, columns 2t, 2t+1 of each 8-column tile
+    const size_t slab = size_t(last - 1);
+    if constexpr (LEAN)
+    {
+      // whole chunk inside the table, N even: 16-byte stores at compile-time offsets from one row pointer;
+      // only the last column tile of the operand can run past N
+      T* row = o.row0 + slab * o.slab_stride;
+      using T2 = typename std::conditional<sizeof(T) == 8, double2, float2>::type;
+      auto pair = [](double x, double y)
+      {
+        T2 v;
+        v.x = static_cast<T>(x);
+        v.y = static_cast<T>(y);
+        return v;
+      };
+      const bool last_ok = o.n0 + (NT - 1) * 8 + 2 * o.t < o.N;
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+      {
+#pragma unroll
+        for (int j = 0; j < NT - 1; ++j)
+          __stcs(reinterpret_cast<T2*>(row + j * 8), pair(acc[m][j][0], acc[m][j][1]));
+        if (last_ok)
+          __stcs(reinterpret_cast<T2*>(row + (NT - 1) * 8), pair(acc[m][NT - 1][0], acc[m][NT - 1][1]));
+        row += size_t(8) * o.N;
+      }
+    }
+    else
+    {
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+      {
+        const size_t q = o.pt + 8 * m;
+        if (q < o.npts)
+        {
+          T* row = o.basis + slab * o.slab_stride + q * o.N;
+#pragma unroll
+          for (int j = 0; j < NT; ++j)
+          {
+            const int n = o.n0 + j * 8 + 2 * o.t;
+            if (n < o.N)
+              __stcs(row + n, static_cast<T>(acc[m][j][0]));
+            if (n + 1 < o.N)
+              __stcs(row + n + 1, static_cast<T>(acc[m][j][1]));
+          }
+        }
+      }
+    }
+  }
+}
+
+// All slabs for one column group of this warp's 16 points.  Two fragment register sets used alternately (the loop is
+// unrolled by two, so nothing is moved between them): the fragments of step s + 1 are in flight during the DMMAs of
+// step s, across slab boundaries too.
 template <int NT, bool LEAN, typename T>
 __device__ __forceinline__ void run_group(const Step* __restrict__ steps, int nsteps, const double* __restrict__ A0,
-                                          const double* __restrict__ A1, const double* __restrict__ Bgt, int n0,
-                                          int g, int t, T* __restrict__ basis, size_t npts, size_t npts_st, int N,
-                                          size_t pt)
+                                          const double* __restrict__ A1, const double* __restrict__ bp,
+                                          const Out<T>& o)
 {
   double acc[2][NT][2];
 #pragma unroll
@@ -245,139 +344,115 @@ __device__ __forceinline__ void run_group(const Step* __restrict__ steps, int ns
 #pragma unroll
     for (int j = 0; j < NT; ++j)
       acc[m][j][0] = acc[m][j][1] = 0.0;
-  Step st = steps[0];
-  double a0, a1, b[NT];
+  double a[2][2], b[2][NT];
+  auto fetch = [&](int set, int st, const double* p)
   {
-    const double* bp = Bgt + st.boff + (n0 + g) * st.kstride;
-    a0 = A0[st.aoff];
-    a1 = A1[st.aoff];
+    const int aoff = (st & kStepKsMask) * 64;
+    a[set][0] = A0[aoff];
+    a[set][1] = A1[aoff];
 #pragma unroll
     for (int j = 0; j < NT; ++j)
-      b[j] = bp[j * 8 * st.kstride];
-  }
+      b[set][j] = p[j * 32];
+  };
+  int st0 = steps[0];
+  fetch(0, st0, bp);
+  int s = 0;
 #pragma unroll 1
-  for (int s = 0; s < nsteps; ++s)
+  for (; s + 1 < nsteps; s += 2)
   {
-    // fragments of the next step (the table ends with a repeat of the last step)
-    const Step nx = steps[s + 1];
-    const double* bp = Bgt + nx.boff + (n0 + g) * nx.kstride;
-    const double an0 = A0[nx.aoff], an1 = A1[nx.aoff];
-    double bn[NT];
-#pragma unroll
-    for (int j = 0; j < NT; ++j)
-      bn[j] = bp[j * 8 * nx.kstride];
-#pragma unroll
-    for (int j = 0; j < NT; ++j)
-    {
-      dmma(acc[0][j][0], acc[0][j][1], a0, b[j]);
-      dmma(acc[1][j][0], acc[1][j][1], a1, b[j]);
-    }
-    if (st.last)
-    {
-      // accumulator fragment: row g = point, columns 2t, 2t+1 of each 8-column tile
-      const size_t slab = size_t(st.last - 1);
-      if constexpr (LEAN)
-      {
-        // whole chunk inside the table, N even: 16-byte stores at compile-time offsets from one row pointer;
-        // only the last column tile of the operand can run past N
-        T* row = basis + (slab * npts + pt) * N + n0 + 2 * t;
-        using T2 = typename std::conditional<sizeof(T) == 8, double2, float2>::type;
-        auto pair = [](double a, double b)
-        {
-          T2 v;
-          v.x = static_cast<T>(a);
-          v.y = static_cast<T>(b);
-          return v;
-        };
-        const bool last_ok = n0 + (NT - 1) * 8 + 2 * t < N;
-#pragma unroll
-        for (int m = 0; m < 2; ++m)
-        {
-#pragma unroll
-          for (int j = 0; j < NT - 1; ++j)
-            __stcs(reinterpret_cast<T2*>(row + j * 8), pair(acc[m][j][0], acc[m][j][1]));
-          if (last_ok)
-            __stcs(reinterpret_cast<T2*>(row + (NT - 1) * 8), pair(acc[m][NT - 1][0], acc[m][NT - 1][1]));
-          row += size_t(8) * N;
-        }
-      }
-      else
-      {
-#pragma unroll
-        for (int m = 0; m < 2; ++m)
-        {
-          const size_t q = pt + 8 * m;
-          if (q < npts_st)
-          {
-            T* row = basis + (slab * npts + q) * N;
-#pragma unroll
-            for (int j = 0; j < NT; ++j)
-            {
-              const int n = n0 + j * 8 + 2 * t;
-              if (n < N)
-                __stcs(row + n, static_cast<T>(acc[m][j][0]));
-              if (n + 1 < N)
-                __stcs(row + n + 1, static_cast<T>(acc[m][j][1]));
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int m = 0; m < 2; ++m)
-#pragma unroll
-        for (int j = 0; j < NT; ++j)
-          acc[m][j][0] = acc[m][j][1] = 0.0;
-    }
-    st = nx;
-    a0 = an0;
-    a1 = an1;
-#pragma unroll
-    for (int j = 0; j < NT; ++j)
-      b[j] = bn[j];
+    const int st1 = steps[s + 1];
+    fetch(1, st1, bp + NT * 32);
+    step_compute<NT, LEAN, T>(st0, acc, a[0][0], a[0][1], b[0], o);
+    bp += 2 * NT * 32;
+    st0 = steps[s + 2];
+    fetch(0, st0, bp);
+    step_compute<NT, LEAN, T>(st1, acc, a[1][0], a[1][1], b[1], o);
   }
+  if (s < nsteps)
+    step_compute<NT, LEAN, T>(st0, acc, a[0][0], a[0][1], b[0], o);
 }
 
 template <bool LEAN, typename T>
 __device__ __forceinline__ void run_groups(const Step* steps, int nsteps, const double* A0, const double* A1,
-                                           const double* Bgt, int g, int t, T* basis, size_t npts, size_t npts_st,
+                                           const double* Bl, int g, int t, T* basis, size_t npts, size_t slab_stride,
                                            int N, size_t pt)
 {
+  Out<T> o;
+  o.basis = basis;
+  o.slab_stride = slab_stride;
+  o.npts = npts;
+  o.pt = pt;
+  o.N = N;
+  o.t = t;
   for (int n0 = 0; n0 < N; n0 += 8 * kMaxNT)
   {
     const int nt = min(kMaxNT, (N - n0 + 7) >> 3);
+    o.n0 = n0;
+    o.row0 = basis + pt * N + n0 + 2 * t;
     switch (nt)
     {
-    case 1: run_group<1, LEAN, T>(steps, nsteps, A0, A1, Bgt, n0, g, t, basis, npts, npts_st, N, pt); break;
-    case 2: run_group<2, LEAN, T>(steps, nsteps, A0, A1, Bgt, n0, g, t, basis, npts, npts_st, N, pt); break;
-    case 3: run_group<3, LEAN, T>(steps, nsteps, A0, A1, Bgt, n0, g, t, basis, npts, npts_st, N, pt); break;
-    case 4: run_group<4, LEAN, T>(steps, nsteps, A0, A1, Bgt, n0, g, t, basis, npts, npts_st, N, pt); break;
-    case 5: run_group<5, LEAN, T>(steps, nsteps, A0, A1, Bgt, n0, g, t, basis, npts, npts_st, N, pt); break;
-    case 6: run_group<6, LEAN, T>(steps, nsteps, A0, A1, Bgt, n0, g, t, basis, npts, npts_st, N, pt); break;
-    default: run_group<7, LEAN, T>(steps, nsteps, A0, A1, Bgt, n0, g, t, basis, npts, npts_st, N, pt); break;
+    case 1: run_group<1, LEAN, T>(steps, nsteps, A0, A1, Bl, o); break;
+    case 2: run_group<2, LEAN, T>(steps, nsteps, A0, A1, Bl, o); break;
+    case 3: run_group<3, LEAN, T>(steps, nsteps, A0, A1, Bl, o); break;
+    case 4: run_group<4, LEAN, T>(steps, nsteps, A0, A1, Bl, o); break;
+    case 5: run_group<5, LEAN, T>(steps, nsteps, A0, A1, Bl, o); break;
+    case 6: run_group<6, LEAN, T>(steps, nsteps, A0, A1, Bl, o); break;
+    default: run_group<7, LEAN, T>(steps, nsteps, A0, A1, Bl, o); break;
     }
+    Bl += size_t(nsteps) * nt * 32; // fragment block of the next column group
   }
 }
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 
 template <int TDIM, int DEG, int WARPS, typename T>
 __global__ void __launch_bounds__(32 * WARPS, 1) tabulate_dop_kernel(const Params<T> p)
 {
-  constexpr int K = jets::psize(TDIM, DEG);
   constexpr int kThreads = 32 * WARPS;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  // [ steps ][ B ][ slab of warp 0 ] ... [ slab of warp WARPS-1 ]
-  Step* steps = reinterpret_cast<Step*>(smem_raw);
-  double* Bs = reinterpret_cast<double*>(steps + p.nsteps + 1);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // [ mbarrier ][ steps ][ B ][ slab of warp 0 ] ... [ slab of warp WARPS-1 ]
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw);
+  Step* steps = reinterpret_cast<Step*>(smem_raw + 16);
+  double* Bs = reinterpret_cast<double*>(smem_raw + 16 + size_t(p.steps_pad) * sizeof(Step));
   const int slab_doubles = p.kpad * 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* slab = Bs + p.b_doubles + warp * slab_doubles;
 
-  for (int i = threadIdx.x; i < p.b_doubles; i += kThreads)
-    Bs[i] = p.B[i];
-  for (int i = threadIdx.x; i <= p.nsteps; i += kThreads)
-    steps[i] = p.steps[i];
+  // the operands (one contiguous block, up to ~190 KB) and the step table enter shared memory as TMA bulk copies
+  // tracked by one mbarrier; meanwhile all threads clear the point slabs
+  if (threadIdx.x == 0)
+  {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t b_bytes = uint32_t(p.b_doubles) * 8u, s_bytes = uint32_t(p.steps_pad) * uint32_t(sizeof(Step));
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(smem_addr(bar)),
+                 "r"(b_bytes + s_bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(steps)),
+                 "l"(p.steps), "r"(s_bytes), "r"(smem_addr(bar))
+                 : "memory");
+    constexpr uint32_t kPiece = 32768;
+    for (uint32_t off = 0; off < b_bytes; off += kPiece)
+    {
+      const uint32_t n = min(kPiece, b_bytes - off);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_addr(Bs) + off),
+                   "l"(reinterpret_cast<const char*>(p.B) + off), "r"(n), "r"(smem_addr(bar))
+                   : "memory");
+    }
+  }
   for (int i = threadIdx.x; i < WARPS * slab_doubles; i += kThreads)
     Bs[p.b_doubles + i] = 0.0; // rows K .. kpad-1 are read by the last k-step of the value slab and must stay finite
-  __syncthreads();
+  __syncthreads(); // barrier initialised and visible, slabs cleared
+  {
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{\n .reg .pred q;\n mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n selp.u32 %0, 1, 0, q;\n}"
+                   : "=r"(done)
+                   : "r"(smem_addr(bar)), "r"(0)
+                   : "memory");
+  }
 
   // chunk c of this warp: points [16 c, 16 c + 16); consecutive warps / CTAs take consecutive chunks
   const size_t nchunks = ceil_div(p.npts, size_t(kChunkPts));
@@ -386,7 +461,7 @@ __global__ void __launch_bounds__(32 * WARPS, 1) tabulate_dop_kernel(const Param
   const bool n_even = (p.N & 1) == 0;
   const double* A0 = slab + t * 16 + (g ^ (t << 2));
   const double* A1 = slab + t * 16 + ((g + 8) ^ (t << 2));
-  const double* Bgt = Bs + t;
+  const double* Bl = Bs + lane;
   const int c = lane & 15;
   const SlabSink sink{{slab + c, slab + (c ^ 4), slab + (c ^ 8), slab + (c ^ 12)}};
 
@@ -423,9 +498,9 @@ __global__ void __launch_bounds__(32 * WARPS, 1) tabulate_dop_kernel(const Param
     const size_t pt = chunk * kChunkPts + g;
     const bool lean = n_even and (chunk + 1) * kChunkPts <= p.npts;
     if (lean)
-      run_groups<true, T>(steps, p.nsteps, A0, A1, Bgt, g, t, p.basis, p.npts, p.npts, p.N, pt);
+      run_groups<true, T>(steps, p.nsteps, A0, A1, Bl, g, t, p.basis, p.npts, p.slab_stride, p.N, pt);
     else
-      run_groups<false, T>(steps, p.nsteps, A0, A1, Bgt, g, t, p.basis, p.npts, p.npts, p.N, pt);
+      run_groups<false, T>(steps, p.nsteps, A0, A1, Bl, g, t, p.basis, p.npts, p.slab_stride, p.N, pt);
     __syncwarp(); // the slab is overwritten by the next chunk
   }
 }
@@ -435,7 +510,7 @@ struct Operand
 {
   double* d_B = nullptr;
   Step* d_steps = nullptr;
-  int b_doubles = 0, nsteps = 0, kpad = 0, warps = 0;
+  int b_doubles = 0, nsteps = 0, steps_pad = 0, kpad = 0, warps = 0;
   bool usable = false;
   size_t smem = 0;
 };
@@ -515,7 +590,13 @@ Operand build_operand(const bx_element& e, int nd, bool upload_to_device)
   const int nder = polyset_nderivs(cell, nd);
   const int npad = int(ceil_div(N, 8) * 8);
   op.kpad = int(ceil_div(K, 4) * 4);
-  Vec B;
+  // dense, zero-padded operand of every slab in step order: Bd[npad][4 ksteps]
+  struct SlabOp
+  {
+    Vec Bd;
+    int ksteps, d;
+  };
+  std::vector<SlabOp> slabs;
   std::vector<Step> steps;
   auto matmul = [K](const Vec& A, const Vec& Bm)
   {
@@ -547,33 +628,51 @@ Operand build_operand(const bx_element& e, int nd, bool upload_to_device)
           for (int r = 0; r < cnt[a]; ++r)
             M = matmul(M, D[a]);
         const int Kd = simplex_dim(tdim, n - m);
-        const int ksteps = std::max(1, int(ceil_div(Kd, 4))); // derivative order above the degree: one zero step
-        const int kp = ksteps * 4;
-        const int kstride = kp % 8 == 4 ? kp : kp + 4;
-        const int boff = int(B.size());
-        B.resize(B.size() + size_t(npad) * kstride, 0.0);
+        SlabOp so;
+        so.ksteps = std::max(1, int(ceil_div(Kd, 4))); // derivative order above the degree: one zero step
+        so.d = d;
+        const int kp = so.ksteps * 4;
+        so.Bd.assign(size_t(npad) * kp, 0.0);
         for (int row = 0; row < N; ++row)
           for (int j = 0; j < Kd; ++j)
           {
-            double s = 0.0;
+            double sum = 0.0;
             for (int k = 0; k < K; ++k)
-              s += e.Cp[size_t(row) * e.Kpad + k] * M[size_t(k) * K + j];
-            B[size_t(boff) + size_t(row) * kstride + j] = s * norm[j];
+              sum += e.Cp[size_t(row) * e.Kpad + k] * M[size_t(k) * K + j];
+            so.Bd[size_t(row) * kp + j] = sum * norm[j];
           }
-        for (int ks = 0; ks < ksteps; ++ks)
-          steps.push_back(Step{boff + 4 * ks, kstride, 64 * ks, ks + 1 == ksteps ? 1 + d : 0});
+        for (int ks = 0; ks < so.ksteps; ++ks)
+          steps.push_back(ks | (ks + 1 == so.ksteps ? (1 + d) << kStepLastShift : 0) | (ks == 0 ? kStepFirst : 0));
+        slabs.push_back(std::move(so));
       }
+  if (nder > 255 or op.kpad / 4 > 256)
+    return op; // outside the packed step encoding
   op.nsteps = int(steps.size());
-  steps.push_back(steps.back()); // prefetch target of the last step
-  op.b_doubles = int((B.size() + 1) & ~size_t(1));
-  B.resize(op.b_doubles, 0.0);
+  steps.push_back(steps.back()); // prefetch targets of the last steps
+  steps.push_back(steps.back());
+  op.steps_pad = int(ceil_div(steps.size(), 4) * 4);
+  steps.resize(op.steps_pad, steps.back());
+  // fragment-major: Bf[column group][step][j < NT][lane] = B_slab[n0 + 8 j + (lane >> 2)][4 ks + (lane & 3)]
+  Vec B;
+  B.reserve(size_t(op.nsteps + 1) * (npad / 8) * 32);
+  for (int n0 = 0; n0 < N; n0 += 8 * kMaxNT)
+  {
+    const int nt = std::min(kMaxNT, (N - n0 + 7) / 8);
+    for (const SlabOp& so : slabs)
+      for (int ks = 0; ks < so.ksteps; ++ks)
+        for (int j = 0; j < nt; ++j)
+          for (int lane = 0; lane < 32; ++lane)
+            B.push_back(so.Bd[size_t(n0 + 8 * j + (lane >> 2)) * (4 * so.ksteps) + 4 * ks + (lane & 3)]);
+  }
+  B.resize(B.size() + size_t(2) * kMaxNT * 32, 0.0); // the loop prefetches up to two steps past the last group
+  op.b_doubles = int(B.size());
   // three warps per SM sub-partition when their slabs fit beside the operands, else two
   static const int warps_env = std::getenv("BX_DOP_WARPS") ? std::atoi(std::getenv("BX_DOP_WARPS")) : 0;
   for (int warps : {12, 8})
   {
     if (warps_env and warps != warps_env)
       continue;
-    const size_t smem = sizeof(Step) * steps.size() + size_t(op.b_doubles) * 8
+    const size_t smem = 16 + sizeof(Step) * steps.size() + size_t(op.b_doubles) * 8
                         + size_t(warps) * op.kpad * 16 * 8;
     if (smem <= 227 * 1024)
     {
@@ -609,6 +708,8 @@ void launch_warps(const Operand& op, const bx_element& e, const T* x, size_t npt
   p.kpad = op.kpad;
   p.b_doubles = op.b_doubles;
   p.nsteps = op.nsteps;
+  p.steps_pad = op.steps_pad;
+  p.slab_stride = npts * size_t(e.N);
   const size_t nblocks = ceil_div(npts, size_t(kChunkPts) * WARPS);
   kern<<<unsigned(std::min<size_t>(nblocks, size_t(sm_count()))), 32 * WARPS, op.smem, s>>>(p);
   BX_LAUNCHED();
