@@ -24,6 +24,7 @@
 //   3. store   the range goes back with coalesced stores.
 // Each global byte of the movable range is read once and written once; nothing else is touched.
 #include "dof_transform_tma.cuh"
+#include "dof_transform_direct.cuh"
 #include "element.cuh"
 
 #include <algorithm>
@@ -274,7 +275,7 @@ EncodeTiled encode_tiled()
 // number of 16-byte units the box is padded by (pad=0: never).
 struct Tune
 {
-  int cpt = 0, nbuf = 0, promo = -1, skip = 0, pad = -1;
+  int cpt = 0, nbuf = 0, promo = -1, skip = 0, pad = -1, direct = -1;
 };
 const Tune& tune()
 {
@@ -295,6 +296,7 @@ const Tune& tune()
       get("promo=", v.promo);
       get("skip=", v.skip);
       get("pad=", v.pad);
+      get("direct=", v.direct);
     }
     return v;
   }();
@@ -378,12 +380,71 @@ void launch_perm_tma_any(const CUtensorMap& map, void* data, const tma::Params& 
 }
 
 // Returns false when the layout does not meet the TMA rules (the caller then takes the register-staged kernel).
+template <int REG>
+void launch_matrix_direct_reg(double* data, const direct::Params& p, size_t smem, cudaStream_t s)
+{
+  auto kern = direct::dof_matrix_direct_kernel<REG>;
+  if (smem > 48 * 1024)
+    BX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  int per_sm = 0;
+  BX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, direct::kThreads, smem));
+  const size_t nitems = p.nc * size_t(p.nslots);
+  const size_t nblocks = ceil_div(nitems, size_t(direct::kThreads));
+  // a few waves of resident CTAs: each CTA pays the table set-up once
+  const size_t cap = size_t(sm_count()) * size_t(std::max(per_sm, 1)) * 8;
+  kern<<<unsigned(std::min(nblocks, cap)), direct::kThreads, smem, s>>>(data, p);
+  BX_LAUNCHED();
+}
+
+// float64, left operators, block size 1, even entity starts, 16-byte aligned cells: the register kernel
+bool try_direct(const bx_element& e, int kind, double* data, size_t nc, size_t cell_size, int maxdim,
+                const uint32_t* cell_info, cudaStream_t s)
+{
+  if (reinterpret_cast<uintptr_t>(data) % 16 != 0 or (cell_size * 8) % 16 != 0 or maxdim > kMaxRegDim or !e.d_mats)
+    return false;
+  for (const auto& sl : e.slots)
+    if (sl.first % 2 != 0)
+      return false;
+  direct::Params p;
+  p.nc = nc;
+  p.cell_size = cell_size;
+  p.nslots = int(e.slots.size());
+  p.table_size = e.mats_size;
+  p.band_size = e.band_size;
+  p.cell_info = cell_info;
+  p.slot_info = e.d_slot_info;
+  p.slot_mat = e.d_slot_mat;
+  p.slot_band = e.d_slot_band;
+  p.band = e.d_band;
+  p.mats = e.d_mats + size_t(kind) * e.mats_size;
+  const size_t smem = size_t(e.mats_size) * 8 + size_t(e.band_size + (e.band_size & 1)) * 8 + size_t(p.nslots) * 32;
+  if (smem > 200 * 1024)
+    return false;
+  if (maxdim <= 4)
+    launch_matrix_direct_reg<4>(data, p, smem, s);
+  else if (maxdim <= 8)
+    launch_matrix_direct_reg<8>(data, p, smem, s);
+  else if (maxdim <= 12)
+    launch_matrix_direct_reg<12>(data, p, smem, s);
+  else if (maxdim <= 16)
+    launch_matrix_direct_reg<16>(data, p, smem, s);
+  else if (maxdim <= 24)
+    launch_matrix_direct_reg<24>(data, p, smem, s);
+  else
+    launch_matrix_direct_reg<32>(data, p, smem, s);
+  return true;
+}
+
 template <typename T>
 bool try_tma(const bx_element& e, int kind, bool right, T* data, size_t nc, size_t cell_size, int n, int r0, int len,
              int maxdim, const uint32_t* cell_info, cudaStream_t s)
 {
   constexpr size_t sz = sizeof(T);
   constexpr int per16 = int(16 / sz);
+  if constexpr (std::is_same<T, double>::value)
+    if (!e.perms and !right and n == 1 and tune().direct > 0 and !tune().skip
+        and try_direct(e, kind, data, nc, cell_size, maxdim, cell_info, s))
+      return true;
   if (reinterpret_cast<uintptr_t>(data) % 16 != 0 or (cell_size * sz) % 16 != 0 or nc >= (size_t(1) << 31))
     return false;
   if (maxdim > kMaxRegDim or e.gather_size >= 65536 or cell_size >= (size_t(1) << 20))

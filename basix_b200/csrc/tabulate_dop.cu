@@ -20,15 +20,19 @@
 // (compile-time (p, q, r): literal coefficients, immediate store offsets) into the warp's private, XOR-swizzled
 // shared-memory slab P[k][16]; then the warp contracts its two m8 row tiles with every slab operand on the FP64 tensor
 // cores (each B-fragment load feeds two DMMAs) and stores each m8n8 accumulator fragment straight as
-// basis[d][pt][n].  The contraction is ONE flat loop over the k-steps of all slabs, driven by a step table in shared
-// memory, with the fragments of step s+1 loaded into a second register set before the DMMAs of step s: a slab
-// boundary costs only its stores, not a pipeline drain (a separate loop per slab reached 65 % of the DMMA peak for
-// one warp per sub-partition and 80 % for two, tools/dmma_loop.cu).  No block barrier and no mbarrier after set-up:
+// basis[d][pt][n].  The contraction is ONE flat loop over the k-steps of all slabs, unrolled by two over two fragment
+// register sets: the fragments of step s+1 are loaded while the DMMAs of step s issue (the compiler spreads the loads
+// between the DMMAs, where they cost nothing), so a slab boundary costs only its stores, not a pipeline drain (a
+// separate loop per slab reached 65 % of the DMMA peak for one warp per sub-partition and 80 % for two,
+// tools/dmma_loop.cu).  The slab operands are stored fragment-major in the order the loop consumes them (one pointer,
+// immediate offsets, no per-step address arithmetic) and enter shared memory as TMA bulk copies on one mbarrier.  No
+// block barrier and no mbarrier after set-up:
 // DFMA and DMMA share one execution pipe on B200 (tools/mixed_fp64.cu: 37 TFLOP/s alone or mixed), so dedicated
 // producer warps starve behind the DMMA stream and stall every consumer waiting on their tile (measured: 2 ms of
 // 12.5 ms per 10 M points); with independent warps a warp that is producing or storing simply leaves the pipe to
-// the other warps of its sub-partition.  Measured on P5 / nd = 2, 10 M points: 10.1 ms (84 % of the DMMA peak on
-// the flops this algorithm executes), against 20.9 ms for the dense fused kernel.
+// the other warps of its sub-partition.  Measured on P5 / nd = 2, 10 M points: 9.9-10.0 ms (0.855 of the DMMA peak on
+// the flops this algorithm executes), against 20.9 ms for the dense fused kernel; with the value production removed
+// 9.42, with the stores removed 9.50, with both removed 9.15 (the loop itself: 0.94 of the executed-flop floor).
 // Parity: 2.8e-14 * max|ref| per slab against the reference on P5 / nd = 2 (bar: 1e-12).
 #include "element.cuh"
 #include "hostmath.cuh"
@@ -61,8 +65,7 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
 // by NT * 32 doubles per step: no per-step address arithmetic, no padding of the operand rows.
 using Step = int;
 constexpr int kStepKsMask = 0xff;   // bits 0..7: ks (slab row 4 ks of the point slab = offset 64 ks doubles)
-constexpr int kStepLastShift = 8;   // bits 8..15: 0, or 1 + derivative slab index when this is the last k-step of it
-constexpr int kStepFirst = 1 << 16; // bit 16: first k-step of its slab (the accumulators start from zero)
+constexpr int kStepLastShift = 8;   // bits 8..: 0, or 1 + derivative slab index when this is the last k-step of it
 
 // T = type of the points and of the table (double, or float for the float32 API: loads widen, stores narrow, the
 // operands and the arithmetic are double either way)
@@ -234,14 +237,6 @@ __device__ __forceinline__ void values_tetrahedron(double x0, double x1, double 
       });
 }
 
-// First k-step of a slab: D = A B (the C operand is the zero register, nothing to clear after the stores).
-__device__ __forceinline__ void dmma_first(double& d0, double& d1, double a, double b)
-{
-  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
-      : "=d"(d0), "=d"(d1)
-      : "d"(a), "d"(b), "d"(0.0), "d"(0.0));
-}
-
 // Everything run_group needs to place an accumulator fragment in the table.
 template <typename T>
 struct Out
@@ -258,25 +253,13 @@ template <int NT, bool LEAN, typename T>
 __device__ __forceinline__ void step_compute(int st, double (&acc)[2][NT][2], double a0, double a1,
                                              const double (&b)[NT], const Out<T>& o)
 {
-  if (st & kStepFirst)
-  {
 #pragma unroll
-    for (int j = 0; j < NT; ++j)
-    {
-      dmma_first(acc[0][j][0], acc[0][j][1], a0, b[j]);
-      dmma_first(acc[1][j][0], acc[1][j][1], a1, b[j]);
-    }
-  }
-  else
+  for (int j = 0; j < NT; ++j)
   {
-#pragma unroll
-    for (int j = 0; j < NT; ++j)
-    {
-      dmma(acc[0][j][0], acc[0][j][1], a0, b[j]);
-      dmma(acc[1][j][0], acc[1][j][1], a1, b[j]);
-    }
+    dmma(acc[0][j][0], acc[0][j][1], a0, b[j]);
+    dmma(acc[1][j][0], acc[1][j][1], a1, b[j]);
   }
-  const int last = (st >> kStepLastShift) & 0xff;
+  const int last = st >> kStepLastShift;
   if (last)
   {
     // accumulator fragment: row g = point, columns 2t, 2t+1 of each 8-column tile
@@ -327,6 +310,13 @@ __device__ __forceinline__ void step_compute(int st, double (&acc)[2][NT][2], do
         }
       }
     }
+    // the next step opens the next slab (a branch-free DMMA block lets the compiler spread the fragment loads of the
+    // next step between the DMMAs; a zero-C first step in its own branch measured the same)
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+        acc[m][j][0] = acc[m][j][1] = 0.0;
   }
 }
 
@@ -354,19 +344,22 @@ __device__ __forceinline__ void run_group(const Step* __restrict__ steps, int ns
     for (int j = 0; j < NT; ++j)
       b[set][j] = p[j * 32];
   };
-  int st0 = steps[0];
+  // table entries are read two steps ahead of their use, fragments one step ahead
+  int st0 = steps[0], st1 = steps[1];
   fetch(0, st0, bp);
   int s = 0;
 #pragma unroll 1
   for (; s + 1 < nsteps; s += 2)
   {
-    const int st1 = steps[s + 1];
+    const int st2 = steps[s + 2];
     fetch(1, st1, bp + NT * 32);
     step_compute<NT, LEAN, T>(st0, acc, a[0][0], a[0][1], b[0], o);
     bp += 2 * NT * 32;
-    st0 = steps[s + 2];
-    fetch(0, st0, bp);
+    const int st3 = steps[s + 3];
+    fetch(0, st2, bp);
     step_compute<NT, LEAN, T>(st1, acc, a[1][0], a[1][1], b[1], o);
+    st0 = st2;
+    st1 = st3;
   }
   if (s < nsteps)
     step_compute<NT, LEAN, T>(st0, acc, a[0][0], a[0][1], b[0], o);
@@ -642,7 +635,7 @@ Operand build_operand(const bx_element& e, int nd, bool upload_to_device)
             so.Bd[size_t(row) * kp + j] = sum * norm[j];
           }
         for (int ks = 0; ks < so.ksteps; ++ks)
-          steps.push_back(ks | (ks + 1 == so.ksteps ? (1 + d) << kStepLastShift : 0) | (ks == 0 ? kStepFirst : 0));
+          steps.push_back(ks | (ks + 1 == so.ksteps ? (1 + d) << kStepLastShift : 0));
         slabs.push_back(std::move(so));
       }
   if (nder > 255 or op.kpad / 4 > 256)
@@ -754,10 +747,14 @@ bool launch_any(const bx_element& e, int nd, const U* x, size_t npts, U* basis, 
   }
   if (!op->usable or (!dry_run and !op->d_B))
     return false;
+#ifdef BX_DOP_DEV // development builds: only the BASELINE element (the full menu takes minutes to compile)
+  BX_DOP(3, 5)
+#else
   BX_DOP(1, 1) BX_DOP(1, 2) BX_DOP(1, 3) BX_DOP(1, 4) BX_DOP(1, 5) BX_DOP(1, 6) BX_DOP(1, 7) BX_DOP(1, 8)
   BX_DOP(1, 9) BX_DOP(1, 10)
   BX_DOP(2, 1) BX_DOP(2, 2) BX_DOP(2, 3) BX_DOP(2, 4) BX_DOP(2, 5) BX_DOP(2, 6) BX_DOP(2, 7) BX_DOP(2, 8)
   BX_DOP(3, 1) BX_DOP(3, 2) BX_DOP(3, 3) BX_DOP(3, 4) BX_DOP(3, 5) BX_DOP(3, 6)
+#endif
   return false;
 }
 template bool launch_any<double>(const bx_element&, int, const double*, size_t, double*, cudaStream_t, bool);

@@ -309,6 +309,39 @@ def test_T_apply_matrix_elements(ref, family, cell, degree, variant, bs):
         assert np.max(np.abs(got - want)) <= 1e-12 * np.max(np.abs(want)), op
 
 
+def test_T_apply_direct_kernel():
+    """The register form of the matrix kernel (dof_transform_direct.cuh) is a development alternative selected with
+    BX_DOF_TUNE="direct=1"; the knob is read once per process, so it is checked in a child process against the
+    default tile kernel of this process's reference run."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import numpy as np, sys\n"
+        "sys.path.insert(0, %r)\n"
+        "import basix_b200 as bx\n"
+        "from oracle import ref\n"
+        "n0 = bx.kernel_launch_count()\n"
+        "for fam, deg in ((2, 4), (3, 3), (2, 2)):\n"
+        "    r, e = ref.RefElement(fam, 3, deg, 11), bx.create_element(fam, 3, deg, 11)\n"
+        "    rng = np.random.default_rng(7)\n"
+        "    ci = rng.integers(0, 2**30, 4001).astype(np.uint32)\n"
+        "    data = rng.standard_normal((4001, r.dim))\n"
+        "    for op in ('T_apply', 'Tt_apply', 'Tinv_apply', 'Tt_inv_apply'):\n"
+        "        want = data.copy()\n"
+        "        r.T_apply_batch(op, want, 1, ci)\n"
+        "        got = data.copy()\n"
+        "        e.T_apply_batch(got, 1, ci, op=op)\n"
+        "        assert np.max(np.abs(got - want)) <= 1e-12 * np.max(np.abs(want)), (fam, deg, op)\n"
+        "assert bx.kernel_launch_count() > n0\n"
+        "print('ok')\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, BX_DOF_TUNE="direct=1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
 def test_T_apply_single_cell_reference_signature(ref):
     """The reference API: one cell per call (finite_element.py:153-166)."""
     r, e = make_pair(ref, RT, TET, 2, LEG)
