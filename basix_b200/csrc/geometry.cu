@@ -43,6 +43,10 @@ constexpr int kThreads = 256;
 #endif
 constexpr int kFusedMaxThreads = 512; // the fused kernel runs 4, 8 or 16 warps per CTA (launch_fused)
 constexpr int kPair = BX_FUSED_PAIR; // row passes per trip of the fused kernel's row loop
+#ifndef BX_FLAT_PAIR
+#define BX_FLAT_PAIR 2
+#endif
+constexpr int kFlatPair = BX_FLAT_PAIR; // 32-row passes per trip of the flat row walk
 
 // Unscaled inverse and its divisor: K = adj / div, detJ = div (square) or sqrt(div) (non-square, div = det(J^T J)).
 //   1 x 1, 2 x 2, 3 x 3: adjugate and determinant (first-row cofactor expansion)
@@ -293,6 +297,7 @@ struct FusedParams
   int nbuf;         // slices per warp (1 or 2)
   int bulk;         // the rows of `batch` consecutive cells are one 16-byte aligned run of `out`: TMA bulk copy-out
   int vec_coords;   // coords is 16-byte aligned: 16-byte loads
+  uint32_t rows_magic; // flat row walk: floor(2^32 / rows) + 1 (0 when rows == 1): cell = umulhi(f, rows_magic) for f < 2^13
   size_t out_pitch; // entries between consecutive cells of `out` (>= rows * OUT_VS: a chunk of a larger point set)
   const int16_t* dof_slot;  // [ndofs] owning slot or -1
   const int4* slot_info;    // [nslots] {shift, mask, dim, _}
@@ -392,7 +397,7 @@ __host__ __device__ constexpr int prefetch_entries()
 //     shared table), pick the reference values of the row's state, map them and write the slice; the rows of the batch
 //     are one contiguous run of `out` and leave as ONE TMA bulk copy, the warp going on with the next batch in the
 //     other slice while the copy engine reads.
-template <typename T, int MAP, int G, int TD, bool GEOM, int VS>
+template <typename T, int MAP, int G, int TD, bool GEOM, int VS, bool FLAT>
 __global__ void __launch_bounds__(kFusedMaxThreads, 1)
     physical_basis_kernel(const T* __restrict__ tab, const T* __restrict__ coords, const T* __restrict__ A,
                           const T* __restrict__ detJ, const FusedParams p, T* __restrict__ out)
@@ -532,7 +537,94 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1)
       }
     }
     __syncwarp();
+    if constexpr (FLAT)
+    {
+      // ---- phase B, flat: the (cell, row) pairs of the warp's cells are ONE index space walked 32 (or 64) at a time, so
+      // every lane has a row whatever rows % 32 is (70 rows: 9 passes per 4 cells instead of 12); the cell's record is
+      // read per lane (at most two different cells per pass when rows >= 32: broadcast loads), the mapped row goes
+      // straight to global memory: a pass writes one contiguous run of 32 * OUT_VS entries of `out` ----
+      static_assert(MAP != BX_MAP_IDENTITY, "the flat row walk is for the Piola maps");
+      const uint32_t total = uint32_t(nb) * uint32_t(rows);
+      T* const obase = out + c0 * p.out_pitch;
+      auto fpass = [&](auto nh, uint32_t f0)
+      {
+        constexpr int NH = decltype(nh)::value;
+        bool ok[NH];
+        const T* u[NH];
+        const T* rc[NH];
+        T* g[NH];
+#pragma unroll
+        for (int h = 0; h < NH; ++h)
+        {
+          const uint32_t f = f0 + 32u * h + lane;
+          ok[h] = f < total;
+          const uint32_t fc = min(f, total - 1u); // lanes past the last row repeat it and do not store
+          const uint32_t cell = p.rows_magic ? __umulhi(fc, p.rows_magic) : fc;
+          const uint32_t row = fc - cell * uint32_t(rows);
+          const uint32_t ci = __shfl_sync(0xffffffffu, my_ci, int(cell));
+          const uint32_t d = s_desc[row];
+          const int st = int(ci >> (d & 31u)) & int(d >> 5);
+          u[h] = s_tab + st * p.tab_stride + row * IN_VS;
+          rc[h] = rec + cell * REC;
+          g[h] = obase + cell * p.out_pitch + row * OUT_VS;
+        }
+        T uu[NH][IN_VS], m[NH][MA], acc[NH][OUT_VS];
+#pragma unroll
+        for (int h = 0; h < NH; ++h)
+        {
+#pragma unroll
+          for (int k = 0; k < IN_VS; ++k)
+            uu[h][k] = u[h][k];
+#pragma unroll
+          for (int k = 0; k < MA; ++k)
+            m[h][k] = rc[h][k];
+        }
+#pragma unroll
+        for (int i = 0; i < OUT_VS; ++i)
+#pragma unroll
+          for (int h = 0; h < NH; ++h)
+          {
+            T a = 0;
+            if constexpr (MAP == BX_MAP_COVARIANT_PIOLA)
+            {
+#pragma unroll
+              for (int k = 0; k < TD; ++k)
+                a += m[h][k * G + i] * uu[h][k]; // out[i] = sum_k K[k][i] in[k]   (maps.h:73-94)
+            }
+            else
+            {
+#pragma unroll
+              for (int k = 0; k < TD; ++k)
+                a += m[h][i * TD + k] * uu[h][k]; // out[i] = (sum_k J[i][k] in[k]) / det   (maps.h:100-124)
+            }
+            acc[h][i] = a;
+          }
+        if constexpr (MAP == BX_MAP_CONTRAVARIANT_PIOLA)
+        {
+#pragma unroll
+          for (int h = 0; h < NH; ++h)
+            div_by<T, OUT_VS>(acc[h], rc[h][MA], rc[h][MA + 1]);
+        }
+#pragma unroll
+        for (int h = 0; h < NH; ++h)
+          if (ok[h])
+          {
+#pragma unroll
+            for (int i = 0; i < OUT_VS; ++i)
+              g[h][i] = acc[h][i];
+          }
+      };
+#pragma unroll 1
+      for (uint32_t f0 = 0; f0 < total; f0 += 32 * kFlatPair)
+      {
+        if (kFlatPair == 2 and f0 + 32 < total)
+          fpass(std::integral_constant<int, kFlatPair>{}, f0);
+        else
+          fpass(std::integral_constant<int, 1>{}, f0);
+      }
+    }
     // ---- phase B ----
+    if constexpr (!FLAT)
     for (int b0 = 0; b0 < nb; b0 += B)
     {
       const int cells = min(B, nb - b0);
@@ -725,7 +817,7 @@ void launch_geometry(const T* coords, const T* dphi, size_t nc, int nv, int npts
 // Tuning aid (development only): BX_FUSED_TUNE="b=2,nbuf=2,nw=8" overrides the cells per slice, the slices per warp and the warps per CTA.
 struct FusedTune
 {
-  int b = 0, nbuf = 0, nw = 0;
+  int b = 0, nbuf = 0, nw = 0, flat = -1;
 };
 inline const FusedTune& fused_tune()
 {
@@ -744,6 +836,7 @@ inline const FusedTune& fused_tune()
       get("b=", v.b);
       get("nbuf=", v.nbuf);
       get("nw=", v.nw);
+      get("flat=", v.flat);
     }
     return v;
   }();
@@ -762,7 +855,6 @@ void launch_fused(const T* tab, const T* coords, const T* A, const T* detJ, Fuse
            + size_t(nw) * (size_t(nbuf) * pad4(batch * E) + pad4(32 * REC) + pad4(32 * prefetch_entries<MAP, G, TD, GEOM>())) * sizeof(T);
   };
   const bool contiguous = p.out_pitch == size_t(E) and reinterpret_cast<uintptr_t>(out) % 16 == 0;
-  auto kern = physical_basis_kernel<T, MAP, G, TD, GEOM, VS>;
   static const size_t smem_max = [&]
   {
     int dev = 0, v = 0;
@@ -770,6 +862,37 @@ void launch_fused(const T* tab, const T* coords, const T* A, const T* detJ, Fuse
     BX_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     return size_t(v);
   }();
+  p.rows_magic = p.rows > 1 ? uint32_t((uint64_t(1) << 32) / uint64_t(p.rows)) + 1u : 0u;
+  if constexpr (MAP != BX_MAP_IDENTITY)
+  {
+    // Piola maps: flat walk over the (cell, row) pairs, rows written straight to global memory (no slices)
+    if (fused_tune().flat != 0)
+    {
+      auto flat = physical_basis_kernel<T, MAP, G, TD, GEOM, VS, true>;
+      const int nw = (fused_tune().nw == 4 or fused_tune().nw == 8 or fused_tune().nw == 16) ? fused_tune().nw : 8;
+      p.batch = 0;
+      p.nbuf = 0;
+      p.bulk = 0;
+      p.vec_coords = reinterpret_cast<uintptr_t>(coords) % 16 == 0;
+      const size_t smem = smem_of(0, 0, nw);
+      if (smem <= smem_max)
+      {
+        if (smem > 48 * 1024)
+          BX_CUDA(cudaFuncSetAttribute(flat, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        int per_sm = 1;
+        BX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flat, nw * 32, smem));
+        if (per_sm >= 1)
+        {
+          const size_t want = ceil_div(p.nc, size_t(nw) * 32);
+          const int grid = int(std::max<size_t>(1, std::min(want, size_t(sm_count()) * per_sm)));
+          flat<<<grid, nw * 32, smem, s>>>(tab, coords, A, detJ, p, out);
+          BX_LAUNCHED();
+          return;
+        }
+      }
+    }
+  }
+  auto kern = physical_basis_kernel<T, MAP, G, TD, GEOM, VS, false>;
   cudaFuncAttributes fa;
   BX_CUDA(cudaFuncGetAttributes(&fa, kern));
   // Warps per CTA (4 / 8 / 16), cells per slice and slices per warp: the configuration with the most resident warps per

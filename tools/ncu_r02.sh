@@ -24,4 +24,13 @@ cap physical_basis_rt4 physical_basis_rt4 physical_basis 2000000
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_ncu_launches_bench_default.csv \
   python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline --no-configs > gpurun_out/ncu_launches.log 2>&1
 tail -1 gpurun_out/ncu_launches.log | cut -c1-200
-ls -la gpurun_out/*.ncu-rep | awk '{print $5, $9}'
+# condense on the box (the reports are too large to travel: 64 MiB limit on gpurun_out/)
+for r in gpurun_out/r02_*.ncu-rep; do
+  n=$(basename "$r" .ncu-rep)
+  python tools/ncu_summary.py "$r" > "gpurun_out/${n/r02_/r02_ncu_}.txt" 2>/dev/null
+  python tools/ncu_stalls.py "$r" > "gpurun_out/${n/r02_/r02_stalls_}.txt" 2>/dev/null
+done
+for r in gpurun_out/r02_*.ncu-rep; do
+  case "$r" in *physical_basis_rt4*|*dof_matrix_rt4.ncu-rep|*small_p1tri*) ;; *) rm -f "$r" ;; esac
+done
+du -sh gpurun_out

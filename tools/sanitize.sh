@@ -16,8 +16,11 @@ run() { # tool  timeout  pytest-args...
     echo "# compute-sanitizer --tool $tool  python -m pytest -m gpu -q -x $*"
     echo "exit code: $rc   (86 = the tool reported errors, 124 = timeout)"
     grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed|error" "$log" | tail -8
-    grep -E "^=========     (at|Invalid|Race|Barrier|Uninit)" "$log" | sort | uniq -c | sort -rn | head -20
+    grep -E "^========= (Invalid|Race|Barrier|Uninit|Program hit|Error|Warning|Hazard|ERROR|WARN)" "$log" | sed -E 's/0x[0-9a-f]+/0x../g; s/thread \([0-9,]+\)/thread (..)/g; s/block \([0-9,]+\)/block (..)/g' | sort | uniq -c | sort -rn | head -20
+    echo "--- first report ---"
+    grep -m1 -A14 -E "^========= (Invalid|Race|Barrier|Uninit|Program hit|Error|Warning|Hazard|ERROR|WARN)" "$log" | cut -c1-220
   } > gpurun_out/sanitizer_$tool.txt
+  head -c 60000 "$log" > "$log.head"; tail -c 60000 "$log" > "$log.tail"; rm -f "$log"
   cat gpurun_out/sanitizer_$tool.txt
 }
 run memcheck ${MEMCHECK_TIMEOUT:-900} $SMALL
