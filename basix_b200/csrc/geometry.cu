@@ -1026,6 +1026,41 @@ void geometry_device(const T* coords, const T* dphi, size_t nc, int nv, int gdim
   }
 }
 
+// push_forward_broadcast through the flat walk of the fused kernel (one slab of reference values U[rows][tdim] for all
+// cells, A = K (covariant) or J (contravariant) per cell, no transformation): the same arithmetic as maps.cu, every lane
+// busy whatever rows % 32 is.  Returns false when the shape is outside the fused kernel's menu (the caller falls back to
+// map_bcast_kernel).
+template <typename T>
+bool push_forward_broadcast_flat(int map_type, const T* U, const T* J, const T* detJ, const T* K, size_t nc, size_t rows,
+                                 int gdim, int tdim, T* out, cudaStream_t s)
+{
+  if (map_type != BX_MAP_COVARIANT_PIOLA and map_type != BX_MAP_CONTRAVARIANT_PIOLA)
+    return false;
+  if (rows > 256 or geo::fused_tune().flat == 0)
+    return false;
+  if (!((gdim == 2 and tdim == 2) or (gdim == 3 and tdim == 3) or (gdim == 3 and tdim == 2)))
+    return false;
+  geo::FusedParams p;
+  p.nc = nc;
+  p.rows = int(rows);
+  p.ndofs = int(rows);
+  p.tab_stride = int(rows) * tdim;
+  p.nstates = 1;
+  p.out_pitch = rows * size_t(gdim);
+  p.dof_slot = nullptr;
+  p.slot_info = nullptr;
+  p.cell_info = nullptr;
+  if (map_type == BX_MAP_COVARIANT_PIOLA)
+    geo::launch_fused_shape<T, BX_MAP_COVARIANT_PIOLA, false>(gdim, tdim, tdim, U, nullptr, K, detJ, p, out, s);
+  else
+    geo::launch_fused_shape<T, BX_MAP_CONTRAVARIANT_PIOLA, false>(gdim, tdim, tdim, U, nullptr, J, detJ, p, out, s);
+  return true;
+}
+template bool push_forward_broadcast_flat<double>(int, const double*, const double*, const double*, const double*, size_t,
+                                                  size_t, int, int, double*, cudaStream_t);
+template bool push_forward_broadcast_flat<float>(int, const float*, const float*, const float*, const float*, size_t, size_t,
+                                                 int, int, float*, cudaStream_t);
+
 // Rows of one kernel pass: at most 256 (eight per lane).  Larger point sets are cut into chunks of whole points.
 int physical_basis_chunk(const bx_element& e, size_t npts)
 {

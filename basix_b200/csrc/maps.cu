@@ -353,6 +353,10 @@ int map_value_size(int map_type, int pull, int in_vs, int gdim, int tdim)
   }
 }
 
+template <typename T>
+bool push_forward_broadcast_flat(int map_type, const T* U, const T* J, const T* detJ, const T* K, size_t nc, size_t rows,
+                                 int gdim, int tdim, T* out, cudaStream_t s); // geometry.cu
+
 // Device pointers.  U[nc][rows][in_vs] (bcast: U[rows][in_vs], shared by all cells), J[nc][gdim][tdim], detJ[nc],
 // K[nc][tdim][gdim].
 template <typename T>
@@ -374,6 +378,10 @@ void map_device(int map_type, int pull, const T* U, const T* J, const T* detJ, c
       fail(BX_ERR_INVALID_ARG, "map: value size of the input (" + std::to_string(in_vs)
                                    + ") does not match the map (" + std::to_string(want) + ")");
   };
+  // push_forward_broadcast with a Piola map: the flat (cell, row) walk of the fused physical-basis kernel
+  if (bcast and !pull and in_vs == tdim and (map_type == BX_MAP_COVARIANT_PIOLA ? K != nullptr : (J != nullptr and detJ != nullptr))
+      and push_forward_broadcast_flat<T>(map_type, U, J, detJ, K, nc, rows, gdim, tdim, out, s))
+    return;
   switch (map_type)
   {
   case BX_MAP_IDENTITY:
