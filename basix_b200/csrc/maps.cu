@@ -19,6 +19,70 @@ namespace
 constexpr int kThreads = 256;
 constexpr int kBcastBatch = 4; // cells per warp iteration of map_bcast_kernel
 
+// One row through the map (the arithmetic of maps.h in its order; `det` is detJ, or 1 / detJ for pull_back, and is
+// only read by the contravariant maps).
+template <typename T, int MAP, int RA, int CA, int IN_VS, int OUT_VS>
+__device__ __forceinline__ void map_row(const T (&a)[RA][CA], const T (&u)[IN_VS], T det, T (&r)[OUT_VS])
+{
+  if constexpr (MAP == BX_MAP_COVARIANT_PIOLA)
+  {
+#pragma unroll
+    for (int i = 0; i < CA; ++i)
+    {
+      T acc = 0;
+#pragma unroll
+      for (int k = 0; k < RA; ++k)
+        acc += a[k][i] * u[k];
+      r[i] = acc;
+    }
+  }
+  else if constexpr (MAP == BX_MAP_CONTRAVARIANT_PIOLA)
+  {
+#pragma unroll
+    for (int i = 0; i < RA; ++i)
+    {
+      T acc = 0;
+#pragma unroll
+      for (int k = 0; k < CA; ++k)
+        acc += a[i][k] * u[k];
+      r[i] = acc / det;
+    }
+  }
+  else if constexpr (MAP == BX_MAP_DOUBLE_COVARIANT_PIOLA)
+  {
+#pragma unroll
+    for (int i = 0; i < CA; ++i)
+#pragma unroll
+      for (int j = 0; j < CA; ++j)
+      {
+        T acc = 0;
+#pragma unroll
+        for (int k = 0; k < RA; ++k)
+#pragma unroll
+          for (int l = 0; l < RA; ++l)
+            acc += a[k][i] * u[k * RA + l] * a[l][j];
+        r[i * CA + j] = acc;
+      }
+  }
+  else
+  {
+    const T det2 = det * det;
+#pragma unroll
+    for (int i = 0; i < RA; ++i)
+#pragma unroll
+      for (int j = 0; j < RA; ++j)
+      {
+        T acc = 0;
+#pragma unroll
+        for (int k = 0; k < CA; ++k)
+#pragma unroll
+          for (int l = 0; l < CA; ++l)
+            acc += a[i][k] * u[k * CA + l] * a[j][l];
+        r[i * RA + j] = acc / det2;
+      }
+  }
+}
+
 // A is the matrix the reference kernel actually reads (RA x CA, row-major):
 //   covariant          A = "K" argument:  out[i] = sum_k A[k][i] in[k]                 maps.h:73-94
 //   contravariant      A = "J" argument:  out[i] = (sum_k A[i][k] in[k]) / det         maps.h:100-124
@@ -77,68 +141,103 @@ __global__ void __launch_bounds__(kThreads)
     for (int i = 0; i < IN_VS; ++i)
       u[i] = in[tin * IN_VS + i];
     T r[OUT_VS];
-    if constexpr (MAP == BX_MAP_COVARIANT_PIOLA)
-    {
-#pragma unroll
-      for (int i = 0; i < CA; ++i)
-      {
-        T acc = 0;
-#pragma unroll
-        for (int k = 0; k < RA; ++k)
-          acc += a[k][i] * u[k];
-        r[i] = acc;
-      }
-    }
-    else if constexpr (MAP == BX_MAP_CONTRAVARIANT_PIOLA)
-    {
-      const T det = invert_det ? T(1.0) / detJ[c] : detJ[c];
-#pragma unroll
-      for (int i = 0; i < RA; ++i)
-      {
-        T acc = 0;
-#pragma unroll
-        for (int k = 0; k < CA; ++k)
-          acc += a[i][k] * u[k];
-        r[i] = acc / det;
-      }
-    }
-    else if constexpr (MAP == BX_MAP_DOUBLE_COVARIANT_PIOLA)
-    {
-#pragma unroll
-      for (int i = 0; i < CA; ++i)
-#pragma unroll
-        for (int j = 0; j < CA; ++j)
-        {
-          T acc = 0;
-#pragma unroll
-          for (int k = 0; k < RA; ++k)
-#pragma unroll
-            for (int l = 0; l < RA; ++l)
-              acc += a[k][i] * u[k * RA + l] * a[l][j];
-          r[i * CA + j] = acc;
-        }
-    }
-    else
-    {
-      const T det = invert_det ? T(1.0) / detJ[c] : detJ[c];
-      const T det2 = det * det;
-#pragma unroll
-      for (int i = 0; i < RA; ++i)
-#pragma unroll
-        for (int j = 0; j < RA; ++j)
-        {
-          T acc = 0;
-#pragma unroll
-          for (int k = 0; k < CA; ++k)
-#pragma unroll
-            for (int l = 0; l < CA; ++l)
-              acc += a[i][k] * u[k * CA + l] * a[j][l];
-          r[i * RA + j] = acc / det2;
-        }
-    }
+    T det = T(1);
+    if constexpr (MAP == BX_MAP_CONTRAVARIANT_PIOLA or MAP == BX_MAP_DOUBLE_CONTRAVARIANT_PIOLA)
+      det = invert_det ? T(1.0) / detJ[c] : detJ[c];
+    map_row<T, MAP, RA, CA, IN_VS, OUT_VS>(a, u, det, r);
 #pragma unroll
     for (int i = 0; i < OUT_VS; ++i)
       out[t * OUT_VS + i] = r[i];
+  }
+}
+
+// Several rows per cell, per-cell input rows (push_forward / pull_back of a [cell][row][value] array): the thread-per-row
+// form without block barriers.  A WARP owns 32 consecutive rows of the flat (cell, row) space per iteration; the
+// matrices of the cells those rows belong to (two at most when rows >= 32) are copied into a warp-private shared slot
+// by the warp itself (one coalesced load), so the tile needs only __syncwarp and the warps of a CTA run independently
+// (the block-staged form above spends a third of its stall samples at its two barriers per tile).  The position of a
+// tile in (cell, row) terms advances incrementally (no 64-bit division in the loop).
+// kMaxCells: cells a 32-row tile can touch; rows >= 2 -> at most 17.
+constexpr int kWarpTileCells = 17;
+template <typename T, int MAP, int RA, int CA>
+__global__ void __launch_bounds__(kThreads)
+    map_warp_kernel(const T* __restrict__ in, const T* __restrict__ A, const T* __restrict__ detJ, int invert_det, size_t nc,
+                    uint32_t rows, T* __restrict__ out)
+{
+  constexpr int IN_VS = MAP == BX_MAP_COVARIANT_PIOLA            ? RA
+                        : MAP == BX_MAP_CONTRAVARIANT_PIOLA      ? CA
+                        : MAP == BX_MAP_DOUBLE_COVARIANT_PIOLA   ? RA * RA
+                                                                 : CA * CA;
+  constexpr int OUT_VS = MAP == BX_MAP_COVARIANT_PIOLA            ? CA
+                         : MAP == BX_MAP_CONTRAVARIANT_PIOLA      ? RA
+                         : MAP == BX_MAP_DOUBLE_COVARIANT_PIOLA   ? CA * CA
+                                                                  : RA * RA;
+  constexpr int MA = RA * CA;
+  constexpr bool kDet = MAP == BX_MAP_CONTRAVARIANT_PIOLA or MAP == BX_MAP_DOUBLE_CONTRAVARIANT_PIOLA;
+  __shared__ T sA_all[kThreads / 32][kWarpTileCells * (MA + 1)];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T* sA = sA_all[warp];
+  const size_t total = nc * size_t(rows);
+  const size_t nwarps = size_t(gridDim.x) * (kThreads / 32);
+  size_t t0 = (size_t(blockIdx.x) * (kThreads / 32) + warp) * 32;
+  if (t0 >= total)
+    return;
+  // (cell, row) of t0 and of the tile stride, advanced incrementally
+  size_t c0 = t0 / rows;
+  uint32_t r0 = uint32_t(t0 - c0 * rows);
+  const size_t stride = nwarps * 32;
+  const size_t dc = stride / rows;
+  const uint32_t dr = uint32_t(stride - dc * rows);
+  const bool wide = rows >= 32; // a tile touches at most two cells
+  for (; t0 < total; t0 += stride)
+  {
+    const uint32_t nrow = uint32_t(min(size_t(32), total - t0));
+    const uint32_t ncell = (r0 + nrow - 1) / rows + 1;
+    // the warp's matrices (and determinants): one coalesced pass
+    for (uint32_t i = lane; i < ncell * MA; i += 32)
+      sA[i] = A[c0 * MA + i];
+    if constexpr (kDet)
+    {
+      if (lane < int(ncell))
+        sA[kWarpTileCells * MA + lane] = detJ[c0 + lane];
+    }
+    const uint32_t rl = r0 + min(uint32_t(lane), nrow - 1); // lanes past the last row repeat it and do not store
+    const uint32_t off = wide ? (rl >= rows ? 1u : 0u) : rl / rows;
+    const size_t t = t0 + min(uint32_t(lane), nrow - 1);
+    T u[IN_VS];
+#pragma unroll
+    for (int i = 0; i < IN_VS; ++i)
+      u[i] = in[t * IN_VS + i];
+    __syncwarp();
+    T a[RA][CA];
+#pragma unroll
+    for (int i = 0; i < RA; ++i)
+#pragma unroll
+      for (int j = 0; j < CA; ++j)
+        a[i][j] = sA[off * MA + i * CA + j];
+    T det = T(1);
+    if constexpr (kDet)
+    {
+      det = sA[kWarpTileCells * MA + off];
+      if (invert_det)
+        det = T(1.0) / det;
+    }
+    T r[OUT_VS];
+    map_row<T, MAP, RA, CA, IN_VS, OUT_VS>(a, u, det, r);
+    if (uint32_t(lane) < nrow)
+    {
+#pragma unroll
+      for (int i = 0; i < OUT_VS; ++i)
+        out[t * OUT_VS + i] = r[i];
+    }
+    __syncwarp(); // the slot is overwritten by the next tile
+    c0 += dc;
+    r0 += dr;
+    if (r0 >= rows)
+    {
+      r0 -= rows;
+      ++c0;
+    }
   }
 }
 
@@ -294,7 +393,21 @@ void launch_one(const T* in, const T* A, const T* detJ, int inv, size_t nc, size
       return;
     }
   }
-  if (rows >= 2)
+  static const int warp_form = []
+  {
+    const char* v = std::getenv("BX_MAP_WARP"); // development knob: 0 selects the block-staged kernel
+    return v ? std::atoi(v) : 1;
+  }();
+  if (rows >= 2 and !bcast and warp_form and rows < (size_t(1) << 31))
+  {
+    auto kern = map_warp_kernel<T, MAP, RA, CA>;
+    int per_sm = 1;
+    BX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0));
+    const size_t want = ceil_div(nc * rows, size_t(kThreads));
+    const size_t cap = size_t(sm_count()) * std::max(per_sm, 1);
+    kern<<<unsigned(std::max<size_t>(1, std::min(want, cap))), kThreads, 0, s>>>(in, A, detJ, inv, nc, uint32_t(rows), out);
+  }
+  else if (rows >= 2)
   {
     auto kern = map_kernel<T, MAP, RA, CA, true>;
     // a tile of kThreads rows touches at most kThreads / rows + 2 cells
