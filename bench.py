@@ -945,6 +945,22 @@ def run_ours(args, w, rank, local_rank, world):
             roofline["copy_same_bytes"] = ("torch copy_ of %d bytes to a second buffer (same bytes read + written as one "
                                            "launch), same L2 flush and event-pair timing" % (int(w.alg_bytes) // 2))
             del src, dst
+            # ... and the event pair around an EMPTY launch under the same rule: what the timing itself costs a kernel
+            # that lives for ~20 us (reported, never subtracted from `achieved` / `frac`)
+            tiny = torch.empty(32, device="cuda")
+
+            class _Empty:
+                flush_l2 = True
+
+                @staticmethod
+                def step():
+                    tiny.fill_(0.0)
+
+            for _ in range(3):
+                _Empty.step()
+            ems, _ = time_steps(_Empty, 20)
+            roofline["event_pair_empty_launch_ms"] = ems / 20
+            roofline["frac_net_of_empty_launch"] = (w.alg_bytes / max((ms_launch - ems / 20) * 1e-3, 1e-9) / 1e9) / hbm_peak
         if hasattr(w, "line_bytes"):
             roofline["line_granular"] = {"bytes": w.line_bytes, "frac": w.line_bytes / (ms_launch * 1e-3) / 1e9 / hbm_peak,
                                          "what": w.line_what}

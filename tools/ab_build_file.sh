@@ -8,6 +8,6 @@ base=$(basename "$file" .cu)
 mkdir -p build/ab build/abobj
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr -Xptxas -v \
   $extra $flags -c "$file" -o build/abobj/$name.o 2> build/abobj/$name.log
-objs=$(ls build/obj/*.o | grep -v "/$base.o")
+objs=$(ls build/obj/*.o | grep -v "/${AB_REPLACES:-$base}.o")
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o build/ab/$name.so $objs build/abobj/$name.o -cudart static
 echo "built build/ab/$name.so"
