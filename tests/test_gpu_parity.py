@@ -187,6 +187,24 @@ def test_push_pull_manifold(ref, family, variant, vs):
     assert np.array_equal(e.pull_back(got, J, detJ, K), r.pull_back(want, J, detJ, K))
 
 
+@pytest.mark.parametrize("family,cell,gdim,vs", [(N1E, TET, 3, 3), (RT, TET, 3, 3), (7, TET, 3, 9), (11, TET, 3, 9),
+                                                (N1E, TRI, 3, 2), (RT, TRI, 3, 2), (RT, TRI, 2, 2), (11, TRI, 3, 4)])
+@pytest.mark.parametrize("rows,nc", [(2, 1003), (3, 77), (31, 130), (32, 65), (33, 129), (64, 33), (100, 41), (700, 5)])
+def test_push_pull_rows_around_the_warp_size(ref, family, cell, gdim, vs, rows, nc):
+    """Several rows per cell: the warp-staged kernel (a warp owns 32 rows of the flat (cell, row) space and stages the
+    matrices of the cells they belong to) for row counts below, at and above the warp size, totals that are not a
+    multiple of 32, square and non-square J, all four Piola maps -- bit for bit against the reference."""
+    degree = 1 if family in (7, 11) else 2
+    r, e = make_pair(ref, family, cell, degree, 0 if family in (7, 11) else LEG)
+    tdim = 3 if cell == TET else 2
+    J, detJ, K = jacobians(nc, gdim, tdim, seed=rows)
+    U = np.random.default_rng(rows + nc).standard_normal((nc, rows, vs))
+    want = r.push_forward(U, J, detJ, K)
+    got = e.push_forward(U, J, detJ, K)
+    assert got.shape == want.shape and np.array_equal(got, want)
+    assert np.array_equal(e.pull_back(got, J, detJ, K), r.pull_back(want, J, detJ, K))
+
+
 @pytest.mark.parametrize("family,cell,degree,variant,vs", [(N1E, TET, 3, LEG, 3), (RT, TET, 4, LEG, 3), (RT, TRI, 2, LEG, 2),
                                                           (P, TET, 2, EQ, 1), (7, TET, 1, 0, 9)])
 def test_push_forward_broadcast(ref, family, cell, degree, variant, vs):
