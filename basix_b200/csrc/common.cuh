@@ -1,6 +1,7 @@
 // Shared host/device helpers for the basix_b200 CUDA library (sm_100a only).
 #pragma once
 
+#include <nvtx3/nvToolsExt.h>
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -41,9 +42,18 @@ inline void cuda_check(cudaError_t e, const char* what, const char* file, int li
     ::bx::cuda_check(cudaGetLastError(), "kernel launch", __FILE__, __LINE__);                           \
   } while (0)
 
-template <typename F>
-int guarded(F&& f)
+// NVTX range named after the C-ABI entry point (header-only NVTX 3: a no-op unless a tool is attached), so that
+// ncu --nvtx / Nsight timelines show which library call a kernel belongs to.
+struct NvtxRange
 {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
+template <typename F>
+int guarded(F&& f, const char* entry = __builtin_FUNCTION())
+{
+  NvtxRange range(entry);
   try
   {
     f();

@@ -12,8 +12,8 @@ cap dop_p5tet tabulate_p5_tet tabulate_dop 2000000
 cap small_p1tri tabulate_p1_tri tabulate_small
 cap tp_q4hex tabulate_q4_hex tabulate_tp_staged 10000000
 cap map_rows1 push_forward_n1curl3 map_kernel
-cap map_rows45 push_forward_n1curl3_rows45 map_kernel 1000000
-cap map_bcast_rows45 push_forward_bcast_n1curl3_rows45 map_bcast 2000000
+cap map_rows45 push_forward_n1curl3_rows45 map_warp_kernel 1000000
+cap map_bcast_rows45 push_forward_bcast_n1curl3_rows45 physical_basis 2000000
 cap dof_matrix_rt4 t_apply_rt4 dof_ 4000000
 cap dof_matrix_rt4_block3 t_apply_rt4_block3 dof_ 2000000
 cap dof_perm_p5tet permute_p5_tet dof_ 4000000
@@ -31,6 +31,6 @@ for r in gpurun_out/r02_*.ncu-rep; do
   python tools/ncu_stalls.py "$r" > "gpurun_out/${n/r02_/r02_stalls_}.txt" 2>/dev/null
 done
 for r in gpurun_out/r02_*.ncu-rep; do
-  case "$r" in *physical_basis_rt4*|*dof_matrix_rt4.ncu-rep|*small_p1tri*) ;; *) rm -f "$r" ;; esac
+  rm -f "$r"
 done
 du -sh gpurun_out
