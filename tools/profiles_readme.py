@@ -6,7 +6,7 @@ import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-rnd = sys.argv[1] if len(sys.argv) > 1 else "r01"
+rnd = sys.argv[1] if len(sys.argv) > 1 else "r02"
 rows = []
 for f in sorted(glob.glob(os.path.join(ROOT, "profiles", f"{rnd}_bench_*.json"))):
     name = os.path.basename(f)[len(rnd) + 7:-5]
@@ -34,6 +34,10 @@ for n, g, ms, v, u, b, fr, hf, e2e, cpu, cores, kind in rows:
                f"{fmt(cpu)}{'' if cpu is None else f' ({cores} cores, {kind})'} |")
 out += ["", "ncu summaries: " + ", ".join(sorted(os.path.basename(f) for f in glob.glob(os.path.join(ROOT, "profiles", f"{rnd}_ncu_*.txt")))), "",
         f"Launch list of the judged command: `{rnd}_ncu_launches_bench_default.csv`; measured DRAM traffic per unit: `{rnd}_traffic.json`;",
-        f"FP64 / HBM / PCIe peaks: `{rnd}_peaks_fp64_hbm_pcie.json`; shared DMMA/DFMA pipe: `{rnd}_mixed_fp64.json`.", ""]
+        "FP64 / HBM / PCIe peaks: `r01_peaks_fp64_hbm_pcie.json`; shared DMMA/DFMA pipe: `r01_mixed_fp64.json`; cuBLAS DGEMM and the",
+        "library-path comparator: `r02_library_comparator.json`; SASS opcode histogram: `r02_sass_opcodes.txt`; per-kernel stall",
+        f"reasons: `{rnd}_stalls_*.txt`; compute-sanitizer status and the guard-zone substitute: `r02_sanitizer.txt`.",
+        "Rows other than `default_*` / `reference` are the `configs` entries of the default line (`r02_bench_default_n1.json`),",
+        "one file each; round-1 files (`r01_*`) are kept for comparison.", ""]
 open(os.path.join(ROOT, "profiles", "README.md"), "w").write("\n".join(out))
 print("\n".join(out))
