@@ -274,6 +274,24 @@ def tp_dof_ordering(family, celltype, degree, lagrange_variant=LagrangeVariant.u
     return order
 
 
+def lex_dof_ordering(family, celltype, degree, lagrange_variant=LagrangeVariant.unset, dpc_variant=DPCVariant.unset,
+                     discontinuous=False):
+    """``basix.finite_element.lex_dof_ordering`` (finite-element.cpp:509-700): the numbering of a P element's dofs in
+    lexicographic order of their points (last coordinate slowest).  Derived from the dof points themselves instead of the
+    reference's index formulas, like ``tp_dof_ordering`` above: ``ordering[dof] = position of the dof's point``."""
+    if int(family) != ElementFamily.P:
+        raise RuntimeError("Lexicographic ordering is built for P elements only")
+    e = create_element(family, celltype, degree,
+                       LagrangeVariant.equispaced if int(lagrange_variant) == LagrangeVariant.unset and degree > 0
+                       else lagrange_variant, dpc_variant, discontinuous)
+    pts = np.round(np.asarray(e.points) * (4 * max(degree, 1)) * 64).astype(np.int64)  # exact keys for lattice points
+    order = np.lexsort(tuple(pts[:, k] for k in range(pts.shape[1])))  # last key = last coordinate = slowest
+    out = [0] * len(order)
+    for position, dof in enumerate(order):
+        out[int(dof)] = position
+    return out
+
+
 def create_tp_element(family, celltype, degree, lagrange_variant=LagrangeVariant.unset, dpc_variant=DPCVariant.unset,
                       discontinuous=False, dtype=np.float64):
     """``basix.create_tp_element`` (finite-element.cpp:327-341)."""

@@ -18,6 +18,17 @@ class QuadratureType(IntEnum):
     strang_fix = 22
 
 
+def gauss_jacobi_rule(alpha, npoints):
+    """``basix.quadrature.gauss_jacobi_rule(alpha, npoints)`` (quadrature.cpp:4955-4965): points and weights on [0, 1] for
+    the weight ``(1 - x)**alpha``."""
+    from basix_b200 import _capi
+
+    pts = np.empty(int(npoints), dtype=np.float64)
+    wts = np.empty(int(npoints), dtype=np.float64)
+    _capi.check(_capi.lib().bx_gauss_jacobi_rule(float(alpha), int(npoints), pts.ctypes.data, wts.ctypes.data))
+    return pts, wts
+
+
 def make_quadrature(cell, degree, rule=QuadratureType.default, polyset_type=PolysetType.standard):
     """``basix.make_quadrature(cell, degree, rule, polyset_type)`` -> (points, weights).  The Gauss-Jacobi scheme
     (quadrature.cpp:215-372) is the one rule built natively; ``default`` resolves to it (the reference picks a tabulated

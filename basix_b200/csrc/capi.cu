@@ -165,6 +165,7 @@ void physical_basis_device(const bx_element& e, int op, const T* U, size_t npts,
                            cudaStream_t s);
 void interpolation_operator_shape(const bx_element& from, const bx_element& to, int32_t shape[2]);
 void interpolation_operator_device(const bx_element& from, const bx_element& to, double* out, cudaStream_t s);
+void gauss_jacobi_rule_unit(double a, int m, std::vector<double>& x, std::vector<double>& w);
 void make_quadrature_gauss_jacobi(int cell, int q, std::vector<double>& x, std::vector<double>& w);
 std::vector<double> create_lattice_points(int cell, int n, int lattice_type, int exterior, int simplex_method);
 bx_element* create_lagrange(int cell, int degree, int variant, bool discontinuous, const int32_t* dof_ordering,
@@ -1219,6 +1220,19 @@ extern "C"
             std::copy(x.begin(), x.end(), points);
           if (weights)
             std::copy(w.begin(), w.end(), weights);
+        });
+  }
+
+  int bx_gauss_jacobi_rule(double alpha, int npoints, double* points, double* weights)
+  {
+    return bx::guarded(
+        [&]()
+        {
+          bx::require(points != nullptr and weights != nullptr, "gauss_jacobi_rule: null argument");
+          std::vector<double> x, w;
+          bx::gauss_jacobi_rule_unit(alpha, npoints, x, w);
+          std::copy(x.begin(), x.end(), points);
+          std::copy(w.begin(), w.end(), weights);
         });
   }
 

@@ -1332,6 +1332,20 @@ std::vector<double> create_lattice_points(int cell, int n, int lattice_type, int
 }
 // quadrature::make_quadrature (quadrature.cpp:4960-5020) with the Gauss-Jacobi scheme (quadrature.cpp:215-372): points
 // [npts][tdim] and weights of a rule exact for polynomials of degree q.
+// quadrature::gauss_jacobi_rule (quadrature.cpp:4955-4965): m points on [0, 1] for the weight (1 - x)^a
+void gauss_jacobi_rule_unit(double a, int m, std::vector<double>& x, std::vector<double>& w)
+{
+  if (m < 1)
+    fail(BX_ERR_INVALID_ARG, "gauss_jacobi_rule: at least one point is needed");
+  gauss_jacobi(a, m, x, w);
+  const double scale = std::pow(2.0, a + 1.0);
+  for (int i = 0; i < m; ++i)
+  {
+    x[i] = (x[i] + 1.0) / 2.0;
+    w[i] /= scale;
+  }
+}
+
 void make_quadrature_gauss_jacobi(int cell, int q, std::vector<double>& x, std::vector<double>& w)
 {
   if (cell < BX_CELL_INTERVAL or cell > BX_CELL_PYRAMID)

@@ -377,6 +377,10 @@ extern "C"
      (the native element factory integrates its moments with it).  points[npts][tdim], weights[npts]; NULL outputs
      return *npts only. */
   int bx_make_quadrature(int cell_type, int degree, double* points, double* weights, size_t* npts);
+  /* quadrature::gauss_jacobi_rule (quadrature.cpp:4955-4965; python basix.quadrature.gauss_jacobi_rule): the npoints-point
+     Gauss-Jacobi rule on [0, 1] for the weight (1 - x)^alpha, alpha > -1 real.  points[npoints], weights[npoints].  Host
+     set-up code. */
+  int bx_gauss_jacobi_rule(double alpha, int npoints, double* points, double* weights);
 
 #ifdef __cplusplus
 }
