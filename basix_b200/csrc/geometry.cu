@@ -371,6 +371,150 @@ __device__ __forceinline__ float safe_reciprocal(float b)
   return ex - 87u > 80u ? __uint_as_float(0x7fc00000u) : 1.0f / b;
 }
 
+// ---- any coordinate element: the warp form of geometry_kernel --------------------------------------------------
+// A warp owns 32 consecutive (cell, point) items of the flat space (their J, K and detJ are one contiguous run of each
+// output array).  The node coordinates of the cells those items belong to -- one contiguous run of `coords` -- arrive
+// with one coalesced pass into a warp-private odd-pitch tile; every lane forms its J from that tile and the derivative
+// table in shared memory (same summation order as geometry_kernel: nodes outermost), inverts it, and the three result
+// tiles leave as one TMA bulk copy each (or lane-consecutive stores when the run is ragged or unaligned).  K = adj / div
+// uses one reciprocal and FMA-corrected quotients (div_by below: bit-equal to IEEE division).  No block
+// barrier after the table is in shared memory; the tile position advances incrementally.
+// xcap: entries of the coordinate tile (>= cells per tile * odd pitch, and >= 32 * G * TD: it is reused for J).
+template <typename T, int G, int TD>
+__global__ void __launch_bounds__(kThreads)
+    geometry_warp_kernel(const T* __restrict__ coords, const T* __restrict__ dphi, size_t nc, int nv, uint32_t npts, int xcap,
+                         T* __restrict__ Jout, T* __restrict__ detout, T* __restrict__ Kout, int bulk)
+{
+  constexpr int MA = G * TD;
+  extern __shared__ __align__(128) unsigned char gw_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ntab = TD * int(npts) * nv;
+  T* s_d = reinterpret_cast<T*>(gw_smem); // [TD][nv][npts]
+  const int per_warp = xcap + ((32 * MA + 3) & ~3) + 32;
+  T* sx = s_d + ((ntab + 3) & ~3) + size_t(warp) * per_warp; // coordinates [cells][XP], then J [32][MA] dense
+  T* sK = sx + xcap;                                          // K [32][MA] dense
+  T* sd = sK + ((32 * MA + 3) & ~3);                          // detJ [32]
+  // the table is kept node-major, [TD][nv][npts]: lanes = consecutive points read consecutive entries (no bank conflicts)
+  for (int i = threadIdx.x; i < ntab; i += kThreads)
+  {
+    const int v = i % nv, ap = i / nv, pp = ap % int(npts), a = ap / int(npts);
+    s_d[(a * nv + v) * int(npts) + pp] = dphi[i];
+  }
+  __syncthreads();
+  const int NX = nv * G, XP = NX | 1;
+  const size_t total = nc * size_t(npts);
+  const size_t stride = size_t(gridDim.x) * (kThreads / 32) * 32;
+  size_t t0 = (size_t(blockIdx.x) * (kThreads / 32) + warp) * 32;
+  if (t0 >= total)
+    return;
+  size_t c0 = t0 / npts;
+  uint32_t p0 = uint32_t(t0 - c0 * npts);
+  const size_t dc = stride / npts;
+  const uint32_t dp = uint32_t(stride - dc * npts);
+  bool pending = false;
+  for (; t0 < total; t0 += stride)
+  {
+    const uint32_t nrow = uint32_t(min(size_t(32), total - t0));
+    const uint32_t ncell = (p0 + nrow - 1) / npts + 1;
+    if (pending)
+    {
+      if (lane < 3)
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+      pending = false;
+    }
+    for (uint32_t q = lane; q < ncell * uint32_t(NX); q += 32)
+      sx[(q / NX) * XP + q % NX] = coords[c0 * NX + q];
+    __syncwarp();
+    const uint32_t il = p0 + min(uint32_t(lane), nrow - 1); // lanes past the last item repeat it and do not store
+    const uint32_t off = il / npts, pt = il - off * npts;
+    const T* xc = sx + off * XP;
+    T J[G][TD];
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+      for (int a = 0; a < TD; ++a)
+        J[g][a] = T(0);
+    for (int v = 0; v < nv; ++v)
+    {
+      T dv[TD];
+#pragma unroll
+      for (int a = 0; a < TD; ++a)
+        dv[a] = s_d[(a * nv + v) * int(npts) + int(pt)];
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+      {
+        const T xg = xc[v * G + g];
+#pragma unroll
+        for (int a = 0; a < TD; ++a)
+          J[g][a] += xg * dv[a];
+      }
+    }
+    __syncwarp(); // the coordinate tile is overwritten by J below
+    T adj[TD][G], div;
+    adjugate<T, G, TD>(J, adj, div);
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+      for (int a = 0; a < TD; ++a)
+        sx[lane * MA + g * TD + a] = J[g][a];
+    {
+      // K = adj / div, correctly rounded: one reciprocal and FMA-corrected quotients (div_by: equal to the IEEE
+      // division bit for bit, tools/div_check.cu), instead of G * TD divisions
+      T q[MA];
+#pragma unroll
+      for (int a = 0; a < TD; ++a)
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+          q[a * G + g] = adj[a][g];
+      div_by<T, MA>(q, div, safe_reciprocal(div));
+#pragma unroll
+      for (int k = 0; k < MA; ++k)
+        sK[lane * MA + k] = q[k];
+    }
+    sd[lane] = det_from_div<T, G, TD>(div);
+    if (bulk and nrow == 32)
+    {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      T* dst = lane == 0 ? Jout : lane == 1 ? Kout : detout;
+      const T* src = lane == 0 ? sx : lane == 1 ? sK : sd;
+      const uint32_t per = lane < 2 ? MA : 1;
+      if (lane < 3 and dst)
+      {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + t0 * per),
+                     "r"(uint32_t(__cvta_generic_to_shared(src))), "r"(uint32_t(32 * per * sizeof(T)))
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      pending = true;
+    }
+    else
+    {
+      __syncwarp();
+      for (uint32_t q = lane; q < nrow * MA; q += 32)
+      {
+        if (Jout)
+          Jout[t0 * MA + q] = sx[q];
+        if (Kout)
+          Kout[t0 * MA + q] = sK[q];
+      }
+      if (detout and uint32_t(lane) < nrow)
+        detout[t0 + lane] = sd[lane];
+      __syncwarp();
+    }
+    c0 += dc;
+    p0 += dp;
+    if (p0 >= npts)
+    {
+      p0 -= npts;
+      ++c0;
+    }
+  }
+  if (pending and lane < 3)
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 __host__ __device__ constexpr int pad4(int n) { return (n + 3) & ~3; }
 // per-cell record of the fused kernel in shared memory: the matrix each row is multiplied by, detJ and 1 / detJ;
 // an odd number of entries, so lane = cell writes are free of bank conflicts
@@ -804,6 +948,29 @@ void launch_geometry(const T* coords, const T* dphi, size_t nc, int nv, int npts
     kern<<<grid, kThreads, smem, s>>>(coords, nc, J, detJ, K, bulk);
     BX_LAUNCHED();
     return;
+  }
+  {
+    // warp form: derivative table and the warps' tiles in shared memory (falls through when they do not fit)
+    constexpr int MA = G * TD;
+    const int cells_per_tile = std::min(32, 31 / npts + 2);
+    const int xcap = (std::max(cells_per_tile * ((nv * G) | 1), 32 * MA) + 3) & ~3;
+    const size_t ntab = (size_t(TD) * npts * nv + 3) & ~size_t(3);
+    const size_t smem = (ntab + size_t(kThreads / 32) * (xcap + ((32 * MA + 3) & ~3) + 32)) * sizeof(T);
+    static const bool warp_form = []
+    {
+      const char* v = std::getenv("BX_GEOM_WARP"); // development knob: 0 selects the thread-per-item kernel
+      return v ? std::atoi(v) != 0 : true;
+    }();
+    if (warp_form and smem <= 100 * 1024 and npts < (1 << 20))
+    {
+      auto kern = geometry_warp_kernel<T, G, TD>;
+      auto aligned = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
+      const int bulk = aligned(J) and aligned(K) and aligned(detJ) and (32 * MA * sizeof(T)) % 16 == 0;
+      const int grid = persistent_grid(kern, ceil_div(nc * size_t(npts), size_t(kThreads)), smem);
+      kern<<<grid, kThreads, smem, s>>>(coords, dphi, nc, nv, uint32_t(npts), xcap, J, detJ, K, bulk);
+      BX_LAUNCHED();
+      return;
+    }
   }
   auto kern = geometry_kernel<T, G, TD>;
   const size_t tbl = size_t(TD) * npts * nv * sizeof(T);

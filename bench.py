@@ -542,7 +542,20 @@ class PhysicalBasis:
         self.units_per_step = self.units_per_launch = nc
         self.launches_per_step = 1
         self.geometry = bx.geometry
-        if self.geometry_only:
+        if self.geometry_only == "hex":
+            # trilinear hexahedra at the 2 x 2 x 2 Gauss points: the general (non-affine) form of bx_geometry
+            q1 = bx.create_element(1, 5, 1, 2)
+            gp = 0.5 + 0.5 * np.array([-1.0, 1.0]) / np.sqrt(3.0)
+            Xq = np.array([[a, b, c] for a in gp for b in gp for c in gp])
+            self.dphi = torch.from_numpy(np.ascontiguousarray(q1.tabulate(1, Xq)[1:4, :, :, 0])).cuda()
+            g = torch.Generator(device="cuda").manual_seed(41 + rank)
+            base = torch.tensor([[i, j, k] for k in (0.0, 1.0) for j in (0.0, 1.0) for i in (0.0, 1.0)], dtype=torch.float64,
+                                device="cuda")
+            self.coords = (base[None] + 0.1 * torch.randn(nc, 8, 3, generator=g, device="cuda", dtype=torch.float64)).contiguous()
+            self.alg_bytes = nc * (192 + 8 * 152)
+            self.config = {"workload": self.desc, "cells_per_gpu": nc, "points_per_cell": 8,
+                           "l2": "arrays are %.2f GB per step (>> 126 MB L2)" % (self.alg_bytes / 1e9)}
+        elif self.geometry_only:
             self.alg_bytes = nc * (96 + 72 + 8 + 72)
             self.config = {"workload": self.desc, "cells_per_gpu": nc,
                            "l2": "arrays are %.2f GB per step (>> 126 MB L2)" % (self.alg_bytes / 1e9)}
@@ -564,7 +577,9 @@ class PhysicalBasis:
             self.ci_host = self.ci.cpu().pin_memory()
 
     def step(self):
-        if self.geometry_only:
+        if self.geometry_only == "hex":
+            self.result = self.geometry(self.coords, self.dphi)
+        elif self.geometry_only:
             self.result = self.geometry(self.coords)
         else:
             self.result = self.e.physical_basis(None, U=self.U, coords=self.coords, cell_info=self.ci)
@@ -610,7 +625,13 @@ class PhysicalBasis:
         self.e2e_units = self.nc
         self.result = None
         torch.cuda.empty_cache()
-        if self.geometry_only:
+        if self.geometry_only == "hex":
+            self.coords_host = self.coords.cpu().pin_memory()
+            self.dphi_host = self.dphi.cpu()
+            self.out_host = [torch.empty(s, dtype=torch.float64).pin_memory() for s in
+                             ((self.nc, 8, 3, 3), (self.nc, 8), (self.nc, 8, 3, 3))]
+            self.h2d, self.d2h = self.nc * 192, self.nc * 8 * 152
+        elif self.geometry_only:
             self.out_host = [torch.empty(s, dtype=torch.float64).pin_memory() for s in
                              ((self.nc, 3, 3), (self.nc,), (self.nc, 3, 3))]
             self.h2d, self.d2h = self.nc * 96, self.nc * 152
@@ -624,7 +645,11 @@ class PhysicalBasis:
         from basix_b200 import _capi
 
         L = _capi.lib()
-        if self.geometry_only:
+        if self.geometry_only == "hex":
+            J, d, K = self.out_host
+            _capi.check(L.bx_geometry_f64(self.coords_host.data_ptr(), self.dphi_host.data_ptr(), self.nc, 8, 3, 3, 8,
+                                          J.data_ptr(), d.data_ptr(), K.data_ptr(), _capi.BX_MEM_HOST, None))
+        elif self.geometry_only:
             J, d, K = self.out_host
             _capi.check(L.bx_geometry_f64(self.coords_host.data_ptr(), None, self.nc, 4, 3, 3, 1, J.data_ptr(), d.data_ptr(),
                                           K.data_ptr(), _capi.BX_MEM_HOST, None))
@@ -645,6 +670,13 @@ class PhysicalBasis:
         base = np.zeros((4, 3))
         base[1:] = np.eye(3)
         coords = base[None] + 0.2 * rng.standard_normal((n, 4, 3))
+        if self.geometry_only == "hex":
+            self.cpu_kind = "port"
+            n = int(min(self.nc, 200_000))
+            base = np.array([[i, j, k] for k in (0.0, 1.0) for j in (0.0, 1.0) for i in (0.0, 1.0)])
+            coords = base[None] + 0.1 * rng.standard_normal((n, 8, 3))
+            self._cpu = (restate, coords, self.dphi.cpu().numpy())
+            return n, f"{n} cells x 8 points per step, oracle/restate.py geometry (numpy, vectorised over cells)"
         if self.geometry_only:
             self.cpu_kind = "port"
             self._cpu = (restate, coords)
@@ -656,6 +688,10 @@ class PhysicalBasis:
                    f"reference values and push_forward, oracle/_ref (unmodified reference, g++ -O2); geometry by numpy")
 
     def cpu_step(self):
+        if self.geometry_only == "hex":
+            restate, coords, dphi = self._cpu
+            self._cpu_out = restate.geometry(coords, dphi)
+            return
         if self.geometry_only:
             restate, coords = self._cpu
             self._cpu_out = restate.geometry(coords)
@@ -762,6 +798,10 @@ WORKLOADS = {
     "geometry_tet": lambda: PhysicalBasis(
         "N1curl3_tetrahedron_legendre", (3, 3, 3, 11), 20_000_000, 1,
         "J, detJ, K of 20M affine tetrahedra from their vertex coordinates", geometry_only=True),
+    "geometry_hex": lambda: PhysicalBasis(
+        "N1curl3_tetrahedron_legendre", (3, 3, 3, 11), 4_000_000, 1,
+        "J, detJ, K of 4M trilinear hexahedra at 8 points each, from node coordinates and the derivatives of the Q1 "
+        "coordinate element (general form of bx_geometry)", geometry_only="hex"),
     "physical_basis_n1curl3": lambda: PhysicalBasis(
         "N1curl3_tetrahedron_legendre", (3, 3, 3, 11), 20_000_000, 1,
         "N1curl degree 3 tetrahedron: tabulate-once -> T_apply -> covariant Piola push_forward fused, geometry from vertex "
@@ -803,6 +843,7 @@ SIDE_CONFIGS = [
     ("permute_p5_tet", {}),
     ("interpolate_n1curl3", {}),
     ("geometry_tet", {}),
+    ("geometry_hex", {}),
     ("physical_basis_n1curl3", {}),
     ("physical_basis_rt4", {}),
 ]

@@ -133,6 +133,28 @@ def test_geometry_higher_order_cells(ref, cell, degree, gdim):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("npts", [1, 8, 33, 64])
+@pytest.mark.parametrize("nc", [1, 101])
+def test_geometry_general_form_tile_edges(ref, npts, nc):
+    """The warp form of the general kernel: point counts below, at and above the 32-item tile, ragged totals, outputs
+    asked for one at a time -- bit for bit against the restatement."""
+    import basix_b200 as bx
+    from oracle import restate as R
+
+    r, _ = make_pair(ref, P, HEX, 1, GLL)
+    X = random_points(HEX, npts, seed=npts)
+    dphi = np.ascontiguousarray(r.tabulate(1, X)[1:, :, :, 0])
+    coords = r.points[None] + 0.05 * np.random.default_rng(nc).standard_normal((nc, 8, 3))
+    want = R.geometry(coords, dphi)
+    got = bx.geometry(coords, dphi)
+    for g, w in zip(got, want):
+        assert g.shape == w.shape and np.array_equal(g, w)
+    for k, name in enumerate(("J", "detJ", "K")):
+        one = bx.geometry(coords, dphi, want=(name,))
+        assert np.array_equal(one[k], want[k]) and all(one[j] is None for j in range(3) if j != k)
+
+
+@pytest.mark.gpu
 def test_geometry_errors():
     import basix_b200 as bx
 
