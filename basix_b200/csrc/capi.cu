@@ -146,6 +146,9 @@ void tabulate_device(const bx_element& e, int nd, const T* x, size_t npts, T* ba
 int tabulate_path(const bx_element& e, int nd);
 template <typename T>
 void interpolate_device(const bx_element& e, int layout, const T* values, size_t nc, T* coefficients, cudaStream_t s);
+template <typename T>
+void interpolate_pulled_device(const bx_element& e, const T* u, const T* J, const T* detJ, const T* K, size_t nc, int gdim,
+                               T* coefficients, cudaStream_t s);
 void closure_permute_device(const bx_element& e, int inverse, int32_t* d, size_t nc, size_t m, const uint32_t* info,
                             int entity_type, int entity_index, cudaStream_t s);
 unsigned tabulate_path_mask(unsigned mask);
@@ -551,6 +554,56 @@ void interpolate_any(const bx_element* e, int layout, const T* values, size_t nc
     cudaStream_t s = st.s[b];
     BX_CUDA(cudaMemcpyAsync(dv[b], values + c0 * K, k * K * sizeof(T), cudaMemcpyHostToDevice, s));
     interpolate_device<T>(*e, layout, dv[b], k, dout[b], s);
+    BX_CUDA(cudaMemcpyAsync(out + c0 * N, dout[b], k * N * sizeof(T), cudaMemcpyDeviceToHost, s));
+  }
+  st.sync();
+  st.trim();
+}
+
+// pull_back fused into the interpolation; host pointers are staged in chunks of cells like every other call
+template <typename T>
+void interpolate_pulled_any(const bx_element* e, const T* u, const T* J, const T* detJ, const T* K, size_t nc, int gdim, T* out,
+                            int mem, bx_stream_t stream)
+{
+  check_mem(mem);
+  require(e != nullptr, "interpolate_pulled: null element");
+  if (mem == BX_MEM_DEVICE)
+  {
+    interpolate_pulled_device<T>(*e, u, J, detJ, K, nc, gdim, out, static_cast<cudaStream_t>(stream));
+    return;
+  }
+  {
+    // validate the element / shapes before staging (no cells: nothing is dereferenced)
+    const T one = T(1);
+    interpolate_pulled_device<T>(*e, &one, J ? &one : nullptr, detJ ? &one : nullptr, K ? &one : nullptr, 0, gdim, nullptr, nullptr);
+  }
+  if (nc == 0)
+    return;
+  require(u and out, "interpolate_pulled: null pointer");
+  const bool cov = e->map_type == BX_MAP_COVARIANT_PIOLA;
+  const size_t D = size_t(e->tdim), U = size_t(e->interp_npts) * D, N = size_t(e->ndofs), M = D * D;
+  const size_t chunk = chunk_units(nc, (U + N + M + 1) * sizeof(T), 1);
+  StagePool& st = stage_pool();
+  DrainOnExit drain{st};
+  T *du[2], *dA[2], *dd[2], *dout[2];
+  for (int b = 0; b < 2; ++b)
+  {
+    du[b] = st.get<T>(0, b, chunk * U * sizeof(T));
+    dA[b] = st.get<T>(1, b, chunk * M * sizeof(T));
+    dd[b] = st.get<T>(2, b, chunk * sizeof(T));
+    dout[b] = st.get<T>(3, b, chunk * N * sizeof(T));
+  }
+  size_t i = 0;
+  for (size_t c0 = 0; c0 < nc; c0 += chunk, ++i)
+  {
+    const int b = int(i & 1);
+    const size_t k = std::min(chunk, nc - c0);
+    cudaStream_t s = st.s[b];
+    BX_CUDA(cudaMemcpyAsync(du[b], u + c0 * U, k * U * sizeof(T), cudaMemcpyHostToDevice, s));
+    BX_CUDA(cudaMemcpyAsync(dA[b], (cov ? J : K) + c0 * M, k * M * sizeof(T), cudaMemcpyHostToDevice, s));
+    if (!cov)
+      BX_CUDA(cudaMemcpyAsync(dd[b], detJ + c0, k * sizeof(T), cudaMemcpyHostToDevice, s));
+    interpolate_pulled_device<T>(*e, du[b], cov ? dA[b] : nullptr, cov ? nullptr : dd[b], cov ? nullptr : dA[b], k, gdim, dout[b], s);
     BX_CUDA(cudaMemcpyAsync(out + c0 * N, dout[b], k * N * sizeof(T), cudaMemcpyDeviceToHost, s));
   }
   st.sync();
@@ -1090,6 +1143,11 @@ extern "C"
                          bx_stream_t stream)
   {
     return bx::guarded([&]() { bx::interpolate_any<double>(e, layout, values, nc, coefficients, mem, stream); });
+  }
+  int bx_interpolate_pulled_f64(const bx_element* e, const double* u, const double* J, const double* detJ, const double* K,
+                                size_t nc, int gdim, double* coefficients, int mem, bx_stream_t stream)
+  {
+    return bx::guarded([&]() { bx::interpolate_pulled_any<double>(e, u, J, detJ, K, nc, gdim, coefficients, mem, stream); });
   }
   int bx_interpolate_f32(const bx_element* e, int layout, const float* values, size_t nc, float* coefficients, int mem,
                          bx_stream_t stream)

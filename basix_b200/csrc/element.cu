@@ -559,6 +559,19 @@ bx_element* element_from_desc(const bx_element_desc& d)
                   = e->interp_M[size_t(n) * K + j * d.npts + p];
         e->d_interp[layout] = upload(B);
       }
+    // blocked component-major operand of the fused pull_back + interpolation (interpolate.cu): Piola elements only
+    if (e->on_device and e->vs == e->tdim and (e->map_type == BX_MAP_COVARIANT_PIOLA or e->map_type == BX_MAP_CONTRAVARIANT_PIOLA))
+    {
+      e->interp_pb = int(ceil_div(d.npts, 8) * 8);
+      const int kb = e->vs * e->interp_pb;
+      e->interp_kstride_blocked = kb % 8 == 4 ? kb : kb + 4;
+      std::vector<double> B(size_t(e->interp_npad) * e->interp_kstride_blocked, 0.0);
+      for (int n = 0; n < e->ndofs; ++n)
+        for (int j = 0; j < e->vs; ++j)
+          for (int p = 0; p < d.npts; ++p)
+            B[size_t(n) * e->interp_kstride_blocked + j * e->interp_pb + p] = e->interp_M[size_t(n) * K + j * d.npts + p];
+      e->d_interp_blocked = upload(B);
+    }
   }
 
   // ---- entity transformations ------------------------------------------------------------------------
@@ -992,4 +1005,5 @@ bx_element::~bx_element()
     cudaFree(cl.d_src);
   cudaFree(d_interp[0]);
   cudaFree(d_interp[1]);
+  cudaFree(d_interp_blocked);
 }

@@ -123,6 +123,9 @@ struct bx_element
   std::vector<double> interp_M; // [ndofs][vs * npts], reference column order (component major)
   int interp_kstride = 0, interp_npad = 0; // operand rows: ndofs padded to 8; row stride == 4 (mod 8) doubles
   double* d_interp[2] = {nullptr, nullptr}; // [layout][npad][kstride]: column order of each value layout
+  // fused pull_back + interpolation (Piola elements): columns k' = i * interp_pb + p, interp_pb = npts padded to 8
+  int interp_pb = 0, interp_kstride_blocked = 0;
+  double* d_interp_blocked = nullptr; // [npad][interp_kstride_blocked]
 
   ~bx_element();
   bx_element() = default;

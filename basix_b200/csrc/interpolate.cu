@@ -218,6 +218,268 @@ void interpolate_device(const bx_element& e, int layout, const T* values, size_t
 }
 template void interpolate_device<double>(const bx_element&, int, const double*, size_t, double*, cudaStream_t);
 template void interpolate_device<float>(const bx_element&, int, const float*, size_t, float*, cudaStream_t);
+// ---- pull_back fused into the interpolation -------------------------------------------------------------------------
+// coefficients[c] = interpolation_matrix * pull_back(u[c], J_c, detJ_c, K_c): the two steps a caller takes to interpolate
+// a physical function into a Piola-mapped element (FiniteElement::pull_back, finite-element.cpp:2007-2042, then the
+// product with interpolation_matrix(), finite-element.h:1183-1226), without the pulled-back values ever touching memory:
+// u[nc][npts][D] (physical values at the mapped interpolation points, the layout push_forward / pull_back use) is read
+// once, 1560 B per N1curl3 cell move instead of 3816.
+//
+// The k axis of the contraction is taken COMPONENT-MAJOR in blocks (k' = i * PB + p, PB = npts padded to 8): during the
+// PB / 4 k-steps of block i every lane needs the same column i of its cell's matrix, so the pulled-back A fragment
+//     covariant       U[p][i] =  sum_k J[k][i] u[p][k]                      (maps.h:73-94 with (K, 1 / detJ, J))
+//     contravariant   U[p][i] = (sum_k K[i][k] u[p][k]) / (1 / detJ)        (maps.h:100-124 with (K, 1 / detJ, J))
+// costs three loads per POINT step (shared by the D blocks) and D * D multiply-adds with the cell's matrix in registers --
+// no selects, no shared-memory staging.  (Folding the map into a point-major k axis needs a different matrix column at
+// every k and is issue-bound.)  The loop walks the point steps; each feeds D k-steps (one per block) of 2 NT DMMAs.
+// The map is evaluated with fused multiply-adds (and the division by 1 / detJ as a multiplication by detJ) and the
+// contraction sums in another k order than bx_interpolate, so the result equals bx_pull_back + bx_interpolate to
+// rounding (observed <= 1e-15 relative, tested at 1e-13), not bit for bit.  Twelve warps (the cell matrices and the
+// three-wide value queue need 160 registers).
+namespace
+{
+constexpr int kPullWarps = 12;
+constexpr int kPullThreads = 32 * kPullWarps;
+
+template <typename T>
+struct PullParams
+{
+  const T* u;      // [nc][npts][D]
+  const T* A;      // [nc][D][D]: J (covariant) or K (contravariant)
+  const T* detJ;   // [nc] (contravariant)
+  const double* B; // [npad][kstride], columns k' = i * PB + p
+  T* out;          // [nc][out_stride]
+  size_t nc;
+  int npts, PB, N, npad, kstride, n_base, out_stride;
+};
+
+template <int NT, int MAP, int D, typename T>
+__device__ __forceinline__ void run_group_pulled(const PullParams<T>& p, const double* __restrict__ Bs, size_t c0, int n0, int g,
+                                                 int t)
+{
+  double acc[2][NT][2];
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+      acc[m][j][0] = acc[m][j][1] = 0.0;
+  const size_t r[2] = {min(c0 + g, p.nc - 1), min(c0 + g + 8, p.nc - 1)}; // a row past the end is computed, never stored
+  double Am[2][D * D];
+  [[maybe_unused]] double det[2];
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+  {
+#pragma unroll
+    for (int k = 0; k < D * D; ++k)
+      Am[m][k] = double(__ldg(p.A + r[m] * (D * D) + k));
+    if constexpr (MAP == BX_MAP_CONTRAVARIANT_PIOLA)
+    {
+      det[m] = double(__ldg(p.detJ + r[m])); // pull_back passes 1 / detJ as the kernel's detJ (finite-element.cpp:2038)
+    }
+  }
+  const T* __restrict__ up[2] = {p.u + r[0] * size_t(p.npts) * D, p.u + r[1] * size_t(p.npts) * D};
+  const int last_pt = p.npts - 1;
+  auto ldu = [&](int m, int ks, double (&dst)[D])
+  {
+    const int pt = min(4 * ks + t, last_pt); // padded points: any finite value, their operand rows are zero
+#pragma unroll
+    for (int k = 0; k < D; ++k)
+      dst[k] = double(__ldg(up[m] + pt * D + k));
+  };
+  const double* __restrict__ bp = Bs + (n0 + g) * p.kstride + t;
+  const int ts = 8 * p.kstride;
+  const int nks = p.PB >> 2; // point steps (even)
+  double uq[2][2][D]; // [slot][row tile][component]: values two point steps ahead
+  double b[2][NT];
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+  {
+    ldu(m, 0, uq[0][m]);
+    ldu(m, 1, uq[1][m]);
+  }
+#pragma unroll
+  for (int j = 0; j < NT; ++j)
+    b[0][j] = bp[j * ts];
+#pragma unroll 1
+  for (int ks = 0; ks < nks; ks += 2)
+  {
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+    {
+      // pulled-back A fragments of this point step, all D blocks
+      double a[2][D];
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+      {
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+        {
+          double v = (MAP == BX_MAP_COVARIANT_PIOLA ? Am[m][i] : Am[m][i * D]) * uq[s][m][0];
+#pragma unroll
+          for (int k = 1; k < D; ++k)
+            v = fma(MAP == BX_MAP_COVARIANT_PIOLA ? Am[m][k * D + i] : Am[m][i * D + k], uq[s][m][k], v);
+          if constexpr (MAP == BX_MAP_CONTRAVARIANT_PIOLA)
+            v *= det[m]; // the reference divides by 1 / detJ
+          a[m][i] = v;
+        }
+        ldu(m, ks + s + 2, uq[s][m]); // two point steps ahead (clamped inside ldu)
+      }
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+      {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int cur = (s * D + i) & 1;
+        // next k-step: the next block of this point step, or block 0 of the next point step
+        const int nb = i + 1 < D ? i + 1 : 0;
+        const int nk = i + 1 < D ? ks + s : min(ks + s + 1, nks - 1);
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+          b[cur ^ 1][j] = bp[j * ts + 4 * (nb * nks + nk)];
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+        {
+          dmma(acc[0][j][0], acc[0][j][1], a[0][i], b[cur][j]);
+          dmma(acc[1][j][0], acc[1][j][1], a[1][i], b[cur][j]);
+        }
+      }
+    }
+  }
+  const bool even = ((p.out_stride | p.n_base) & 1) == 0;
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+  {
+    const size_t c = c0 + g + 8 * m;
+    if (c < p.nc)
+    {
+      T* row = p.out + c * size_t(p.out_stride) + p.n_base;
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+      {
+        const int n = n0 + j * 8 + 2 * t;
+        if constexpr (sizeof(T) == 8)
+        {
+          if (even)
+          {
+            if (n < p.N)
+              __stcs(reinterpret_cast<double2*>(row + n), make_double2(acc[m][j][0], acc[m][j][1]));
+            continue;
+          }
+        }
+        if (n < p.N)
+          __stcs(row + n, static_cast<T>(acc[m][j][0]));
+        if (n + 1 < p.N)
+          __stcs(row + n + 1, static_cast<T>(acc[m][j][1]));
+      }
+    }
+  }
+}
+
+template <int MAP, int D, typename T>
+__global__ void __launch_bounds__(kPullThreads, 1) interpolate_pulled_kernel(const PullParams<T> p)
+{
+  extern __shared__ __align__(16) double interp_smem[];
+  double* Bs = interp_smem;
+  for (int i = threadIdx.x; i < p.npad * p.kstride; i += kPullThreads)
+    Bs[i] = p.B[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const size_t nchunks = ceil_div(p.nc, size_t(kCells));
+  const size_t stride = size_t(gridDim.x) * kPullWarps;
+  for (size_t chunk = size_t(blockIdx.x) * kPullWarps + warp; chunk < nchunks; chunk += stride)
+  {
+    const size_t c0 = chunk * kCells;
+    for (int n0 = 0; n0 < p.N; n0 += 8 * kMaxNT)
+    {
+      const int nt = min(kMaxNT, (p.N - n0 + 7) >> 3);
+      switch (nt)
+      {
+      case 1: run_group_pulled<1, MAP, D, T>(p, Bs, c0, n0, g, t); break;
+      case 2: run_group_pulled<2, MAP, D, T>(p, Bs, c0, n0, g, t); break;
+      case 3: run_group_pulled<3, MAP, D, T>(p, Bs, c0, n0, g, t); break;
+      case 4: run_group_pulled<4, MAP, D, T>(p, Bs, c0, n0, g, t); break;
+      case 5: run_group_pulled<5, MAP, D, T>(p, Bs, c0, n0, g, t); break;
+      case 6: run_group_pulled<6, MAP, D, T>(p, Bs, c0, n0, g, t); break;
+      default: run_group_pulled<7, MAP, D, T>(p, Bs, c0, n0, g, t); break;
+      }
+    }
+  }
+}
+
+template <int MAP, int D, typename T>
+void launch_pulled(const bx_element& e, PullParams<T> p, cudaStream_t s)
+{
+  const size_t row_bytes = size_t(p.kstride) * sizeof(double);
+  const int rows_fit = int(std::min<size_t>(size_t(e.interp_npad), (size_t(200) * 1024 / row_bytes) / 8 * 8));
+  if (rows_fit < 8)
+    fail(BX_ERR_UNSUPPORTED, "interpolate: a block of eight rows of the interpolation matrix does not fit in shared memory");
+  const size_t nblocks = ceil_div(p.nc, size_t(kCells) * kPullWarps);
+  const unsigned grid = unsigned(std::min<size_t>(nblocks, size_t(sm_count())));
+  auto kern = interpolate_pulled_kernel<MAP, D, T>;
+  for (int n0 = 0; n0 < e.ndofs; n0 += rows_fit)
+  {
+    p.n_base = n0;
+    p.N = std::min(rows_fit, e.ndofs - n0);
+    p.npad = std::min(rows_fit, e.interp_npad - n0);
+    p.B = e.d_interp_blocked + size_t(n0) * p.kstride;
+    const size_t smem = size_t(p.npad) * row_bytes;
+    BX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    kern<<<grid, kPullThreads, smem, s>>>(p);
+    BX_LAUNCHED();
+  }
+}
+} // namespace
+
+// u[nc][npts][gdim] physical values at the interpolation points; J[nc][gdim][tdim], detJ[nc], K[nc][tdim][gdim] per cell
+// -> coefficients[nc][ndofs] = interpolation_matrix * pull_back(u).  Covariant and contravariant Piola maps on square
+// Jacobians (gdim == tdim == value size); other elements: bx_pull_back + bx_interpolate.
+template <typename T>
+void interpolate_pulled_device(const bx_element& e, const T* u, const T* J, const T* detJ, const T* K, size_t nc, int gdim,
+                               T* coefficients, cudaStream_t s)
+{
+  if (e.interp_npts == 0)
+    fail(BX_ERR_RUNTIME, "interpolate: the element was built without points() / interpolation_matrix()");
+  const int map = e.map_type, D = e.tdim;
+  if ((map != BX_MAP_COVARIANT_PIOLA and map != BX_MAP_CONTRAVARIANT_PIOLA) or gdim != D or e.vs != D or (D != 2 and D != 3)
+      or !e.d_interp_blocked)
+    fail(BX_ERR_UNSUPPORTED, "interpolate_pulled: covariant / contravariant Piola elements on square Jacobians (gdim == tdim "
+                             "== value size) are fused; use pull_back and interpolate separately otherwise");
+  if (map == BX_MAP_COVARIANT_PIOLA ? !J : (!K or !detJ))
+    fail(BX_ERR_INVALID_ARG, "interpolate_pulled: the covariant pull_back needs J, the contravariant one K and detJ");
+  if (nc == 0)
+    return;
+  if (!u or !coefficients)
+    fail(BX_ERR_INVALID_ARG, "interpolate_pulled: null pointer");
+  require_device(e);
+  PullParams<T> p;
+  p.u = u;
+  p.A = map == BX_MAP_COVARIANT_PIOLA ? J : K;
+  p.detJ = detJ;
+  p.out = coefficients;
+  p.nc = nc;
+  p.npts = e.interp_npts;
+  p.PB = e.interp_pb;
+  p.kstride = e.interp_kstride_blocked;
+  p.out_stride = e.ndofs;
+  if (map == BX_MAP_COVARIANT_PIOLA)
+  {
+    if (D == 3)
+      launch_pulled<BX_MAP_COVARIANT_PIOLA, 3, T>(e, p, s);
+    else
+      launch_pulled<BX_MAP_COVARIANT_PIOLA, 2, T>(e, p, s);
+  }
+  else
+  {
+    if (D == 3)
+      launch_pulled<BX_MAP_CONTRAVARIANT_PIOLA, 3, T>(e, p, s);
+    else
+      launch_pulled<BX_MAP_CONTRAVARIANT_PIOLA, 2, T>(e, p, s);
+  }
+}
+template void interpolate_pulled_device<double>(const bx_element&, const double*, const double*, const double*, const double*,
+                                                size_t, int, double*, cudaStream_t);
+
 // ---- compute_interpolation_operator (reference cpp/basix/interpolation.cpp:16-116) --------------------------------
 // The matrix that maps the coefficients of a function in `from` to the coefficients of its interpolant in `to`:
 // tabulate `from` at the interpolation points of `to`, apply `to`'s interpolation matrix.  Composition of two device

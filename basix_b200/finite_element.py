@@ -936,6 +936,30 @@ class FiniteElement:
         check(fn(self._h, lay, va.ptr, va.shape[0], _ptr_of(out), va.mem, stream))
         return out
 
+    def interpolate_pulled_batch(self, u, J, detJ, K):
+        """coefficients[c] = interpolation_matrix @ pull_back(u[c], J[c], detJ[c], K[c]) in one fused pass
+        (``bx_interpolate_pulled_f64``): the two steps of interpolating a physical function into a Piola-mapped element,
+        without the pulled-back values ever being written.  ``u``: (ncells, npts, gdim) values at the mapped
+        interpolation points (the layout ``pull_back`` takes); ``J`` (ncells, gdim, tdim), ``detJ`` (ncells,), ``K``
+        (ncells, tdim, gdim).  Covariant / contravariant Piola elements with gdim == tdim; equal to
+        ``interpolate_batch(pull_back(u, J, detJ, K).reshape(ncells, -1), "point-major")`` to rounding (1e-13).
+        Returns (ncells, ndofs)."""
+        if self._points is None:
+            raise RuntimeError("interpolate: the element was built without points() / interpolation_matrix()")
+        ua, Ja = _Arg(u, np.float64, "u"), _Arg(J, np.float64, "J")
+        da, Ka = _Arg(detJ, np.float64, "detJ"), _Arg(K, np.float64, "K")
+        mem = _same_mem(ua, Ja, da, Ka)
+        npts = self._points.shape[0]
+        if len(ua.shape) != 3 or ua.shape[1] != npts or len(Ja.shape) != 3:
+            raise RuntimeError(f"u must have shape (ncells, {npts}, gdim) and J (ncells, gdim, tdim)")
+        nc, gdim, tdim = Ja.shape
+        if ua.shape[0] != nc or ua.shape[2] != gdim or da.shape != (nc,) or Ka.shape != (nc, tdim, gdim):
+            raise RuntimeError("interpolate_pulled: inconsistent array shapes")
+        stream, alloc = _stream_and_like(ua)
+        out = alloc((nc, self._ndofs), np.float64)
+        check(lib().bx_interpolate_pulled_f64(self._h, ua.ptr, Ja.ptr, da.ptr, Ka.ptr, nc, gdim, _ptr_of(out), mem, stream))
+        return out
+
     # ---- sub-entity closure permutations ---------------------------------------------------------------
     def subentity_closure_size(self, entity_type) -> int:
         """Number of dofs on the closure of a sub-entity of this type (0 when the cell has none)."""

@@ -710,8 +710,9 @@ class Interpolate:
     bound = "tensor"
     cpu_kind = "port"  # numpy dgemm with the reference's matrix: the reference has no batched call to time
 
-    def __init__(self, element, ref_args, nc, desc):
+    def __init__(self, element, ref_args, nc, desc, pulled=False):
         self.element_name, self.ref_args, self.nc, self.desc = element, ref_args, nc, desc
+        self.pulled = pulled  # pull_back fused into the interpolation (bx_interpolate_pulled)
 
     def setup(self, rank, device_only=False):
         import torch
@@ -734,9 +735,52 @@ class Interpolate:
         self.config = {"workload": self.desc, "cells_per_gpu": nc, "values_per_cell": self.K, "ndofs": self.N,
                        "fp64_flops_per_cell": 2 * self.K * self.N,
                        "l2": "arrays are %.2f GB per step (>> 126 MB L2)" % (self.alg_bytes / 1e9)}
+        if self.pulled:
+            # physical values u[nc][npts][3] and the Jacobians; the pulled-back values never exist in memory
+            self.u = self.values.reshape(nc, e.points.shape[0], 3)
+            self.J = torch.eye(3, device="cuda", dtype=torch.float64)[None] + 0.3 * torch.randn(
+                nc, 3, 3, generator=g, device="cuda", dtype=torch.float64)
+            self.detJ = torch.linalg.det(self.J)
+            self.Kinv = torch.linalg.inv(self.J).contiguous()
+            self.alg_bytes = nc * (self.K + 9 + self.N) * 8
+            self.flops = (2.0 * self.K * self.N + 5.0 * self.K) * nc
+            self.config["fp64_flops_per_cell"] = 2 * self.K * self.N + 5 * self.K
+            self.config["bytes_per_cell_fused"] = (self.K + 9 + self.N) * 8
+            self.config["bytes_per_cell_two_calls"] = (2 * self.K + 9) * 8 + (self.K + self.N) * 8
 
     def step(self):
-        self.result = self.e.interpolate_batch(self.values)
+        if self.pulled:
+            self.result = self.e.interpolate_pulled_batch(self.u, self.J, self.detJ, self.Kinv)
+        else:
+            self.result = self.e.interpolate_batch(self.values)
+
+    def extra(self):
+        """The same coefficients through the two separate calls (pull_back, interpolate): what the fusion saves."""
+        import torch
+
+        if not self.pulled:
+            return None
+        n = min(self.nc, 4_000_000)
+        u, J, d, K = self.u[:n], self.J[:n], self.detJ[:n], self.Kinv[:n]
+
+        def two_calls():
+            return self.e.interpolate_batch(self.e.pull_back(u, J, d, K).reshape(n, -1), "point-major")
+
+        for _ in range(2):
+            out = two_calls()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            out = two_calls()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 3
+        fused = self.e.interpolate_pulled_batch(u, J, d, K)
+        rel = float((fused - out).abs().max() / out.abs().max())
+        del out, fused
+        return {"two_calls_ns_per_cell": ms * 1e6 / n, "two_calls": "pull_back + interpolate_batch(point-major) on %d cells, "
+                "device-resident" % n, "fused_vs_two_calls_max_rel_difference": rel}
 
     def e2e_setup(self, avail_bytes):
         import torch
@@ -745,11 +789,19 @@ class Interpolate:
         self.out_host = torch.empty((self.nc, self.N), dtype=torch.float64).pin_memory()
         self.e2e_units = self.nc
         self.h2d, self.d2h = self.values_host.numel() * 8, self.out_host.numel() * 8
+        if self.pulled:
+            self.J_host, self.detJ_host, self.K_host = (a.cpu().pin_memory() for a in (self.J, self.detJ, self.Kinv))
+            self.h2d += self.nc * 9 * 8
         return {"cells_per_gpu": self.nc}
 
     def e2e_step(self):
         from basix_b200 import _capi
 
+        if self.pulled:
+            _capi.check(_capi.lib().bx_interpolate_pulled_f64(self.e._h, self.values_host.data_ptr(), self.J_host.data_ptr(),
+                                                             self.detJ_host.data_ptr(), self.K_host.data_ptr(), self.nc, 3,
+                                                             self.out_host.data_ptr(), _capi.BX_MEM_HOST, None))
+            return
         _capi.check(_capi.lib().bx_interpolate_f64(self.e._h, 0, self.values_host.data_ptr(), self.nc,
                                                    self.out_host.data_ptr(), _capi.BX_MEM_HOST, None))
 
@@ -761,10 +813,24 @@ class Interpolate:
         r = ref.RefElement(*self.ref_args)
         n = int(min(self.nc, 2_000_000))
         self._cpu = (np.ascontiguousarray(r.interpolation_matrix.T), np.random.default_rng(21).standard_normal((n, self.K)))
+        if self.pulled:
+            n = int(min(n, 500_000))
+            rng = np.random.default_rng(22)
+            J = np.eye(3)[None] + 0.3 * rng.standard_normal((n, 3, 3))
+            self._cpu = (self._cpu[0], rng.standard_normal((n, self.K // 3, 3)), r, J, np.linalg.det(J),
+                         np.ascontiguousarray(np.linalg.inv(J)), cores)
+            self.cpu_kind = "reference"
+            return n, (f"{n} cells per step: the reference's pull_back over {cores} std::threads (oracle/_ref, unmodified "
+                       f"reference), then values @ interpolation_matrix.T with numpy (OpenBLAS dgemm)")
         return n, (f"{n} cells per step, values @ interpolation_matrix.T with numpy (OpenBLAS dgemm, all threads), the "
                    f"reference's documented usage of interpolation_matrix()")
 
     def cpu_step(self):
+        if self.pulled:
+            Mt, u, r, J, d, K, cores = self._cpu
+            U = r.pull_back(u, J, d, K, nthreads=cores)
+            self._cpu_out = U.transpose(0, 2, 1).reshape(len(u), -1) @ Mt
+            return
         Mt, v = self._cpu
         self._cpu_out = v @ Mt
 
@@ -816,6 +882,10 @@ WORKLOADS = {
     "interpolate_n1curl3": lambda: Interpolate(
         "N1curl3_tetrahedron_legendre", (3, 3, 3, 11), 20_000_000,
         "N1curl degree 3 tetrahedron, interpolation_matrix (45 x 141) applied to 20M cells of point values"),
+    "interpolate_pulled_n1curl3": lambda: Interpolate(
+        "N1curl3_tetrahedron_legendre", (3, 3, 3, 11), 20_000_000,
+        "N1curl degree 3 tetrahedron, covariant Piola pull_back fused into the interpolation (45 x 141 matrix), 20M cells of "
+        "physical point values", pulled=True),
     "push_forward_bcast_n1curl3_rows45": lambda: PushForward(
         "N1curl3_tetrahedron_legendre", (3, 3, 3, 11), 8_000_000, 45, False,
         "N1curl degree 3 tetrahedron, covariant Piola push_forward of ONE 45-row slab of reference values onto 8M cells "
@@ -842,6 +912,7 @@ SIDE_CONFIGS = [
     ("t_apply_rt4_block3", {"nc": 50_000_000}),
     ("permute_p5_tet", {}),
     ("interpolate_n1curl3", {}),
+    ("interpolate_pulled_n1curl3", {}),
     ("geometry_tet", {}),
     ("geometry_hex", {}),
     ("physical_basis_n1curl3", {}),

@@ -354,6 +354,15 @@ extern "C"
   int bx_element_interpolation_matrix(const bx_element* e, double* out); /* [ndofs][value_size * npts] */
   int bx_interpolate_f64(const bx_element* e, int layout, const double* values, size_t nc, double* coefficients,
                          int mem, bx_stream_t stream);
+  /* pull_back fused into the interpolation: coefficients[c] = interpolation_matrix * pull_back(u[c], J_c, detJ_c, K_c) --
+     FiniteElement::pull_back (finite-element.cpp:2007-2042) followed by the product with interpolation_matrix()
+     (finite-element.h:1183-1226) -- in one pass that reads the physical values once and never writes the pulled-back
+     ones.  u[nc][npts][gdim]: values of the function at the mapped interpolation points, the layout pull_back takes.
+     Covariant (needs J) and contravariant (needs K and detJ) Piola elements with gdim == tdim == value size; other
+     elements: BX_ERR_UNSUPPORTED (call bx_pull_back and bx_interpolate).  Equal to those two calls to rounding (fused
+     multiply-adds in the map, another summation order in the contraction: <= 1e-13 relative). */
+  int bx_interpolate_pulled_f64(const bx_element* e, const double* u, const double* J, const double* detJ, const double* K,
+                                size_t nc, int gdim, double* coefficients, int mem, bx_stream_t stream);
   /* float32 values / coefficients (the reference's FiniteElement<float>); the matrix and the arithmetic are float64 */
   int bx_interpolate_f32(const bx_element* e, int layout, const float* values, size_t nc, float* coefficients,
                          int mem, bx_stream_t stream);

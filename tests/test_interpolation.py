@@ -195,3 +195,46 @@ def test_compute_interpolation_operator_errors_and_native_elements(ref):
     want = ref.compute_interpolation_operator(ref.RefElement(1, 3, 2, 2), ref.RefElement(1, 3, 3, 2))
     got = bx.compute_interpolation_operator(bx.create_element(1, 3, 2, 2), bx.create_element(1, 3, 3, 2))
     assert np.max(np.abs(got - want)) <= 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("family,cell,degree", [(3, 3, 3), (2, 3, 4), (3, 3, 1), (2, 3, 1), (3, 2, 2), (2, 2, 3), (3, 2, 1)])
+@pytest.mark.parametrize("nc", [1, 16, 1000 + 13])
+def test_interpolate_pulled_equals_pull_back_then_interpolate(family, cell, degree, nc):
+    """pull_back fused into the interpolation (bx_interpolate_pulled_f64): the library's own pull_back followed by
+    interpolate_batch to 1e-13 (another summation order in the contraction), host and device pointers bit-equal; and within
+    1e-12 of the reference's pull_back times the matrix."""
+    import torch
+
+    import basix_b200 as bx
+    from oracle import ref
+
+    e = bx.create_element(family, cell, degree, 11)
+    r = ref.RefElement(family, cell, degree, 11)
+    tdim = 3 if cell == 3 else 2
+    rng = np.random.default_rng(nc + degree)
+    J = np.eye(tdim)[None] + 0.25 * rng.standard_normal((nc, tdim, tdim))
+    detJ, K = np.linalg.det(J), np.ascontiguousarray(np.linalg.inv(J))
+    npts = e.points.shape[0]
+    u = rng.standard_normal((nc, npts, tdim))
+    two = e.interpolate_batch(e.pull_back(u, J, detJ, K).reshape(nc, -1), "point-major")
+    got = e.interpolate_pulled_batch(u, J, detJ, K)
+    # fused multiply-adds in the map and another k order in the contraction: equal to rounding
+    scale = max(np.max(np.abs(two)), 1.0)
+    assert got.shape == (nc, e.dim) and np.max(np.abs(got - two)) <= 1e-13 * scale, np.max(np.abs(got - two)) / scale
+    dev = e.interpolate_pulled_batch(*[torch.from_numpy(a).cuda() for a in (u, J, detJ, K)])
+    assert np.array_equal(dev.cpu().numpy(), got)
+    # the reference: its own pull_back, then our element's matrix in the reference's column order (the native element's
+    # interpolation points differ from the reference element's, the map arithmetic does not)
+    U = r.pull_back(u, J, detJ, K)  # (nc, npts, tdim)
+    want = np.einsum("nk,ck->cn", e.interpolation_matrix, U.transpose(0, 2, 1).reshape(nc, -1))
+    assert np.max(np.abs(got - want)) <= 1e-12 * max(np.max(np.abs(want)), 1.0)
+
+
+@pytest.mark.gpu
+def test_interpolate_pulled_rejects_what_it_does_not_fuse():
+    import basix_b200 as bx
+
+    p = bx.create_element(1, 3, 2, 2)
+    with pytest.raises(RuntimeError):
+        p.interpolate_pulled_batch(np.zeros((2, p.points.shape[0], 3)), np.zeros((2, 3, 3)), np.ones(2), np.zeros((2, 3, 3)))
