@@ -244,3 +244,22 @@ def test_interpolate_stays_inside_its_arrays(family, cell, degree, variant, nc, 
         assert L.bx_interpolate_f64(e._h, layout, vals.ptr, nc, coef.ptr, capi.BX_MEM_DEVICE, None) == 0, L.bx_last_error()
 
     _run_twice(call, [coef], [vals])
+
+
+@pytest.mark.parametrize("family,degree,nc", [(3, 3, 1000 + 9), (2, 2, 77), (3, 1, 17)])
+def test_interpolate_pulled_stays_inside_its_arrays(family, degree, nc):
+    import basix_b200 as bx
+
+    capi, L = _lib()
+    e = bx.create_element(family, 3, degree, 11)
+    npts = e.points.shape[0]
+    Jn, dn, Kn = _jac(nc, 3, 3, degree)
+    u = Guarded(nc * npts * 3, np.float64, np.random.default_rng(6).standard_normal(nc * npts * 3))
+    J, d, K = Guarded(Jn.size, np.float64, Jn), Guarded(dn.size, np.float64, dn), Guarded(Kn.size, np.float64, Kn)
+    coef = Guarded(nc * e.dim, np.float64)
+
+    def call():
+        assert L.bx_interpolate_pulled_f64(e._h, u.ptr, J.ptr, d.ptr, K.ptr, nc, 3, coef.ptr, capi.BX_MEM_DEVICE, None) == 0, \
+            L.bx_last_error()
+
+    _run_twice(call, [coef], [u, J, d, K])
