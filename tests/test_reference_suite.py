@@ -32,6 +32,11 @@ def test_compat_package_imports_and_host_helpers():
         "assert hasattr(cpp, 'FiniteElement_float64') and hasattr(cpp, 'tabulate_polynomial_set_float64')\n"
         "t = basix.create_tp_element(basix.ElementFamily.P, basix.CellType.quadrilateral, 2, basix.LagrangeVariant.gll_warped)\n"
         "assert t.has_tensor_product_factorisation and t.dof_ordering == [0, 3, 1, 4, 6, 2, 5, 7, 8]\n"
+        "assert basix.finite_element.lex_dof_ordering(basix.ElementFamily.P, basix.CellType.triangle, 3) == [0, 3, 9, 6, 8, 4, 7, 1, 2, 5]\n"
+        "pts, wts = basix.quadrature.gauss_jacobi_rule(1.5, 4)\n"
+        "assert abs(sum(w * (1 - x) ** 3 for x, w in zip(pts, wts)) - 1 / 5.5) < 1e-14\n"
+        "assert basix.cell.volume(basix.CellType.pyramid) == 1 / 3 and basix.cell.facet_orientations(basix.CellType.triangle) == [False, True, False]\n"
+        "assert np.allclose(basix.cell.facet_outward_normals(basix.CellType.tetrahedron)[0], np.ones(3) / np.sqrt(3))\n"
         "try:\n"
         "    basix.create_element(basix.ElementFamily.Regge, basix.CellType.triangle, 1)\n"
         "    raise SystemExit('Regge should not be built natively')\n"
@@ -55,4 +60,4 @@ def test_reference_pytest_files_pass_against_the_shim():
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
     counts = {k: int(v) for v, k in re.findall(r"(\d+) (passed|skipped|failed|xfailed|error)", tail)}
     assert counts.get("failed", 0) == 0 and counts.get("error", 0) == 0
-    assert counts.get("passed", 0) >= 5000, tail
+    assert counts.get("passed", 0) >= 6000, tail
