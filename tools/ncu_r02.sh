@@ -19,6 +19,8 @@ cap dof_matrix_rt4_block3 t_apply_rt4_block3 dof_ 2000000
 cap dof_perm_p5tet permute_p5_tet dof_ 4000000
 cap interp_n1curl3 interpolate_n1curl3 interpolate_kernel 4000000
 cap geometry_tet geometry_tet geometry_affine 4000000
+cap geometry_hex geometry_hex geometry_warp 1000000
+cap interp_pulled_n1curl3 interpolate_pulled_n1curl3 interpolate_pulled 4000000
 cap physical_basis_n1curl3 physical_basis_n1curl3 physical_basis 2000000
 cap physical_basis_rt4 physical_basis_rt4 physical_basis 2000000
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_ncu_launches_bench_default.csv \

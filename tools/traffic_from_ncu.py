@@ -23,6 +23,8 @@ CAPTURES = {
     "permute_p5_tet": ("dof_perm_p5tet", 4_000_000, "cell"),
     "interpolate_n1curl3": ("interp_n1curl3", 4_000_000, "cell"),
     "geometry_tet": ("geometry_tet", 4_000_000, "cell"),
+    "geometry_hex": ("geometry_hex", 1_000_000, "cell"),
+    "interpolate_pulled_n1curl3": ("interp_pulled_n1curl3", 4_000_000, "cell"),
     "physical_basis_n1curl3": ("physical_basis_n1curl3", 2_000_000, "cell"),
     "physical_basis_rt4": ("physical_basis_rt4", 2_000_000, "cell"),
 }
