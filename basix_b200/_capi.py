@@ -91,6 +91,8 @@ SIGNATURES = {
     "bx_push_forward_fused_f64": (_I, [_P, _I, _P, _SIZE, _P, _P, _P, _P, _P, _SIZE, _I, _P, _I, _P]),
     "bx_push_forward_fused_f32": (_I, [_P, _I, _P, _SIZE, _P, _P, _P, _P, _P, _SIZE, _I, _P, _I, _P]),
     "bx_physical_basis_f64": (_I, [_P, _I, _P, _SIZE, _I, _P, _P, _P, _P, _P, _SIZE, _I, _P, _I, _P]),
+    "bx_physical_basis_pointwise_f64": (_I, [_P, _I, _P, _SIZE, _I, _P, _P, _P, _P, _SIZE, _I, _P, _I, _P]),
+    "bx_push_forward_fused_pointwise_f64": (_I, [_P, _I, _P, _SIZE, _P, _P, _P, _P, _SIZE, _I, _P, _I, _P]),
     "bx_T_apply_f64": (_I, [_P, _I, _P, _SIZE, _SIZE, _I, _P, _I, _P]),
     "bx_T_apply_f32": (_I, [_P, _I, _P, _SIZE, _SIZE, _I, _P, _I, _P]),
     "bx_T_apply_i32": (_I, [_P, _I, _P, _SIZE, _SIZE, _I, _P, _I, _P]),

@@ -165,7 +165,7 @@ void geometry_device(const T* coords, const T* dphi, size_t nc, int nv, int gdim
 template <typename T>
 void physical_basis_device(const bx_element& e, int op, const T* U, size_t npts, const T* coords, const T* J,
                            const T* detJ, const T* K, const uint32_t* cell_info, size_t nc, int gdim, T* out,
-                           cudaStream_t s);
+                           cudaStream_t s, int per_point = 0);
 void interpolation_operator_shape(const bx_element& from, const bx_element& to, int32_t shape[2]);
 void interpolation_operator_device(const bx_element& from, const bx_element& to, double* out, cudaStream_t s);
 void gauss_jacobi_rule_unit(double a, int m, std::vector<double>& x, std::vector<double>& w);
@@ -674,7 +674,7 @@ void geometry_any(const T* coords, const T* dphi, size_t nc, int nv, int gdim, i
 template <typename T>
 void physical_basis_any(const bx_element* e, int op, const T* X, const T* U, size_t npts, const T* coords, const T* J,
                         const T* detJ, const T* K, const uint32_t* cell_info, size_t nc, int gdim, T* out, int mem,
-                        bx_stream_t stream)
+                        bx_stream_t stream, int per_point = 0)
 {
   check_mem(mem);
   require(e != nullptr, "physical_basis: null element");
@@ -685,7 +685,7 @@ void physical_basis_any(const bx_element* e, int op, const T* X, const T* U, siz
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (!X or npts == 0 or nc == 0)
     {
-      physical_basis_device<T>(*e, op, U, npts, coords, J, detJ, K, cell_info, nc, gdim, out, s);
+      physical_basis_device<T>(*e, op, U, npts, coords, J, detJ, K, cell_info, nc, gdim, out, s, per_point);
       return;
     }
     T* dU = nullptr;
@@ -693,7 +693,7 @@ void physical_basis_any(const bx_element* e, int op, const T* X, const T* U, siz
     try
     {
       tabulate_device<T>(*e, 0, X, npts, dU, npts, s);
-      physical_basis_device<T>(*e, op, dU, npts, coords, J, detJ, K, cell_info, nc, gdim, out, s);
+      physical_basis_device<T>(*e, op, dU, npts, coords, J, detJ, K, cell_info, nc, gdim, out, s, per_point);
     }
     catch (...)
     {
@@ -703,16 +703,18 @@ void physical_basis_any(const bx_element* e, int op, const T* X, const T* U, siz
     BX_CUDA(cudaFreeAsync(dU, s));
     return;
   }
-  physical_basis_device<T>(*e, op, U, 0, coords, J, detJ, K, cell_info, 0, gdim, out, nullptr); // validate
+  physical_basis_device<T>(*e, op, U, 0, coords, J, detJ, K, cell_info, 0, gdim, out, nullptr, per_point); // validate
   if (nc == 0 or npts == 0)
     return;
   require(out != nullptr, "physical_basis: null pointer");
   const int tdim = e->tdim, map = e->map_type;
   const int out_vs = map == BX_MAP_IDENTITY ? e->vs : gdim;
-  const size_t xsz = coords ? size_t(tdim + 1) * gdim : 0, jsz = size_t(gdim) * tdim;
+  // per-point geometry: every cell brings npts matrices (and determinants)
+  const size_t pp = per_point ? npts : 1;
+  const size_t xsz = coords ? size_t(tdim + 1) * gdim : 0, jsz = size_t(gdim) * tdim * pp;
   const bool need_K = !coords and map == BX_MAP_COVARIANT_PIOLA, need_J = !coords and map == BX_MAP_CONTRAVARIANT_PIOLA;
   const size_t orow = npts * size_t(e->ndofs) * out_vs;
-  const size_t per_cell = (xsz + ((need_K or need_J) ? jsz : 0) + (need_J ? 1 : 0) + orow) * sizeof(T) + sizeof(uint32_t);
+  const size_t per_cell = (xsz + ((need_K or need_J) ? jsz : 0) + (need_J ? pp : 0) + orow) * sizeof(T) + sizeof(uint32_t);
   const size_t chunk = chunk_units(nc, per_cell, 1);
   StagePool& st = stage_pool();
   DrainOnExit drain{st};
@@ -721,7 +723,7 @@ void physical_basis_any(const bx_element* e, int op, const T* X, const T* U, siz
   for (int b = 0; b < 2; ++b)
   {
     dg[b] = st.get<T>(0, b, chunk * std::max(xsz, jsz) * sizeof(T));
-    dd[b] = need_J ? st.get<T>(1, b, chunk * sizeof(T)) : nullptr;
+    dd[b] = need_J ? st.get<T>(1, b, chunk * pp * sizeof(T)) : nullptr;
     dci[b] = cell_info ? st.get<uint32_t>(2, b, chunk * sizeof(uint32_t)) : nullptr;
     dout[b] = st.get<T>(3, b, chunk * orow * sizeof(T));
   }
@@ -755,12 +757,12 @@ void physical_basis_any(const bx_element* e, int op, const T* X, const T* U, siz
     else if (need_J)
     {
       BX_CUDA(cudaMemcpyAsync(dg[b], J + c0 * jsz, n * jsz * sizeof(T), cudaMemcpyHostToDevice, s));
-      BX_CUDA(cudaMemcpyAsync(dd[b], detJ + c0, n * sizeof(T), cudaMemcpyHostToDevice, s));
+      BX_CUDA(cudaMemcpyAsync(dd[b], detJ + c0 * pp, n * pp * sizeof(T), cudaMemcpyHostToDevice, s));
     }
     if (cell_info)
       BX_CUDA(cudaMemcpyAsync(dci[b], cell_info + c0, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     physical_basis_device<T>(*e, op, dU, npts, coords ? dg[b] : nullptr, need_J ? dg[b] : nullptr, dd[b],
-                             need_K ? dg[b] : nullptr, dci[b], n, gdim, dout[b], s);
+                             need_K ? dg[b] : nullptr, dci[b], n, gdim, dout[b], s, per_point);
     BX_CUDA(cudaMemcpyAsync(out + c0 * orow, dout[b], n * orow * sizeof(T), cudaMemcpyDeviceToHost, s));
   }
   st.sync();
@@ -1223,6 +1225,30 @@ extern "C"
           bx::require(X != nullptr or npts == 0, "physical_basis: null points");
           bx::physical_basis_any<double>(e, op, X, nullptr, npts, coords, J, detJ, K, cell_info, nc, gdim, out, mem, stream);
         });
+  }
+
+  int bx_physical_basis_pointwise_f64(const bx_element* e, int op, const double* X, size_t npts, int tdim_x, const double* J,
+                                      const double* detJ, const double* K, const uint32_t* cell_info, size_t nc, int gdim,
+                                      double* out, int mem, bx_stream_t stream)
+  {
+    return bx::guarded(
+        [&]()
+        {
+          bx::require(e != nullptr, "physical_basis: null element");
+          if (tdim_x != e->tdim)
+            bx::fail(BX_ERR_INVALID_ARG, "Point dim (" + std::to_string(tdim_x) + ") does not match element dim ("
+                                             + std::to_string(e->tdim) + ").");
+          bx::require(X != nullptr or npts == 0, "physical_basis: null points");
+          bx::physical_basis_any<double>(e, op, X, nullptr, npts, nullptr, J, detJ, K, cell_info, nc, gdim, out, mem, stream, 1);
+        });
+  }
+  int bx_push_forward_fused_pointwise_f64(const bx_element* e, int op, const double* U, size_t npts, const double* J,
+                                          const double* detJ, const double* K, const uint32_t* cell_info, size_t nc, int gdim,
+                                          double* out, int mem, bx_stream_t stream)
+  {
+    return bx::guarded(
+        [&]()
+        { bx::physical_basis_any<double>(e, op, nullptr, U, npts, nullptr, J, detJ, K, cell_info, nc, gdim, out, mem, stream, 1); });
   }
 
   int bx_compute_interpolation_operator_f64(const bx_element* from, const bx_element* to, int32_t shape[2], double* out,

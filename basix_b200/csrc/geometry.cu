@@ -298,6 +298,7 @@ struct FusedParams
   int nbuf;         // slices per warp (1 or 2)
   int bulk;         // the rows of `batch` consecutive cells are one 16-byte aligned run of `out`: TMA bulk copy-out
   int vec_coords;   // coords is 16-byte aligned: 16-byte loads
+  int ppc;          // points per cell when the kernel's "cells" are (cell, point) items with their own matrix (else 1)
   uint32_t rows_magic; // flat row walk: floor(2^32 / rows) + 1 (0 when rows == 1): cell = umulhi(f, rows_magic) for f < 2^13
   size_t out_pitch; // entries between consecutive cells of `out` (>= rows * OUT_VS: a chunk of a larger point set)
   const int16_t* dof_slot;  // [ndofs] owning slot or -1
@@ -563,7 +564,9 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1)
   for (size_t c0 = first; c0 < p.nc; c0 += warps * 32)
   {
     const int nb = int(min(size_t(32), p.nc - c0));
-    const uint32_t my_ci = (p.cell_info and lane < nb) ? p.cell_info[c0 + lane] : 0u;
+    // items of a per-point geometry share the cell_info of their cell and take the table rows of their point
+    const uint32_t my_ci = (p.cell_info and lane < nb) ? p.cell_info[p.ppc > 1 ? (c0 + lane) / size_t(p.ppc) : c0 + lane] : 0u;
+    [[maybe_unused]] const uint32_t pt0 = p.ppc > 1 ? uint32_t(c0 % size_t(p.ppc)) : 0u;
     // ---- phase A: lane = cell ----
     if constexpr (MAP != BX_MAP_IDENTITY)
     {
@@ -645,7 +648,8 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1)
           const uint32_t ci = __shfl_sync(0xffffffffu, my_ci, int(cell));
           const uint32_t d = s_desc[row];
           const int st = int(ci >> (d & 31u)) & int(d >> 5);
-          u[h] = s_tab + st * p.tab_stride + row * IN_VS;
+          const uint32_t trow = p.ppc > 1 ? ((pt0 + cell) % uint32_t(p.ppc)) * uint32_t(rows) + row : row;
+          u[h] = s_tab + st * p.tab_stride + trow * IN_VS;
           rc[h] = rec + cell * REC;
           g[h] = obase + cell * p.out_pitch + row * OUT_VS;
         }
@@ -970,7 +974,7 @@ void launch_fused(const T* tab, const T* coords, const T* A, const T* detJ, Fuse
   if constexpr (MAP != BX_MAP_IDENTITY)
   {
     // Piola maps: flat walk over the (cell, row) pairs, rows written straight to global memory (no slices)
-    if (fused_tune().flat != 0)
+    if (fused_tune().flat != 0 or p.ppc > 1)
     {
       auto flat = physical_basis_kernel<T, MAP, G, TD, GEOM, VS, true>;
       const int nw = (fused_tune().nw == 4 or fused_tune().nw == 8 or fused_tune().nw == 16) ? fused_tune().nw : 8;
@@ -994,6 +998,9 @@ void launch_fused(const T* tab, const T* coords, const T* A, const T* detJ, Fuse
           return;
         }
       }
+      if (p.ppc > 1)
+        fail(BX_ERR_UNSUPPORTED, "physical_basis: the state tables of this many points do not fit in shared memory (split "
+                                 "the point set)");
     }
   }
   auto kern = physical_basis_kernel<T, MAP, G, TD, GEOM, VS, false>;
@@ -1150,6 +1157,7 @@ bool push_forward_broadcast_flat(int map_type, const T* U, const T* J, const T* 
   p.ndofs = int(rows);
   p.tab_stride = int(rows) * tdim;
   p.nstates = 1;
+  p.ppc = 1;
   p.out_pitch = rows * size_t(gdim);
   p.dof_slot = nullptr;
   p.slot_info = nullptr;
@@ -1179,7 +1187,7 @@ int physical_basis_chunk(const bx_element& e, size_t npts)
 template <typename T>
 void physical_basis_device(const bx_element& e, int op, const T* U, size_t npts, const T* coords, const T* J,
                            const T* detJ, const T* K, const uint32_t* cell_info, size_t nc, int gdim, T* out,
-                           cudaStream_t s)
+                           cudaStream_t s, int per_point)
 {
   const int tdim = e.tdim, vs = e.vs, map = e.map_type;
   if (op < 0 or op > 3)
@@ -1207,7 +1215,14 @@ void physical_basis_device(const bx_element& e, int op, const T* U, size_t npts,
   if (transform)
     require_device(e);
   const int out_vs = map == BX_MAP_IDENTITY ? vs : gdim;
-  const int chunk = physical_basis_chunk(e, npts);
+  // per-point geometry (non-affine cells): J[nc][npts][gdim][tdim], detJ[nc][npts], K[nc][npts][tdim][gdim].  The kernel's
+  // "cells" are the (cell, point) items: rows = ndofs, one state table for all points, every item with its own matrix.
+  const bool items = per_point != 0 and map != BX_MAP_IDENTITY and npts > 1;
+  if (per_point and geom)
+    fail(BX_ERR_INVALID_ARG, "physical_basis: per-point geometry is given as J / detJ / K, not as vertex coordinates");
+  if (items and npts * size_t(e.ndofs) >= 8192)
+    fail(BX_ERR_UNSUPPORTED, "physical_basis: too many points for one pass (split the point set)");
+  const int chunk = items ? int(npts) : physical_basis_chunk(e, npts);
   const size_t slab = size_t(chunk) * e.ndofs * vs; // entries of one state's table
   // scratch: the 8 state tables and their cell_info words (stream-ordered allocation: capturable, no host sync)
   T* tab = nullptr;
@@ -1244,8 +1259,14 @@ void physical_basis_device(const bx_element& e, int op, const T* U, size_t npts,
         // what bx_T_apply gives a caller who transforms the replicated reference values cell by cell
         dof_transform_device<T>(e, op, tab, size_t(8) * np, size_t(e.ndofs) * vs, vs, st_ci, s);
       }
-      p.rows = np * e.ndofs;
+      p.rows = items ? e.ndofs : np * e.ndofs;
       p.tab_stride = int(period);
+      p.ppc = items ? np : 1;
+      if (items)
+      {
+        p.nc = nc * npts;
+        p.out_pitch = size_t(e.ndofs) * out_vs;
+      }
       T* o = out + p0 * size_t(e.ndofs) * out_vs;
       const T* A = map == BX_MAP_COVARIANT_PIOLA ? K : J;
       if (map == BX_MAP_IDENTITY)
@@ -1282,7 +1303,8 @@ template void geometry_device<float>(const float*, const float*, size_t, int, in
                                      cudaStream_t);
 template void physical_basis_device<double>(const bx_element&, int, const double*, size_t, const double*, const double*,
                                             const double*, const double*, const uint32_t*, size_t, int, double*,
-                                            cudaStream_t);
+                                            cudaStream_t, int);
 template void physical_basis_device<float>(const bx_element&, int, const float*, size_t, const float*, const float*,
-                                           const float*, const float*, const uint32_t*, size_t, int, float*, cudaStream_t);
+                                           const float*, const float*, const uint32_t*, size_t, int, float*, cudaStream_t,
+                                           int);
 } // namespace bx

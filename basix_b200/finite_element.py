@@ -720,10 +720,13 @@ class FiniteElement:
         -- the reference's three calls (``tabulate`` once; per cell ``T_apply`` on the reference values with block size =
         value size, then ``push_forward``).  Geometry: ``coords`` (ncells, tdim + 1, gdim) of affine triangle / tetrahedron
         cells (J, detJ, K are computed on chip), or ``J`` (ncells, gdim, tdim), ``detJ`` (ncells,), ``K`` (ncells, tdim,
-        gdim) per cell.  ``cell_info``: (ncells,) uint32 or None.  Pass ``U`` = ``tabulate(0, X)[0]`` (npts, ndofs,
-        value_size) instead of ``X`` to reuse a table.  Returns (ncells, npts, ndofs, physical value size)."""
+        gdim) per cell -- or, for non-affine cells, per (cell, point): ``J`` (ncells, npts, gdim, tdim), ``detJ`` (ncells,
+        npts), ``K`` (ncells, npts, tdim, gdim), what ``geometry(coords, dphi)`` returns.  ``cell_info``: (ncells,) uint32 or
+        None.  Pass ``U`` = ``tabulate(0, X)[0]`` (npts, ndofs, value_size) instead of ``X`` to reuse a table.  Returns
+        (ncells, npts, ndofs, physical value size)."""
         given = U if X is None else X
         dt = _float_dtype(given)
+        pointwise = False
         geo = [a for a in (coords, J, detJ, K) if a is not None]
         if not geo and int(self._map_type) != 0:
             raise TypeError("physical_basis: pass coords, or J / detJ / K")
@@ -740,10 +743,12 @@ class FiniteElement:
             nc, gdim = args["coords"].shape[0], args["coords"].shape[2]
         elif args["K"] is not None or args["J"] is not None:
             m = args["K"] if args["K"] is not None else args["J"]
-            if len(m.shape) != 3:
-                raise TypeError("J must have shape (ncells, gdim, tdim) and K (ncells, tdim, gdim)")
+            if len(m.shape) == 4:
+                pointwise = True  # non-affine cells: one Jacobian per (cell, point), as bx.geometry(coords, dphi) returns
+            elif len(m.shape) != 3:
+                raise TypeError("J must have shape (ncells, [npts,] gdim, tdim) and K (ncells, [npts,] tdim, gdim)")
             nc = m.shape[0]
-            gdim = m.shape[2] if args["K"] is not None else m.shape[1]
+            gdim = m.shape[-1] if args["K"] is not None else m.shape[-2]
         else:
             if ci is None:
                 raise TypeError("physical_basis: the number of cells is unknown (no geometry, no cell_info)")
@@ -753,6 +758,29 @@ class FiniteElement:
         out_vs = self._vs if int(self._map_type) == 0 else gdim
         stream, alloc = _stream_and_like(ga)
         ptr = {k: (None if a is None else a.ptr) for k, a in args.items()}
+        if pointwise:
+            npts = ga.shape[0]
+            for name in ("J", "K"):
+                if args[name] is not None and (len(args[name].shape) != 4 or args[name].shape[:2] != (nc, npts)):
+                    raise RuntimeError("per-point geometry: J (ncells, npts, gdim, tdim), detJ (ncells, npts), K (ncells, npts, "
+                                       "tdim, gdim) with npts = the number of points")
+            if args["detJ"] is not None and args["detJ"].shape != (nc, npts):
+                raise RuntimeError("per-point geometry: detJ must have shape (ncells, npts)")
+            if dt is not np.float64:
+                raise TypeError("per-point geometry: float64 only")
+            out = alloc((nc, npts, self._ndofs, out_vs), dt)
+            cip = None if ci is None else ci.ptr
+            if U is None:
+                if len(ga.shape) != 2:
+                    raise TypeError("X must have shape (npts, tdim)")
+                check(lib().bx_physical_basis_pointwise_f64(self._h, T_OPS[op], ga.ptr, npts, ga.shape[1], ptr["J"], ptr["detJ"],
+                                                            ptr["K"], cip, nc, gdim, _ptr_of(out), mem, stream))
+            else:
+                if len(ga.shape) != 3 or ga.shape[1:] != (self._ndofs, self._vs):
+                    raise TypeError("U must have shape (npts, ndofs, value_size)")
+                check(lib().bx_push_forward_fused_pointwise_f64(self._h, T_OPS[op], ga.ptr, npts, ptr["J"], ptr["detJ"], ptr["K"],
+                                                                cip, nc, gdim, _ptr_of(out), mem, stream))
+            return out
         if U is None:
             if len(ga.shape) != 2:
                 raise TypeError("X must have shape (npts, tdim)")

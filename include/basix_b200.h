@@ -367,6 +367,19 @@ extern "C"
   int bx_interpolate_f32(const bx_element* e, int layout, const float* values, size_t nc, float* coefficients,
                          int mem, bx_stream_t stream);
 
+  /* The same fused pass for NON-AFFINE cells (hexahedra, curved simplices): the Jacobian varies from point to point, so the
+     geometry is J[nc][npts][gdim][tdim], detJ[nc][npts], K[nc][npts][tdim][gdim] -- exactly what bx_geometry writes when it
+     is given the derivatives of the coordinate element --
+         out[c][p][dof][:] = push_forward( T_op(cell_info[c]) U[p] , J[c][p], detJ[c][p], K[c][p] ).
+     Covariant and contravariant Piola maps (the identity map has no geometry: use bx_push_forward_fused); the state tables
+     of all points must fit in shared memory (npts * ndofs below about 900 rows for 3-component float64 values).  Equal,
+     bit for bit, to T_apply on the replicated reference values followed by push_forward with nc * npts Jacobians. */
+  int bx_physical_basis_pointwise_f64(const bx_element* e, int op, const double* X, size_t npts, int tdim_x, const double* J,
+                                      const double* detJ, const double* K, const uint32_t* cell_info, size_t nc, int gdim,
+                                      double* out, int mem, bx_stream_t stream);
+  int bx_push_forward_fused_pointwise_f64(const bx_element* e, int op, const double* U, size_t npts, const double* J,
+                                          const double* detJ, const double* K, const uint32_t* cell_info, size_t nc, int gdim,
+                                          double* out, int mem, bx_stream_t stream);
   /* Replaces basix::compute_interpolation_operator (interpolation.cpp:16-116; python
      basix.compute_interpolation_operator): the matrix taking the coefficients of a function in `from` to those of its
      interpolant in `to` -- `from` tabulated at to's points(), to's interpolation_matrix() applied -- composed on the

@@ -230,6 +230,49 @@ def test_physical_basis_against_three_calls(ref, family, cell, degree, variant, 
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("family,cell,degree,variant", [(N1E, TET, 3, LEG), (RT, TET, 2, LEG), (RT, TRI, 2, LEG), (N1E, TRI, 1, LEG)])
+@pytest.mark.parametrize("npts,nc", [(2, 5), (5, 517), (13, 100)])
+def test_physical_basis_per_point_geometry(ref, family, cell, degree, variant, npts, nc):
+    """Non-affine cells (curved P2 simplices): the Jacobian varies from point to point.  bx.geometry(coords, dphi) feeds
+    the fused pass, which must equal -- bit for bit -- T_apply on the replicated reference values followed by
+    push_forward with one Jacobian per (cell, point); and the reference's own calls to 1e-12.  Host and device pointers."""
+    import torch
+
+    import basix_b200 as bx
+
+    r, e = make_pair(ref, family, cell, degree, variant)
+    rg, _ = make_pair(ref, P, cell, 2, GLL)  # the P2 coordinate element
+    tdim, nd, vs = r.tdim, r.dim, r.value_size
+    rng = np.random.default_rng(npts + nc)
+    X = random_points(cell, npts, seed=9)
+    dphi = np.ascontiguousarray(rg.tabulate(1, X)[1:, :, :, 0])
+    coords = rg.points[None] + 0.04 * rng.standard_normal((nc, rg.dim, tdim))
+    J, detJ, K = bx.geometry(coords, dphi)  # (nc, npts, ...)
+    ci = cell_infos(nc)
+    got = e.physical_basis(X, J=J, detJ=detJ, K=K, cell_info=ci)
+    assert got.shape == (nc, npts, nd, tdim)
+    # the library's own separate calls
+    Ub = e.tabulate(0, X)[0]
+    rep = np.ascontiguousarray(np.broadcast_to(Ub.reshape(1, npts, nd * vs), (nc, npts, nd * vs))).reshape(nc * npts, nd * vs)
+    e.T_apply_batch(rep, vs, np.repeat(ci, npts))
+    two = e.push_forward(rep.reshape(nc * npts, nd, vs), J.reshape(nc * npts, tdim, tdim), detJ.reshape(-1),
+                         K.reshape(nc * npts, tdim, tdim)).reshape(nc, npts, nd, tdim)
+    assert np.array_equal(got, two)
+    # the reference's
+    Ur = r.tabulate(0, X)[0]
+    repr_ = np.ascontiguousarray(np.broadcast_to(Ur.reshape(1, npts, nd * vs), (nc, npts, nd * vs))).reshape(nc * npts, nd * vs)
+    r.T_apply_batch("T_apply", repr_, vs, np.repeat(ci, npts))
+    want = r.push_forward(repr_.reshape(nc * npts, nd, vs), J.reshape(nc * npts, tdim, tdim), detJ.reshape(-1),
+                          K.reshape(nc * npts, tdim, tdim)).reshape(nc, npts, nd, tdim)
+    assert np.max(np.abs(got - want)) <= 1e-12 * np.max(np.abs(want))
+    # device pointers, and the table given instead of the points
+    dev = [torch.from_numpy(a).cuda() for a in (J, detJ, K)]
+    got_dev = e.physical_basis(None, U=torch.from_numpy(Ub).cuda(), J=dev[0], detJ=dev[1], K=dev[2],
+                               cell_info=torch.from_numpy(ci.view(np.int32)).cuda())
+    assert np.array_equal(got_dev.cpu().numpy(), got)
+
+
+@pytest.mark.gpu
 def test_physical_basis_other_operators_manifold_and_float32(ref):
     import basix_b200 as bx
 
