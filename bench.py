@@ -524,9 +524,10 @@ class PhysicalBasis:
     metric, unit = METRIC_CELLS, "cells/s"
     bound = "hbm"
 
-    def __init__(self, element, ref_args, nc, npts, desc, geometry_only=False):
+    def __init__(self, element, ref_args, nc, npts, desc, geometry_only=False, pointwise=False):
         self.element_name, self.ref_args, self.nc, self.npts, self.desc = element, ref_args, nc, npts, desc
         self.geometry_only = geometry_only
+        self.pointwise = pointwise  # per-(cell, point) Jacobians given (non-affine cells)
 
     def setup(self, rank, device_only=False):
         import torch
@@ -571,6 +572,14 @@ class PhysicalBasis:
             self.config = {"workload": self.desc, "cells_per_gpu": nc, "points_per_cell": self.npts, "rows_per_cell": rows,
                            "bytes_per_cell_fused": 100 + self.out_bytes, "bytes_per_cell_three_calls": unfused,
                            "l2": "arrays are %.2f GB per step (>> 126 MB L2)" % (self.alg_bytes / 1e9)}
+        if self.pointwise:
+            g = torch.Generator(device="cuda").manual_seed(51 + rank)
+            self.Jp = (torch.eye(3, device="cuda", dtype=torch.float64)[None, None]
+                       + 0.2 * torch.randn(nc, self.npts, 3, 3, generator=g, device="cuda", dtype=torch.float64)).contiguous()
+            self.dp = torch.linalg.det(self.Jp)
+            self.Kp = torch.linalg.inv(self.Jp).contiguous()
+            self.alg_bytes = nc * (self.npts * 72 + 4 + self.out_bytes)
+            self.config["geometry"] = "one Jacobian per (cell, point): K[nc][npts][3][3] read, nothing computed on chip"
         self.flops = 0.0
         if not device_only:
             self.coords_host = self.coords.cpu().pin_memory()
@@ -581,6 +590,8 @@ class PhysicalBasis:
             self.result = self.geometry(self.coords, self.dphi)
         elif self.geometry_only:
             self.result = self.geometry(self.coords)
+        elif self.pointwise:
+            self.result = self.e.physical_basis(None, U=self.U, J=self.Jp, detJ=self.dp, K=self.Kp, cell_info=self.ci)
         else:
             self.result = self.e.physical_basis(None, U=self.U, coords=self.coords, cell_info=self.ci)
 
@@ -589,7 +600,7 @@ class PhysicalBasis:
         push_forward), timed on a 2M-cell slice: what the fusion saves."""
         import torch
 
-        if self.geometry_only:
+        if self.geometry_only or self.pointwise:
             return None
         import basix_b200 as bx
 
@@ -879,6 +890,10 @@ WORKLOADS = {
     "physical_basis_n1curl3_4pts": lambda: PhysicalBasis(
         "N1curl3_tetrahedron_legendre", (3, 3, 3, 11), 5_000_000, 4,
         "N1curl degree 3 tetrahedron: fused physical basis at 4 points per cell (180 rows), 5M cells"),
+    "physical_basis_n1curl3_pointwise_4pts": lambda: PhysicalBasis(
+        "N1curl3_tetrahedron_legendre", (3, 3, 3, 11), 5_000_000, 4,
+        "N1curl degree 3 tetrahedron: fused physical basis at 4 points per cell with one Jacobian per (cell, point) "
+        "(non-affine cells), 5M cells", pointwise=True),
     "interpolate_n1curl3": lambda: Interpolate(
         "N1curl3_tetrahedron_legendre", (3, 3, 3, 11), 20_000_000,
         "N1curl degree 3 tetrahedron, interpolation_matrix (45 x 141) applied to 20M cells of point values"),
@@ -917,6 +932,7 @@ SIDE_CONFIGS = [
     ("geometry_hex", {}),
     ("physical_basis_n1curl3", {}),
     ("physical_basis_rt4", {}),
+    ("physical_basis_n1curl3_4pts", {}),
 ]
 
 
