@@ -305,6 +305,32 @@ public:
     check(bx_interpolate_f64(_h, layout, values, nc, coefficients, mem, stream));
   }
 
+  /// coefficients[c] = interpolation_matrix() * pull_back(u[c], J[c], detJ[c], K[c]) in one pass (u[nc][npts][gdim])
+  void interpolate_pulled_batch(const double* u, const double* J, const double* detJ, const double* K, std::size_t nc,
+                                int gdim, double* coefficients, int mem = BX_MEM_HOST, bx_stream_t stream = nullptr) const
+  {
+    check(bx_interpolate_pulled_f64(_h, u, J, detJ, K, nc, gdim, coefficients, mem, stream));
+  }
+  /// out[c][p][dof][:] = push_forward(T_op(cell_info[c]) tabulate(0, X)[0][p], geometry of cell c): tabulate once, T_apply
+  /// and push_forward fused.  Geometry: coords[nc][tdim + 1][gdim] of affine simplex cells (J, detJ, K computed on chip),
+  /// or J / detJ / K per cell (coords == nullptr), or -- per_point -- per (cell, point) for non-affine cells.
+  void physical_basis(const double* X, std::size_t npts, const double* coords, const double* J, const double* detJ,
+                      const double* K, const std::uint32_t* cell_info, std::size_t nc, int gdim, double* out,
+                      int op = BX_T_APPLY, bool per_point = false, int mem = BX_MEM_HOST, bx_stream_t stream = nullptr) const
+  {
+    if (per_point)
+      check(bx_physical_basis_pointwise_f64(_h, op, X, npts, _tdim, J, detJ, K, cell_info, nc, gdim, out, mem, stream));
+    else
+      check(bx_physical_basis_f64(_h, op, X, npts, _tdim, coords, J, detJ, K, cell_info, nc, gdim, out, mem, stream));
+  }
+  /// J, detJ, K of nc cells at npts points from node coordinates and the coordinate element's derivatives
+  /// (dphi == nullptr: affine simplex cells, npts = 1)
+  static void geometry(const double* coords, const double* dphi, std::size_t nc, int nv, int gdim, int tdim, int npts,
+                       double* J, double* detJ, double* K, int mem = BX_MEM_HOST, bx_stream_t stream = nullptr)
+  {
+    check(bx_geometry_f64(coords, dphi, nc, nv, gdim, tdim, npts, J, detJ, K, mem, stream));
+  }
+
 private:
   FiniteElement() = default;
   void read_info()
