@@ -93,6 +93,7 @@ SIGNATURES = {
     "bx_physical_basis_f64": (_I, [_P, _I, _P, _SIZE, _I, _P, _P, _P, _P, _P, _SIZE, _I, _P, _I, _P]),
     "bx_physical_basis_pointwise_f64": (_I, [_P, _I, _P, _SIZE, _I, _P, _P, _P, _P, _SIZE, _I, _P, _I, _P]),
     "bx_push_forward_fused_pointwise_f64": (_I, [_P, _I, _P, _SIZE, _P, _P, _P, _P, _SIZE, _I, _P, _I, _P]),
+    "bx_push_forward_fused_pointwise_f32": (_I, [_P, _I, _P, _SIZE, _P, _P, _P, _P, _SIZE, _I, _P, _I, _P]),
     "bx_T_apply_f64": (_I, [_P, _I, _P, _SIZE, _SIZE, _I, _P, _I, _P]),
     "bx_T_apply_f32": (_I, [_P, _I, _P, _SIZE, _SIZE, _I, _P, _I, _P]),
     "bx_T_apply_i32": (_I, [_P, _I, _P, _SIZE, _SIZE, _I, _P, _I, _P]),
@@ -103,6 +104,7 @@ SIGNATURES = {
     "bx_interpolate_f64": (_I, [_P, _I, _P, _SIZE, _P, _I, _P]),
     "bx_interpolate_f32": (_I, [_P, _I, _P, _SIZE, _P, _I, _P]),
     "bx_interpolate_pulled_f64": (_I, [_P, _P, _P, _P, _P, _SIZE, _I, _P, _I, _P]),
+    "bx_interpolate_pulled_f32": (_I, [_P, _P, _P, _P, _P, _SIZE, _I, _P, _I, _P]),
     "bx_compute_interpolation_operator_f64": (_I, [_P, _P, _P, _P, _I, _P]),
     "bx_make_quadrature": (_I, [_I, _I, _P, _P, C.POINTER(C.c_size_t)]),
     "bx_gauss_jacobi_rule": (_I, [C.c_double, _I, _P, _P]),

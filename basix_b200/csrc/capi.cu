@@ -1151,6 +1151,11 @@ extern "C"
   {
     return bx::guarded([&]() { bx::interpolate_pulled_any<double>(e, u, J, detJ, K, nc, gdim, coefficients, mem, stream); });
   }
+  int bx_interpolate_pulled_f32(const bx_element* e, const float* u, const float* J, const float* detJ, const float* K, size_t nc,
+                                int gdim, float* coefficients, int mem, bx_stream_t stream)
+  {
+    return bx::guarded([&]() { bx::interpolate_pulled_any<float>(e, u, J, detJ, K, nc, gdim, coefficients, mem, stream); });
+  }
   int bx_interpolate_f32(const bx_element* e, int layout, const float* values, size_t nc, float* coefficients, int mem,
                          bx_stream_t stream)
   {
@@ -1241,6 +1246,14 @@ extern "C"
           bx::require(X != nullptr or npts == 0, "physical_basis: null points");
           bx::physical_basis_any<double>(e, op, X, nullptr, npts, nullptr, J, detJ, K, cell_info, nc, gdim, out, mem, stream, 1);
         });
+  }
+  int bx_push_forward_fused_pointwise_f32(const bx_element* e, int op, const float* U, size_t npts, const float* J,
+                                          const float* detJ, const float* K, const uint32_t* cell_info, size_t nc, int gdim,
+                                          float* out, int mem, bx_stream_t stream)
+  {
+    return bx::guarded(
+        [&]()
+        { bx::physical_basis_any<float>(e, op, nullptr, U, npts, nullptr, J, detJ, K, cell_info, nc, gdim, out, mem, stream, 1); });
   }
   int bx_push_forward_fused_pointwise_f64(const bx_element* e, int op, const double* U, size_t npts, const double* J,
                                           const double* detJ, const double* K, const uint32_t* cell_info, size_t nc, int gdim,

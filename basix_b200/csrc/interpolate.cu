@@ -479,6 +479,8 @@ void interpolate_pulled_device(const bx_element& e, const T* u, const T* J, cons
 }
 template void interpolate_pulled_device<double>(const bx_element&, const double*, const double*, const double*, const double*,
                                                 size_t, int, double*, cudaStream_t);
+template void interpolate_pulled_device<float>(const bx_element&, const float*, const float*, const float*, const float*, size_t,
+                                               int, float*, cudaStream_t);
 
 // ---- compute_interpolation_operator (reference cpp/basix/interpolation.cpp:16-116) --------------------------------
 // The matrix that maps the coefficients of a function in `from` to the coefficients of its interpolant in `to`:

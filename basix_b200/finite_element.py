@@ -766,10 +766,14 @@ class FiniteElement:
                                        "tdim, gdim) with npts = the number of points")
             if args["detJ"] is not None and args["detJ"].shape != (nc, npts):
                 raise RuntimeError("per-point geometry: detJ must have shape (ncells, npts)")
-            if dt is not np.float64:
-                raise TypeError("per-point geometry: float64 only")
             out = alloc((nc, npts, self._ndofs, out_vs), dt)
             cip = None if ci is None else ci.ptr
+            if dt is np.float32:
+                Ut = self.tabulate(0, X)[0] if U is None else U
+                ta = _Arg(Ut, dt, "U")
+                check(lib().bx_push_forward_fused_pointwise_f32(self._h, T_OPS[op], ta.ptr, npts, ptr["J"], ptr["detJ"], ptr["K"],
+                                                                cip, nc, gdim, _ptr_of(out), mem, stream))
+                return out
             if U is None:
                 if len(ga.shape) != 2:
                     raise TypeError("X must have shape (npts, tdim)")
@@ -974,8 +978,9 @@ class FiniteElement:
         Returns (ncells, ndofs)."""
         if self._points is None:
             raise RuntimeError("interpolate: the element was built without points() / interpolation_matrix()")
-        ua, Ja = _Arg(u, np.float64, "u"), _Arg(J, np.float64, "J")
-        da, Ka = _Arg(detJ, np.float64, "detJ"), _Arg(K, np.float64, "K")
+        dt = _float_dtype(u)
+        ua, Ja = _Arg(u, dt, "u"), _Arg(J, dt, "J")
+        da, Ka = _Arg(detJ, dt, "detJ"), _Arg(K, dt, "K")
         mem = _same_mem(ua, Ja, da, Ka)
         npts = self._points.shape[0]
         if len(ua.shape) != 3 or ua.shape[1] != npts or len(Ja.shape) != 3:
@@ -984,8 +989,9 @@ class FiniteElement:
         if ua.shape[0] != nc or ua.shape[2] != gdim or da.shape != (nc,) or Ka.shape != (nc, tdim, gdim):
             raise RuntimeError("interpolate_pulled: inconsistent array shapes")
         stream, alloc = _stream_and_like(ua)
-        out = alloc((nc, self._ndofs), np.float64)
-        check(lib().bx_interpolate_pulled_f64(self._h, ua.ptr, Ja.ptr, da.ptr, Ka.ptr, nc, gdim, _ptr_of(out), mem, stream))
+        out = alloc((nc, self._ndofs), dt)
+        fn = lib().bx_interpolate_pulled_f32 if dt is np.float32 else lib().bx_interpolate_pulled_f64
+        check(fn(self._h, ua.ptr, Ja.ptr, da.ptr, Ka.ptr, nc, gdim, _ptr_of(out), mem, stream))
         return out
 
     # ---- sub-entity closure permutations ---------------------------------------------------------------

@@ -363,6 +363,9 @@ extern "C"
      multiply-adds in the map, another summation order in the contraction: <= 1e-13 relative). */
   int bx_interpolate_pulled_f64(const bx_element* e, const double* u, const double* J, const double* detJ, const double* K,
                                 size_t nc, int gdim, double* coefficients, int mem, bx_stream_t stream);
+  /* float32 arrays (loads widen, stores narrow; matrix and arithmetic float64) */
+  int bx_interpolate_pulled_f32(const bx_element* e, const float* u, const float* J, const float* detJ, const float* K, size_t nc,
+                                int gdim, float* coefficients, int mem, bx_stream_t stream);
   /* float32 values / coefficients (the reference's FiniteElement<float>); the matrix and the arithmetic are float64 */
   int bx_interpolate_f32(const bx_element* e, int layout, const float* values, size_t nc, float* coefficients,
                          int mem, bx_stream_t stream);
@@ -380,6 +383,9 @@ extern "C"
   int bx_push_forward_fused_pointwise_f64(const bx_element* e, int op, const double* U, size_t npts, const double* J,
                                           const double* detJ, const double* K, const uint32_t* cell_info, size_t nc, int gdim,
                                           double* out, int mem, bx_stream_t stream);
+  int bx_push_forward_fused_pointwise_f32(const bx_element* e, int op, const float* U, size_t npts, const float* J,
+                                          const float* detJ, const float* K, const uint32_t* cell_info, size_t nc, int gdim,
+                                          float* out, int mem, bx_stream_t stream);
   /* Replaces basix::compute_interpolation_operator (interpolation.cpp:16-116; python
      basix.compute_interpolation_operator): the matrix taking the coefficients of a function in `from` to those of its
      interpolant in `to` -- `from` tabulated at to's points(), to's interpolation_matrix() applied -- composed on the

@@ -270,6 +270,9 @@ def test_physical_basis_per_point_geometry(ref, family, cell, degree, variant, n
     got_dev = e.physical_basis(None, U=torch.from_numpy(Ub).cuda(), J=dev[0], detJ=dev[1], K=dev[2],
                                cell_info=torch.from_numpy(ci.view(np.int32)).cuda())
     assert np.array_equal(got_dev.cpu().numpy(), got)
+    got32 = e.physical_basis(X.astype(np.float32), J=J.astype(np.float32), detJ=detJ.astype(np.float32), K=K.astype(np.float32),
+                             cell_info=ci)
+    assert got32.dtype == np.float32 and np.allclose(got32, want, rtol=3e-4, atol=3e-4 * np.max(np.abs(want)))
 
 
 @pytest.mark.gpu

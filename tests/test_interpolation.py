@@ -229,6 +229,9 @@ def test_interpolate_pulled_equals_pull_back_then_interpolate(family, cell, degr
     U = r.pull_back(u, J, detJ, K)  # (nc, npts, tdim)
     want = np.einsum("nk,ck->cn", e.interpolation_matrix, U.transpose(0, 2, 1).reshape(nc, -1))
     assert np.max(np.abs(got - want)) <= 1e-12 * max(np.max(np.abs(want)), 1.0)
+    # float32 arrays: the float64 result to float32 accuracy
+    got32 = e.interpolate_pulled_batch(*[a.astype(np.float32) for a in (u, J, detJ, K)])
+    assert got32.dtype == np.float32 and np.allclose(got32, want, rtol=2e-4, atol=2e-4 * np.max(np.abs(want)))
 
 
 @pytest.mark.gpu
