@@ -317,7 +317,7 @@ using fpdiv::safe_reciprocal;
 // tiles leave as one TMA bulk copy each (or lane-consecutive stores when the run is ragged or unaligned).  K = adj / div
 // uses one reciprocal and FMA-corrected quotients (div_by below: bit-equal to IEEE division).  No block
 // barrier after the table is in shared memory; the tile position advances incrementally.
-// xcap: entries of the coordinate tile (>= cells per tile * odd pitch, and >= 32 * G * TD: it is reused for J).
+// xcap: entries of one coordinate buffer (>= cells per tile * odd pitch); a warp has two, filled by cp.async one tile ahead.
 template <typename T, int G, int TD>
 __global__ void __launch_bounds__(kThreads)
     geometry_warp_kernel(const T* __restrict__ coords, const T* __restrict__ dphi, size_t nc, int nv, uint32_t npts, int xcap,
@@ -328,10 +328,12 @@ __global__ void __launch_bounds__(kThreads)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ntab = TD * int(npts) * nv;
   T* s_d = reinterpret_cast<T*>(gw_smem); // [TD][nv][npts]
-  const int per_warp = xcap + ((32 * MA + 3) & ~3) + 32;
-  T* sx = s_d + ((ntab + 3) & ~3) + size_t(warp) * per_warp; // coordinates [cells][XP], then J [32][MA] dense
-  T* sK = sx + xcap;                                          // K [32][MA] dense
-  T* sd = sK + ((32 * MA + 3) & ~3);                          // detJ [32]
+  constexpr int TP = (32 * MA + 3) & ~3;
+  const int per_warp = 2 * xcap + 2 * TP + 32;
+  T* cb = s_d + ((ntab + 3) & ~3) + size_t(warp) * per_warp; // coordinates [2][cells][XP]: this tile's and the next one's
+  T* sx = cb + 2 * xcap;                                      // J [32][MA] dense
+  T* sK = sx + TP;                                            // K [32][MA] dense
+  T* sd = sK + TP;                                            // detJ [32]
   // the table is kept node-major, [TD][nv][npts]: lanes = consecutive points read consecutive entries (no bank conflicts)
   for (int i = threadIdx.x; i < ntab; i += kThreads)
   {
@@ -349,24 +351,39 @@ __global__ void __launch_bounds__(kThreads)
   uint32_t p0 = uint32_t(t0 - c0 * npts);
   const size_t dc = stride / npts;
   const uint32_t dp = uint32_t(stride - dc * npts);
+  // node coordinates of a tile's cells: global -> shared by cp.async, one tile ahead of the arithmetic
+  auto fetch = [&](size_t ft0, size_t fc0, uint32_t fp0, T* buf)
+  {
+    const uint32_t fr = uint32_t(min(size_t(32), total - ft0));
+    const uint32_t fcells = (fp0 + fr - 1) / npts + 1;
+    for (uint32_t q = lane; q < fcells * uint32_t(NX); q += 32)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(uint32_t(__cvta_generic_to_shared(buf + (q / NX) * XP + q % NX))),
+                   "l"(coords + fc0 * NX + q), "n"(sizeof(T))
+                   : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  fetch(t0, c0, p0, cb);
   bool pending = false;
+  int cur = 0;
   for (; t0 < total; t0 += stride)
   {
     const uint32_t nrow = uint32_t(min(size_t(32), total - t0));
-    const uint32_t ncell = (p0 + nrow - 1) / npts + 1;
-    if (pending)
-    {
-      if (lane < 3)
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      __syncwarp();
-      pending = false;
-    }
-    for (uint32_t q = lane; q < ncell * uint32_t(NX); q += 32)
-      sx[(q / NX) * XP + q % NX] = coords[c0 * NX + q];
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
+    // position of the next tile; its coordinates travel while this tile is computed
+    size_t cn = c0 + dc;
+    uint32_t pn = p0 + dp;
+    if (pn >= npts)
+    {
+      pn -= npts;
+      ++cn;
+    }
+    if (t0 + stride < total)
+      fetch(t0 + stride, cn, pn, cb + (cur ^ 1) * xcap);
+    const T* sxc = cb + cur * xcap;
     const uint32_t il = p0 + min(uint32_t(lane), nrow - 1); // lanes past the last item repeat it and do not store
     const uint32_t off = il / npts, pt = il - off * npts;
-    const T* xc = sx + off * XP;
+    const T* xc = sxc + off * XP;
     T J[G][TD];
 #pragma unroll
     for (int g = 0; g < G; ++g)
@@ -388,9 +405,16 @@ __global__ void __launch_bounds__(kThreads)
           J[g][a] += xg * dv[a];
       }
     }
-    __syncwarp(); // the coordinate tile is overwritten by J below
     T adj[TD][G], div;
     adjugate<T, G, TD>(J, adj, div);
+    if (pending)
+    {
+      // the result tiles of the previous item tile have been read by the copy engine
+      if (lane < 3)
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+      pending = false;
+    }
 #pragma unroll
     for (int g = 0; g < G; ++g)
 #pragma unroll
@@ -441,13 +465,9 @@ __global__ void __launch_bounds__(kThreads)
         detout[t0 + lane] = sd[lane];
       __syncwarp();
     }
-    c0 += dc;
-    p0 += dp;
-    if (p0 >= npts)
-    {
-      p0 -= npts;
-      ++c0;
-    }
+    c0 = cn;
+    p0 = pn;
+    cur ^= 1;
   }
   if (pending and lane < 3)
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -894,9 +914,9 @@ void launch_geometry(const T* coords, const T* dphi, size_t nc, int nv, int npts
     // warp form: derivative table and the warps' tiles in shared memory (falls through when they do not fit)
     constexpr int MA = G * TD;
     const int cells_per_tile = std::min(32, 31 / npts + 2);
-    const int xcap = (std::max(cells_per_tile * ((nv * G) | 1), 32 * MA) + 3) & ~3;
+    const int xcap = (cells_per_tile * ((nv * G) | 1) + 3) & ~3; // one coordinate buffer (two per warp)
     const size_t ntab = (size_t(TD) * npts * nv + 3) & ~size_t(3);
-    const size_t smem = (ntab + size_t(kThreads / 32) * (xcap + ((32 * MA + 3) & ~3) + 32)) * sizeof(T);
+    const size_t smem = (ntab + size_t(kThreads / 32) * (2 * xcap + 2 * ((32 * MA + 3) & ~3) + 32)) * sizeof(T);
     static const bool warp_form = []
     {
       const char* v = std::getenv("BX_GEOM_WARP"); // development knob: 0 selects the thread-per-item kernel
