@@ -1228,6 +1228,8 @@ def run_ours(args, w, rank, local_rank, world):
                     sw.step()
                 torch.cuda.synchronize()
                 ksteps = max(3, min(args.steps, 10))
+                if getattr(sw, "flush_l2", False):
+                    ksteps = 50  # a 20-microsecond launch timed step by step: many samples, each behind its own L2 flush
                 tms, nl = time_steps(sw, ksteps)
                 sms = tms / ksteps
                 rf = roofline_of(sw, name, sms)
@@ -1237,6 +1239,7 @@ def run_ours(args, w, rank, local_rank, world):
                                  "roofline": {k: rf[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic",
                                                                  "ms_per_launch", "launches_per_step",
                                                                  "frac_of_copy_same_bytes", "copy_same_bytes_ms",
+                                                                 "event_pair_empty_launch_ms", "frac_net_of_empty_launch",
                                                                  "line_granular") if k in rf},
                                  "l2": sw.config.get("l2")}
                 if rf["bound"] == "tensor":
