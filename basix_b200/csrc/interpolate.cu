@@ -327,8 +327,6 @@ __device__ __forceinline__ void run_group_pulled(const PullParams<T>& p, const d
 #pragma unroll
       for (int i = 0; i < D; ++i)
       {
-        constexpr int dummy = 0;
-        (void)dummy;
         const int cur = (s * D + i) & 1;
         // next k-step: the next block of this point step, or block 0 of the next point step
         const int nb = i + 1 < D ? i + 1 : 0;
