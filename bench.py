@@ -650,6 +650,9 @@ class PhysicalBasis:
             self.out_host = torch.empty((self.nc, self.npts, self.e.dim, 3), dtype=torch.float64).pin_memory()
             self.X_host = self.X.cpu()
             self.h2d, self.d2h = self.nc * 100 + self.X_host.numel() * 8, self.out_host.numel() * 8
+            if self.pointwise:
+                self.K_host = self.Kp.cpu().pin_memory()
+                self.h2d = self.nc * (self.npts * 72 + 4) + self.X_host.numel() * 8
         return {"cells_per_gpu": self.nc}
 
     def e2e_step(self):
@@ -664,6 +667,10 @@ class PhysicalBasis:
             J, d, K = self.out_host
             _capi.check(L.bx_geometry_f64(self.coords_host.data_ptr(), None, self.nc, 4, 3, 3, 1, J.data_ptr(), d.data_ptr(),
                                           K.data_ptr(), _capi.BX_MEM_HOST, None))
+        elif self.pointwise:
+            _capi.check(L.bx_physical_basis_pointwise_f64(self.e._h, 0, self.X_host.data_ptr(), self.npts, 3, None, None,
+                                                          self.K_host.data_ptr(), self.ci_host.data_ptr(), self.nc, 3,
+                                                          self.out_host.data_ptr(), _capi.BX_MEM_HOST, None))
         else:
             # points in, physical basis functions out: the reference values never exist on the host
             _capi.check(L.bx_physical_basis_f64(self.e._h, 0, self.X_host.data_ptr(), self.npts, 3,
@@ -1133,6 +1140,8 @@ def run_ours(args, w, rank, local_rank, world):
         host = getattr(w, "out_host", None)
         if host is None:
             host = getattr(w, "data_host", None)
+        if isinstance(host, (list, tuple)):  # several result arrays (geometry): the largest one stands for the leg
+            host = max(host, key=lambda h: h.numel())
         if host is not None and host.numel() * host.element_size() >= (64 << 20):
             flat = host.view(-1).view(torch.uint8) if host.is_contiguous() else None
         else:
