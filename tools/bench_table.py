@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """Print the headline and the per-config figures of one bench.py JSON line as a table."""
 import json
+import signal
 import sys
+
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)  # `| head` closes the pipe early
 
 d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
 r = d.get("roofline") or {}
