@@ -156,6 +156,27 @@ def interpolate_sharded(element, values, layout: str = "component-major", gather
     return gather_cells(local, values.shape[0], dst, group) if gather else local
 
 
+def interpolate_pulled_sharded(element, u, J, detJ, K, gather: bool = False, dst: int | None = None, group=None):
+    """``interpolate_pulled_batch`` (pull_back fused into the interpolation) on this rank's slice of the cells."""
+    _, world, rank = _dist(group)
+    lo, hi = shard_bounds(u.shape[0], world, rank)
+    local = element.interpolate_pulled_batch(u[lo:hi], J[lo:hi], detJ[lo:hi], K[lo:hi])
+    return gather_cells(local, u.shape[0], dst, group) if gather else local
+
+
+def physical_basis_sharded(element, X, coords=None, J=None, detJ=None, K=None, cell_info=None, op: str = "T_apply",
+                           gather: bool = False, dst: int | None = None, group=None):
+    """``physical_basis`` (tabulate once, T_apply and push_forward fused) on this rank's slice of the cells; the points
+    ``X`` are the same on every rank, every per-cell array is sliced."""
+    _, world, rank = _dist(group)
+    first = next(a for a in (coords, J, K, detJ, cell_info) if a is not None)
+    nc = first.shape[0]
+    lo, hi = shard_bounds(nc, world, rank)
+    cut = lambda a: None if a is None else a[lo:hi]  # noqa: E731
+    local = element.physical_basis(X, coords=cut(coords), J=cut(J), detJ=cut(detJ), K=cut(K), cell_info=cut(cell_info), op=op)
+    return gather_cells(local, nc, dst, group) if gather else local
+
+
 def T_apply_sharded(element, data, block_size: int, cell_info, op: str = "T_apply", group=None):
     """In-place DOF transformation of this rank's slice of the cells of ``data[ncells][ndofs*block_size]``;
     returns the slice bounds.  (In place: there is nothing to gather unless the caller wants the slices

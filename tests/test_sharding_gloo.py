@@ -66,6 +66,23 @@ class _OracleElement:
         assert layout == "component-major"
         return torch.from_numpy(values.numpy() @ self.M.T)
 
+    def interpolate_pulled_batch(self, u, J, detJ, K):
+        U = self.pull_back(u, J, detJ, K).numpy()  # (nc, npts, vs) -> the reference's component-major columns
+        return self.interpolate_batch(__import__("torch").from_numpy(np.ascontiguousarray(U.transpose(0, 2, 1)).reshape(len(U), -1)))
+
+    def physical_basis(self, X, coords=None, J=None, detJ=None, K=None, cell_info=None, op="T_apply"):
+        import torch
+
+        from oracle import restate as R
+
+        U = self.e.tabulate(0, X.numpy())[0]  # (npts, ndofs, vs)
+        npts, nd, vs = U.shape
+        Jn, dn, Kn = R.geometry(coords.numpy())
+        nc = len(Jn)
+        rep = np.ascontiguousarray(np.broadcast_to(U.reshape(1, npts, nd * vs), (nc, npts, nd * vs))).reshape(nc * npts, nd * vs)
+        self.e.T_apply_batch(op, rep, vs, np.repeat(cell_info.numpy(), npts))
+        return torch.from_numpy(self.e.push_forward(rep.reshape(nc, npts * nd, vs), Jn, dn, Kn).reshape(nc, npts, nd, -1))
+
 
 def _worker(rank, world, port, out_dir):
     sys.path.insert(0, ROOT)
@@ -104,6 +121,20 @@ def _worker(rank, world, port, out_dir):
         vals = torch.from_numpy(rng.standard_normal((33, e.M.shape[1])))
         # (the stand-in's dgemm blocks a slice differently from the whole array: compare to rounding)
         assert torch.allclose(sharding.interpolate_sharded(e, vals, gather=True), e.interpolate_batch(vals), rtol=0, atol=1e-12)
+        # the fused calls: pull_back + interpolation, and tabulate-once -> T_apply -> push_forward from vertex coordinates
+        npts = e.M.shape[1] // 3
+        u = torch.from_numpy(rng.standard_normal((33, npts, 3)))
+        assert torch.allclose(sharding.interpolate_pulled_sharded(e, u, *args[1:], gather=True),
+                              e.interpolate_pulled_batch(u, *args[1:]), rtol=0, atol=1e-11)
+        verts = np.zeros((4, 3))
+        verts[1:] = np.eye(3)
+        coords = torch.from_numpy(verts[None] + 0.1 * rng.standard_normal((33, 4, 3)))
+        ci33 = torch.from_numpy(rng.integers(0, 2 ** 18, 33).astype(np.int64))
+        X = torch.from_numpy(rng.random((3, 3)) / 4)
+        want = e.physical_basis(X, coords=coords, cell_info=ci33)
+        assert torch.equal(sharding.physical_basis_sharded(e, X, coords=coords, cell_info=ci33, gather=True), want)
+        lo, hi = sharding.shard_bounds(33, world, rank)
+        assert torch.equal(sharding.physical_basis_sharded(e, X, coords=coords, cell_info=ci33), want[lo:hi])
         # in-place sharded T_apply, then exchange of the slices
         e = _OracleElement("RT2_tetrahedron_legendre")
         data = torch.from_numpy(rng.standard_normal((21, 15)))
