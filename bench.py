@@ -915,6 +915,9 @@ WORKLOADS = {
     "t_apply_rt4": lambda: TApply(
         "RT4_tetrahedron_legendre", (2, 3, 4, 11), 50_000_000, 1, False,
         "RT degree 4 tetrahedron, T_apply(block 1) over 50M cells, random cell_info"),
+    "t_apply_p5_tet": lambda: TApply(
+        "P5_tetrahedron_gll", (1, 3, 5, 2), 50_000_000, 1, False,
+        "P5 Lagrange tetrahedron, T_apply<double>(block 1) over 50M cells (permutation element), random cell_info"),
     "permute_p5_tet": lambda: TApply(
         "P5_tetrahedron_gll", (1, 3, 5, 2), 50_000_000, 1, True,
         "P5 Lagrange tetrahedron, permute (int32) over 50M cells, random cell_info"),
@@ -933,6 +936,7 @@ SIDE_CONFIGS = [
     ("t_apply_rt4", {}),
     ("t_apply_rt4_block3", {"nc": 50_000_000}),
     ("permute_p5_tet", {}),
+    ("t_apply_p5_tet", {}),
     ("interpolate_n1curl3", {}),
     ("interpolate_pulled_n1curl3", {}),
     ("geometry_tet", {}),
