@@ -9,7 +9,7 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 
-template <int MODE>
+template <int MODE, int ST = 0>
 __global__ void k(const int4* __restrict__ src, int4* __restrict__ dst, size_t nc, int cs16, int off16, int len16, int* sink)
 {
   const size_t total = nc * size_t(len16), stride = size_t(gridDim.x) * blockDim.x;
@@ -26,24 +26,31 @@ __global__ void k(const int4* __restrict__ src, int4* __restrict__ dst, size_t n
     else
     {
       v.x += 1;
-      dst[i] = v;
+      if (ST == 1)
+        __stcs(dst + i, v); // evict-first
+      else if (ST == 2)
+        __stwt(dst + i, v); // write-through
+      else if (ST == 3)
+        __stcg(dst + i, v); // cache at L2 only
+      else
+        dst[i] = v;
     }
   }
   if (MODE == 0 and acc == 0x7fffffff)
     *sink = acc;
 }
 
-template <int MODE>
+template <int MODE, int ST = 0>
 float run(const int4* src, int4* dst, size_t nc, int cs16, int off16, int len16, int* sink)
 {
   cudaEvent_t a, b;
   cudaEventCreate(&a);
   cudaEventCreate(&b);
   for (int i = 0; i < 3; ++i)
-    k<MODE><<<148 * 8, 256>>>(src, dst, nc, cs16, off16, len16, sink);
+    k<MODE, ST><<<148 * 8, 256>>>(src, dst, nc, cs16, off16, len16, sink);
   cudaEventRecord(a);
   for (int i = 0; i < 10; ++i)
-    k<MODE><<<148 * 8, 256>>>(src, dst, nc, cs16, off16, len16, sink);
+    k<MODE, ST><<<148 * 8, 256>>>(src, dst, nc, cs16, off16, len16, sink);
   cudaEventRecord(b);
   cudaEventSynchronize(b);
   float ms;
@@ -75,11 +82,15 @@ int main()
     const int cs16 = c.cs / 16, off16 = c.off / 16, len16 = c.len / 16;
     const float rd = run<0>(a, a, c.nc, cs16, off16, len16, sink), wr = run<1>(a, a, c.nc, cs16, off16, len16, sink),
                 in = run<2>(a, a, c.nc, cs16, off16, len16, sink), out = run<2>(a, b, c.nc, cs16, off16, len16, sink),
-                whole = run<2>(a, a, c.nc, cs16, 0, cs16, sink);
+                whole = run<2>(a, a, c.nc, cs16, 0, cs16, sink), in_cs = run<2, 1>(a, a, c.nc, cs16, off16, len16, sink),
+                in_wt = run<2, 2>(a, a, c.nc, cs16, off16, len16, sink), in_cg = run<2, 3>(a, a, c.nc, cs16, off16, len16, sink),
+                wr_cs = run<1, 1>(a, a, c.nc, cs16, off16, len16, sink), wr_wt = run<1, 2>(a, a, c.nc, cs16, off16, len16, sink);
     const double gb = double(c.nc) * c.len / 1e9;
     printf(" {\"case\": \"%s\", \"cells\": %zu, \"read_ms\": %.3f, \"write_ms\": %.3f, \"inplace_ms\": %.3f, \"outplace_ms\": %.3f, "
-           "\"whole_cells_inplace_ms\": %.3f, \"inplace_GBps_on_movable_bytes\": %.0f, \"cuda\": \"%s\"}%s\n",
-           c.name, c.nc, rd, wr, in, out, whole, 2 * gb / (in * 1e-3), cudaGetErrorString(cudaGetLastError()), ci < 2 ? "," : "");
+           "\"whole_cells_inplace_ms\": %.3f, \"inplace_stcs_ms\": %.3f, \"inplace_stwt_ms\": %.3f, \"inplace_stcg_ms\": %.3f, "
+           "\"write_stcs_ms\": %.3f, \"write_stwt_ms\": %.3f, \"inplace_GBps_on_movable_bytes\": %.0f, \"cuda\": \"%s\"}%s\n",
+           c.name, c.nc, rd, wr, in, out, whole, in_cs, in_wt, in_cg, wr_cs, wr_wt, 2 * gb / (in * 1e-3),
+           cudaGetErrorString(cudaGetLastError()), ci < 2 ? "," : "");
     cudaFree(a);
     cudaFree(b);
     cudaFree(sink);
